@@ -1,0 +1,91 @@
+"""ctypes loader for libblast_cuda.so (the C ABI declared in include/blast_cuda.h).
+
+There is no fallback: if the shared library is missing this module raises ImportError telling
+the user to build it (python -c "import __graft_entry__ as g; g.build()" or make -C
+audio_decoder_b200/csrc).  No compute ever happens in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libblast_cuda.so")
+
+OK = 0
+ERR_IO, ERR_UNSUPPORTED_FORMAT, ERR_UNEXPECTED_EOF, ERR_INVALID_DATA, ERR_REF_PANIC = 1, 2, 3, 4, 5
+ERR_CUDA, ERR_ARG, ERR_NO_DEVICE, ERR_CAPACITY, ERR_UNSUPPORTED = 100, 101, 102, 103, 104
+
+
+class PcmDesc(C.Structure):
+    _fields_ = [("sample_rate", C.c_uint32), ("num_channels", C.c_uint32), ("bits_per_sample", C.c_uint32),
+                ("big_endian", C.c_uint32), ("data_off", C.c_uint64), ("data_len", C.c_uint64)]
+
+
+class PcmJob(C.Structure):
+    _fields_ = [("d_src", C.c_void_p), ("d_dst", C.c_void_p), ("n_words", C.c_uint64), ("big_endian", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class Pcm24Job(C.Structure):
+    _fields_ = [("d_src", C.c_void_p), ("d_dst", C.c_void_p), ("n_samples", C.c_uint64), ("big_endian", C.c_uint32),
+                ("out_kind", C.c_uint32)]
+
+
+# name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
+_vp, _u64, _u32, _sz = C.c_void_p, C.c_uint64, C.c_uint32, C.c_size_t
+SIGNATURES = {
+    "blast_abi_version": (C.c_int, []),
+    "blast_last_error": (C.c_char_p, []),
+    "blast_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "blast_ctx_destroy": (None, [_vp]),
+    "blast_ctx_set_stream": (C.c_int, [_vp, _vp]),
+    "blast_ctx_stream": (_vp, [_vp]),
+    "blast_ctx_sync": (C.c_int, [_vp]),
+    "blast_ctx_device": (C.c_int, [_vp]),
+    "blast_ctx_sm_count": (C.c_int, [_vp]),
+    "blast_ctx_launch_count": (_u64, [_vp]),
+    "blast_dev_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
+    "blast_dev_free": (C.c_int, [_vp, _vp]),
+    "blast_host_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
+    "blast_host_free": (C.c_int, [_vp, _vp]),
+    "blast_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, _sz]),
+    "blast_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, _sz]),
+    "blast_memset_dev": (C.c_int, [_vp, _vp, C.c_int, _sz]),
+    "blast_event_create": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "blast_event_destroy": (None, [_vp]),
+    "blast_event_record": (C.c_int, [_vp, _vp]),
+    "blast_event_elapsed_ms": (C.c_int, [_vp, _vp, C.POINTER(C.c_float)]),
+    "blast_wav_probe": (C.c_int, [_vp, _sz, C.POINTER(PcmDesc)]),
+    "blast_aiff_probe": (C.c_int, [_vp, _sz, C.POINTER(PcmDesc)]),
+    "blast_pcm_out_len": (_sz, [C.POINTER(PcmDesc)]),
+    "blast_file_name": (C.c_int, [C.c_char_p, C.c_char_p, _sz]),
+    "blast_pcm_plan_create": (C.c_int, [_vp, C.POINTER(PcmJob), _u32, C.POINTER(_vp)]),
+    "blast_pcm_plan_run_dev": (C.c_int, [_vp, _vp]),
+    "blast_pcm_plan_destroy": (None, [_vp, _vp]),
+    "blast_pcm_plan_words": (_u64, [_vp]),
+    "blast_pcm_decode_dev": (C.c_int, [_vp, C.POINTER(PcmJob), _u32]),
+    "blast_pcm_decode_batch": (C.c_int, [_vp, _u32, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(PcmDesc),
+                                         C.POINTER(_vp), C.POINTER(_vp)]),
+    "blast_pcm24_unpack_dev": (C.c_int, [_vp, C.POINTER(Pcm24Job), _u32]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libblast_cuda.so and set the prototypes.  Raises ImportError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(
+            f"{SO_PATH} is missing: build the CUDA extension first (make -C audio_decoder_b200/csrc, or "
+            "__graft_entry__.build()).  audio_decoder_b200 has no CPU fallback.")
+    L = C.CDLL(SO_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)          # AttributeError here == header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L

@@ -1,0 +1,153 @@
+/*
+ * blast_cuda.h — C ABI of libblast_cuda.so, the B200 (sm_100a) implementation of BLAST's
+ * data-parallel hot path (gitxandert/audio_decoder).  This is the drop-in boundary: a
+ * Rust (or any FFI) host binds exactly these symbols; INTEGRATION.md shows the
+ * `extern "C"` block and the replacement bodies of file_parsing::{wav,aiff,mpeg}::parse,
+ * Conductor::coordinate and X128P that sit on top of it.
+ *
+ * Each entry point cites the reference interface it replaces (file:line relative to the
+ * reference root).  The reference has no FFI of its own (its only extern "C" item is the
+ * SIGTERM handler, blast/src/audio_processing/runtime.rs:400), so the seam is the Rust
+ * function/struct surface; this header is its C projection.
+ *
+ * Conventions
+ *  - every function returns a status code (0 = OK); codes 1..4 are the reference's
+ *    DecodeError variants (blast/src/file_parsing/decode_helpers.rs:1-7); code 5 marks inputs
+ *    on which the reference PANICS (index out of bounds, usize underflow) — never UB here;
+ *    codes >= 100 are this library's own.  blast_last_error() gives the message
+ *    (thread-local).
+ *  - all buffers are caller-owned.  "d_" parameters are device pointers on the context's
+ *    GPU, everything else is host memory.
+ *  - one blast_ctx is bound to one GPU and may be driven by one host thread at a time
+ *    (the reference's callers are single-threaded: main.rs:18-89, runtime.rs:320-380).
+ *    Work is enqueued on the context's CUDA stream; functions named *_dev are
+ *    asynchronous, the host-buffer entry points synchronise before returning.
+ *  - there is NO CPU compute fallback: without a usable CUDA device blast_ctx_create fails
+ *    with BLAST_ERR_NO_DEVICE and nothing else can be called.
+ */
+#ifndef BLAST_CUDA_H
+#define BLAST_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLAST_ABI_VERSION 1
+
+enum {
+    BLAST_OK = 0,
+    BLAST_ERR_IO = 1,                 /* DecodeError::Io */
+    BLAST_ERR_UNSUPPORTED_FORMAT = 2, /* DecodeError::UnsupportedFormat */
+    BLAST_ERR_UNEXPECTED_EOF = 3,     /* DecodeError::UnexpectedEof */
+    BLAST_ERR_INVALID_DATA = 4,       /* DecodeError::InvalidData */
+    BLAST_ERR_REF_PANIC = 5,          /* the reference would panic on this input */
+    BLAST_ERR_CUDA = 100,
+    BLAST_ERR_ARG = 101,
+    BLAST_ERR_NO_DEVICE = 102,
+    BLAST_ERR_CAPACITY = 103,
+    BLAST_ERR_UNSUPPORTED = 104
+};
+
+typedef struct blast_ctx blast_ctx;
+
+/* ------------------------------------------------------------------ lifecycle */
+int  blast_abi_version(void);
+const char* blast_last_error(void);
+/* Binds a context to CUDA device `device` and creates its stream.  Fails loudly
+ * (BLAST_ERR_NO_DEVICE) if there is no sm_100 device: there is no CPU path. */
+int  blast_ctx_create(blast_ctx** out, int device);
+void blast_ctx_destroy(blast_ctx* ctx);
+/* Use an existing cudaStream_t (e.g. torch's current stream) instead of the context's own. */
+int  blast_ctx_set_stream(blast_ctx* ctx, void* cuda_stream);
+void* blast_ctx_stream(blast_ctx* ctx);
+int  blast_ctx_sync(blast_ctx* ctx);
+int  blast_ctx_device(const blast_ctx* ctx);
+int  blast_ctx_sm_count(const blast_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t blast_ctx_launch_count(const blast_ctx* ctx);
+
+/* memory helpers (device allocations are 256-byte aligned and padded to 256 bytes) */
+int blast_dev_alloc(blast_ctx* ctx, size_t bytes, void** out);
+int blast_dev_free(blast_ctx* ctx, void* d_ptr);
+int blast_host_alloc(blast_ctx* ctx, size_t bytes, void** out);   /* pinned */
+int blast_host_free(blast_ctx* ctx, void* ptr);
+int blast_memcpy_h2d(blast_ctx* ctx, void* d_dst, const void* src, size_t bytes);   /* async */
+int blast_memcpy_d2h(blast_ctx* ctx, void* dst, const void* d_src, size_t bytes);   /* async */
+int blast_memset_dev(blast_ctx* ctx, void* d_dst, int value, size_t bytes);         /* async */
+
+/* CUDA-event timing on the context's stream (the stream the kernels are launched on) */
+typedef struct blast_event blast_event;
+int  blast_event_create(blast_ctx* ctx, blast_event** out);
+void blast_event_destroy(blast_event* ev);
+int  blast_event_record(blast_ctx* ctx, blast_event* ev);
+int  blast_event_elapsed_ms(blast_event* start, blast_event* stop, float* ms_out);  /* syncs on stop */
+
+/* ------------------------------------------------------------------ L0: PCM decode
+ * replaces file_parsing::wav::parse (blast/src/file_parsing/wav.rs:69-167) and
+ * file_parsing::aiff::parse (blast/src/file_parsing/aiff.rs:99-183). */
+typedef struct {
+    uint32_t sample_rate;      /* AudioFile.sample_rate  (decode_helpers.rs:21) */
+    uint32_t num_channels;     /* AudioFile.num_channels */
+    uint32_t bits_per_sample;  /* AudioFile.bits_per_sample (reported, never used to unpack) */
+    uint32_t big_endian;       /* 0 = "wav" (i16::from_le_bytes), 1 = "aiff" (i16::from_be_bytes) */
+    uint64_t data_off;         /* offset of the first payload byte in the file image */
+    uint64_t data_len;         /* declared payload bytes (data_size / ssnd_size) */
+} blast_pcm_desc;
+
+/* Host header walks: wav.rs:69-138 and aiff.rs:99-154, every quirk kept (ids never
+ * compared, the +91 extensible skip, COMM size must be 18, 80-bit rate -> f64 -> u32).
+ * They also apply the sample loop's bounds rule (wav.rs:143-151, aiff.rs:159-167): if any
+ * byte pair of the declared payload is missing the whole parse is UnexpectedEof. */
+int    blast_wav_probe(const uint8_t* file, size_t len, blast_pcm_desc* out);
+int    blast_aiff_probe(const uint8_t* file, size_t len, blast_pcm_desc* out);
+size_t blast_pcm_out_len(const blast_pcm_desc* desc);   /* ceil(data_len / 2) i16 words */
+/* file-name rule applied after decoding (wav.rs:156-164, aiff.rs:172-180) */
+int    blast_file_name(const char* path, char* out, size_t cap);
+
+/* One decode job on device-resident bytes: n_words byte pairs at d_src (ANY byte
+ * alignment) -> int16 at d_dst (2-byte aligned).  d_src must be readable up to the next
+ * 16-byte boundary past its last byte (true for blast_dev_alloc / cudaMalloc buffers). */
+typedef struct {
+    const uint8_t* d_src;
+    int16_t*       d_dst;
+    uint64_t       n_words;
+    uint32_t       big_endian;
+    uint32_t       reserved;
+} blast_pcm_job;
+
+/* A plan holds the device-side job + tile tables so that a batch can be (re)launched as a
+ * single kernel with nothing but the launch inside the timed region. */
+typedef struct blast_pcm_plan blast_pcm_plan;
+int  blast_pcm_plan_create(blast_ctx* ctx, const blast_pcm_job* jobs, uint32_t n_jobs, blast_pcm_plan** out);
+int  blast_pcm_plan_run_dev(blast_ctx* ctx, blast_pcm_plan* plan);          /* async, 1 launch */
+void blast_pcm_plan_destroy(blast_ctx* ctx, blast_pcm_plan* plan);
+uint64_t blast_pcm_plan_words(const blast_pcm_plan* plan);
+/* one-shot: create + run + destroy */
+int  blast_pcm_decode_dev(blast_ctx* ctx, const blast_pcm_job* jobs, uint32_t n_jobs);
+
+/* The parse() drop-in for a batch of in-memory file images (host buffers, ideally pinned):
+ * copies each payload to the GPU, decodes, and delivers AudioFile.samples to
+ *   host_out[i]  (nullable array / nullable entries; blast_pcm_out_len(descs[i]) words) and/or
+ *   d_out[i]     (nullable array / nullable entries; device, stays resident for the render).
+ * Copies and kernels are pipelined over internal streams; returns after everything landed. */
+int  blast_pcm_decode_batch(blast_ctx* ctx, uint32_t n, const uint8_t* const* files, const size_t* lens,
+                            const blast_pcm_desc* descs, int16_t* const* host_out, int16_t* const* d_out);
+
+/* Extension (not in the reference): true packed 24-bit unpack.
+ * out_kind 0: sign-extended int32 per sample; 1: top 16 bits as int16. */
+typedef struct {
+    const uint8_t* d_src;      /* 3 bytes per sample, any alignment */
+    void*          d_dst;      /* int32* or int16*, naturally aligned */
+    uint64_t       n_samples;
+    uint32_t       big_endian;
+    uint32_t       out_kind;
+} blast_pcm24_job;
+int  blast_pcm24_unpack_dev(blast_ctx* ctx, const blast_pcm24_job* jobs, uint32_t n_jobs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLAST_CUDA_H */

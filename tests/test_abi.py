@@ -1,0 +1,149 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol the header declares,
+refuses to run without a GPU, and its host logic (header walks, file-name rule) matches the oracle."""
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+import audio_decoder_b200 as blast
+from audio_decoder_b200 import _lib, file_parsing as fp
+import oracle
+import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = set()
+    for fn in os.listdir(os.path.join(ROOT, "include")):
+        if fn.endswith(".h"):
+            text = open(os.path.join(ROOT, "include", fn)).read()
+            text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+            names |= set(re.findall(r"\b(blast_[a-z0-9_]+)\s*\(", text))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) > 20
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, missing
+    # and the ctypes table covers the whole header (no unbound entry points)
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert L.blast_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(blast.BlastError) as e:
+        blast.Context()
+    assert e.value.code == _lib.ERR_NO_DEVICE
+    assert "no CPU fallback" in str(e.value)
+
+
+def _same_probe(kind, image):
+    """product probe == oracle probe, including the error variant"""
+    o_fn = oracle.wav_probe if kind == "wav" else oracle.aiff_probe
+    try:
+        o = o_fn(image)
+        o_err = None
+    except oracle.OracleError as e:
+        o, o_err = None, e.code
+    try:
+        p = fp.probe(kind, image)
+        p_err = None
+    except blast.BlastError as e:
+        p, p_err = None, e.code
+    assert o_err == p_err, (kind, o_err, p_err)
+    if o is not None:
+        for f, _ in _lib.PcmDesc._fields_:
+            assert getattr(o, f) == getattr(p, f), f
+    return p, p_err
+
+
+def test_probe_canonical_headers():
+    p, _ = _same_probe("wav", synth.wav_image(1, 4000))
+    assert (p.data_off, p.data_len, p.sample_rate, p.num_channels, p.bits_per_sample) == (44, 4000, 44100, 2, 16)
+    p, _ = _same_probe("aiff", synth.aiff_image(2, 6000))
+    assert (p.data_off, p.data_len, p.sample_rate, p.num_channels, p.bits_per_sample, p.big_endian) == \
+        (54, 6000, 48000, 2, 24, 1)
+    assert _lib.load().blast_pcm_out_len(p) == 3000
+
+
+def test_probe_truncations_and_quirks():
+    w = synth.wav_image(3, 101)            # odd payload, no byte after it -> EOF
+    _, err = _same_probe("wav", w)
+    assert err == _lib.ERR_UNEXPECTED_EOF
+    _same_probe("wav", np.concatenate([w, np.zeros(1, np.uint8)]))
+    a = synth.aiff_image(4, 64)
+    for cut in range(0, len(a) + 1):
+        _same_probe("aiff", a[:cut])
+    w = synth.wav_image(5, 64)
+    for cut in range(0, len(w) + 1):
+        _same_probe("wav", w[:cut])
+    # extensible fmt: +91 skip
+    ext = struct.pack("<HHIH", 22, 16, 3, 1) + bytes(91)
+    img = (b"RIFF" + struct.pack("<I", 0) + b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 40, 0xFFFE, 2, 48000, 0, 4, 16) +
+           ext + b"data" + struct.pack("<I", 32) + bytes(32))
+    p, err = _same_probe("wav", img)
+    assert err is None and p.data_off == 145
+    for cut in range(30, len(img)):
+        _same_probe("wav", img[:cut])
+    # bad tag, bad COMM size, SSND size < 8
+    bad = bytearray(synth.wav_image(6, 16)); bad[20] = 2
+    assert _same_probe("wav", bytes(bad))[1] == _lib.ERR_UNSUPPORTED_FORMAT
+    bad = bytearray(synth.aiff_image(7, 16)); bad[19] = 20
+    assert _same_probe("aiff", bytes(bad))[1] == _lib.ERR_INVALID_DATA
+    bad = bytearray(synth.aiff_image(8, 16)); bad[42:46] = struct.pack(">I", 4)
+    assert _same_probe("aiff", bytes(bad))[1] == _lib.ERR_UNEXPECTED_EOF
+
+
+def test_probe_fuzz_matches_oracle():
+    rng = np.random.default_rng(99)
+    base_w = synth.wav_image(9, 40)
+    base_a = synth.aiff_image(10, 40)
+    for _ in range(1500):
+        for kind, base in (("wav", base_w), ("aiff", base_a)):
+            img = base.copy()
+            k = int(rng.integers(1, 5))
+            pos = rng.integers(0, 60, size=k)
+            img[pos] = rng.integers(0, 256, size=k, dtype=np.uint8)
+            cut = int(rng.integers(0, len(img) + 1)) if rng.random() < 0.3 else len(img)
+            _same_probe(kind, img[:cut])
+
+
+def test_aiff_rate_conversion_matches_oracle():
+    rng = np.random.default_rng(5)
+    L = _lib.load()
+    for _ in range(2000):
+        ext = rng.integers(0, 256, size=10, dtype=np.uint8)
+        if rng.random() < 0.5:            # plausible exponents around 2^0 .. 2^40
+            e = 16383 + int(rng.integers(-4, 40))
+            ext[0] = (e >> 8) & 0x7F
+            ext[1] = e & 0xFF
+        img = synth.aiff_image(1, 8)
+        img[28:38] = ext
+        _same_probe("aiff", img)
+    assert L is not None
+
+
+def test_file_name_rule():
+    for path in ["blast/assets/fairies.wav", "a/b.c/d.e.aif", "x/.wav", "/abs/path/t.aiff"]:
+        assert fp.file_name(path) == oracle.file_name(path)
+    for bad in ["fairies.wav", "noext", ".wav", "dir/name.", "a.b/c"]:
+        with pytest.raises(blast.InvalidData) as e:
+            fp.file_name(bad)
+        with pytest.raises(oracle.OracleError) as oe:
+            oracle.file_name(bad)
+        assert oe.value.code == oracle.INVALID_DATA
+        assert oracle.lib().orc_last_error().decode() in str(e.value)
+
+
+def test_parse_missing_file_is_io_error():
+    with pytest.raises(blast.Io):
+        fp.wav.parse("/nonexistent/dir/file.wav")
