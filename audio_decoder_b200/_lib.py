@@ -32,6 +32,16 @@ class Pcm24Job(C.Structure):
                 ("out_kind", C.c_uint32)]
 
 
+class Track(C.Structure):
+    _fields_ = [("d_samples", C.c_void_p), ("n_samples", C.c_uint64), ("num_channels", C.c_uint32),
+                ("sample_rate", C.c_uint32)]
+
+
+class Voice(C.Structure):
+    _fields_ = [("track", C.c_uint32), ("active", C.c_uint32), ("position", C.c_float), ("velocity", C.c_float),
+                ("gain", C.c_float), ("reserved", C.c_uint32)]
+
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
 _vp, _u64, _u32, _sz = C.c_void_p, C.c_uint64, C.c_uint32, C.c_size_t
 SIGNATURES = {
@@ -68,6 +78,15 @@ SIGNATURES = {
     "blast_pcm_decode_batch": (C.c_int, [_vp, _u32, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(PcmDesc),
                                          C.POINTER(_vp), C.POINTER(_vp)]),
     "blast_pcm24_unpack_dev": (C.c_int, [_vp, C.POINTER(Pcm24Job), _u32]),
+    "blast_scene_create": (C.c_int, [_vp, C.POINTER(Track), _u32, C.POINTER(Voice), _u32, _u32, C.POINTER(_vp)]),
+    "blast_scene_destroy": (None, [_vp, _vp]),
+    "blast_scene_set_voices": (C.c_int, [_vp, _vp, C.POINTER(Voice), _u32]),
+    "blast_scene_get_voices": (C.c_int, [_vp, _vp, C.POINTER(Voice), _u32]),
+    "blast_scene_render_dev": (C.c_int, [_vp, _vp, _u64, _vp]),
+    "blast_scene_check": (C.c_int, [_vp, _vp]),
+    "blast_bus_finalize_dev": (C.c_int, [_vp, _vp, _vp, _u64]),
+    "blast_render": (C.c_int, [_vp, C.POINTER(Track), _u32, C.POINTER(Voice), _u32, _u32, _u64, _vp,
+                               C.POINTER(Voice)]),
 }
 
 _lib = None

@@ -147,6 +147,49 @@ typedef struct {
 } blast_pcm24_job;
 int  blast_pcm24_unpack_dev(blast_ctx* ctx, const blast_pcm24_job* jobs, uint32_t n_jobs);
 
+/* ------------------------------------------------------------------ L1: voice render / mix-down
+ * replaces Conductor::coordinate (blast/src/audio_processing/engine.rs:46-81) and Voice::process
+ * (engine.rs:386-448) for a set of voices over `frames` output frames.  Output is bit-exact with
+ * the reference's release-build semantics (saturating `as i16`, wrapping i16 accumulate). */
+typedef struct {
+    const int16_t* d_samples;  /* device, interleaved, 4-byte aligned (AudioFile.samples) */
+    uint64_t n_samples;        /* samples.len() */
+    uint32_t num_channels;     /* AudioFile.num_channels */
+    uint32_t sample_rate;      /* informational */
+} blast_track;
+
+typedef struct {               /* VoiceState (engine.rs:279-286), flattened; `end` is derived like */
+    uint32_t track;            /* Voice::new does: samples.len()/channels - 1 (engine.rs:302)      */
+    uint32_t active;
+    float    position;
+    float    velocity;
+    float    gain;             /* no Command sets it; exposed here as a plain field */
+    uint32_t reserved;
+} blast_voice;
+
+typedef struct blast_scene blast_scene;
+/* Uploads the voice table.  BLAST_ERR_REF_PANIC for inputs on which Voice::new / load panic
+ * (track index out of range, 0 channels, empty track). out_channels 1..8. */
+int  blast_scene_create(blast_ctx* ctx, const blast_track* tracks, uint32_t n_tracks, const blast_voice* voices,
+                        uint32_t n_voices, uint32_t out_channels, blast_scene** out);
+void blast_scene_destroy(blast_ctx* ctx, blast_scene* scene);
+int  blast_scene_set_voices(blast_ctx* ctx, blast_scene* scene, const blast_voice* voices, uint32_t n_voices);
+/* reads the voice states back (positions as left by the last render); synchronises */
+int  blast_scene_get_voices(blast_ctx* ctx, blast_scene* scene, blast_voice* out, uint32_t n_voices);
+/* Renders `frames` frames of all active voices into the int32 partial bus
+ * d_partial_bus[frames * out_channels] (overwritten) and advances the voices, exactly as `frames`
+ * iterations of coordinate()'s outer loop would.  Async: position scan + render/mix launches.
+ * Partial buses of several GPUs may be summed (int32) before blast_bus_finalize_dev. */
+int  blast_scene_render_dev(blast_ctx* ctx, blast_scene* scene, uint64_t frames, int32_t* d_partial_bus);
+/* synchronises and reports deferred device-side errors of the last render (BLAST_ERR_CAPACITY) */
+int  blast_scene_check(blast_ctx* ctx, blast_scene* scene);
+/* S16 bus = low 16 bits of the int32 partial sums (== i16 wrapping accumulate, engine.rs:441) */
+int  blast_bus_finalize_dev(blast_ctx* ctx, const int32_t* d_partial, int16_t* d_bus, uint64_t n_slots);
+/* one-shot with a host bus (interleaved S16_LE like the ALSA area, runtime.rs:272-276) */
+int  blast_render(blast_ctx* ctx, const blast_track* tracks, uint32_t n_tracks, const blast_voice* voices,
+                  uint32_t n_voices, uint32_t out_channels, uint64_t frames, int16_t* host_bus_out,
+                  blast_voice* voices_after /* nullable */);
+
 #ifdef __cplusplus
 }
 #endif

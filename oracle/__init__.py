@@ -136,6 +136,8 @@ def lib():
                                           C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.orc_clock_current.argtypes = [C.c_void_p]
     L.orc_clock_current.restype = C.c_uint64
+    L.orc_position_walk.argtypes = [C.c_float, C.c_float, C.c_uint64, C.c_uint64, C.c_void_p]
+    L.orc_position_walk.restype = None
     L.orc_mpeg_parse_header.argtypes = [C.c_uint32, C.POINTER(MpegHeader)]
     L.orc_mpeg_parse_header.restype = None
     L.orc_mpeg_match_ref.argtypes = [C.POINTER(MpegHeader), C.POINTER(MpegHeader)]
@@ -379,6 +381,12 @@ class Conductor:
 
     def clock(self):
         return lib().orc_clock_current(self.h)
+
+
+def position_walk(p0, velocity, end, n) -> np.ndarray:
+    out = np.empty(n + 1, dtype=np.float32)
+    lib().orc_position_walk(p0, velocity, end, n, out.ctypes.data)
+    return out
 
 
 # ---------------- MPEG ----------------

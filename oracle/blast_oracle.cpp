@@ -742,6 +742,19 @@ int orc_conductor_set_voice(orc_conductor* c, int group, uint32_t idx, const flo
 }
 uint64_t orc_clock_current(orc_conductor* c) { return c->clock; }
 
+// The position recurrence of Voice::process in isolation (engine.rs:407-410, 445-447):
+// out[s] = position seen by advance-event s (s = 0..n inclusive; out[n] is the state afterwards).
+// The advance is skipped, forever, from the first step whose trunc(position) >= end.
+void orc_position_walk(float p0, float velocity, uint64_t end, uint64_t n, float* out) {
+    float p = p0;
+    for (uint64_t s = 0; s <= n; ++s) {
+        out[s] = p;
+        if (f32_as_usize(p) >= end) continue;
+        p += velocity;
+    }
+}
+
+
 // ===================== MPEG: mpeg.rs =====================
 static const uint32_t BITRATES_COL4[15] = {8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160, 0};   // mpeg.rs:255-271
 

@@ -162,6 +162,8 @@ int orc_conductor_n_groups(orc_conductor*);
 int orc_conductor_get_voice(orc_conductor*, int group, uint32_t idx, orc_voice_state* out);
 int orc_conductor_set_voice(orc_conductor*, int group, uint32_t idx, const float* position, const float* velocity, const float* gain, const int* active);
 uint64_t orc_clock_current(orc_conductor*);
+/* position recurrence alone (engine.rs:407-410,445-447): out[0..n], freeze at trunc(pos) >= end */
+void orc_position_walk(float p0, float velocity, uint64_t end, uint64_t n, float* out);
 
 /* ---------------- MPEG: mpeg.rs ---------------- */
 typedef struct {

@@ -1,0 +1,119 @@
+"""Python model of K3 `voice_position_scan` (audio_decoder_b200/csrc/render.cu): builds the
+arithmetic-segment list of a voice's f32 position trajectory.  Mirrors the CUDA code line by line so
+that the ALGORITHM can be validated on the CPU against the sequential recurrence (the CUDA
+transliteration itself is validated by the GPU parity tests)."""
+import numpy as np
+
+f32 = np.float32
+MAXSEG = 160
+
+
+def bits(x) -> int:
+    return int(np.array(x, dtype=np.float32).view(np.uint32))
+
+
+def f2u_sat(x) -> int:
+    x = float(x)
+    if x != x or x <= 0:
+        return 0
+    if x >= 4294967295.0:
+        return 0xFFFFFFFF
+    return int(x)
+
+
+def decompose(x):
+    b = bits(x)
+    sign, E = b >> 31, (b >> 23) & 0xFF
+    if E == 255:
+        return None
+    M = b & 0x7FFFFF
+    return sign, E, (M | 0x800000) if E else M
+
+
+def ulp(E) -> np.float32:
+    return f32(2.0 ** ((E if E else 1) - 150))
+
+
+def seg_eval(p0, d, scale, k):
+    # exact in float64: |k*d| < 2^24, scale a power of two, result representable in f32
+    if d == 0:
+        return f32(p0)
+    return f32(np.float64(k * d) * np.float64(scale) + np.float64(p0))
+
+
+def build_segments(pos, vel, end, total):
+    """-> (segments [(step0, p0, d, scale)], final position)"""
+    segs = []
+    p, vel = f32(pos), f32(vel)
+    s = 0
+    if total == 0:
+        segs.append((0, p, 0, f32(0)))
+    with np.errstate(all="ignore"):
+        while s < total:
+            if f2u_sat(p) >= end:
+                segs.append((s, p, 0, f32(0)))
+                break
+            p1 = f32(p + vel)
+            if bits(p1) == bits(p):
+                segs.append((s, p, 0, f32(0)))
+                break
+            p2 = f32(p1 + vel)
+            a, b, c = decompose(p), decompose(p1), decompose(p2)
+            run = a and b and c and a[0] == b[0] == c[0] and a[1] == b[1] == c[1]
+            if run:
+                s0, E0, q0 = a
+                q1, q2 = b[2], c[2]
+                d = q2 - q1
+                from_p = (q1 - q0) == d
+                qs = q0 if from_p else q1
+                s_run = s if from_p else s + 1
+                p_run = p if from_p else p1
+                if d == 0:
+                    kmax = 0xFFFFFFFF
+                elif d > 0:
+                    qhi = (0xFFFFFF if E0 else 0x7FFFFF) - 1
+                    kmax = (qhi - qs) // d if qs <= qhi else 0
+                else:
+                    qlo = 0x800001 if E0 else 0
+                    kmax = (qs - qlo) // (-d) if qs >= qlo else 0
+                if s0 == 0 and d > 0:
+                    e = (E0 if E0 else 1) - 150
+                    if e >= 0:
+                        thr = 1 if e >= 32 else (end + (1 << e) - 1) >> e
+                    else:
+                        thr = (1 << 64) - 1 if -e >= 40 else end << (-e)
+                    if thr > qs:
+                        kf = (thr - qs + d - 1) // d
+                        kmax = min(kmax, kf)
+                    else:
+                        kmax = 0
+                kmax = min(kmax, total - s_run)
+                if kmax >= 1:
+                    if not from_p:
+                        segs.append((s, p, 0, f32(0)))
+                    ds = -d if s0 else d
+                    sc = ulp(E0)
+                    segs.append((s_run, p_run, ds, sc))
+                    p = seg_eval(p_run, ds, sc, kmax)
+                    s = s_run + kmax
+                    continue
+            segs.append((s, p, 0, f32(0)))
+            p = p1
+            s += 1
+    return segs, p
+
+
+def expand(segs, total):
+    """positions for steps 0..total-1 from the segment list (vectorised)"""
+    out = np.empty(total, dtype=np.float32)
+    for i, (step0, p0, d, scale) in enumerate(segs):
+        nxt = segs[i + 1][0] if i + 1 < len(segs) else total
+        nxt = min(nxt, total)
+        if nxt <= step0:
+            continue
+        k = np.arange(nxt - step0, dtype=np.float64)
+        if d == 0:
+            out[step0:nxt] = p0
+        else:
+            out[step0:nxt] = (k * d * np.float64(scale) + np.float64(p0)).astype(np.float32)
+    return out

@@ -1,0 +1,85 @@
+"""The time-parallel position formulation (K3) against the sequential f32 recurrence of the reference
+(engine.rs:446 `position += velocity`), on the CPU: random velocities incl. rounding ties, tiny and huge
+ratios, negative velocities, zero crossings, the 2^24 stall, freezing at `end`, NaN / inf."""
+import numpy as np
+import pytest
+
+import oracle
+import seg_model as sm
+
+f32 = np.float32
+
+
+def _check(p0, v, end, total):
+    segs, final = sm.build_segments(p0, v, end, total)
+    assert len(segs) <= sm.MAXSEG, (p0, v, len(segs))
+    ref = oracle.position_walk(p0, v, end, total)
+    got = sm.expand(segs, total)
+    a, b = got.view(np.uint32), ref[:total].view(np.uint32)
+    # -0.0 vs +0.0 is the one tolerated difference (render output cannot tell them apart)
+    bad = (a != b) & ~((got == 0) & (ref[:total] == 0))
+    assert not bad.any(), (p0, v, end, int(np.argmax(bad)), got[np.argmax(bad)], ref[np.argmax(bad)])
+    fb, rb = sm.bits(final), int(ref[total:total + 1].view(np.uint32)[0])
+    assert fb == rb or (float(final) == 0.0 and float(ref[total]) == 0.0), (p0, v, end, final, ref[total])
+    return len(segs)
+
+
+def test_named_cases():
+    N = 1 << 18
+    big = 1 << 31
+    assert _check(0.0, 1.0, big, N) <= 48
+    _check(16777000.0, 1.0, big, 1000)            # runs into the 2^24 stall
+    _check(16777215.0, 3.0, big, 1000)            # v/u = 1.5 tie at 2^24
+    _check(0.0, 0.75, 1000, N)                    # freezes at end
+    _check(0.0, 0.3, 5, 100)
+    _check(100.0, -1.0, big, 500)                 # down through zero, negative forever
+    _check(100.25, -0.37, big, N)
+    _check(0.0, -1.0, big, 100)
+    _check(5.0, 0.0, big, 100)
+    _check(1e9, 1.0, 1 << 31, 100)                # velocity below half an ulp: fixed point
+    _check(7.0, 3.0, 0, 10)                       # end == 0: frozen at step 0
+    _check(0.0, 1e-30, big, N)
+    _check(0.0, 1e-45, big, 1000)                 # denormal increments are exact
+    _check(1e-40, 1e-42, big, 5000)
+    _check(0.0, 1e30, big, 100)                   # frozen after one step (idx saturates)
+    _check(3.0, float("inf"), big, 10)
+    _check(3.0, float("nan"), big, 10)
+    _check(float("nan"), 1.0, big, 10)
+    _check(float("-inf"), 1.0, big, 10)
+    _check(-0.0, 0.0, big, 10)
+    _check(2.5, 1.0, big, 1 << 16)                # v == 1 with a fractional start
+    _check(0.1, 1.0, big, 1 << 16)
+
+
+def test_random_velocities_with_ties():
+    rng = np.random.default_rng(123)
+    N = 200_000
+    big = (1 << 31) - 1
+    worst = 0
+    for i in range(400):
+        kind = i % 8
+        if kind == 0:
+            v = float(f32(rng.uniform(0.5, 1.5)))
+        elif kind == 1:
+            v = float(f32(rng.integers(1, 1 << 24)) * f32(2.0) ** int(rng.integers(-30, 3)))   # 24-bit mantissas: ties
+        elif kind == 2:
+            v = float(f32(rng.uniform(0, 1)) * f32(10.0) ** int(rng.integers(-12, 6)))
+        elif kind == 3:
+            v = -float(f32(rng.uniform(0.01, 3.0)))
+        elif kind == 4:
+            v = float(f32(2.0) ** int(rng.integers(-10, 4)) * f32(1.5))                         # k + 1/2 patterns
+        elif kind == 5:
+            v = float(f32(rng.integers(1, 64)) / f32(rng.integers(1, 64)))
+        elif kind == 6:
+            v = float(f32(rng.normal()))
+        else:
+            v = float(f32(rng.uniform(0.9999, 1.0001)))
+        p0 = float(f32(rng.choice([0.0, 0.0, 0.5, 123.456, 16777000.0, 1e-3, 70000.7, -5.5])))
+        end = int(rng.choice([big, big, 100_000, 5000]))
+        worst = max(worst, _check(p0, v, end, N))
+    assert worst <= sm.MAXSEG
+
+
+@pytest.mark.parametrize("v", [1.0, 0.5, 1.5, 0.3, 3.0, 0.1, 7.0 / 3.0])
+def test_long_runs(v):
+    _check(0.0, v, (1 << 31) - 1, 1 << 21)

@@ -1,0 +1,183 @@
+"""GPU parity: voice render / mix-down (K3 + K4 + K5) through the C ABI vs the oracle Conductor."""
+import numpy as np
+import pytest
+
+import audio_decoder_b200 as blast
+from audio_decoder_b200 import audio_processing as ap
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = blast.Context(0)
+    yield c
+    c.close()
+
+
+def oracle_render(voices, out_channels, frames, chunks=None):
+    """voices: list of dict(samples, channels, position, velocity, gain, active)"""
+    c = oracle.Conductor(out_channels, 44100, [(v["samples"], v["channels"], 44100) for v in voices])
+    for i, v in enumerate(voices):
+        c.load(i)
+        c.set_voice(i, position=v["position"], velocity=v["velocity"], gain=v["gain"], active=v["active"])
+    if chunks is None:
+        out = c.coordinate(frames)
+    else:
+        out = np.concatenate([c.coordinate(n) for n in chunks])
+    return out, [c.get_voice(i).position for i in range(len(voices))]
+
+
+def gpu_render(ctx, voices, out_channels, frames):
+    tracks = [ap.Track.from_host(ctx, v["samples"], v["channels"]) for v in voices]
+    vp = [ap.VoiceParams(i, v["active"], v["position"], v["velocity"], v["gain"]) for i, v in enumerate(voices)]
+    bus, after = ap.render(ctx, tracks, vp, out_channels, frames)
+    return bus, [a.position for a in after]
+
+
+def same_pos(a, b):
+    a, b = np.float32(a), np.float32(b)
+    return a.view(np.uint32) == b.view(np.uint32) or (a == 0 and b == 0) or (np.isnan(a) and np.isnan(b))
+
+
+def V(samples, channels, velocity=1.0, gain=1.0, position=0.0, active=True):
+    return dict(samples=np.asarray(samples, dtype=np.int16), channels=channels, velocity=velocity, gain=gain,
+                position=position, active=active)
+
+
+ST = np.array([[1000 * k + 7, -1000 * k - 13] for k in range(16)], dtype=np.int16).reshape(-1)
+MONO = np.array([300 * k - 5 for k in range(16)], dtype=np.int16)
+KATS = {
+    "A": ([V(ST, 2)], [7, -13, 1007, -1013, 2007, -2013, 3007, -3013, 4007, -4013, 5007, -5013]),
+    "B": ([V(ST, 2, 0.75, 0.5)], [3, -6, 378, -381, 753, -756, 1128, -1131, 1503, -1506, 1878, -1881]),
+    "C": ([V(MONO, 1)], [-5, 295, 595, 895, 1195, 1495, 1795, 2095, 2395, 2695, 2995, 3295]),
+    "D": ([V(MONO, 1, 0.3, 1.7)], [-8, 144, 297, 450, 603, 756, 909, 1062, 1215, 1368, 1521, 1674]),
+    "E": ([V(ST, 2), V(ST, 2, 0.75, 0.5), V(MONO, 1), V(MONO, 1, 0.3, 1.7)],
+          [-3, 420, 2277, -49, 4558, -518, 6839, -987, 9120, -1456, 11401, -1925]),
+    "F": ([V(np.full(32, 30000), 2), V(np.full(32, 30000), 2)], [-5536] * 12),
+    "G": ([V(np.full(32, 30000), 2, 1.0, 2.0)], [32767] * 12),
+    "H": ([V(ST, 2, -1.0, 1.0, position=15.0)], [0] * 12),
+}
+
+
+@pytest.mark.parametrize("name", list(KATS))
+def test_render_kats(ctx, name):
+    voices, expect = KATS[name]
+    bus, _ = gpu_render(ctx, voices, 2, 6)
+    assert list(bus) == expect
+
+
+def test_stereo_voice_on_mono_bus_never_advances(ctx):
+    bus, pos = gpu_render(ctx, [V(ST, 2)], 1, 6)
+    assert list(bus) == [7] * 6 and pos[0] == 0.0
+
+
+def test_cast_semantics_pinned(ctx):
+    """(sample*gain) as i16: saturating, truncating toward zero, NaN -> 0 (SURVEY hard part 2)"""
+    clip = np.array([1, 1, 1, 1], dtype=np.int16)
+    for gain, want in [(float("inf"), 32767), (float("-inf"), -32768), (float("nan"), 0), (32768.5, 32767),
+                       (-32768.5, -32768), (-0.9, 0), (0.9, 0), (-1.9, -1), (32767.99, 32767), (-32769.0, -32768)]:
+        bus, _ = gpu_render(ctx, [V(clip, 1, 1.0, gain)], 1, 1)
+        exp, _ = oracle_render([V(clip, 1, 1.0, gain)], 1, 1)
+        assert bus[0] == want == exp[0], gain
+
+
+def _random_voice(rng, long_clip=False):
+    ch = int(rng.choice([1, 1, 2, 2, 2, 3, 4]))
+    nfr = int(rng.integers(2, 60)) if not long_clip else int(rng.integers(3000, 20000))
+    s = rng.integers(-32768, 32768, size=nfr * ch).astype(np.int16)
+    vel = float(np.float32(rng.choice([1.0, 1.0, 0.5, 1.5, 0.3, 2.25, -1.0, 0.0, 3.7, 0.999, 1e-3, float("nan")])))
+    gain = float(np.float32(rng.choice([1.0, 0.5, 1.7, 2.0, -0.75, 0.001, 40.0])))
+    pos = float(np.float32(rng.choice([0.0, 0.0, 0.0, 0.5, 3.25, 1e9, -2.5, nfr - 2.0])))
+    return V(s, ch, vel, gain, pos, active=bool(rng.random() < 0.9))
+
+
+@pytest.mark.parametrize("out_channels", [1, 2, 3, 4])
+def test_random_small_scenes(ctx, out_channels):
+    rng = np.random.default_rng(100 + out_channels)
+    for trial in range(25):
+        voices = [_random_voice(rng) for _ in range(int(rng.integers(1, 9)))]
+        frames = int(rng.integers(1, 80))
+        bus, pos = gpu_render(ctx, voices, out_channels, frames)
+        exp, epos = oracle_render(voices, out_channels, frames)
+        assert np.array_equal(bus, exp), (out_channels, trial)
+        assert all(same_pos(a, b) for a, b in zip(pos, epos)), (out_channels, trial, pos, epos)
+
+
+@pytest.mark.parametrize("out_channels", [1, 2])
+def test_multi_tile_scenes_and_freeze(ctx, out_channels):
+    """several 2048-frame tiles, clips that end mid-render (freeze), segment boundaries inside tiles"""
+    rng = np.random.default_rng(7 + out_channels)
+    for trial in range(6):
+        voices = [_random_voice(rng, long_clip=True) for _ in range(int(rng.integers(2, 24)))]
+        frames = int(rng.integers(4097, 9000))
+        bus, pos = gpu_render(ctx, voices, out_channels, frames)
+        exp, epos = oracle_render(voices, out_channels, frames)
+        assert np.array_equal(bus, exp), (out_channels, trial, int(np.argmax(bus != exp)))
+        assert all(same_pos(a, b) for a, b in zip(pos, epos))
+
+
+def test_binade_crossings_and_stall(ctx):
+    """positions near 2^24 (the f32 stall) and velocities that tie: exact trajectory required"""
+    n = 1 << 15
+    clip = (np.arange(n * 2) % 2001 - 1000).astype(np.int16)
+    voices = [V(clip, 2, 1.0, 1.0, position=0.0), V(clip, 2, 3.0, 0.5, position=5.0), V(clip, 2, 0.1, 1.0),
+              V(clip, 1, 1.0, 1.0, position=100.0), V(clip, 1, 0.37, 0.8), V(clip, 2, 7.0 / 3.0, 0.3),
+              V(clip, 2, 1.0, 1.0, position=16777000.0)]
+    frames = 10000
+    bus, pos = gpu_render(ctx, voices, 2, frames)
+    exp, epos = oracle_render(voices, 2, frames)
+    assert np.array_equal(bus, exp)
+    assert all(same_pos(a, b) for a, b in zip(pos, epos))
+
+
+def test_chained_renders_equal_one_long_render(ctx):
+    rng = np.random.default_rng(5)
+    voices = [_random_voice(rng, long_clip=True) for _ in range(12)]
+    tracks = [ap.Track.from_host(ctx, v["samples"], v["channels"]) for v in voices]
+    vp = [ap.VoiceParams(i, v["active"], v["position"], v["velocity"], v["gain"]) for i, v in enumerate(voices)]
+    sc = ap.Scene(ctx, tracks, vp, 2)
+    chunks = [128, 1, 2047, 2048, 3000, 5]
+    got = np.concatenate([sc.render(n) for n in chunks])
+    exp, epos = oracle_render(voices, 2, sum(chunks), chunks=chunks)
+    assert np.array_equal(got, exp)
+    assert all(same_pos(a.position, b) for a, b in zip(sc.voices(), epos))
+    sc.close()
+
+
+def test_scaled_c3_scene_vs_oracle_and_linearity(ctx):
+    """C3-shaped scene scaled to what the oracle finishes in seconds: 256 voices x 32768 frames, plus the
+    size-independent property: mix(all) == wrap16(mix(A) + mix(B)) for a voice partition A | B"""
+    rng = np.random.default_rng(0xC3)
+    nv, frames = 256, 1 << 15
+    voices = []
+    for v in range(nv):
+        vel = 1.0 if v % 2 == 0 else float(np.float32(0.5 + rng.random()))
+        nfr = int(np.ceil(max(1.0, vel) * frames * 1.5)) + 2 if v % 5 else frames // 2      # every 5th clip ends early
+        s = rng.integers(-32768, 32768, size=nfr * 2).astype(np.int16)
+        voices.append(V(s, 2, vel, float(np.float32(rng.random() * 2.0 ** -5)), 0.0))
+    tracks = [ap.Track.from_host(ctx, v["samples"], 2) for v in voices]
+    vp = [ap.VoiceParams(i, True, 0.0, v["velocity"], v["gain"]) for i, v in enumerate(voices)]
+    bus, _ = ap.render(ctx, tracks, vp, 2, frames)
+    exp, _ = oracle_render(voices, 2, frames)
+    assert np.array_equal(bus, exp)
+    a, _ = ap.render(ctx, tracks, [p if i < 100 else ap.VoiceParams(i, False) for i, p in enumerate(vp)], 2, frames)
+    b, _ = ap.render(ctx, tracks, [p if i >= 100 else ap.VoiceParams(i, False) for i, p in enumerate(vp)], 2, frames)
+    assert np.array_equal((a.astype(np.int32) + b.astype(np.int32)).astype(np.int16), bus)
+
+
+def test_reference_panics_become_error_codes(ctx):
+    t = ap.Track.from_host(ctx, np.zeros(4, np.int16), 2)
+    with pytest.raises(blast.ReferencePanic):
+        ap.render(ctx, [t], [ap.VoiceParams(3, True)], 2, 4)                    # track index out of bounds
+    empty = ap.Track(ctx.alloc(16), 0, 2)
+    with pytest.raises(blast.ReferencePanic):
+        ap.render(ctx, [empty], [ap.VoiceParams(0, True)], 2, 4)                # usize underflow in Voice::new
+    zero_ch = ap.Track(ctx.alloc(16), 4, 0)
+    with pytest.raises(blast.ReferencePanic):
+        ap.render(ctx, [zero_ch], [ap.VoiceParams(0, True)], 2, 4)              # divide by zero
+    with pytest.raises(blast.BlastError):
+        ap.render(ctx, [t], [ap.VoiceParams(0, True)], 9, 4)                    # > 8 output channels
+    bus, _ = ap.render(ctx, [t], [], 2, 4)                                      # no voices: silence
+    assert list(bus) == [0] * 8
