@@ -12,6 +12,7 @@ from .errors import (BlastError, DecodeError, Io, UnsupportedFormat, UnexpectedE
 from . import file_parsing  # noqa: F401
 from .file_parsing import AudioFile, DeviceTrack  # noqa: F401
 from . import audio_processing  # noqa: F401
+from . import blast_rand  # noqa: F401
 
 __all__ = ["Context", "DevBuf", "HostBuf", "Event", "file_parsing", "AudioFile", "DeviceTrack", "BlastError",
            "DecodeError", "Io", "UnsupportedFormat", "UnexpectedEof", "InvalidData", "ReferencePanic"]

@@ -42,6 +42,10 @@ class Voice(C.Structure):
                 ("gain", C.c_float), ("reserved", C.c_uint32)]
 
 
+class X128PState(C.Structure):
+    _fields_ = [("s0", C.c_uint64), ("s1", C.c_uint64)]
+
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
 _vp, _u64, _u32, _sz = C.c_void_p, C.c_uint64, C.c_uint32, C.c_size_t
 SIGNATURES = {
@@ -85,6 +89,11 @@ SIGNATURES = {
     "blast_scene_render_dev": (C.c_int, [_vp, _vp, _u64, _vp]),
     "blast_scene_check": (C.c_int, [_vp, _vp]),
     "blast_bus_finalize_dev": (C.c_int, [_vp, _vp, _vp, _u64]),
+    "blast_x128p_seed": (None, [_u64, C.POINTER(X128PState)]),
+    "blast_x128p_advance": (C.c_int, [C.POINTER(X128PState), _u64, C.POINTER(X128PState)]),
+    "blast_x128p_jump_dev": (C.c_int, [_vp, C.POINTER(X128PState), _u64, _u64, _vp]),
+    "blast_x128p_fill_dev": (C.c_int, [_vp, _vp, _u64, _u64, C.c_int64, C.c_int64, _vp, _vp, _vp]),
+    "blast_x128p_fill": (C.c_int, [_vp, _u64, _u64, _u64, _u64, C.c_int64, C.c_int64, _vp, _vp, _vp]),
     "blast_render": (C.c_int, [_vp, C.POINTER(Track), _u32, C.POINTER(Voice), _u32, _u32, _u64, _vp,
                                C.POINTER(Voice)]),
 }

@@ -190,6 +190,28 @@ int  blast_render(blast_ctx* ctx, const blast_track* tracks, uint32_t n_tracks, 
                   uint32_t n_voices, uint32_t out_channels, uint64_t frames, int16_t* host_bus_out,
                   blast_voice* voices_after /* nullable */);
 
+/* ------------------------------------------------------------------ RNG parameter streams
+ * replaces X128P (blast/src/audio_processing/blast_rand.rs:4-60): xoroshiro128+ with the 55/14/36
+ * constants, SplitMix64 seeding, Lemire multiply-shift range WITHOUT rejection. */
+typedef struct { uint64_t s0, s1; } blast_x128p;
+/* X128P::new(seed) (blast_rand.rs:10-24) */
+void blast_x128p_seed(uint64_t seed, blast_x128p* out);
+/* host-side jump of one generator by n_draws (table construction only, no GPU needed) */
+int  blast_x128p_advance(const blast_x128p* in, uint64_t n_draws, blast_x128p* out);
+/* Jump-ahead (not in the reference; GF(2) matrix powers): d_states_out[s] = `base` advanced by
+ * s * stride draws, so draw j of stream s is draw s*stride + j of the CPU's sequential sequence. */
+int  blast_x128p_jump_dev(blast_ctx* ctx, const blast_x128p* base, uint64_t stride, uint64_t n_streams,
+                          blast_x128p* d_states_out);
+/* draws_per_stream draws from every stream, states advanced in place.  Nullable outputs:
+ *   d_raw    [n_streams * draws]  next_u64()                      (blast_rand.rs:31-39)
+ *   d_ranged [n_streams * draws]  next_i64_range(lower, upper)    (blast_rand.rs:50-59)
+ *   d_checks [n_streams * 4]      {xor raw, sum raw, xor ranged, sum ranged} per stream (wrapping) */
+int  blast_x128p_fill_dev(blast_ctx* ctx, blast_x128p* d_states, uint64_t n_streams, uint64_t draws_per_stream,
+                          int64_t lower, int64_t upper, uint64_t* d_raw, int64_t* d_ranged, uint64_t* d_checks);
+/* host one-shot: seed -> jump -> fill -> copy back (outputs nullable) */
+int  blast_x128p_fill(blast_ctx* ctx, uint64_t seed, uint64_t stride, uint64_t n_streams, uint64_t draws_per_stream,
+                      int64_t lower, int64_t upper, uint64_t* raw_out, int64_t* ranged_out, uint64_t* checks_out);
+
 #ifdef __cplusplus
 }
 #endif

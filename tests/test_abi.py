@@ -147,3 +147,22 @@ def test_file_name_rule():
 def test_parse_missing_file_is_io_error():
     with pytest.raises(blast.Io):
         fp.wav.parse("/nonexistent/dir/file.wav")
+
+
+def test_x128p_seed_and_host_jump_match_oracle():
+    from audio_decoder_b200 import blast_rand as br
+    for seed in (0, 1, 42, 0xDEADBEEFCAFEBABE, 2**64 - 1):
+        assert br.seed_state(seed) == oracle.Rng(seed).state
+    base = br.seed_state(42)
+    for n in (0, 1, 2, 3, 65536, 1_000_000, 12_345_678):
+        g = oracle.Rng(42)
+        g.discard(n)
+        assert br.advance(base, n) == g.state, n
+    assert br.advance(base, 65536) == (0x7642b3b57ffb2a57, 0xc7c3ecc7c44024b3)
+    # composition: jump(a) then jump(b) == jump(a + b), for jumps far beyond what can be walked
+    assert br.advance(br.advance(base, 2**40), 2**40) == br.advance(base, 2**41)
+    # against the Python GF(2) model
+    import pyref
+    T = pyref.transition_columns()
+    st = pyref.mat_vec(pyref.mat_pow(T, 2**40 + 7), base[0] | (base[1] << 64))
+    assert br.advance(base, 2**40 + 7) == (st & pyref.M64, st >> 64)
