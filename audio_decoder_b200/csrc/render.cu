@@ -27,6 +27,7 @@
 // 8 frames x out_channels int32 accumulators in registers over all voices of its group and issues one
 // RED.ADD.S32 per bus slot at the end.  Roofline: HBM (2 B per voice-frame-channel of source, read once).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -207,15 +208,21 @@ struct VoiceS {            // what K4 needs per voice, staged in shared memory
     TileRec rec;
 };
 
-__device__ __forceinline__ float position_at(const VoiceS& v, const Seg* __restrict__ sg, bool fast,
-                                             uint32_t tile_step0, uint32_t step_local) {
-    if (fast) return seg_eval(v.rec.p0, v.rec.d, v.rec.scale, step_local);
+__device__ __forceinline__ float position_eval(bool fast, float p0, int32_t d, float scale, uint32_t recmeta,
+                                               const Seg* __restrict__ sg, uint32_t nseg, uint32_t tile_step0,
+                                               uint32_t step_local) {
+    if (fast) return seg_eval(p0, d, scale, step_local);
     // the tile straddles a segment boundary: walk the (short) segment list from the tile's segment
     const uint32_t abs_step = tile_step0 + step_local;
-    uint32_t j = v.rec.meta >> 24;
-    while (j + 1 < v.nseg && sg[j + 1].step0 <= abs_step) ++j;
+    uint32_t j = recmeta >> 24;
+    while (j + 1 < nseg && sg[j + 1].step0 <= abs_step) ++j;
     const Seg g = sg[j];
     return seg_eval(g.p0, g.d, g.scale, abs_step - g.step0);
+}
+
+__device__ __forceinline__ float position_at(const VoiceS& v, const Seg* __restrict__ sg, bool fast,
+                                             uint32_t tile_step0, uint32_t step_local) {
+    return position_eval(fast, v.rec.p0, v.rec.d, v.rec.scale, v.rec.meta, sg, v.nseg, tile_step0, step_local);
 }
 
 // (sample * gain) as i16 for one source channel at position p (engine.rs:429-442)
@@ -331,6 +338,459 @@ voice_render_mix(const VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_
 #pragma unroll
     for (int j = 0; j < kFPT; ++j) {
         const uint32_t fl = threadIdx.x + j * kThreads;
+        if (fl < nf) {
+            int32_t* out = bus + (size_t)(f0 + fl) * OC;
+#pragma unroll
+            for (int c = 0; c < OC; ++c) {
+                if (use_atomic) atomicAdd(out + c, acc[j][c]);
+                else out[c] = acc[j][c];
+            }
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------- K4 (TMA pipeline, out_channels <= 2)
+// Warp-specialised render/mix tile: one producer warp walks the voices of the group and cuts each
+// voice's part of the tile into PIECES — maximal frame ranges that lie inside one arithmetic
+// position segment (normally one piece = the whole tile; more only where the f32 trajectory crosses
+// a binade, retriggers or freezes inside the tile).  For every audible piece it issues ONE bulk async
+// copy (cp.async.bulk -> UBLKCP) of the contiguous source span into a 4-deep shared-memory ring,
+// signalled through mbarriers.  Eight consumer warps (lanes = consecutive frames) read the staged
+// samples with conflict-free LDS, interpolate, scale, cast and accumulate int32 in registers.
+// Memory latency is decoupled from arithmetic, arbitrary velocities gather from shared memory instead
+// of HBM, and every source byte crosses HBM once per tile.  Spans that do not fit a stage
+// (|velocity| > 2 on stereo), NaN trajectories and frames that straddle two segments fall back to
+// direct global gathers inside the same kernel.
+//
+// Measured on B200 (tools/micro/pipe_rates.cu): F2I / I2F.S16 / FRND run on the XU pipe at 16
+// lanes/clk/SM, PRMT / LOP3 at 64, FADD / FMUL / FMNMX / IADD at 128.  The hot paths therefore keep
+// XU work to the two final saturating casts per frame: i16 -> f32 uses the 2^23 magic-number trick
+// (exact) and positions are carried as the integer significand of their segment.
+constexpr int kStages = 4;
+constexpr int kStageBytes = 16 * 1024 + 256;
+constexpr int kConsumers = 256;
+constexpr int kTmaThreads = kConsumers + 32;
+enum : uint32_t { kModeStaged = 1, kModeDirect = 2, kModeEnd = 3 };
+enum : uint32_t { kPathGeneric = 0, kPathStereoUnit = 1, kPathStereoLerp = 2 };
+
+struct StageMeta {            // written by the producer before it arrives on the stage's full barrier
+    // hot header (one LDS.128)
+    uint32_t mode;            // kMode* | path << 8 | full-range flag << 16 | slow flag << 17
+    float gain;
+    uint32_t a0_off;          // byte offset in the stage such that frame fl of the tile maps to a0_off + fl*4 (unit path)
+    uint32_t frange;          // fa | fb << 16: the piece covers tile frames [fa, fb)
+    // integer trajectory of the fast paths (second LDS.128)
+    int32_t q0;               // significand at tile frame 0 (extrapolated), q(fl) = q0 + fl * d
+    int32_t d;
+    uint32_t sh;              // position = q * 2^-sh
+    float scale;              // 2^-sh as float (segment ulp)
+    // generic path
+    const int16_t* smp;
+    const Seg* sg;
+    float p0;                 // position at the first step of the piece
+    float vel;
+    uint32_t end;
+    uint32_t base_idx;        // frame index staged at byte_off
+    uint32_t byte_off;
+    uint32_t shape;           // C | S << 8 | nch << 16
+    uint32_t nseg;
+    uint32_t seg_hint;        // segment index at the piece start (slow pieces walk from here)
+};
+static_assert(sizeof(StageMeta) == 80, "StageMeta layout");
+constexpr size_t kMetaStride = 80;
+constexpr size_t kTmaSmem = (size_t)kStages * kStageBytes + kStages * kMetaStride + 2 * kStages * sizeof(uint64_t);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int32_t lds_s16(uint32_t addr) {
+    int32_t v;
+    asm volatile("{\n\t.reg .s16 t;\n\tld.shared.s16 t, [%1];\n\tcvt.s32.s16 %0, t;\n\t}" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// packed stereo frame (L | R << 16) -> two exact floats without the XU pipe
+__device__ __forceinline__ void unpack_pair(uint32_t w, float& l, float& r) {
+    const uint32_t x = w ^ 0x80008000u;                                   // bias both halves to unsigned
+    l = __fsub_rn(__uint_as_float(__byte_perm(x, 0x4B400000u, 0x7610)), 12615680.0f);   // 1.5*2^23 + 32768
+    r = __fsub_rn(__uint_as_float(__byte_perm(x, 0x4B400000u, 0x7632)), 12615680.0f);
+}
+
+// velocity == 1.0 inside a unit-step run: frame index advances by one per frame, no interpolation
+template <bool kFull>
+__device__ __forceinline__ void consume_stereo_unit(uint32_t stage_addr, uint32_t a0_off, float gain, uint32_t frange,
+                                                    int32_t (&acc)[kFPT][2]) {
+    const uint32_t a0 = stage_addr + a0_off + threadIdx.x * 4u;
+    const uint32_t fa = frange & 0xFFFF, span = (frange >> 16) - fa;
+    uint32_t w[kFPT];
+#pragma unroll
+    for (int j = 0; j < kFPT; ++j) {
+        const bool on = kFull || (threadIdx.x + j * kConsumers - fa) < span;
+        w[j] = on ? lds_u32(a0 + (uint32_t)j * kConsumers * 4u) : 0x0u;
+    }
+#pragma unroll
+    for (int j = 0; j < kFPT; ++j) {
+        const bool on = kFull || (threadIdx.x + j * kConsumers - fa) < span;
+        float l, r;
+        unpack_pair(w[j], l, r);
+        const int32_t il = f2i16_sat(__fmul_rn(l, gain)), ir = f2i16_sat(__fmul_rn(r, gain));
+        acc[j][0] += on ? il : 0;
+        acc[j][1] += on ? ir : 0;
+    }
+}
+
+// any velocity inside one arithmetic segment with positions in [0, 2^24)
+template <bool kFull>
+__device__ __forceinline__ void consume_stereo_lerp(uint32_t stage_addr, const StageMeta& m, int32_t (&acc)[kFPT][2]) {
+    const uint32_t mask = (1u << m.sh) - 1u;
+    const uint32_t fa = m.frange & 0xFFFF, span = (m.frange >> 16) - fa;
+    const uint32_t sbase = stage_addr + m.byte_off - m.base_idx * 4u;
+    uint32_t w0[kFPT], w1[kFPT], fb[kFPT];
+#pragma unroll
+    for (int j = 0; j < kFPT; ++j) {
+        const uint32_t fl = threadIdx.x + j * kConsumers;
+        const bool on = kFull || (fl - fa) < span;
+        const uint32_t q = (uint32_t)(m.q0 + (int32_t)fl * m.d);
+        const uint32_t a = sbase + (q >> m.sh) * 4u;
+        fb[j] = q & mask;
+        w0[j] = on ? lds_u32(a) : 0u;
+        w1[j] = on ? lds_u32(a + 4u) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < kFPT; ++j) {
+        const bool on = kFull || (threadIdx.x + j * kConsumers - fa) < span;
+        // fract = position - trunc(position), exactly (engine.rs:433)
+        const float frac = __fmul_rn(__int2float_rn((int)fb[j]), m.scale);       // fb < 2^24: exact (I2FP, not XU)
+        const float om = __fsub_rn(1.0f, frac);
+        float l0, r0, l1, r1;
+        unpack_pair(w0[j], l0, r0);
+        unpack_pair(w1[j], l1, r1);
+        const float l = __fadd_rn(__fmul_rn(l0, om), __fmul_rn(l1, frac));
+        const float r = __fadd_rn(__fmul_rn(r0, om), __fmul_rn(r1, frac));
+        const int32_t il = f2i16_sat(__fmul_rn(l, m.gain)), ir = f2i16_sat(__fmul_rn(r, m.gain));
+        acc[j][0] += on ? il : 0;
+        acc[j][1] += on ? ir : 0;
+    }
+}
+
+// generic piece: any channel layout; samples from the stage (kStaged) or straight from global memory.
+// Slow pieces (a frame whose advance events straddle two segments) walk the segment list per step.
+template <int OC, bool kStaged>
+__device__ __forceinline__ void consume_generic(const StageMeta& m, uint32_t stage_addr, uint32_t f0,
+                                                int32_t (&acc)[kFPT][OC]) {
+    const uint32_t C = m.shape & 0xFF, S = (m.shape >> 8) & 0xFF, nch = (m.shape >> 16) & 0xFF;
+    const uint32_t fa = m.frange & 0xFFFF, span = (m.frange >> 16) - fa;
+    const bool slow = (m.mode >> 17) & 1;
+    const bool lerp = m.vel != 1.0f;
+    const uint32_t sbase = stage_addr + m.byte_off;
+#pragma unroll
+    for (int j = 0; j < kFPT; ++j) {
+        const uint32_t fl = threadIdx.x + j * kConsumers;
+        if ((fl - fa) < span) {
+#pragma unroll
+            for (int c = 0; c < OC; ++c) {
+                if ((uint32_t)c < nch) {
+                    const uint32_t step = (fl - fa) * S + ((C == 1) ? (uint32_t)c : 0u);   // steps since the piece start
+                    float p;
+                    if (!slow) {
+                        p = seg_eval(m.p0, m.d, m.scale, step);
+                    } else {
+                        const uint32_t abs_step = (f0 + fa) * S + step;
+                        uint32_t k = m.seg_hint;
+                        while (k + 1 < m.nseg && m.sg[k + 1].step0 <= abs_step) ++k;
+                        const Seg g = m.sg[k];
+                        p = seg_eval(g.p0, g.d, g.scale, abs_step - g.step0);
+                    }
+                    const uint32_t idx = f2u_sat(p);
+                    if (idx < m.end) {
+                        const uint32_t sc = (C == 1) ? 0u : (uint32_t)c;
+                        float s0, s1 = 0.0f;
+                        if (kStaged) {
+                            const uint32_t a = sbase + ((idx - m.base_idx) * C + sc) * 2u;
+                            s0 = (float)lds_s16(a);
+                            if (lerp) s1 = (float)lds_s16(a + C * 2u);
+                        } else {
+                            const int16_t* sp = m.smp + (size_t)idx * C + sc;
+                            s0 = (float)sp[0];
+                            if (lerp) s1 = (float)sp[C];
+                        }
+                        float smp = s0;
+                        if (lerp) {
+                            const float frac = __fsub_rn(p, truncf(p));                  // f32::fract
+                            smp = __fadd_rn(__fmul_rn(s0, __fsub_rn(1.0f, frac)), __fmul_rn(s1, frac));
+                        }
+                        acc[j][c] += f2i16_sat(__fmul_rn(smp, m.gain));
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int OC>
+__global__ void __launch_bounds__(kTmaThreads)
+voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t voices_per_group,
+                     const Seg* __restrict__ segs, const uint32_t* __restrict__ nsegs,
+                     const TileRec* __restrict__ recs, uint32_t frames, int32_t* __restrict__ bus, int use_atomic) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* stages = smem;
+    uint8_t* meta_base = smem + (size_t)kStages * kStageBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(meta_base + kStages * kMetaStride);
+    uint64_t* empty = full + kStages;
+
+    const uint32_t tile = blockIdx.x;
+    const uint32_t f0 = tile * (uint32_t)kFT;
+    const uint32_t nf = min((uint32_t)kFT, frames - f0);
+    const uint32_t vbeg = blockIdx.y * voices_per_group;
+    const uint32_t vend = min(n_voices, vbeg + voices_per_group);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, kConsumers / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kConsumers / 32) {
+        // ------------------------------------------------ producer warp
+        uint32_t o = 0;                                   // items enqueued so far (uniform across the warp)
+        for (uint32_t vb = vbeg; vb < vend; vb += 32) {
+            const uint32_t vi = vb + lane;
+            // per-lane voice state for the piece walk
+            VoiceDev v{};
+            const Seg* sg = nullptr;
+            uint32_t nseg = 0, seg_j = 0, cur = nf;        // cur = next tile frame not yet covered
+            TileRec r{};
+            if (vi < vend) {
+                v = voices[vi];
+                if (v.active) {
+                    r = recs[(size_t)tile * n_voices + vi];
+                    sg = segs + (size_t)vi * kMaxSeg;
+                    nseg = nsegs[vi];
+                    seg_j = r.meta >> 24;
+                    cur = 0;
+                }
+            }
+            bool first_round = true;
+            while (__any_sync(0xFFFFFFFFu, cur < nf)) {
+                // ---- every lane cuts its next piece
+                StageMeta m{};
+                uint32_t bytes = 0;
+                unsigned long long src = 0;
+                bool unit_tile = false;
+                if (first_round && cur < nf && OC == 2 && v.C == 2 && v.nch == 2 && v.vel == 1.0f && r.p0 >= 0.0f) {
+                    // velocity 1.0: while position + frames stays below 2^24 and the start is a multiple of the
+                    // coarsest ulp it will meet, every `position += 1.0` is exact, whatever binades it crosses:
+                    // the whole tile is one unit-step piece (frame index = floor(p0) + frame).
+                    const float top = __fadd_rn(r.p0, (float)nf);
+                    if (top < 16777216.0f) {
+                        const float u = ulp_of_binade((__float_as_uint(top) >> 23) & 0xFF);
+                        const float qf = __fdiv_rn(r.p0, u);
+                        const uint32_t idx_a = f2u_sat(r.p0);
+                        if (truncf(qf) == qf && idx_a + nf <= v.end) {
+                            const unsigned long long base = (unsigned long long)v.smp;
+                            const unsigned long long b0 = base + (unsigned long long)idx_a * 4ull;
+                            const unsigned long long b1 = base + ((unsigned long long)idx_a + nf) * 4ull;
+                            const unsigned long long a0 = b0 & ~15ull, a1 = (b1 + 15ull) & ~15ull;
+                            unit_tile = true;
+                            src = a0;
+                            bytes = (uint32_t)(a1 - a0);
+                            m.a0_off = (uint32_t)(b0 - a0);
+                            m.mode = kModeStaged | (kPathStereoUnit << 8) | ((nf == (uint32_t)kFT ? 1u : 0u) << 16);
+                            m.gain = v.gain;
+                            m.frange = 0u | (nf << 16);
+                            cur = nf;
+                        }
+                    }
+                }
+                first_round = false;
+                if (!unit_tile && cur < nf) {
+                    uint32_t fa = cur, fb;
+                    float p_a;
+                    int32_t d;
+                    float scale;
+                    bool slow = false;
+                    const uint32_t tile_step0 = f0 * v.S;
+                    if (v.S == 0) {
+                        fb = nf; p_a = r.p0; d = 0; scale = 0.0f;
+                    } else if (cur == 0 && (r.meta & 0xFFFFFFu) >= nf * v.S) {
+                        fb = nf; p_a = r.p0; d = r.d; scale = r.scale;           // the common case: one piece
+                    } else {
+                        const uint32_t abs0 = tile_step0 + cur * v.S;
+                        while (seg_j + 1 < nseg && sg[seg_j + 1].step0 <= abs0) ++seg_j;
+                        const Seg g = sg[seg_j];
+                        const uint32_t seg_end = (seg_j + 1 < nseg) ? sg[seg_j + 1].step0 : 0xFFFFFFFFu;
+                        const uint32_t whole = (seg_end - abs0) / v.S;           // frames entirely inside the segment
+                        p_a = seg_eval(g.p0, g.d, g.scale, abs0 - g.step0);
+                        d = g.d; scale = g.scale;
+                        if (whole >= 1) {
+                            fb = min(nf, cur + whole);
+                        } else {
+                            fb = cur + 1;                                        // frame straddles two segments
+                            slow = true;
+                        }
+                    }
+                    cur = fb;
+                    const uint32_t last_step = v.S ? (fb - fa) * v.S - 1 : 0;
+                    float p_last;
+                    if (!slow) {
+                        p_last = seg_eval(p_a, d, scale, last_step);
+                    } else {
+                        const uint32_t abs_last = tile_step0 + fa * v.S + last_step;
+                        uint32_t k = seg_j;
+                        while (k + 1 < nseg && sg[k + 1].step0 <= abs_last) ++k;
+                        const Seg g = sg[k];
+                        p_last = seg_eval(g.p0, g.d, g.scale, abs_last - g.step0);
+                    }
+                    const bool weird = (p_a != p_a) || (p_last != p_last) || (v.vel != v.vel);
+                    const uint32_t idx_lo = f2u_sat(fminf(p_a, p_last));
+                    const uint32_t idx_hi = f2u_sat(fmaxf(p_a, p_last));
+                    uint32_t mode = 0, path = kPathGeneric;
+                    if (weird) {
+                        mode = kModeDirect;
+                    } else if (idx_lo < v.end) {
+                        const uint32_t hi_c = min(idx_hi, v.end - 1);
+                        const unsigned long long base = (unsigned long long)v.smp;
+                        const unsigned long long b0 = base + (unsigned long long)idx_lo * v.C * 2ull;
+                        const unsigned long long b1 = base + ((unsigned long long)hi_c + 2ull) * v.C * 2ull;
+                        const unsigned long long a0 = b0 & ~15ull, a1 = (b1 + 15ull) & ~15ull;
+                        if (a1 - a0 <= (unsigned long long)kStageBytes) {
+                            mode = kModeStaged;
+                            src = a0;
+                            bytes = (uint32_t)(a1 - a0);
+                            m.base_idx = idx_lo;
+                            m.byte_off = (uint32_t)(b0 - a0);
+                            // fast consumer paths: one segment, every frame audible, stereo voice on a
+                            // stereo bus, positions in [0, 2^24)
+                            if (OC == 2 && v.C == 2 && v.nch == 2 && !slow && idx_hi < v.end && p_a >= 0.0f && p_last >= 0.0f) {
+                                if (v.vel == 1.0f && __fmul_rn((float)d, scale) == 1.0f) {
+                                    path = kPathStereoUnit;
+                                    m.a0_off = m.byte_off + (f2u_sat(p_a) - idx_lo - fa) * 4u;
+                                } else if (v.vel != 1.0f && d != 0) {
+                                    const uint32_t eb = (__float_as_uint(scale) >> 23) & 0xFF;     // scale = 2^(eb-127)
+                                    if (eb >= 96 && eb <= 127) {
+                                        path = kPathStereoLerp;
+                                        m.sh = 127 - eb;
+                                        const int32_t qa = __float2int_rz(__fmul_rn(p_a, __uint_as_float((127u + m.sh) << 23)));
+                                        m.q0 = qa - (int32_t)fa * d;
+                                    }
+                                }
+                            }
+                        } else {
+                            mode = kModeDirect;
+                        }
+                    }                                     // else: silent piece, nothing to enqueue
+                    const bool fullr = (fa == 0 && fb == (uint32_t)kFT);
+                    m.mode = mode | (path << 8) | ((fullr ? 1u : 0u) << 16) | ((slow ? 1u : 0u) << 17);
+                    m.gain = v.gain;
+                    m.frange = fa | (fb << 16);
+                    m.d = d;
+                    m.scale = scale;
+                    m.smp = v.smp;
+                    m.sg = sg;
+                    m.p0 = p_a;
+                    m.vel = v.vel;
+                    m.end = v.end;
+                    m.shape = v.C | (v.S << 8) | (v.nch << 16);
+                    m.nseg = nseg;
+                    m.seg_hint = seg_j;
+                }
+                // ---- issue the pieces of this round in lane order
+                const uint32_t have = __ballot_sync(0xFFFFFFFFu, (m.mode & 0xFF) != 0);
+                for (uint32_t rest = have; rest; rest &= rest - 1) {
+                    const int i = __ffs(rest) - 1;
+                    const uint32_t st = o % kStages, round = o / kStages;
+                    if (lane == i) {
+                        if (round > 0) mbar_wait(empty + st, (round - 1) & 1);
+                        *reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride) = m;
+                        if ((m.mode & 0xFF) == kModeStaged) {
+                            mbar_arrive_expect_tx(full + st, bytes);
+                            bulk_g2s(stages + (size_t)st * kStageBytes, reinterpret_cast<const void*>(src), bytes, full + st);
+                        } else {
+                            mbar_arrive(full + st);
+                        }
+                    }
+                    __syncwarp();
+                    o += 1;
+                }
+            }
+        }
+        if (lane == 0) {
+            const uint32_t st = o % kStages, round = o / kStages;
+            if (round > 0) mbar_wait(empty + st, (round - 1) & 1);
+            reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride)->mode = kModeEnd;
+            mbar_arrive(full + st);
+        }
+        return;
+    }
+
+    // ---------------------------------------------------- consumer warps
+    int32_t acc[kFPT][OC];
+#pragma unroll
+    for (int j = 0; j < kFPT; ++j)
+#pragma unroll
+        for (int c = 0; c < OC; ++c) acc[j][c] = 0;
+
+    const uint32_t stage0 = smem_u32(stages), meta0 = smem_u32(meta_base);
+    for (uint32_t o = 0;; ++o) {
+        const uint32_t st = o % kStages;
+        mbar_wait(full + st, (o / kStages) & 1);
+        const uint32_t stage_addr = stage0 + st * (uint32_t)kStageBytes;
+        const StageMeta* mp = reinterpret_cast<const StageMeta*>(meta_base + st * kMetaStride);
+        uint32_t mode; float gain; uint32_t a0_off, frange;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(mode), "=f"(gain), "=r"(a0_off), "=r"(frange) : "r"(meta0 + st * (uint32_t)kMetaStride));
+        if ((mode & 0xFF) == kModeEnd) break;
+        const uint32_t path = (mode >> 8) & 0xFF;
+        const bool fullr = (mode >> 16) & 1;
+        if (OC == 2 && path == kPathStereoUnit) {
+            auto& a2 = reinterpret_cast<int32_t (&)[kFPT][2]>(acc);
+            if (fullr) consume_stereo_unit<true>(stage_addr, a0_off, gain, frange, a2);
+            else consume_stereo_unit<false>(stage_addr, a0_off, gain, frange, a2);
+        } else if (OC == 2 && path == kPathStereoLerp) {
+            auto& a2 = reinterpret_cast<int32_t (&)[kFPT][2]>(acc);
+            if (fullr) consume_stereo_lerp<true>(stage_addr, *mp, a2);
+            else consume_stereo_lerp<false>(stage_addr, *mp, a2);
+        } else if ((mode & 0xFF) == kModeStaged) {
+            consume_generic<OC, true>(*mp, stage_addr, f0, acc);
+        } else {
+            consume_generic<OC, false>(*mp, 0u, f0, acc);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + st);
+    }
+
+#pragma unroll
+    for (int j = 0; j < kFPT; ++j) {
+        const uint32_t fl = threadIdx.x + j * kConsumers;
         if (fl < nf) {
             int32_t* out = bus + (size_t)(f0 + fl) * OC;
 #pragma unroll
@@ -528,21 +988,35 @@ int blast_scene_render_dev(blast_ctx* ctx, blast_scene* sc, uint64_t frames, int
     const int use_atomic = groups > 1;
     if (use_atomic) BLAST_CUDA_TRY(cudaMemsetAsync(d_partial_bus, 0, slots * sizeof(int32_t), ctx->stream));
     dim3 grid(n_tiles, groups);
+    static const bool legacy = getenv("BLAST_RENDER_LEGACY") != nullptr;
+    if (oc <= 2 && !legacy) {
+        // TMA pipeline kernel (one producer warp + eight consumer warps)
+        if (oc == 1) {
+            BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
+            voice_render_mix_tma<1><<<grid, kTmaThreads, kTmaSmem, ctx->stream>>>(sc->d_voices, sc->n_voices, per_group, sc->d_segs,
+                                                                                  sc->d_nsegs, sc->d_recs, (uint32_t)frames, d_partial_bus, use_atomic);
+        } else {
+            BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
+            voice_render_mix_tma<2><<<grid, kTmaThreads, kTmaSmem, ctx->stream>>>(sc->d_voices, sc->n_voices, per_group, sc->d_segs,
+                                                                                  sc->d_nsegs, sc->d_recs, (uint32_t)frames, d_partial_bus, use_atomic);
+        }
+    } else {
 #define BLAST_LAUNCH_MIX(OCV)                                                                              \
     voice_render_mix<OCV><<<grid, kThreads, 0, ctx->stream>>>(sc->d_voices, sc->n_voices, per_group, sc->d_segs, \
                                                                sc->d_nsegs, sc->d_recs, (uint32_t)frames,       \
                                                                d_partial_bus, use_atomic)
-    switch (oc) {
-        case 1: BLAST_LAUNCH_MIX(1); break;
-        case 2: BLAST_LAUNCH_MIX(2); break;
-        case 3: BLAST_LAUNCH_MIX(3); break;
-        case 4: BLAST_LAUNCH_MIX(4); break;
-        case 5: BLAST_LAUNCH_MIX(5); break;
-        case 6: BLAST_LAUNCH_MIX(6); break;
-        case 7: BLAST_LAUNCH_MIX(7); break;
-        default: BLAST_LAUNCH_MIX(8); break;
-    }
+        switch (oc) {
+            case 1: BLAST_LAUNCH_MIX(1); break;
+            case 2: BLAST_LAUNCH_MIX(2); break;
+            case 3: BLAST_LAUNCH_MIX(3); break;
+            case 4: BLAST_LAUNCH_MIX(4); break;
+            case 5: BLAST_LAUNCH_MIX(5); break;
+            case 6: BLAST_LAUNCH_MIX(6); break;
+            case 7: BLAST_LAUNCH_MIX(7); break;
+            default: BLAST_LAUNCH_MIX(8); break;
+        }
 #undef BLAST_LAUNCH_MIX
+    }
     BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
     return BLAST_OK;
