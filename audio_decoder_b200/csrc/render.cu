@@ -372,7 +372,8 @@ constexpr int kStageBytes = 16 * 1024 + 256;
 constexpr int kConsumers = 256;
 constexpr int kTmaThreads = kConsumers + 32;
 enum : uint32_t { kModeStaged = 1, kModeDirect = 2, kModeEnd = 3 };
-enum : uint32_t { kPathGeneric = 0, kPathStereoUnit = 1, kPathStereoLerp = 2 };
+enum : uint32_t { kPathGeneric = 0, kPathStereoUnit = 1, kPathStereoLerp = 2, kPathStereoMulti = 3 };
+constexpr int kMaxPieces = 32;                // pieces of one voice in one tile handled by a single staged item
 
 struct StageMeta {            // written by the producer before it arrives on the stage's full barrier
     // hot header (one LDS.128)
@@ -399,7 +400,8 @@ struct StageMeta {            // written by the producer before it arrives on th
 };
 static_assert(sizeof(StageMeta) == 80, "StageMeta layout");
 constexpr size_t kMetaStride = 80;
-constexpr size_t kTmaSmem = (size_t)kStages * kStageBytes + kStages * kMetaStride + 2 * kStages * sizeof(uint64_t);
+constexpr size_t kTmaSmem = (size_t)kStages * kStageBytes + kStages * kMetaStride + 2 * kStages * sizeof(uint64_t) +
+                            (size_t)kStages * kMaxPieces * sizeof(uint4);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -447,55 +449,117 @@ template <bool kFull>
 __device__ __forceinline__ void consume_stereo_unit(uint32_t stage_addr, uint32_t a0_off, float gain, uint32_t frange,
                                                     int32_t (&acc)[kFPT][2]) {
     const uint32_t a0 = stage_addr + a0_off + threadIdx.x * 4u;
-    const uint32_t fa = frange & 0xFFFF, span = (frange >> 16) - fa;
-    uint32_t w[kFPT];
+    if (kFull) {
+        uint32_t w[kFPT];
 #pragma unroll
-    for (int j = 0; j < kFPT; ++j) {
-        const bool on = kFull || (threadIdx.x + j * kConsumers - fa) < span;
-        w[j] = on ? lds_u32(a0 + (uint32_t)j * kConsumers * 4u) : 0x0u;
-    }
+        for (int j = 0; j < kFPT; ++j) w[j] = lds_u32(a0 + (uint32_t)j * kConsumers * 4u);
 #pragma unroll
-    for (int j = 0; j < kFPT; ++j) {
-        const bool on = kFull || (threadIdx.x + j * kConsumers - fa) < span;
-        float l, r;
-        unpack_pair(w[j], l, r);
-        const int32_t il = f2i16_sat(__fmul_rn(l, gain)), ir = f2i16_sat(__fmul_rn(r, gain));
-        acc[j][0] += on ? il : 0;
-        acc[j][1] += on ? ir : 0;
+        for (int j = 0; j < kFPT; ++j) {
+            float l, r;
+            unpack_pair(w[j], l, r);
+            acc[j][0] += f2i16_sat(__fmul_rn(l, gain));
+            acc[j][1] += f2i16_sat(__fmul_rn(r, gain));
+        }
+    } else {
+        // partial piece: only the 256-frame slabs it touches are visited (uniform skip), lanes predicated
+        const uint32_t fa = frange & 0xFFFF, fb = frange >> 16, span = fb - fa;
+        const uint32_t j_lo = fa / kConsumers, j_hi = (fb - 1) / kConsumers;
+#pragma unroll
+        for (int j = 0; j < kFPT; ++j) {
+            if ((uint32_t)j < j_lo || (uint32_t)j > j_hi) continue;
+            if ((threadIdx.x + j * kConsumers - fa) < span) {
+                float l, r;
+                unpack_pair(lds_u32(a0 + (uint32_t)j * kConsumers * 4u), l, r);
+                acc[j][0] += f2i16_sat(__fmul_rn(l, gain));
+                acc[j][1] += f2i16_sat(__fmul_rn(r, gain));
+            }
+        }
     }
 }
 
 // any velocity inside one arithmetic segment with positions in [0, 2^24)
+__device__ __forceinline__ void lerp_frame(uint32_t w0, uint32_t w1, uint32_t fbits, float scale, float gain,
+                                           int32_t& al, int32_t& ar) {
+    // fract = position - trunc(position), exactly (engine.rs:433); fbits < 2^24 so I2FP is exact
+    const float frac = __fmul_rn(__int2float_rn((int)fbits), scale);
+    const float om = __fsub_rn(1.0f, frac);
+    float l0, r0, l1, r1;
+    unpack_pair(w0, l0, r0);
+    unpack_pair(w1, l1, r1);
+    const float l = __fadd_rn(__fmul_rn(l0, om), __fmul_rn(l1, frac));
+    const float r = __fadd_rn(__fmul_rn(r0, om), __fmul_rn(r1, frac));
+    al += f2i16_sat(__fmul_rn(l, gain));
+    ar += f2i16_sat(__fmul_rn(r, gain));
+}
+
 template <bool kFull>
 __device__ __forceinline__ void consume_stereo_lerp(uint32_t stage_addr, const StageMeta& m, int32_t (&acc)[kFPT][2]) {
     const uint32_t mask = (1u << m.sh) - 1u;
-    const uint32_t fa = m.frange & 0xFFFF, span = (m.frange >> 16) - fa;
     const uint32_t sbase = stage_addr + m.byte_off - m.base_idx * 4u;
-    uint32_t w0[kFPT], w1[kFPT], fb[kFPT];
+    const int32_t q0 = m.q0, d = m.d;
+    const uint32_t sh = m.sh;
+    const float scale = m.scale, gain = m.gain;
+    if (kFull) {
+        uint32_t w0[kFPT], w1[kFPT], fb[kFPT];
 #pragma unroll
-    for (int j = 0; j < kFPT; ++j) {
-        const uint32_t fl = threadIdx.x + j * kConsumers;
-        const bool on = kFull || (fl - fa) < span;
-        const uint32_t q = (uint32_t)(m.q0 + (int32_t)fl * m.d);
-        const uint32_t a = sbase + (q >> m.sh) * 4u;
-        fb[j] = q & mask;
-        w0[j] = on ? lds_u32(a) : 0u;
-        w1[j] = on ? lds_u32(a + 4u) : 0u;
+        for (int j = 0; j < kFPT; ++j) {
+            const uint32_t q = (uint32_t)(q0 + (int32_t)(threadIdx.x + j * kConsumers) * d);
+            const uint32_t a = sbase + (q >> sh) * 4u;
+            fb[j] = q & mask;
+            w0[j] = lds_u32(a);
+            w1[j] = lds_u32(a + 4u);
+        }
+#pragma unroll
+        for (int j = 0; j < kFPT; ++j) lerp_frame(w0[j], w1[j], fb[j], scale, gain, acc[j][0], acc[j][1]);
+    } else {
+        const uint32_t fa = m.frange & 0xFFFF, fe = m.frange >> 16, span = fe - fa;
+        const uint32_t j_lo = fa / kConsumers, j_hi = (fe - 1) / kConsumers;
+#pragma unroll
+        for (int j = 0; j < kFPT; ++j) {
+            if ((uint32_t)j < j_lo || (uint32_t)j > j_hi) continue;
+            const uint32_t fl = threadIdx.x + j * kConsumers;
+            if ((fl - fa) < span) {
+                const uint32_t q = (uint32_t)(q0 + (int32_t)fl * d);
+                const uint32_t a = sbase + (q >> sh) * 4u;
+                lerp_frame(lds_u32(a), lds_u32(a + 4u), q & mask, scale, gain, acc[j][0], acc[j][1]);
+            }
+        }
     }
+}
+
+// several pieces of one stereo voice inside one tile, all staged by ONE bulk copy: the producer leaves a
+// table of (frame range, q0, d, sh) per piece; every piece is visited with uniform slab skipping
+template <bool kLerp>
+__device__ __forceinline__ void consume_stereo_multi(uint32_t stage_addr, const StageMeta& m, uint32_t ptab, uint32_t n_p,
+                                                     int32_t (&acc)[kFPT][2]) {
+    const uint32_t sbase = stage_addr + m.byte_off - m.base_idx * 4u;
+    const float gain = m.gain;
+    for (uint32_t k = 0; k < n_p; ++k) {
+        uint32_t frange, q0u, du, shf;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(frange), "=r"(q0u), "=r"(du), "=r"(shf) : "r"(ptab + k * 16u));
+        if (shf & 0x100u) continue;                                      // silent piece (frozen / past the end)
+        const uint32_t sh = shf & 0xFFu, mask = (1u << sh) - 1u;
+        const float scale = __uint_as_float((127u - sh) << 23);
+        const int32_t q0 = (int32_t)q0u, d = (int32_t)du;
+        const uint32_t fa = frange & 0xFFFF, fe = frange >> 16, span = fe - fa;
+        const uint32_t j_lo = fa / kConsumers, j_hi = (fe - 1) / kConsumers;
 #pragma unroll
-    for (int j = 0; j < kFPT; ++j) {
-        const bool on = kFull || (threadIdx.x + j * kConsumers - fa) < span;
-        // fract = position - trunc(position), exactly (engine.rs:433)
-        const float frac = __fmul_rn(__int2float_rn((int)fb[j]), m.scale);       // fb < 2^24: exact (I2FP, not XU)
-        const float om = __fsub_rn(1.0f, frac);
-        float l0, r0, l1, r1;
-        unpack_pair(w0[j], l0, r0);
-        unpack_pair(w1[j], l1, r1);
-        const float l = __fadd_rn(__fmul_rn(l0, om), __fmul_rn(l1, frac));
-        const float r = __fadd_rn(__fmul_rn(r0, om), __fmul_rn(r1, frac));
-        const int32_t il = f2i16_sat(__fmul_rn(l, m.gain)), ir = f2i16_sat(__fmul_rn(r, m.gain));
-        acc[j][0] += on ? il : 0;
-        acc[j][1] += on ? ir : 0;
+        for (int j = 0; j < kFPT; ++j) {
+            if ((uint32_t)j < j_lo || (uint32_t)j > j_hi) continue;
+            const uint32_t fl = threadIdx.x + j * kConsumers;
+            if ((fl - fa) < span) {
+                const uint32_t q = (uint32_t)(q0 + (int32_t)fl * d);
+                const uint32_t a = sbase + (q >> sh) * 4u;
+                if (kLerp) {
+                    lerp_frame(lds_u32(a), lds_u32(a + 4u), q & mask, scale, gain, acc[j][0], acc[j][1]);
+                } else {
+                    float l, r;
+                    unpack_pair(lds_u32(a), l, r);
+                    acc[j][0] += f2i16_sat(__fmul_rn(l, gain));
+                    acc[j][1] += f2i16_sat(__fmul_rn(r, gain));
+                }
+            }
+        }
     }
 }
 
@@ -509,8 +573,10 @@ __device__ __forceinline__ void consume_generic(const StageMeta& m, uint32_t sta
     const bool slow = (m.mode >> 17) & 1;
     const bool lerp = m.vel != 1.0f;
     const uint32_t sbase = stage_addr + m.byte_off;
+    const uint32_t j_lo = fa / kConsumers, j_hi = (fa + span - 1) / kConsumers;
 #pragma unroll
     for (int j = 0; j < kFPT; ++j) {
+        if ((uint32_t)j < j_lo || (uint32_t)j > j_hi) continue;
         const uint32_t fl = threadIdx.x + j * kConsumers;
         if ((fl - fa) < span) {
 #pragma unroll
@@ -556,18 +622,22 @@ __device__ __forceinline__ void consume_generic(const StageMeta& m, uint32_t sta
 template <int OC>
 __global__ void __launch_bounds__(kTmaThreads)
 voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t voices_per_group,
-                     const Seg* __restrict__ segs, const uint32_t* __restrict__ nsegs,
+                     uint32_t n_groups, const Seg* __restrict__ segs, const uint32_t* __restrict__ nsegs,
                      const TileRec* __restrict__ recs, uint32_t frames, int32_t* __restrict__ bus, int use_atomic) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stages = smem;
     uint8_t* meta_base = smem + (size_t)kStages * kStageBytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(meta_base + kStages * kMetaStride);
     uint64_t* empty = full + kStages;
+    uint4* ptabs = reinterpret_cast<uint4*>(empty + kStages);          // [kStages][kMaxPieces]
 
-    const uint32_t tile = blockIdx.x;
+    // tile-major block order: all voice groups of tile 0 first.  Early tiles are the expensive ones (a
+    // voice that starts at position 0 crosses ~20 binades inside its first tile), so they must not be
+    // the last CTAs to be scheduled.
+    const uint32_t tile = blockIdx.x / n_groups;
     const uint32_t f0 = tile * (uint32_t)kFT;
     const uint32_t nf = min((uint32_t)kFT, frames - f0);
-    const uint32_t vbeg = blockIdx.y * voices_per_group;
+    const uint32_t vbeg = (blockIdx.x % n_groups) * voices_per_group;
     const uint32_t vend = min(n_voices, vbeg + voices_per_group);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -601,6 +671,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                 }
             }
             bool first_round = true;
+            bool hold_multi = false;      // stereo voice whose tile spans several segments: try ONE staged item first
             while (__any_sync(0xFFFFFFFFu, cur < nf)) {
                 // ---- every lane cuts its next piece
                 StageMeta m{};
@@ -632,8 +703,10 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                         }
                     }
                 }
-                first_round = false;
-                if (!unit_tile && cur < nf) {
+                if (first_round && !unit_tile && cur < nf && OC == 2 && v.C == 2 && v.nch == 2 &&
+                    (r.meta & 0xFFFFFFu) < nf * v.S)
+                    hold_multi = true;
+                if (!unit_tile && cur < nf && !hold_multi) {
                     uint32_t fa = cur, fb;
                     float p_a;
                     int32_t d;
@@ -742,6 +815,92 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                     __syncwarp();
                     o += 1;
                 }
+                // ---- after the first round: voices held back for the multi-piece path, one at a time, with
+                // the whole warp cooperating (lane l looks at segment j0 + l of that voice)
+                if (first_round) {
+                    for (uint32_t rest = __ballot_sync(0xFFFFFFFFu, hold_multi); rest; rest &= rest - 1) {
+                        const int i = __ffs(rest) - 1;
+                        const Seg* sgi = reinterpret_cast<const Seg*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)sg, i));
+                        const uint32_t nseg_i = __shfl_sync(0xFFFFFFFFu, nseg, i), j0 = __shfl_sync(0xFFFFFFFFu, seg_j, i);
+                        const uint32_t end_i = __shfl_sync(0xFFFFFFFFu, v.end, i);
+                        const float gain_i = __shfl_sync(0xFFFFFFFFu, v.gain, i), vel_i = __shfl_sync(0xFFFFFFFFu, v.vel, i);
+                        const unsigned long long smp_i = __shfl_sync(0xFFFFFFFFu, (unsigned long long)v.smp, i);
+                        const uint32_t last_abs = f0 + nf - 1;                      // S == 1 for these voices
+                        const uint32_t jl = j0 + lane;
+                        bool ex = jl < nseg_i;
+                        Seg g{};
+                        uint32_t nxt = 0xFFFFFFFFu;
+                        if (ex) {
+                            g = sgi[jl];
+                            if (jl + 1 < nseg_i) nxt = sgi[jl + 1].step0;
+                        }
+                        ex = ex && (lane == 0 || g.step0 <= last_abs);
+                        const uint32_t exm = __ballot_sync(0xFFFFFFFFu, ex);
+                        const bool overflow = exm == 0xFFFFFFFFu && __shfl_sync(0xFFFFFFFFu, nxt, 31) <= last_abs;
+                        bool ok = true, silent = true;
+                        uint32_t idx_lo = 0xFFFFFFFFu, idx_hi = 0, shv = 0, fa = 0, fe = 0;
+                        int32_t q0v = 0;
+                        if (ex) {
+                            const uint32_t ls = max(g.step0, f0), le = min(nxt, f0 + nf);
+                            fa = ls - f0; fe = le - f0;
+                            const float p_a = seg_eval(g.p0, g.d, g.scale, ls - g.step0);
+                            const float p_l = seg_eval(g.p0, g.d, g.scale, le - 1 - g.step0);
+                            const bool weird = (p_a != p_a) || (p_l != p_l);
+                            const uint32_t lo = f2u_sat(fminf(p_a, p_l)), hi = f2u_sat(fmaxf(p_a, p_l));
+                            silent = !weird && lo >= end_i;
+                            ok = silent;
+                            if (!silent && !weird && p_a >= 0.0f && p_l >= 0.0f && hi < end_i) {
+                                if (g.d != 0) {
+                                    const uint32_t eb = (__float_as_uint(g.scale) >> 23) & 0xFF;
+                                    if (eb >= 96 && eb <= 127) { shv = 127 - eb; ok = true; }
+                                } else {
+                                    const int E = (int)((__float_as_uint(p_a) >> 23) & 0xFF);
+                                    const int s_ = p_a == 0.0f ? 0 : max(0, 150 - E);
+                                    if (s_ <= 31) { shv = (uint32_t)s_; ok = true; }
+                                }
+                                if (ok) {
+                                    const int32_t qa = __float2int_rz(__fmul_rn(p_a, __uint_as_float((127u + shv) << 23)));
+                                    q0v = qa - (int32_t)fa * g.d;
+                                    idx_lo = lo; idx_hi = hi;
+                                }
+                            }
+                        }
+                        const bool all_ok = __all_sync(0xFFFFFFFFu, ok) && !overflow;
+                        const uint32_t lo_all = __reduce_min_sync(0xFFFFFFFFu, idx_lo);
+                        const uint32_t hi_all = __reduce_max_sync(0xFFFFFFFFu, (ex && !silent) ? idx_hi : 0u);
+                        const bool audible = lo_all != 0xFFFFFFFFu;
+                        const unsigned long long b0 = smp_i + (unsigned long long)lo_all * 4ull;
+                        const unsigned long long b1 = smp_i + ((unsigned long long)hi_all + 2ull) * 4ull;
+                        const unsigned long long a0 = b0 & ~15ull, a1 = (b1 + 15ull) & ~15ull;
+                        if (all_ok && (!audible || a1 - a0 <= (unsigned long long)kStageBytes)) {
+                            if (audible) {
+                                const uint32_t st = o % kStages, round = o / kStages;
+                                if (lane == 0 && round > 0) mbar_wait(empty + st, (round - 1) & 1);
+                                __syncwarp();
+                                if (ex) ptabs[st * kMaxPieces + lane] = make_uint4(fa | (fe << 16), (uint32_t)q0v, (uint32_t)g.d, shv | (silent ? 0x100u : 0u));
+                                if (lane == 0) {
+                                    StageMeta mm{};
+                                    mm.mode = kModeStaged | (kPathStereoMulti << 8);
+                                    mm.gain = gain_i;
+                                    mm.a0_off = (uint32_t)__popc(exm);
+                                    mm.frange = (vel_i != 1.0f) ? 1u : 0u;
+                                    mm.base_idx = lo_all;
+                                    mm.byte_off = (uint32_t)(b0 - a0);
+                                    *reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride) = mm;
+                                }
+                                __syncwarp();
+                                if (lane == 0) {
+                                    mbar_arrive_expect_tx(full + st, (uint32_t)(a1 - a0));
+                                    bulk_g2s(stages + (size_t)st * kStageBytes, reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0), full + st);
+                                }
+                                o += 1;
+                            }
+                            if (lane == i) cur = nf;
+                        }
+                    }
+                    hold_multi = false;            // whoever is left walks piece by piece below
+                }
+                first_round = false;
             }
         }
         if (lane == 0) {
@@ -779,6 +938,11 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
             auto& a2 = reinterpret_cast<int32_t (&)[kFPT][2]>(acc);
             if (fullr) consume_stereo_lerp<true>(stage_addr, *mp, a2);
             else consume_stereo_lerp<false>(stage_addr, *mp, a2);
+        } else if (OC == 2 && path == kPathStereoMulti) {
+            auto& a2 = reinterpret_cast<int32_t (&)[kFPT][2]>(acc);
+            const uint32_t ptab = smem_u32(ptabs + st * kMaxPieces);
+            if (frange & 1u) consume_stereo_multi<true>(stage_addr, *mp, ptab, a0_off, a2);
+            else consume_stereo_multi<false>(stage_addr, *mp, ptab, a0_off, a2);
         } else if ((mode & 0xFF) == kModeStaged) {
             consume_generic<OC, true>(*mp, stage_addr, f0, acc);
         } else {
@@ -988,16 +1152,17 @@ int blast_scene_render_dev(blast_ctx* ctx, blast_scene* sc, uint64_t frames, int
     const int use_atomic = groups > 1;
     if (use_atomic) BLAST_CUDA_TRY(cudaMemsetAsync(d_partial_bus, 0, slots * sizeof(int32_t), ctx->stream));
     dim3 grid(n_tiles, groups);
+    dim3 grid_tma(n_tiles * groups, 1);      // 1-D, decoded tile-major inside the kernel
     static const bool legacy = getenv("BLAST_RENDER_LEGACY") != nullptr;
     if (oc <= 2 && !legacy) {
         // TMA pipeline kernel (one producer warp + eight consumer warps)
         if (oc == 1) {
             BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
-            voice_render_mix_tma<1><<<grid, kTmaThreads, kTmaSmem, ctx->stream>>>(sc->d_voices, sc->n_voices, per_group, sc->d_segs,
+            voice_render_mix_tma<1><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(sc->d_voices, sc->n_voices, per_group, groups, sc->d_segs,
                                                                                   sc->d_nsegs, sc->d_recs, (uint32_t)frames, d_partial_bus, use_atomic);
         } else {
             BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
-            voice_render_mix_tma<2><<<grid, kTmaThreads, kTmaSmem, ctx->stream>>>(sc->d_voices, sc->n_voices, per_group, sc->d_segs,
+            voice_render_mix_tma<2><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(sc->d_voices, sc->n_voices, per_group, groups, sc->d_segs,
                                                                                   sc->d_nsegs, sc->d_recs, (uint32_t)frames, d_partial_bus, use_atomic);
         }
     } else {
