@@ -85,6 +85,7 @@ SIGNATURES = {
     "blast_scene_create": (C.c_int, [_vp, C.POINTER(Track), _u32, C.POINTER(Voice), _u32, _u32, C.POINTER(_vp)]),
     "blast_scene_destroy": (None, [_vp, _vp]),
     "blast_scene_set_voices": (C.c_int, [_vp, _vp, C.POINTER(Voice), _u32]),
+    "blast_scene_restore_dev": (C.c_int, [_vp, _vp]),
     "blast_scene_get_voices": (C.c_int, [_vp, _vp, C.POINTER(Voice), _u32]),
     "blast_scene_render_dev": (C.c_int, [_vp, _vp, _u64, _vp]),
     "blast_scene_check": (C.c_int, [_vp, _vp]),

@@ -71,6 +71,10 @@ class Scene:
         v = (_lib.Voice * max(1, len(voices)))(*[x.c() for x in voices])
         check(self.ctx.lib.blast_scene_set_voices(self.ctx.h, self.h, v, len(voices)))
 
+    def restore_dev(self):
+        """async rewind to the voice table of the last create / set_voices"""
+        check(self.ctx.lib.blast_scene_restore_dev(self.ctx.h, self.h))
+
     def voices(self):
         v = (_lib.Voice * max(1, self.n_voices))()
         check(self.ctx.lib.blast_scene_get_voices(self.ctx.h, self.h, v, self.n_voices))

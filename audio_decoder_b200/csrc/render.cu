@@ -995,6 +995,7 @@ struct blast_scene {
     std::vector<blast_track> tracks;
     std::vector<blast_voice> voices;     // host mirror of the ABI voices (positions refreshed on get)
     VoiceDev* d_voices = nullptr;
+    VoiceDev* d_voices0 = nullptr;       // the table as last uploaded (blast_scene_restore_dev)
     Seg* d_segs = nullptr;
     uint32_t* d_nsegs = nullptr;
     uint32_t* d_err = nullptr;
@@ -1041,6 +1042,7 @@ int upload_voices(blast_ctx* ctx, blast_scene* sc) {
         if (int rc = make_voice_dev(sc, sc->voices[i], i, &hv[i])) return rc;
     if (sc->n_voices) {
         BLAST_CUDA_TRY(cudaMemcpyAsync(sc->d_voices, hv.data(), hv.size() * sizeof(VoiceDev), cudaMemcpyHostToDevice, ctx->stream));
+        BLAST_CUDA_TRY(cudaMemcpyAsync(sc->d_voices0, sc->d_voices, hv.size() * sizeof(VoiceDev), cudaMemcpyDeviceToDevice, ctx->stream));
         BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
     return BLAST_OK;
@@ -1065,6 +1067,7 @@ int blast_scene_create(blast_ctx* ctx, const blast_track* tracks, uint32_t n_tra
     auto fail = [&](int rc) { blast_scene_destroy(ctx, sc); return rc; };
     const size_t nv = n_voices ? n_voices : 1;
     if (cudaMalloc(&sc->d_voices, nv * sizeof(VoiceDev)) != cudaSuccess ||
+        cudaMalloc(&sc->d_voices0, nv * sizeof(VoiceDev)) != cudaSuccess ||
         cudaMalloc(&sc->d_segs, nv * kMaxSeg * sizeof(Seg)) != cudaSuccess ||
         cudaMalloc(&sc->d_nsegs, nv * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&sc->d_err, sizeof(uint32_t)) != cudaSuccess)
@@ -1081,6 +1084,7 @@ void blast_scene_destroy(blast_ctx* ctx, blast_scene* sc) {
         cudaStreamSynchronize(ctx->stream);
     }
     if (sc->d_voices) cudaFree(sc->d_voices);
+    if (sc->d_voices0) cudaFree(sc->d_voices0);
     if (sc->d_segs) cudaFree(sc->d_segs);
     if (sc->d_nsegs) cudaFree(sc->d_nsegs);
     if (sc->d_err) cudaFree(sc->d_err);
@@ -1098,6 +1102,15 @@ int blast_scene_set_voices(blast_ctx* ctx, blast_scene* sc, const blast_voice* v
     int rc = upload_voices(ctx, sc);
     if (rc != BLAST_OK) sc->voices = keep;
     return rc;
+}
+
+int blast_scene_restore_dev(blast_ctx* ctx, blast_scene* sc) {
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_REQUIRE(sc != nullptr, BLAST_ERR_ARG, "blast_scene_restore_dev: null scene");
+    if (sc->n_voices)
+        BLAST_CUDA_TRY(cudaMemcpyAsync(sc->d_voices, sc->d_voices0, (size_t)sc->n_voices * sizeof(VoiceDev),
+                                       cudaMemcpyDeviceToDevice, ctx->stream));
+    return BLAST_OK;
 }
 
 int blast_scene_get_voices(blast_ctx* ctx, blast_scene* sc, blast_voice* out, uint32_t n_voices) {

@@ -127,16 +127,22 @@ def barrier(dist, local):
 # ------------------------------------------------------------------ our arm
 def run_ours(args):
     import audio_decoder_b200 as blast
-    from audio_decoder_b200 import _lib, file_parsing as fp
+    from audio_decoder_b200 import _lib, audio_processing as ap, blast_rand as br, file_parsing as fp
 
     rank, world, local, dist = dist_setup(args.gpus)
-    ctx = blast.Context(local)
+    torch = None
+    if world > 1:
+        import torch
+        ctx = blast.Context(local, stream=torch.cuda.current_stream().cuda_stream)
+    else:
+        ctx = blast.Context(local)
     L = ctx.lib
     n_files, data_len = args.files, args.data_len
     hdr = np.frombuffer(synth.aiff_header(data_len), dtype=np.uint8)
     image_len = len(hdr) + data_len
     slot = (image_len + 255) // 256 * 256                      # file images at 256-byte aligned slots in HBM
     words_per_file = (data_len + 1) // 2
+    frames_per_file = words_per_file // 2                      # stereo
 
     # ---- synthetic file images: pinned host slab (e2e input) + HBM slab (device-resident input)
     h_in = ctx.pinned(n_files * slot)
@@ -152,65 +158,116 @@ def run_ours(args):
     ctx.sync()
     descs = [fp.probe("aiff", view[0, :image_len])] * n_files
     off = descs[0].data_off
-    src_extra = off if args.layout == "image" else 0
     if args.layout == "payload":
         # payload-only layout: what blast_pcm_decode_batch stages (16-byte aligned payloads)
         d_pay = ctx.alloc(n_files * slot)
         for i in range(n_files):
             L.blast_memcpy_h2d(ctx.h, d_pay.ptr + i * slot, h_in.ptr + i * slot + off, data_len)
         ctx.sync()
-        d_src_base = d_pay.ptr
+        d_src_base, src_extra = d_pay.ptr, 0
     else:
-        d_src_base = d_in.ptr
+        d_src_base, src_extra = d_in.ptr, off
     jobs = [(d_src_base + i * slot + src_extra, d_out.ptr + i * words_per_file * 2, words_per_file, True)
             for i in range(n_files)]
     plan = fp.PcmPlan(ctx, jobs)
     samples_per_step = n_files * words_per_file
     alg_bytes_decode = 4 * samples_per_step                      # 2 B read + 2 B written per i16 word
 
-    def step():
+    # ---- mix: every decoded file is one stereo voice (velocity 1, per-voice gain) on one stereo bus
+    mix = not args.no_mix
+    if mix:
+        tracks, voices = [], []
+        g = br.fill(ctx, 0xC2, 0, 1, n_files, 0, 100, ranged=False, checks=False)[0][0]
+        for i in range(n_files):
+            buf = blast.DevBuf.__new__(blast.DevBuf)
+            buf.ctx, buf.ptr, buf.nbytes = ctx, d_out.ptr + i * words_per_file * 2, words_per_file * 2
+            buf.free = lambda: None
+            tracks.append(ap.Track(buf, words_per_file, 2, 48000))
+            gain = float(np.float32((int(g[i]) >> 11) * 2.0 ** -53) * np.float32(2.0 ** -5))
+            voices.append(ap.VoiceParams(i, True, 0.0, 1.0, gain))
+        scene = ap.Scene(ctx, tracks, voices, 2)
+        n_slots = frames_per_file * 2
+        if world > 1:
+            t_part = torch.empty(n_slots, dtype=torch.int32, device=f"cuda:{local}")
+            part_ptr = t_part.data_ptr()
+        else:
+            d_part = ctx.alloc(4 * n_slots)
+            part_ptr = d_part.ptr
+        d_bus = ctx.alloc(2 * n_slots)
+        alg_bytes_mix = 4 * (frames_per_file - 1) * n_files + 2 * n_slots   # source frames touched + S16 bus
+    n_ev = 3 if mix else 2
+
+    def step(evs=None):
+        if evs:
+            evs[0].record()
         plan.run()
+        if evs:
+            evs[1].record()
+        if mix:
+            scene.restore_dev()
+            scene.render_partial_dev(frames_per_file, part_ptr)
+            if world > 1:
+                dist.all_reduce(t_part, op=dist.ReduceOp.SUM)      # the one collective: int32 partial buses
+            ap.finalize_bus(ctx, part_ptr, d_bus.ptr, n_slots)
+            if evs:
+                evs[2].record()
 
     for _ in range(args.warmup):
         step()
     ctx.sync()
+    if mix:
+        scene.check()
     barrier(dist, local)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count
-    e0, e1 = ctx.event(), ctx.event()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    ms_total = e0.elapsed_ms(e1)
+    evs = [[ctx.event() for _ in range(n_ev)] for _ in range(args.steps)]
+    e_end = ctx.event()
+    for k in range(args.steps):
+        step(evs[k])
+    e_end.record()
+    ms_total = evs[0][0].elapsed_ms(e_end)
     ctx.sync()
     barrier(dist, local)
     launches = ctx.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
+    ms_decode = sum(e[0].elapsed_ms(e[1]) for e in evs) / args.steps
+    ms_mix = sum(e[1].elapsed_ms(e[2]) for e in evs) / args.steps if mix else 0.0
     ms_total = max_over_ranks(dist, local, ms_total)
     ms_step = ms_total / args.steps
     value = world * samples_per_step / (ms_step * 1e-3) / 1e9
 
-    # ---- roofline of the dominant kernel (decode): per-launch average over the timed region
+    # ---- roofline of the dominant kernel (decode moves 2x the bytes of the mix), per-launch average
     peak, peak_src = measured_peaks()
-    kern_ms = ms_step                                             # one launch per step
-    achieved = alg_bytes_decode / (kern_ms * 1e-3) / 1e9
+    achieved = alg_bytes_decode / (ms_decode * 1e-3) / 1e9
     roofline = {"kernel": "pcm16_decode_batch", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "frac_of_nominal_8000": round(achieved / 8000.0, 4),
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_decode}
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_decode,
+                "ms_per_launch": round(ms_decode, 4)}
+    traffic = {}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roofline["traffic"] = json.load(open(tr)).get("pcm16_decode_batch")
+            traffic = json.load(open(tr))
         except Exception:
-            pass
+            traffic = {}
+    roofline["traffic"] = traffic.get("pcm16_decode_batch")
+    roofline_mix = None
+    if mix:
+        ach = alg_bytes_mix / (ms_mix * 1e-3) / 1e9
+        roofline_mix = {"kernel": "voice_position_scan + voice_render_mix_tma + bus_finalize" +
+                                  (" + NCCL all-reduce(int32)" if world > 1 else ""),
+                        "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                        "frac": round(ach / peak, 4), "algorithmic_bytes_per_step": alg_bytes_mix,
+                        "ms_per_step": round(ms_mix, 4), "traffic": traffic.get("voice_render_mix_tma_c2")}
 
-    # ---- e2e: host file images (pinned) -> blast_pcm_decode_batch -> host AudioFile.samples (pinned)
+    # ---- e2e: host file images (pinned) -> blast_pcm_decode_batch (host AudioFile.samples out, tracks stay in
+    #      HBM) -> render of the decoded tracks -> S16 bus copied back to the host
     e2e = None
     if not args.no_e2e:
         h_out = ctx.pinned(n_files * words_per_file * 2)
+        h_bus = ctx.pinned(2 * frames_per_file * 2) if mix else None
         files = (C.c_void_p * n_files)(*[h_in.ptr + i * slot for i in range(n_files)])
         lens = (C.c_size_t * n_files)(*([image_len] * n_files))
         dd = (_lib.PcmDesc * n_files)(*descs)
@@ -221,8 +278,16 @@ def run_ours(args):
             rc = L.blast_pcm_decode_batch(ctx.h, n_files, files, lens, dd, host_out, dev_out)
             if rc != 0:
                 raise RuntimeError(L.blast_last_error().decode())
+            if mix:
+                scene.restore_dev()
+                scene.render_partial_dev(frames_per_file, part_ptr)
+                if world > 1:
+                    dist.all_reduce(t_part, op=dist.ReduceOp.SUM)
+                ap.finalize_bus(ctx, part_ptr, d_bus.ptr, n_slots)
+                L.blast_memcpy_d2h(ctx.h, h_bus.ptr, d_bus.ptr, 2 * n_slots)
+                ctx.sync()
 
-        for _ in range(max(1, min(2, args.warmup))):
+        for _ in range(2):
             e2e_step()
         barrier(dist, local)
         t0 = time.perf_counter()
@@ -235,66 +300,95 @@ def run_ours(args):
         got = h_out.view(np.int16, words_per_file, 0)
         assert np.array_equal(got, view[0, off:off + data_len].view(">i2").astype(np.int16)), "e2e output mismatch"
         e2e = {"value": round(world * samples_per_step / dt / 1e9, 3), "unit": UNIT,
-               "h2d_bytes_per_step": n_files * data_len, "d2h_bytes_per_step": n_files * words_per_file * 2,
-               "ms_per_step": round(dt * 1e3, 3), "api": "blast_pcm_decode_batch (host images in, host samples out)"}
+               "h2d_bytes_per_step": n_files * data_len,
+               "d2h_bytes_per_step": n_files * words_per_file * 2 + (2 * n_slots if mix else 0),
+               "ms_per_step": round(dt * 1e3, 3),
+               "api": "blast_pcm_decode_batch (pinned host images in, host AudioFile.samples out, tracks kept in HBM)"
+                      + (" + blast_scene_render_dev + blast_bus_finalize_dev + bus D2H" if mix else "")}
 
+    workload = (f"C2: batch decode {n_files} x 24-bit BE 48 kHz stereo AIFF ({data_len} payload B each), reference-exact "
+                "byte-pair decode to i16" + (f", then mix of the {n_files} decoded tracks (stereo voices, velocity 1, "
+                                             "per-voice gain) into one stereo S16 bus" if mix else ""))
     out = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "i16", "data": "synthetic",
-        "config": {"workload": f"C2: batch decode {n_files} x 24-bit BE 48 kHz stereo AIFF ({data_len} payload B each), "
-                               "reference-exact byte-pair decode to i16",
-                   "files_per_gpu": n_files, "samples_per_step_per_gpu": samples_per_step, "layout": args.layout,
-                   "l2": f"input {n_files * data_len / 1e6:.0f} MB + output per step, far larger than the 126 MB L2 (no flush needed)",
-                   "parallelism": f"files sharded, {world} rank(s), no collective"},
-        "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
+        "config": {"workload": workload, "files_per_gpu": n_files, "samples_per_step_per_gpu": samples_per_step,
+                   "sample_definition": "one i16 PCM word that is decoded" + (" and then mixed" if mix else ""),
+                   "layout": args.layout,
+                   "l2": f"per step {n_files * data_len / 1e6:.0f} MB of file images are read and {samples_per_step * 2 / 1e6:.0f} MB of "
+                         "samples written then re-read: far larger than the 126 MB L2 (no flush needed)",
+                   "parallelism": f"files / voices sharded over {world} rank(s)" +
+                                  ("; one int32 all-reduce of the partial bus per step (NCCL)" if world > 1 and mix else "; no collective")},
+        "roofline": roofline, "roofline_mix": roofline_mix,
+        "kernel_ms": {"decode": round(ms_decode, 4), "mix": round(ms_mix, 4)},
+        "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
     }
     if rank == 0 and not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(view, image_len, n_files, threads=1, budget_s=args.cpu_seconds)
+        out["cpu_baseline"] = cpu_baseline(view, image_len, n_files, threads=1, budget_s=args.cpu_seconds, mix=mix)
     if rank == 0:
         print(json.dumps(out))
     plan.close()
+    if mix:
+        scene.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------ CPU arms (oracle = checker, timed as the baseline)
-def _cpu_parse_files(view, image_len, idx):
+def _cpu_decode_mix(view, image_len, idx, mix):
+    """faithful aiff::parse of files idx, then (mix) Conductor::coordinate over them as voices -> words"""
     import oracle
     L = oracle.lib()
     d = oracle.PcmDesc()
-    out = C.c_void_p()
-    cnt = C.c_size_t()
     words = 0
+    bufs = []
     for i in idx:
+        out = C.c_void_p()
+        cnt = C.c_size_t()
         rc = L.orc_aiff_parse(view[i].ctypes.data, image_len, C.byref(d), C.byref(out), C.byref(cnt))
         assert rc == 0
         words += cnt.value
-        L.orc_free(out)
+        bufs.append((out, cnt.value))
+    if mix and bufs:
+        arr = (oracle.Track * len(bufs))(*[oracle.Track(b.value, n, 2, 48000) for b, n in bufs])
+        h = L.orc_conductor_new(2, 48000, arr, len(bufs))
+        for k in range(len(bufs)):
+            L.orc_conductor_apply(h, C.byref(oracle.Command(kind=oracle.CMD_LOAD, idx=k, tempo=oracle.tempo_repr())))
+            L.orc_conductor_apply(h, C.byref(oracle.Command(kind=oracle.CMD_START, idx_kind=oracle.IDX_VOICE, idx=k)))
+            L.orc_conductor_set_voice(h, -1, k, None, None, C.byref(C.c_float(0.01)), None)
+        frames = bufs[0][1] // 2
+        bus = np.empty(frames * 2, dtype=np.int16)
+        L.orc_conductor_coordinate(h, frames, bus.ctypes.data)
+        L.orc_conductor_free(h)
+    for b, _ in bufs:
+        L.orc_free(b)
     return words
 
 
-def cpu_baseline(view, image_len, n_files, threads: int, budget_s: float):
-    """faithful CPU restatement (per-pair bounds-checked reads, Vec growth) on a bounded sample"""
+def cpu_baseline(view, image_len, n_files, threads: int, budget_s: float, mix: bool = True):
+    """faithful CPU restatement (per-pair bounds-checked reads, Vec growth; frame->channel->voice scalar
+    render loop) on a bounded sample; threads > 1 shard the files / voices (generous comparison)"""
     import oracle
     oracle.lib()
     t0 = time.perf_counter()
-    w = _cpu_parse_files(view, image_len, [0])
+    _cpu_decode_mix(view, image_len, [0], mix)
     per_file = max(1e-4, time.perf_counter() - t0)
     n = int(max(threads, min(n_files, budget_s / per_file * threads)))
-    n = n // threads * threads
+    n = max(threads, n // threads * threads)
     idx = list(range(n))
     t0 = time.perf_counter()
     if threads == 1:
-        words = _cpu_parse_files(view, image_len, idx)
+        words = _cpu_decode_mix(view, image_len, idx, mix)
     else:
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(threads) as ex:
-            words = sum(ex.map(lambda k: _cpu_parse_files(view, image_len, idx[k::threads]), range(threads)))
+            words = sum(ex.map(lambda k: _cpu_decode_mix(view, image_len, idx[k::threads], mix), range(threads)))
     dt = time.perf_counter() - t0
+    what = "aiff::parse" + (" + Conductor::coordinate (each thread mixes its own voice shard)" if mix else "")
     return {"value": round(words / dt / 1e9, 4), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{n} of {n_files} files ({words} i16 words) through the faithful C++ restatement of aiff::parse "
-                      f"(oracle/blast_oracle.cpp, g++ -O2), {dt:.1f} s",
+            "sample": f"{n} of {n_files} files ({words} i16 words) through the faithful C++ restatement of {what} "
+                      f"(oracle/blast_oracle.cpp, g++ -O2 -ffp-contract=off), {dt:.1f} s",
             "note": "CPU restatement of the reference, not the Rust binary (no rustc in the image)"}
 
 
@@ -304,32 +398,31 @@ def run_reference(args):
     if rank != 0:
         return
     n_files, data_len = args.files, args.data_len
+    mix = not args.no_mix
     threads = os.cpu_count() or 1
     hdr = np.frombuffer(synth.aiff_header(data_len), dtype=np.uint8)
     image_len = len(hdr) + data_len
-    sample_files = min(n_files, max(threads, 4 * threads))
+    sample_files = min(n_files, args.ref_files_per_thread * threads)
     view = np.empty((sample_files, image_len), dtype=np.uint8)
     rng = np.random.default_rng(0xC20000)
     view[:, :len(hdr)] = hdr
     view[:, len(hdr):] = rng.integers(0, 256, size=(sample_files, data_len), dtype=np.uint8)
-    res = None
-    times = []
+    res, times = None, []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        res = cpu_baseline(view, image_len, sample_files, threads=threads, budget_s=1e9)
+        res = cpu_baseline(view, image_len, sample_files, threads=threads, budget_s=1e9, mix=mix)
         if it >= args.warmup:
             times.append(time.perf_counter() - t0)
-    value = res["value"]
     words = sample_files * ((data_len + 1) // 2)
     value = words / (sum(times) / len(times)) / 1e9
     res["value"] = round(value, 4)
+    workload = (f"C2: batch decode {n_files} x 24-bit BE 48 kHz stereo AIFF ({data_len} payload B each), reference-exact "
+                "byte-pair decode to i16" + (", then mix of the decoded tracks into one stereo S16 bus" if mix else ""))
     out = {
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * sum(times) / len(times), 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16", "data": "synthetic",
-        "config": {"workload": f"C2: batch decode {n_files} x 24-bit BE 48 kHz stereo AIFF ({data_len} payload B each), "
-                               "reference-exact byte-pair decode to i16",
-                   "sample_files_per_step": sample_files, "threads": threads},
+        "config": {"workload": workload, "sample_files_per_step": sample_files, "threads": threads},
         "cpu_baseline": res,
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -349,6 +442,8 @@ def main():
                     help="HBM-resident input: whole file images (payload at +54, misaligned) or 16B-aligned payloads")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-mix", action="store_true", help="decode only (no render/mix of the decoded tracks)")
+    ap.add_argument("--ref-files-per-thread", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()

@@ -174,6 +174,8 @@ int  blast_scene_create(blast_ctx* ctx, const blast_track* tracks, uint32_t n_tr
                         uint32_t n_voices, uint32_t out_channels, blast_scene** out);
 void blast_scene_destroy(blast_ctx* ctx, blast_scene* scene);
 int  blast_scene_set_voices(blast_ctx* ctx, blast_scene* scene, const blast_voice* voices, uint32_t n_voices);
+/* async: puts every voice back to the state uploaded by the last create / set_voices (rewind) */
+int  blast_scene_restore_dev(blast_ctx* ctx, blast_scene* scene);
 /* reads the voice states back (positions as left by the last render); synchronises */
 int  blast_scene_get_voices(blast_ctx* ctx, blast_scene* scene, blast_voice* out, uint32_t n_voices);
 /* Renders `frames` frames of all active voices into the int32 partial bus
