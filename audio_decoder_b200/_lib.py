@@ -46,6 +46,13 @@ class X128PState(C.Structure):
     _fields_ = [("s0", C.c_uint64), ("s1", C.c_uint64)]
 
 
+class MpegHeader(C.Structure):
+    _fields_ = [("ok", C.c_uint32), ("status", C.c_uint32), ("version_id", C.c_uint32), ("layer", C.c_uint32),
+                ("is_protected", C.c_uint32), ("padded", C.c_uint32), ("channel_mode", C.c_uint32),
+                ("bitrate", C.c_uint32), ("sample_rate", C.c_double), ("frame_len_ok", C.c_uint32),
+                ("payload_len", C.c_uint32), ("skip", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
 _vp, _u64, _u32, _sz = C.c_void_p, C.c_uint64, C.c_uint32, C.c_size_t
 SIGNATURES = {
@@ -95,6 +102,13 @@ SIGNATURES = {
     "blast_x128p_jump_dev": (C.c_int, [_vp, C.POINTER(X128PState), _u64, _u64, _vp]),
     "blast_x128p_fill_dev": (C.c_int, [_vp, _vp, _u64, _u64, C.c_int64, C.c_int64, _vp, _vp, _vp]),
     "blast_x128p_fill": (C.c_int, [_vp, _u64, _u64, _u64, _u64, C.c_int64, C.c_int64, _vp, _vp, _vp]),
+    "blast_mpeg_header_info": (C.c_int, [_u32, C.POINTER(MpegHeader)]),
+    "blast_mpeg_scan_dev": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _u64, C.POINTER(_u64)]),
+    "blast_mpeg_index_dev": (C.c_int, [_vp, _vp, _u64, C.c_int, _vp, _u64, C.POINTER(_u64), C.POINTER(_u32),
+                                       C.POINTER(_u64)]),
+    "blast_mpeg_gather_dev": (C.c_int, [_vp, _vp, _u64, _vp, _u64, _vp, _u64, C.POINTER(_u64)]),
+    "blast_mpeg_parse": (C.c_int, [_vp, _vp, _u64, C.c_int, _vp, _u64, C.POINTER(_u64), C.POINTER(_u32),
+                                   C.POINTER(_u64), _vp, _u64, C.POINTER(_u64)]),
     "blast_render": (C.c_int, [_vp, C.POINTER(Track), _u32, C.POINTER(Voice), _u32, _u32, _u64, _vp,
                                C.POINTER(Voice)]),
 }

@@ -161,3 +161,79 @@ def pcm24_unpack_dev(ctx: Context, jobs):
     """Extension: jobs = [(d_src, d_dst, n_samples, big_endian, out_kind)]"""
     arr = (_lib.Pcm24Job * max(1, len(jobs)))(*[_lib.Pcm24Job(s, d, n, int(be), k) for s, d, n, be, k in jobs])
     check(ctx.lib.blast_pcm24_unpack_dev(ctx.h, arr, len(jobs)))
+
+
+# ---------------------------------------------------------------------------------- mpeg
+def mpeg_header_info(header: int) -> _lib.MpegHeader:
+    """parse_header + Header::format + compute_frame_len for one header word (mpeg.rs:154-234, 367-496)"""
+    o = _lib.MpegHeader()
+    check(_lib.load().blast_mpeg_header_info(header & 0xFFFFFFFF, C.byref(o)))
+    return o
+
+
+class _Mpeg:
+    """file_parsing::mpeg (blast/src/file_parsing/mpeg.rs)"""
+
+    @staticmethod
+    def scan_dev(ctx: Context, d_bytes: int, length: int, cap: int | None = None):
+        """greedy sync scan of device-resident bytes -> (positions uint64, headers uint32) in file order"""
+        cap = length // 32 + 4096 if cap is None else cap
+        d_pos, d_hdr = ctx.alloc(max(16, 8 * cap)), ctx.alloc(max(16, 4 * cap))
+        n = C.c_uint64()
+        check(ctx.lib.blast_mpeg_scan_dev(ctx.h, d_bytes, length, d_pos.ptr, d_hdr.ptr, cap, C.byref(n)))
+        return d_pos.download(np.uint64, n.value), d_hdr.download(np.uint32, n.value)
+
+    @staticmethod
+    def index_dev(ctx: Context, d_bytes: int, length: int, reference_compat: bool = True):
+        """-> dict(offsets uint64 (frames[*].file_pos, sorted), ref_header, n_candidates)"""
+        n, ncand, ref = C.c_uint64(), C.c_uint64(), C.c_uint32()
+        check(ctx.lib.blast_mpeg_index_dev(ctx.h, d_bytes, length, int(reference_compat), None, 0, C.byref(n),
+                                           C.byref(ref), C.byref(ncand)))
+        d_off = ctx.alloc(max(16, 8 * n.value))
+        check(ctx.lib.blast_mpeg_index_dev(ctx.h, d_bytes, length, int(reference_compat), d_off.ptr, n.value,
+                                           C.byref(n), C.byref(ref), C.byref(ncand)))
+        return dict(offsets=d_off.download(np.uint64, n.value), ref_header=ref.value, n_candidates=ncand.value,
+                    d_offsets=d_off)
+
+    @staticmethod
+    def gather_dev(ctx: Context, d_bytes: int, length: int, d_offsets: int, n_offsets: int) -> np.ndarray:
+        plen = C.c_uint64()
+        check(ctx.lib.blast_mpeg_gather_dev(ctx.h, d_bytes, length, d_offsets, n_offsets, None, 0, C.byref(plen)))
+        d_pay = ctx.alloc(max(16, plen.value))
+        check(ctx.lib.blast_mpeg_gather_dev(ctx.h, d_bytes, length, d_offsets, n_offsets, d_pay.ptr, plen.value,
+                                            C.byref(plen)))
+        return d_pay.download(np.uint8, plen.value)
+
+    @staticmethod
+    def parse_bytes(image, ctx: Context | None = None, reference_compat: bool = True, want_payload: bool = True):
+        """blast_mpeg_parse on a host buffer -> dict(offsets, ref_header, n_candidates, payload)"""
+        own = ctx is None
+        ctx = ctx or Context()
+        try:
+            a = _as_u8(image)
+            n, ncand, ref, plen = C.c_uint64(), C.c_uint64(), C.c_uint32(), C.c_uint64()
+            ptr = a.ctypes.data if a.size else None
+            check(ctx.lib.blast_mpeg_parse(ctx.h, ptr, a.size, int(reference_compat), None, 0, C.byref(n), C.byref(ref),
+                                           C.byref(ncand), None, 0, C.byref(plen) if want_payload else None))
+            offs = np.empty(n.value, dtype=np.uint64)
+            pay = np.empty(plen.value if want_payload else 0, dtype=np.uint8)
+            check(ctx.lib.blast_mpeg_parse(ctx.h, ptr, a.size, int(reference_compat), offs.ctypes.data, offs.size,
+                                           C.byref(n), C.byref(ref), C.byref(ncand),
+                                           pay.ctypes.data if want_payload and pay.size else None, pay.size,
+                                           C.byref(plen) if want_payload else None))
+            return dict(offsets=offs, ref_header=ref.value, n_candidates=ncand.value, payload=pay)
+        finally:
+            if own:
+                ctx.close()
+
+    def parse(self, path: str, ctx: Context | None = None) -> np.ndarray:
+        """`pub fn parse(path: &str) -> DecodeResult<Vec<u8>>` (mpeg.rs:7): the concatenated frame payloads"""
+        try:
+            with open(path, "rb") as f:
+                image = f.read()
+        except OSError as e:
+            raise Io(_lib.ERR_IO, str(e)) from e
+        return self.parse_bytes(image, ctx)["payload"]
+
+
+mpeg = _Mpeg()

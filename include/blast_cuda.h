@@ -214,6 +214,48 @@ int  blast_x128p_fill_dev(blast_ctx* ctx, blast_x128p* d_states, uint64_t n_stre
 int  blast_x128p_fill(blast_ctx* ctx, uint64_t seed, uint64_t stride, uint64_t n_streams, uint64_t draws_per_stream,
                       int64_t lower, int64_t upper, uint64_t* raw_out, int64_t* ranged_out, uint64_t* checks_out);
 
+/* ------------------------------------------------------------------ MPEG frame-sync scan / index
+ * replaces file_parsing::mpeg::parse (blast/src/file_parsing/mpeg.rs:7-128). */
+typedef struct {               /* parse_header + Header::format + compute_frame_len for one 32-bit header */
+    uint32_t ok;               /* parse_header returned Ok (mpeg.rs:367-496) */
+    uint32_t status;           /* otherwise BLAST_ERR_UNSUPPORTED_FORMAT / BLAST_ERR_INVALID_DATA */
+    uint32_t version_id;       /* the 2-bit id as the reference computes it (low bit = protection bit) */
+    uint32_t layer;            /* 1 / 2 / 3 */
+    uint32_t is_protected;
+    uint32_t padded;
+    uint32_t channel_mode;
+    uint32_t bitrate;          /* kbit/s, always column 4 of BITRATES (mpeg.rs:273-284) */
+    double   sample_rate;
+    uint32_t frame_len_ok;     /* compute_frame_len returned Ok (mpeg.rs:207-234) */
+    uint32_t payload_len;      /* its value */
+    uint32_t skip;             /* payload starts at pos + skip (6 if protected else 4, mpeg.rs:86-89) */
+    uint32_t reserved;
+} blast_mpeg_header;
+int  blast_mpeg_header_info(uint32_t header, blast_mpeg_header* out);        /* host */
+
+/* Greedy non-overlapping sync scan (mpeg.rs:17-50) over device-resident bytes (16-byte aligned):
+ * candidates (position, big-endian header) in file order, WITHOUT the duplicate-first quirk.
+ * *n_out is the number found even when it exceeds cap (then BLAST_ERR_CAPACITY).
+ * BLAST_ERR_REF_PANIC if the scan reaches a trailing 0xFF (the reference indexes out of bounds). */
+int  blast_mpeg_scan_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, uint64_t* d_pos_out,
+                         uint32_t* d_hdr_out, uint64_t cap, uint64_t* n_out);
+/* The frame-offset index = frames[*].file_pos after the sort (mpeg.rs:53-116): reference header = most
+ * frequent header value that parses (ties: smallest value; the reference follows HashMap order), frames =
+ * candidates whose header parses, match_ref()s and has a valid length.  reference_compat != 0 duplicates
+ * the first position of every distinct header value (mpeg.rs:39) and reports payloads past EOF as
+ * BLAST_ERR_REF_PANIC.  d_offsets_out nullable (count only). */
+int  blast_mpeg_index_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, int reference_compat,
+                          uint64_t* d_offsets_out, uint64_t cap, uint64_t* n_offsets_out, uint32_t* ref_header_out,
+                          uint64_t* n_candidates_out);
+/* Payload gather (mpeg.rs:86-121): concatenated b[pos+skip .. pos+skip+len] of the indexed frames.
+ * d_payload_out nullable (size only). */
+int  blast_mpeg_gather_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, const uint64_t* d_offsets,
+                           uint64_t n_offsets, uint8_t* d_payload_out, uint64_t cap, uint64_t* payload_len_out);
+/* mpeg::parse on a host buffer: upload + scan + index + gather; every output nullable except n_offsets_out */
+int  blast_mpeg_parse(blast_ctx* ctx, const uint8_t* bytes, uint64_t len, int reference_compat, uint64_t* offsets_out,
+                      uint64_t offsets_cap, uint64_t* n_offsets_out, uint32_t* ref_header_out, uint64_t* n_candidates_out,
+                      uint8_t* payload_out, uint64_t payload_cap, uint64_t* payload_len_out);
+
 #ifdef __cplusplus
 }
 #endif

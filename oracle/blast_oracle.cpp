@@ -870,14 +870,14 @@ int orc_mpeg_parse(const uint8_t* r, uint64_t file_len, int reference_compat,
         cur += 1;
     }
     if (n_candidates_out) *n_candidates_out = ncand;
-    // mpeg.rs:53-58: sort by count descending.  Ties follow HashMap order in the reference;
-    // the oracle breaks them by smallest first position (documented deviation, deterministic).
+    // mpeg.rs:53-58: sort by count descending.  Ties follow HashMap order in the reference
+    // (nondeterministic); the oracle breaks them by smallest header value (documented, deterministic).
     std::vector<std::pair<uint32_t, const std::vector<uint64_t>*>> vecs;
     vecs.reserve(possibles.size());
     for (auto& kv : possibles) vecs.push_back({kv.first, &kv.second});
     std::sort(vecs.begin(), vecs.end(), [](auto& a, auto& b) {
         if (a.second->size() != b.second->size()) return a.second->size() > b.second->size();
-        return (*a.second)[0] < (*b.second)[0];
+        return a.first < b.first;
     });
     // mpeg.rs:61-73: first header that parses is the reference; none -> index panic
     orc_mpeg_header ref;

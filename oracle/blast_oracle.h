@@ -192,8 +192,8 @@ int  orc_mpeg_match_ref(const orc_mpeg_header* ref, const orc_mpeg_header* other
 int orc_mpeg_sync_scan(const uint8_t* bytes, uint64_t len, uint64_t* pos_out, uint32_t* hdr_out, uint64_t cap, uint64_t* n_out);
 
 /* the full mpeg::parse (mpeg.rs:7-128).  tie_break: when several headers share the top
- * count the reference follows HashMap order (nondeterministic); the oracle picks the one
- * whose FIRST position is smallest.  offsets_out receives frames[*].file_pos after the sort
+ * count the reference follows HashMap order (nondeterministic); the oracle picks the
+ * smallest header value.  offsets_out receives frames[*].file_pos after the sort
  * (first position of each header duplicated when reference_compat != 0); payload_out (nullable)
  * receives the concatenated payload. */
 int orc_mpeg_parse(const uint8_t* bytes, uint64_t len, int reference_compat,

@@ -166,3 +166,25 @@ def test_x128p_seed_and_host_jump_match_oracle():
     T = pyref.transition_columns()
     st = pyref.mat_vec(pyref.mat_pow(T, 2**40 + 7), base[0] | (base[1] << 64))
     assert br.advance(base, 2**40 + 7) == (st & pyref.M64, st >> 64)
+
+
+def test_mpeg_header_info_matches_oracle_exhaustively():
+    """all 2^21 header values with the 11 sync bits set: host classifier == oracle parse_header/format/frame_len"""
+    L = _lib.load()
+    o = _lib.MpegHeader()
+    import ctypes as C
+    ol = oracle.lib()
+    oh = oracle.MpegHeader()
+    for idx in list(range(0, 1 << 21, 7)) + list(range(0x1B9000, 0x1B9400)):
+        h = 0xFFE00000 | idx
+        L.blast_mpeg_header_info(h, C.byref(o))
+        ol.orc_mpeg_parse_header(h, C.byref(oh))
+        assert o.ok == oh.ok, hex(h)
+        if not oh.ok:
+            assert o.status == oh.err, hex(h)
+            continue
+        assert (o.layer, o.is_protected, o.padded, o.channel_mode, o.bitrate, o.sample_rate, o.skip) == \
+            (oh.layer, int(oh.not_protected == 0), oh.padded, oh.channel_mode, oh.bitrate, oh.sr, oh.skip), hex(h)
+        assert o.frame_len_ok == oh.frame_len_ok, hex(h)
+        if oh.frame_len_ok:
+            assert o.payload_len == oh.payload_len, hex(h)
