@@ -278,16 +278,32 @@ mpeg_sync_scan(const uint8_t* __restrict__ bytes, unsigned long long n, TileDesc
                     }
                     const uint32_t incm = __ballot_sync(0xFFFFFFFFu, flag == 2);     // lanes past tile 0 count as inclusive(0,0)
                     const int first = incm ? __ffs(incm) - 1 : 32;
-                    for (int i = 0; i < first; ++i) {                                  // nearest tile first
-                        const uint32_t m_i = __shfl_sync(0xFFFFFFFFu, amap, i);
-                        const uint32_t c01_i = __shfl_sync(0xFFFFFFFFu, a01, i), c23_i = __shfl_sync(0xFFFFFFFFu, a23, i);
-                        // F' = (tile i) then F
-                        unsigned long long nc[4];
+                    // "simple" aggregate: constant map and a count that does not depend on the entry state —
+                    // every tile that contains a 3-byte gap without a raw sync, i.e. practically all of them
+                    const bool simple = map_is_const(amap) && a01 == (a01 & 0xFFFFu) * 0x10001u && a23 == a01;
+                    const uint32_t need = first >= 32 ? 0xFFFFFFFFu : ((1u << first) - 1u);
+                    const uint32_t simple_m = __ballot_sync(0xFFFFFFFFu, simple) & need;
+                    if (simple_m == need) {
+                        if (first > 0) {
+                            // fold the whole window at once: counts add up, the nearest tile fixes the state
+                            const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, (int)lane < first ? (a01 & 0xFFFFu) : 0u);
+                            const uint32_t e0 = __shfl_sync(0xFFFFFFFFu, amap, 0) & 3u;
+                            const unsigned long long nc = tot + pick4(fc[0], fc[1], fc[2], fc[3], e0);
+                            fc[0] = fc[1] = fc[2] = fc[3] = nc;
+                            fmap = map_get(fmap, e0) * 0x55u;
+                        }
+                    } else {
+                        for (int i = 0; i < first; ++i) {                              // nearest tile first
+                            const uint32_t m_i = __shfl_sync(0xFFFFFFFFu, amap, i);
+                            const uint32_t c01_i = __shfl_sync(0xFFFFFFFFu, a01, i), c23_i = __shfl_sync(0xFFFFFFFFu, a23, i);
+                            // F' = (tile i) then F
+                            unsigned long long nc[4];
 #pragma unroll
-                        for (int s = 0; s < 4; ++s) nc[s] = cnt16(c01_i, c23_i, s) + pick4(fc[0], fc[1], fc[2], fc[3], map_get(m_i, s));
+                            for (int s = 0; s < 4; ++s) nc[s] = cnt16(c01_i, c23_i, s) + pick4(fc[0], fc[1], fc[2], fc[3], map_get(m_i, s));
 #pragma unroll
-                        for (int s = 0; s < 4; ++s) fc[s] = nc[s];
-                        fmap = map_after(m_i, fmap);
+                            for (int s = 0; s < 4; ++s) fc[s] = nc[s];
+                            fmap = map_after(m_i, fmap);
+                        }
                     }
                     if (first < 32) {
                         const uint32_t sigma = __shfl_sync(0xFFFFFFFFu, st, first);
