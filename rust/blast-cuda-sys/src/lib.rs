@@ -1,0 +1,70 @@
+//! Raw bindings of include/blast_cuda.h.  Written by hand (no bindgen in the image) and NOT compiled here:
+//! the build image has no Rust toolchain.  Every item mirrors the C declaration one to one.
+#![allow(non_camel_case_types)]
+use core::ffi::{c_char, c_int, c_void};
+
+pub const BLAST_OK: c_int = 0;
+pub const BLAST_ERR_IO: c_int = 1;
+pub const BLAST_ERR_UNSUPPORTED_FORMAT: c_int = 2;
+pub const BLAST_ERR_UNEXPECTED_EOF: c_int = 3;
+pub const BLAST_ERR_INVALID_DATA: c_int = 4;
+pub const BLAST_ERR_REF_PANIC: c_int = 5;
+
+#[repr(C)] pub struct blast_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct blast_scene { _p: [u8; 0] }
+#[repr(C)] pub struct blast_pcm_plan { _p: [u8; 0] }
+
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct blast_pcm_desc {
+    pub sample_rate: u32, pub num_channels: u32, pub bits_per_sample: u32, pub big_endian: u32,
+    pub data_off: u64, pub data_len: u64,
+}
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct blast_pcm_job { pub d_src: *const u8, pub d_dst: *mut i16, pub n_words: u64, pub big_endian: u32, pub reserved: u32 }
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct blast_track { pub d_samples: *const i16, pub n_samples: u64, pub num_channels: u32, pub sample_rate: u32 }
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct blast_voice { pub track: u32, pub active: u32, pub position: f32, pub velocity: f32, pub gain: f32, pub reserved: u32 }
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct blast_x128p { pub s0: u64, pub s1: u64 }
+
+extern "C" {
+    pub fn blast_last_error() -> *const c_char;
+    pub fn blast_ctx_create(out: *mut *mut blast_ctx, device: c_int) -> c_int;
+    pub fn blast_ctx_destroy(ctx: *mut blast_ctx);
+    pub fn blast_ctx_sync(ctx: *mut blast_ctx) -> c_int;
+    pub fn blast_dev_alloc(ctx: *mut blast_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn blast_dev_free(ctx: *mut blast_ctx, p: *mut c_void) -> c_int;
+    pub fn blast_host_alloc(ctx: *mut blast_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn blast_host_free(ctx: *mut blast_ctx, p: *mut c_void) -> c_int;
+
+    pub fn blast_wav_probe(file: *const u8, len: usize, out: *mut blast_pcm_desc) -> c_int;
+    pub fn blast_aiff_probe(file: *const u8, len: usize, out: *mut blast_pcm_desc) -> c_int;
+    pub fn blast_pcm_out_len(desc: *const blast_pcm_desc) -> usize;
+    pub fn blast_file_name(path: *const c_char, out: *mut c_char, cap: usize) -> c_int;
+    pub fn blast_pcm_decode_batch(ctx: *mut blast_ctx, n: u32, files: *const *const u8, lens: *const usize,
+                                  descs: *const blast_pcm_desc, host_out: *const *mut i16, d_out: *const *mut i16) -> c_int;
+    pub fn blast_pcm_decode_dev(ctx: *mut blast_ctx, jobs: *const blast_pcm_job, n_jobs: u32) -> c_int;
+
+    pub fn blast_scene_create(ctx: *mut blast_ctx, tracks: *const blast_track, n_tracks: u32, voices: *const blast_voice,
+                              n_voices: u32, out_channels: u32, out: *mut *mut blast_scene) -> c_int;
+    pub fn blast_scene_destroy(ctx: *mut blast_ctx, scene: *mut blast_scene);
+    pub fn blast_scene_set_voices(ctx: *mut blast_ctx, scene: *mut blast_scene, voices: *const blast_voice, n: u32) -> c_int;
+    pub fn blast_scene_get_voices(ctx: *mut blast_ctx, scene: *mut blast_scene, out: *mut blast_voice, n: u32) -> c_int;
+    pub fn blast_scene_render_dev(ctx: *mut blast_ctx, scene: *mut blast_scene, frames: u64, d_partial_bus: *mut i32) -> c_int;
+    pub fn blast_scene_check(ctx: *mut blast_ctx, scene: *mut blast_scene) -> c_int;
+    pub fn blast_bus_finalize_dev(ctx: *mut blast_ctx, d_partial: *const i32, d_bus: *mut i16, n_slots: u64) -> c_int;
+    pub fn blast_render(ctx: *mut blast_ctx, tracks: *const blast_track, n_tracks: u32, voices: *const blast_voice,
+                        n_voices: u32, out_channels: u32, frames: u64, host_bus_out: *mut i16,
+                        voices_after: *mut blast_voice) -> c_int;
+
+    pub fn blast_x128p_seed(seed: u64, out: *mut blast_x128p);
+    pub fn blast_x128p_advance(state: *const blast_x128p, n_draws: u64, out: *mut blast_x128p) -> c_int;
+    pub fn blast_x128p_fill(ctx: *mut blast_ctx, seed: u64, stride: u64, n_streams: u64, draws_per_stream: u64,
+                            lower: i64, upper: i64, raw_out: *mut u64, ranged_out: *mut i64, checks_out: *mut u64) -> c_int;
+
+    pub fn blast_mpeg_parse(ctx: *mut blast_ctx, bytes: *const u8, len: u64, reference_compat: c_int,
+                            offsets_out: *mut u64, offsets_cap: u64, n_offsets_out: *mut u64, ref_header_out: *mut u32,
+                            n_candidates_out: *mut u64, payload_out: *mut u8, payload_cap: u64,
+                            payload_len_out: *mut u64) -> c_int;
+}
