@@ -31,6 +31,11 @@ struct blast_ctx {
     };
     Lane lane[kPipe];
     size_t lane_bytes = 0, lane_jobs = 0, lane_tiles = 0;
+    // grow-only device scratch slots + a small pinned mailbox: hot entry points never cudaMalloc / cudaFree
+    static constexpr int kScratch = 12;
+    void* scratch[kScratch] = {nullptr};
+    size_t scratch_cap[kScratch] = {0};
+    void* mailbox = nullptr;          // 4 KiB pinned host memory for small read-backs
 };
 
 struct blast_event {
@@ -64,6 +69,9 @@ inline int bind(blast_ctx* ctx) {
 int ensure_pipe(blast_ctx* ctx, size_t chunk_bytes, size_t max_jobs, size_t max_tiles, size_t job_size,
                 size_t tile_size);
 void release_pipe(blast_ctx* ctx);
+// device scratch slot `slot` with at least `bytes` bytes (contents undefined); nullptr + error on failure
+void* scratch(blast_ctx* ctx, int slot, size_t bytes);
+void* mailbox(blast_ctx* ctx);
 
 // 128-bit streaming accessors (read-only path, no L1 allocation: every byte is touched once)
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {

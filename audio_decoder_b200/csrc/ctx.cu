@@ -55,6 +55,33 @@ int ensure_pipe(blast_ctx* ctx, size_t chunk_bytes, size_t max_jobs, size_t max_
     return BLAST_OK;
 }
 
+void* scratch(blast_ctx* ctx, int slot, size_t bytes) {
+    if (slot < 0 || slot >= blast_ctx::kScratch) { set_error(BLAST_ERR_ARG, "bad scratch slot"); return nullptr; }
+    if (ctx->scratch_cap[slot] >= bytes && ctx->scratch[slot]) return ctx->scratch[slot];
+    if (ctx->scratch[slot]) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->scratch[slot]);
+        ctx->scratch[slot] = nullptr;
+        ctx->scratch_cap[slot] = 0;
+    }
+    size_t want = (bytes + (bytes >> 2) + 255) & ~(size_t)255;      // 25 % head-room
+    if (cudaMalloc(&ctx->scratch[slot], want) != cudaSuccess) {
+        ctx->scratch[slot] = nullptr;
+        set_error(BLAST_ERR_CUDA, "scratch allocation of %zu bytes failed: %s", want, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    ctx->scratch_cap[slot] = want;
+    return ctx->scratch[slot];
+}
+
+void* mailbox(blast_ctx* ctx) {
+    if (!ctx->mailbox && cudaHostAlloc(&ctx->mailbox, 4096, cudaHostAllocDefault) != cudaSuccess) {
+        ctx->mailbox = nullptr;
+        set_error(BLAST_ERR_CUDA, "pinned mailbox allocation failed");
+    }
+    return ctx->mailbox;
+}
+
 }  // namespace blast
 
 using blast::set_error;
@@ -101,6 +128,9 @@ void blast_ctx_destroy(blast_ctx* ctx) {
     blast::release_pipe(ctx);
     for (int i = 0; i < blast_ctx::kPipe; ++i)
         if (ctx->lane[i].stream) cudaStreamDestroy(ctx->lane[i].stream);
+    for (int i = 0; i < blast_ctx::kScratch; ++i)
+        if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

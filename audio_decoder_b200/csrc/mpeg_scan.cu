@@ -28,17 +28,20 @@ namespace {
 
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
-constexpr int kChunk = 64;                                  // bytes per thread
-constexpr int kTileBytes = kScanThreads * kChunk;           // 16 KiB
+constexpr int kChunk = 64;                                  // bytes per thread per round
+constexpr int kRounds = 16;                                 // rounds per tile: a warp walks 16 x 2 KiB = 32 KiB
+constexpr int kSpanBytes = kRounds * 32 * kChunk;           // contiguous bytes per warp per tile
+constexpr int kTileBytes = kScanWarps * kSpanBytes;         // 256 KiB
 constexpr uint32_t kIdentityMap = 0xE4;                     // s -> s for s = 0..3, two bits each
 
-struct TileDesc {             // 32 bytes
+struct TileDesc {             // 64 bytes
     uint32_t flag;            // 0 = nothing, 1 = aggregate valid, 2 = inclusive prefix valid
     uint32_t map;             // aggregate: exit state per entry state (4 x 2 bits)
-    uint32_t c01, c23;        // aggregate: candidates per entry state (4 x 16 bits)
+    uint32_t c[4];            // aggregate: candidates per entry state
     uint32_t state;           // inclusive: exit state of this tile under the true entry state
-    uint32_t pad;
+    uint32_t pad0;
     uint32_t cnt_lo, cnt_hi;  // inclusive: candidates in tiles 0..this
+    uint32_t pad[6];
 };
 
 struct ScanCtl {
@@ -129,11 +132,13 @@ __global__ void __launch_bounds__(kScanThreads)
 mpeg_sync_scan(const uint8_t* __restrict__ bytes, unsigned long long n, TileDesc* __restrict__ desc,
                unsigned long long n_tiles, ScanCtl* __restrict__ ctl, unsigned long long* __restrict__ out_pos,
                uint32_t* __restrict__ out_hdr, unsigned long long cap) {
+    // per (warp, round, lane): raw-sync mask and the lane's pre-map relative to the warp span's entry state
+    __shared__ unsigned long long s_mask[kScanWarps * kRounds * 32];
+    __shared__ uint8_t s_tpre[kScanWarps * kRounds * 32];
     __shared__ unsigned long long s_tile;
-    __shared__ uint32_t s_wmap[kScanWarps], s_wc01[kScanWarps], s_wc23[kScanWarps];   // warp aggregates
-    __shared__ uint32_t s_wpre[kScanWarps], s_wp01[kScanWarps], s_wp23[kScanWarps];   // prefix before each warp
-    __shared__ uint32_t s_entry;
-    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_wmap[kScanWarps], s_wc[kScanWarps][4];      // warp-span aggregates
+    __shared__ uint32_t s_wentry[kScanWarps];                          // true entry state of every warp span
+    __shared__ unsigned long long s_wbase[kScanWarps];                 // global candidate index at the span start
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     for (;;) {
@@ -141,152 +146,148 @@ mpeg_sync_scan(const uint8_t* __restrict__ bytes, unsigned long long n, TileDesc
         __syncthreads();
         const unsigned long long tile = s_tile;
         if (tile >= n_tiles) return;
-        const unsigned long long base = tile * (unsigned long long)kTileBytes + (unsigned long long)threadIdx.x * kChunk;
+        const unsigned long long span0 = tile * (unsigned long long)kTileBytes + (unsigned long long)warp * kSpanBytes;
 
-        // ---- load 64 bytes (+ the next word) as 32-bit words, zero beyond n
-        uint32_t w[17];
-        {
-            const uint4* v = reinterpret_cast<const uint4*>(bytes + base);
+        // ================= pass 1: masks + summaries, one warp walks its contiguous 32 KiB span
+        uint32_t wrun = kIdentityMap;          // span entry state -> entry state of the current round (uniform)
+        uint32_t wc01 = 0, wc23 = 0;           // candidates so far per span-entry hypothesis (uniform, 4 x 16 bit)
+#pragma unroll 1
+        for (int r = 0; r < kRounds; ++r) {
+            const unsigned long long base = span0 + (unsigned long long)r * (32 * kChunk) + (unsigned long long)lane * kChunk;
+            uint32_t w[17];
+            {
+                const uint4* v = reinterpret_cast<const uint4*>(bytes + base);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint4 x = make_uint4(0, 0, 0, 0);
-                if (base + 16ull * q < n) x = __ldg(v + q);
-                w[4 * q] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w;
-            }
-            w[16] = (base + 64 < n) ? __ldg(reinterpret_cast<const uint32_t*>(bytes + base + 64)) : 0u;
-            if (base + 68 > n) {                                     // the buffer ends inside this window
+                for (int q = 0; q < 4; ++q) {
+                    uint4 x = make_uint4(0, 0, 0, 0);
+                    if (base + 16ull * q < n) x = __ldg(v + q);
+                    w[4 * q] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w;
+                }
+                w[16] = (base + 64 < n) ? __ldg(reinterpret_cast<const uint32_t*>(bytes + base + 64)) : 0u;
+                if (base + 68 > n) {                                     // the buffer ends inside this window
 #pragma unroll
-                for (int k = 0; k < 17; ++k) {
-                    const unsigned long long p = base + 4ull * k;
-                    if (p >= n) w[k] = 0;
-                    else if (p + 4 > n) w[k] &= (1u << (8 * (uint32_t)(n - p))) - 1u;
+                    for (int k = 0; k < 17; ++k) {
+                        const unsigned long long p = base + 4ull * k;
+                        if (p >= n) w[k] = 0;
+                        else if (p + 4 > n) w[k] &= (1u << (8 * (uint32_t)(n - p))) - 1u;
+                    }
                 }
             }
-        }
-
-        // ---- raw sync mask: bit i <=> b[i]==0xFF && (b[i+1]&0xE0)==0xE0
-        uint32_t mlo = 0, mhi = 0;
-        {
-            uint32_t e_next = is_e0(w[16]);
+            // raw sync mask: bit i <=> b[i]==0xFF && (b[i+1]&0xE0)==0xE0; two words per multiply
+            uint32_t mlo, mhi;
+            {
+                uint32_t raw[16];
+                uint32_t e_next = is_e0(w[16]);
 #pragma unroll
-            for (int k = 15; k >= 0; --k) {
-                const uint32_t e = is_e0(w[k]);
-                const uint32_t raw = is_ff(w[k]) & __funnelshift_r(e, e_next, 8);
-                const uint32_t nib = nibble_of(raw);
-                if (k < 8) mlo |= nib << (4 * k); else mhi |= nib << (4 * (k - 8));
-                e_next = e;
+                for (int k = 15; k >= 0; --k) {
+                    const uint32_t e = is_e0(w[k]);
+                    raw[k] = is_ff(w[k]) & __funnelshift_r(e, e_next, 8);
+                    e_next = e;
+                }
+                uint32_t b8[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) b8[k] = (((raw[2 * k] >> 7) | (raw[2 * k + 1] >> 3)) * 0x01020408u);   // byte 3 = 8 flags
+                mlo = __byte_perm(__byte_perm(b8[0], b8[1], 0x0073), __byte_perm(b8[2], b8[3], 0x0073), 0x5410);
+                mhi = __byte_perm(__byte_perm(b8[4], b8[5], 0x0073), __byte_perm(b8[6], b8[7], 0x0073), 0x5410);
             }
-        }
-        const unsigned long long M = ((unsigned long long)mhi << 32) | mlo;
-        // candidates whose 4 header bytes are inside the buffer are emitted (mpeg.rs:25-37)
-        unsigned long long okmask = ~0ull;
-        if (base + 67 >= n) {
-            const unsigned long long lim = n > base + 3 ? n - 3 - base : 0;    // positions base+i with i < lim emit
-            okmask = lim >= 64 ? ~0ull : ((1ull << lim) - 1ull);
-        }
-
-        // ---- per-thread summary: exit state and candidate count for every entry state
-        uint32_t my_map, my_cnt;      // 4 x 2 bits, 4 x 8 bits
-        {
-            uint32_t e0;
-            const unsigned long long sel0 = resolve(M, 0, e0);
-            const uint32_t c0 = __popcll(sel0 & okmask);
-            my_map = e0 * 0x55u;
-            my_cnt = c0 * 0x01010101u;
-            if (M & 7ull) {           // a raw sync in the first 3 bytes: the entry state matters
+            const unsigned long long M = ((unsigned long long)mhi << 32) | mlo;
+            unsigned long long okmask = ~0ull;
+            if (base + 67 >= n) {
+                const unsigned long long lim = n > base + 3 ? n - 3 - base : 0;
+                okmask = lim >= 64 ? ~0ull : ((1ull << lim) - 1ull);
+            }
+            // per-thread summary
+            uint32_t my_map, my_cnt;
+            {
+                uint32_t e0;
+                const unsigned long long sel0 = resolve(M, 0, e0);
+                my_map = e0 * 0x55u;
+                my_cnt = (uint32_t)__popcll(sel0 & okmask) * 0x01010101u;
+                if (M & 7ull) {
 #pragma unroll
-                for (uint32_t s = 1; s < 4; ++s) {
-                    uint32_t es;
-                    const unsigned long long sel = resolve(M, s, es);
-                    my_map = (my_map & ~(3u << (2 * s))) | (es << (2 * s));
-                    my_cnt = (my_cnt & ~(0xFFu << (8 * s))) | ((uint32_t)__popcll(sel & okmask) << (8 * s));
+                    for (uint32_t s = 1; s < 4; ++s) {
+                        uint32_t es;
+                        const unsigned long long sel = resolve(M, s, es);
+                        my_map = (my_map & ~(3u << (2 * s))) | (es << (2 * s));
+                        my_cnt = (my_cnt & ~(0xFFu << (8 * s))) | ((uint32_t)__popcll(sel & okmask) << (8 * s));
+                    }
                 }
             }
-        }
-
-        // ---- lane's pre-map: warp entry state -> this lane's entry state
-        uint32_t pre = kIdentityMap;
-        bool known = lane == 0;
-        {
-            const uint32_t pm = __shfl_up_sync(0xFFFFFFFFu, my_map, 1);
-            if (lane > 0 && map_is_const(pm)) { pre = pm; known = true; }
-            while (!__all_sync(0xFFFFFFFFu, known)) {
-                const uint32_t ppre = __shfl_up_sync(0xFFFFFFFFu, pre, 1);
-                const bool pknown = __shfl_up_sync(0xFFFFFFFFu, (int)known, 1) != 0;
-                if (!known && pknown) { pre = map_after(ppre, pm); known = true; }
+            // lane's pre-map within this round: round entry state -> lane entry state
+            uint32_t pre = kIdentityMap;
+            {
+                bool known = lane == 0;
+                const uint32_t pm = __shfl_up_sync(0xFFFFFFFFu, my_map, 1);
+                if (lane > 0 && map_is_const(pm)) { pre = pm; known = true; }
+                while (!__all_sync(0xFFFFFFFFu, known)) {
+                    const uint32_t ppre = __shfl_up_sync(0xFFFFFFFFu, pre, 1);
+                    const bool pknown = __shfl_up_sync(0xFFFFFFFFu, (int)known, 1) != 0;
+                    if (!known && pknown) { pre = map_after(ppre, pm); known = true; }
+                }
             }
+            const uint32_t tpre = map_after(wrun, pre);              // span entry -> lane entry
+            const uint32_t slot = (warp * kRounds + r) * 32 + lane;
+            s_mask[slot] = M;
+            s_tpre[slot] = (uint8_t)tpre;
+            {
+                const uint32_t k0 = (my_cnt >> (8 * map_get(tpre, 0))) & 0xFF, k1 = (my_cnt >> (8 * map_get(tpre, 1))) & 0xFF;
+                const uint32_t k2 = (my_cnt >> (8 * map_get(tpre, 2))) & 0xFF, k3 = (my_cnt >> (8 * map_get(tpre, 3))) & 0xFF;
+                wc01 += __reduce_add_sync(0xFFFFFFFFu, k0 | (k1 << 16));
+                wc23 += __reduce_add_sync(0xFFFFFFFFu, k2 | (k3 << 16));
+            }
+            const uint32_t round_map = __shfl_sync(0xFFFFFFFFu, map_after(pre, my_map), 31);
+            wrun = map_after(wrun, round_map);
         }
-        // counts per warp-entry hypothesis, packed 2 x 16 bits, inclusive scan over the warp
-        uint32_t h01, h23;
-        {
-            const uint32_t k0 = (my_cnt >> (8 * map_get(pre, 0))) & 0xFF, k1 = (my_cnt >> (8 * map_get(pre, 1))) & 0xFF;
-            const uint32_t k2 = (my_cnt >> (8 * map_get(pre, 2))) & 0xFF, k3 = (my_cnt >> (8 * map_get(pre, 3))) & 0xFF;
-            h01 = k0 | (k1 << 16);
-            h23 = k2 | (k3 << 16);
-        }
-        const uint32_t own01 = h01, own23 = h23;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, h01, d), b = __shfl_up_sync(0xFFFFFFFFu, h23, d);
-            if ((int)lane >= d) { h01 += a; h23 += b; }
-        }
-        if (lane == 31) {
-            s_wmap[warp] = map_after(pre, my_map);
-            s_wc01[warp] = h01;
-            s_wc23[warp] = h23;
+        if (lane == 0) {
+            s_wmap[warp] = wrun;
+            s_wc[warp][0] = wc01 & 0xFFFF; s_wc[warp][1] = wc01 >> 16; s_wc[warp][2] = wc23 & 0xFFFF; s_wc[warp][3] = wc23 >> 16;
         }
         __syncthreads();
 
-        // ---- warp 0: combine the warp summaries, publish the tile aggregate, look back, publish inclusive
+        // ================= warp 0: combine the spans, publish the aggregate, look back, publish inclusive
         if (warp == 0) {
-            Agg run;                      // composition of warps 0..k-1 (prefix before warp k)
+            Agg run;
             run.map = kIdentityMap;
             run.c[0] = run.c[1] = run.c[2] = run.c[3] = 0;
-            // every lane computes the same tiny chain (8 steps); lane k keeps prefix k
-            uint32_t keep_map = kIdentityMap, keep01 = 0, keep23 = 0;
+            Agg keep = run;                        // prefix before span `lane`
 #pragma unroll
             for (int k = 0; k < kScanWarps; ++k) {
-                if ((int)lane == k) { keep_map = run.map; keep01 = run.c[0] | (run.c[1] << 16); keep23 = run.c[2] | (run.c[3] << 16); }
+                if ((int)lane == k) keep = run;
                 Agg wk;
                 wk.map = s_wmap[k];
-                wk.c[0] = s_wc01[k] & 0xFFFF; wk.c[1] = s_wc01[k] >> 16; wk.c[2] = s_wc23[k] & 0xFFFF; wk.c[3] = s_wc23[k] >> 16;
+                wk.c[0] = s_wc[k][0]; wk.c[1] = s_wc[k][1]; wk.c[2] = s_wc[k][2]; wk.c[3] = s_wc[k][3];
                 run = agg_then(run, wk);
             }
-            if (lane < kScanWarps) { s_wpre[lane] = keep_map; s_wp01[lane] = keep01; s_wp23[lane] = keep23; }
             TileDesc* me = desc + tile;
             uint32_t entry = 0;
             unsigned long long cbase = 0;
             if (tile > 0) {
                 if (lane == 0) {
                     me->map = run.map;
-                    me->c01 = run.c[0] | (run.c[1] << 16);
-                    me->c23 = run.c[2] | (run.c[3] << 16);
+                    me->c[0] = run.c[0]; me->c[1] = run.c[1]; me->c[2] = run.c[2]; me->c[3] = run.c[3];
                     st_release(&me->flag, 1u);
                 }
-                // F = composition of the tiles between the nearest inclusive tile and this one
                 uint32_t fmap = kIdentityMap;
                 unsigned long long fc[4] = {0, 0, 0, 0};
                 long long look = (long long)tile - 1;
                 for (;;) {
                     const long long t = look - (long long)lane;
-                    uint32_t flag = 2, amap = kIdentityMap, a01 = 0, a23 = 0, st = 0, clo = 0, chi = 0;
+                    uint32_t flag = 2, amap = kIdentityMap, a0 = 0, a1 = 0, a2 = 0, a3 = 0, st = 0, clo = 0, chi = 0;
                     if (t >= 0) {
                         const TileDesc* dsc = desc + t;
                         do { flag = ld_acquire(&dsc->flag); } while (flag == 0);
                         if (flag == 2) { st = ld_relaxed(&dsc->state); clo = ld_relaxed(&dsc->cnt_lo); chi = ld_relaxed(&dsc->cnt_hi); }
-                        else { amap = ld_relaxed(&dsc->map); a01 = ld_relaxed(&dsc->c01); a23 = ld_relaxed(&dsc->c23); }
+                        else { amap = ld_relaxed(&dsc->map); a0 = ld_relaxed(&dsc->c[0]); a1 = ld_relaxed(&dsc->c[1]); a2 = ld_relaxed(&dsc->c[2]); a3 = ld_relaxed(&dsc->c[3]); }
                     }
                     const uint32_t incm = __ballot_sync(0xFFFFFFFFu, flag == 2);     // lanes past tile 0 count as inclusive(0,0)
                     const int first = incm ? __ffs(incm) - 1 : 32;
-                    // "simple" aggregate: constant map and a count that does not depend on the entry state —
-                    // every tile that contains a 3-byte gap without a raw sync, i.e. practically all of them
-                    const bool simple = map_is_const(amap) && a01 == (a01 & 0xFFFFu) * 0x10001u && a23 == a01;
+                    // "simple" aggregate: constant map, count independent of the entry state (practically every tile)
+                    const bool simple = map_is_const(amap) && a0 == a1 && a1 == a2 && a2 == a3;
                     const uint32_t need = first >= 32 ? 0xFFFFFFFFu : ((1u << first) - 1u);
                     const uint32_t simple_m = __ballot_sync(0xFFFFFFFFu, simple) & need;
                     if (simple_m == need) {
                         if (first > 0) {
-                            // fold the whole window at once: counts add up, the nearest tile fixes the state
-                            const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, (int)lane < first ? (a01 & 0xFFFFu) : 0u);
+                            const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, (int)lane < first ? a0 : 0u);
                             const uint32_t e0 = __shfl_sync(0xFFFFFFFFu, amap, 0) & 3u;
                             const unsigned long long nc = tot + pick4(fc[0], fc[1], fc[2], fc[3], e0);
                             fc[0] = fc[1] = fc[2] = fc[3] = nc;
@@ -295,11 +296,11 @@ mpeg_sync_scan(const uint8_t* __restrict__ bytes, unsigned long long n, TileDesc
                     } else {
                         for (int i = 0; i < first; ++i) {                              // nearest tile first
                             const uint32_t m_i = __shfl_sync(0xFFFFFFFFu, amap, i);
-                            const uint32_t c01_i = __shfl_sync(0xFFFFFFFFu, a01, i), c23_i = __shfl_sync(0xFFFFFFFFu, a23, i);
-                            // F' = (tile i) then F
+                            const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, a0, i), b1 = __shfl_sync(0xFFFFFFFFu, a1, i);
+                            const uint32_t b2 = __shfl_sync(0xFFFFFFFFu, a2, i), b3 = __shfl_sync(0xFFFFFFFFu, a3, i);
                             unsigned long long nc[4];
 #pragma unroll
-                            for (int s = 0; s < 4; ++s) nc[s] = cnt16(c01_i, c23_i, s) + pick4(fc[0], fc[1], fc[2], fc[3], map_get(m_i, s));
+                            for (int s = 0; s < 4; ++s) nc[s] = pick4(b0, b1, b2, b3, (uint32_t)s) + pick4(fc[0], fc[1], fc[2], fc[3], map_get(m_i, s));
 #pragma unroll
                             for (int s = 0; s < 4; ++s) fc[s] = nc[s];
                             fmap = map_after(m_i, fmap);
@@ -322,47 +323,85 @@ mpeg_sync_scan(const uint8_t* __restrict__ bytes, unsigned long long n, TileDesc
                 me->cnt_hi = (uint32_t)(cend >> 32);
                 st_release(&me->flag, 2u);
                 if (tile + 1 == n_tiles) ctl->total = cend;
-                s_entry = entry;
-                s_base = cbase;
+            }
+            if (lane < kScanWarps) {
+                s_wentry[lane] = map_get(keep.map, entry);
+                s_wbase[lane] = cbase + pick4(keep.c[0], keep.c[1], keep.c[2], keep.c[3], entry);
             }
         }
         __syncthreads();
 
-        // ---- every thread: true entry state, global index of its first candidate, emission
-        const uint32_t tile_entry = s_entry;
-        const uint32_t warp_entry = map_get(s_wpre[warp], tile_entry);
-        const uint32_t my_entry = map_get(pre, warp_entry);
-        unsigned long long idx = s_base + cnt16(s_wp01[warp], s_wp23[warp], tile_entry) +
-                                 (cnt16(h01, h23, warp_entry) - cnt16(own01, own23, warp_entry));
-        if (M) {
-            uint32_t dummy;
-            unsigned long long sel = resolve(M, my_entry, dummy) & okmask;
-            while (sel) {
-                const int i = __ffsll((long long)sel) - 1;
-                sel &= sel - 1;
-                const int kk = i >> 2;
-                uint32_t lo = 0, hi = 0;
-#pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    if (k == kk) { lo = w[k]; hi = w[k + 1]; }
-                const uint32_t le = __funnelshift_r(lo, hi, 8 * (i & 3));
-                if (idx < cap) {
-                    out_pos[idx] = base + (unsigned long long)i;
-                    out_hdr[idx] = __byte_perm(le, 0, 0x0123);               // big-endian header (mpeg.rs:22-38)
-                }
-                idx += 1;
-            }
-        }
-        // mpeg.rs:20: `reader[cur + 1]` with cur == n-1 panics when the scan reaches a trailing 0xFF
-        if (n > 0 && n - 1 >= base && n - 1 < base + kChunk) {
-            const uint32_t il = (uint32_t)(n - 1 - base);
-            if (bytes[n - 1] == 0xFF) {
+        // ================= pass 2: true entry states are known; emit candidates at their final indices
+        {
+            const uint32_t span_entry = s_wentry[warp];
+            unsigned long long run_base = s_wbase[warp];
+            const bool near_end = span0 + kSpanBytes + 4 > n;       // this span touches the end of the buffer
+#pragma unroll 1
+            for (int r = 0; r < kRounds; ++r) {
+                const unsigned long long base = span0 + (unsigned long long)r * (32 * kChunk) + (unsigned long long)lane * kChunk;
+                const uint32_t slot = (warp * kRounds + r) * 32 + lane;
+                const unsigned long long M = s_mask[slot];
+                const uint32_t my_entry = map_get((uint32_t)s_tpre[slot], span_entry);
                 uint32_t dummy;
-                const unsigned long long sel = resolve(M, my_entry, dummy);
-                const unsigned long long before = il ? (sel & ((il >= 64 ? ~0ull : (1ull << il)) - 1ull)) : 0ull;
-                bool skipped = il < my_entry;
-                if (before) skipped = skipped || (il - (uint32_t)(63 - __clzll((long long)before)) <= 3);
-                if (!skipped) ctl->panic = 1;
+                const unsigned long long sel_all = M ? resolve(M, my_entry, dummy) : 0ull;
+                unsigned long long okmask = ~0ull;
+                if (near_end && base + 67 >= n) {
+                    const unsigned long long lim = n > base + 3 ? n - 3 - base : 0;
+                    okmask = lim >= 64 ? ~0ull : ((1ull << lim) - 1ull);
+                }
+                unsigned long long sel = sel_all & okmask;
+                const uint32_t cnt = (uint32_t)__popcll(sel);
+                uint32_t inc = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                    if ((int)lane >= d) inc += a;
+                }
+                unsigned long long idx = run_base + (inc - cnt);
+                run_base += __shfl_sync(0xFFFFFFFFu, inc, 31);
+                // header = 4 bytes at base+i, read as two aligned words (L2 hits: the tile was just scanned).
+                // The first two candidates' loads are issued together; more than two per 64 bytes is rare.
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(bytes + base);
+                int i0 = -1, i1 = -1;
+                uint32_t a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+                if (sel) { i0 = __ffsll((long long)sel) - 1; sel &= sel - 1; }
+                if (sel) { i1 = __ffsll((long long)sel) - 1; sel &= sel - 1; }
+                if (i0 >= 0) { a0 = __ldg(wp + (i0 >> 2)); if (i0 & 3) b0 = __ldg(wp + (i0 >> 2) + 1); }
+                if (i1 >= 0) { a1 = __ldg(wp + (i1 >> 2)); if (i1 & 3) b1 = __ldg(wp + (i1 >> 2) + 1); }
+                if (i0 >= 0) {
+                    if (idx < cap) {
+                        out_pos[idx] = base + (unsigned long long)i0;
+                        out_hdr[idx] = __byte_perm(__funnelshift_r(a0, b0, 8 * (i0 & 3)), 0, 0x0123);    // big-endian (mpeg.rs:22-38)
+                    }
+                    idx += 1;
+                }
+                if (i1 >= 0) {
+                    if (idx < cap) {
+                        out_pos[idx] = base + (unsigned long long)i1;
+                        out_hdr[idx] = __byte_perm(__funnelshift_r(a1, b1, 8 * (i1 & 3)), 0, 0x0123);
+                    }
+                    idx += 1;
+                }
+                while (sel) {
+                    const int i = __ffsll((long long)sel) - 1;
+                    sel &= sel - 1;
+                    if (idx < cap) {
+                        const uint32_t a = __ldg(wp + (i >> 2)), b = (i & 3) ? __ldg(wp + (i >> 2) + 1) : 0u;
+                        out_pos[idx] = base + (unsigned long long)i;
+                        out_hdr[idx] = __byte_perm(__funnelshift_r(a, b, 8 * (i & 3)), 0, 0x0123);
+                    }
+                    idx += 1;
+                }
+                // mpeg.rs:20: `reader[cur + 1]` with cur == n-1 panics when the scan reaches a trailing 0xFF
+                if (near_end && n > 0 && n - 1 >= base && n - 1 < base + kChunk) {
+                    const uint32_t il = (uint32_t)(n - 1 - base);
+                    if (bytes[n - 1] == 0xFF) {
+                        const unsigned long long before = il ? (sel_all & ((1ull << il) - 1ull)) : 0ull;
+                        bool skipped = il < my_entry;
+                        if (before) skipped = skipped || (il - (uint32_t)(63 - __clzll((long long)before)) <= 3);
+                        if (!skipped) ctl->panic = 1;
+                    }
+                }
             }
         }
         __syncthreads();            // shared scratch is reused by the next tile
@@ -592,23 +631,23 @@ int run_scan(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, uint64_t* d_p
     *n_out = 0;
     if (len == 0) return BLAST_OK;
     const unsigned long long n_tiles = (len + kTileBytes - 1) / kTileBytes;
-    DevFree mem;
-    TileDesc* desc = nullptr;
-    ScanCtl* ctl = nullptr;
-    BLAST_CUDA_TRY(mem.alloc(&desc, n_tiles * sizeof(TileDesc)));
-    BLAST_CUDA_TRY(mem.alloc(&ctl, sizeof(ScanCtl)));
-    BLAST_CUDA_TRY(cudaMemsetAsync(desc, 0, n_tiles * sizeof(TileDesc), ctx->stream));
-    BLAST_CUDA_TRY(cudaMemsetAsync(ctl, 0, sizeof(ScanCtl), ctx->stream));
-    int per_sm = 0;
-    BLAST_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpeg_sync_scan, kScanThreads, 0));
+    // tile descriptors + control block live in context scratch (no cudaMalloc / cudaFree on this path)
+    TileDesc* desc = static_cast<TileDesc*>(blast::scratch(ctx, 0, n_tiles * sizeof(TileDesc) + 256));
+    if (!desc) return BLAST_ERR_CUDA;
+    ScanCtl* ctl = reinterpret_cast<ScanCtl*>(reinterpret_cast<uint8_t*>(desc) + ((n_tiles * sizeof(TileDesc) + 127) & ~127ull));
+    ScanCtl* h_ctl = static_cast<ScanCtl*>(blast::mailbox(ctx));
+    if (!h_ctl) return BLAST_ERR_CUDA;
+    BLAST_CUDA_TRY(cudaMemsetAsync(desc, 0, ((n_tiles * sizeof(TileDesc) + 127) & ~127ull) + sizeof(ScanCtl), ctx->stream));
+    static int per_sm = 0;
+    if (per_sm == 0) BLAST_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpeg_sync_scan, kScanThreads, 0));
     const unsigned grid = (unsigned)std::min<unsigned long long>(n_tiles, (unsigned long long)ctx->sm_count * std::max(per_sm, 1));
     mpeg_sync_scan<<<grid, kScanThreads, 0, ctx->stream>>>(d_bytes, len, desc, n_tiles, ctl,
                                                            reinterpret_cast<unsigned long long*>(d_pos), d_hdr, cap);
     BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
-    ScanCtl h{};
-    BLAST_CUDA_TRY(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    BLAST_CUDA_TRY(cudaMemcpyAsync(h_ctl, ctl, sizeof(ScanCtl), cudaMemcpyDeviceToHost, ctx->stream));
     BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const ScanCtl h = *h_ctl;
     *n_out = h.total;
     if (h.panic) return blast::set_error(BLAST_ERR_REF_PANIC, "index out of bounds: the scan reaches a trailing 0xFF (mpeg.rs:20)");
     if (h.total > cap) return blast::set_error(BLAST_ERR_CAPACITY, "mpeg scan: %llu candidates, capacity %llu",
