@@ -31,42 +31,11 @@
 #include <cstring>
 #include <vector>
 
-#include "blast_internal.h"
+#include "render_internal.h"
+
+using namespace blast_rdr;
 
 namespace {
-
-constexpr int kMaxSeg = 160;
-constexpr int kFT = 2048;                      // frames per tile
-constexpr int kThreads = 256;
-constexpr int kFPT = kFT / kThreads;           // frames per thread
-constexpr int kVoiceBatch = 64;                // voices staged in shared memory at a time
-constexpr int kMaxOut = 8;
-
-struct VoiceDev {
-    const int16_t* smp;
-    uint32_t end;          // Voice::new: samples.len()/channels - 1 (engine.rs:302)
-    uint32_t C;            // track channels
-    float pos, vel, gain;
-    uint32_t active;
-    uint32_t S;            // advance events per frame for this voice on this bus: 0, 1 or 2
-    uint32_t nch;          // bus channels this voice feeds
-    uint32_t pad0, pad1;
-};
-static_assert(sizeof(VoiceDev) == 48, "VoiceDev layout");
-
-struct Seg {               // positions for steps [step0, next.step0): p0 + (step-step0)*d*scale
-    uint32_t step0;
-    float p0;
-    int32_t d;
-    float scale;
-};
-
-struct TileRec {           // state of one voice at the first step of one tile
-    float p0;
-    int32_t d;
-    float scale;
-    uint32_t meta;         // [23:0] steps this segment still covers (saturating), [31:24] segment index
-};
 
 __device__ __forceinline__ uint32_t f2u_sat(float x) {       // Rust `as usize` on f32, clamped to u32
     uint32_t r;
@@ -98,28 +67,142 @@ __device__ __forceinline__ float seg_eval(float p0, int32_t d, float scale, uint
     return __fmaf_rn((float)(int32_t)(k * (uint32_t)d), scale, p0);
 }
 
+// ---- advance map of voices that carry Seq processes.  Their step unit is the CALL (frame * oc + channel)
+// because a retrigger can land between the channels of one frame; A(c) = advance events before call c.
+__device__ __forceinline__ uint32_t adv_count(uint32_t c, uint32_t adv) {
+    if (adv == 0) return c;
+    const uint32_t oc = adv & 0xFF, lo = (adv >> 8) & 0xFF, na = (adv >> 16) & 0xFF;
+    const uint32_t f = c / oc, r = c - f * oc;
+    const uint32_t in = r > lo ? min(r - lo, na) : 0u;
+    return f * na + in;
+}
+__device__ __forceinline__ uint32_t adv_first_call(uint32_t a, uint32_t adv) {   // smallest c with A(c) >= a
+    if (adv == 0 || a == 0) return a;
+    const uint32_t oc = adv & 0xFF, lo = (adv >> 8) & 0xFF, na = (adv >> 16) & 0xFF;
+    if (na == 0) return 0xFFFFFFFFu;
+    const uint32_t f = (a - 1) / na, r = (a - 1) - f * na;
+    const unsigned long long c = (unsigned long long)f * oc + lo + r + 1;
+    return c > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c;
+}
+__device__ __forceinline__ float seg_pos(const Seg& g, uint32_t abs_step, uint32_t adv) {
+    return seg_eval(g.p0, g.d, g.scale, adv_count(abs_step, adv) - adv_count(g.step0, adv));
+}
+
+// ---------------------------------------------------------------- K3a: Seq event scan (processes.rs:69-90)
+// One thread per voice that carries Seq processes.  A Seq fires at call c when
+//   fmodf((tempo.current as f32) / interval, period as f32) == steps[idx]        (exact f32 equality)
+// with tempo.current = base + rate * c (u32, wrapping), then draws next_i64_range(0, 100) and, if the draw is
+// below chance[idx], retriggers the voice.  x(c) = f32(current) / interval is monotone in c (rate >= 1, no
+// wrap), and fmodf is exact, so a hit needs x(c) == steps[idx] + k * period for an integer k: for each k the
+// first call reaching that value is found by bisection.  Other cases (rate 0, wrap, odd intervals) walk
+// call by call.  Output: the sorted, de-duplicated retrigger calls of the voice.
+__device__ __forceinline__ uint64_t xo_rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+__device__ __forceinline__ uint64_t xo_next(unsigned long long& s0, unsigned long long& s1) {   // blast_rand.rs:31-39
+    const uint64_t r = s0 + s1;
+    const uint64_t t = s1 ^ s0;
+    s0 = xo_rotl(s0, 55) ^ t ^ (t << 14);
+    s1 = xo_rotl(t, 36);
+    return r;
+}
+__device__ __forceinline__ long long f32_as_i64(float x) {      // Rust `as i64`
+    if (x != x) return 0;
+    if (x >= 9223372036854775808.0f) return 0x7FFFFFFFFFFFFFFFll;
+    if (x <= -9223372036854775808.0f) return (long long)0x8000000000000000ull;
+    return (long long)x;
+}
+__device__ __forceinline__ float seq_cur(uint32_t base, uint32_t rate, uint32_t c, float interval, float period_f) {
+    const uint32_t cur = base + rate * c;                                        // u32 wrapping (blast_time.rs:113-115)
+    return fmodf(__fdiv_rn((float)cur, interval), period_f);                      // blast_time.rs:118-121, processes.rs:77
+}
+
+__global__ void seq_event_scan(const VoiceDev* __restrict__ voices, uint32_t n_voices, SeqDev* __restrict__ seqs,
+                               uint32_t n_calls, uint32_t* __restrict__ events, uint32_t* __restrict__ nevents,
+                               uint32_t* __restrict__ err) {
+    const uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vi >= n_voices) return;
+    const VoiceDev v = voices[vi];
+    const uint32_t n_seq = v.first_seq >> 24, s_first = v.first_seq & 0xFFFFFFu;
+    uint32_t* ev = events + (size_t)vi * kMaxEvents;
+    uint32_t n_ev = 0;
+    if (!v.active || n_seq == 0) { nevents[vi] = 0; return; }
+    for (uint32_t si = 0; si < n_seq && n_ev <= (uint32_t)kMaxEvents; ++si) {
+        SeqDev q = seqs[s_first + si];
+        // n_steps == 0: the host parks Seqs whose tempo is inactive this way (processes.rs:74-75).
+        // period 0: x % 0.0 is NaN, which equals nothing.
+        if (q.n_steps == 0 || !(q.period_f > 0.0f)) continue;
+        const float P = q.period_f;
+        const unsigned long long last_tick = (unsigned long long)q.base + (unsigned long long)q.rate * (n_calls - 1);
+        // x(c) = f32(current) / interval is monotone in c, and a period spans >= 16 calls (bounds the k walk)
+        const bool monotone = q.rate >= 1 && q.interval > 0.0f && q.interval < 3.0e38f && last_tick <= 0xFFFFFFFFull &&
+                              __fmul_rn(q.interval, P) >= __fmul_rn(16.0f, (float)q.rate);
+        uint32_t c = 0;
+        while (c < n_calls && n_ev <= (uint32_t)kMaxEvents) {
+            const float t = q.steps[q.idx];
+            uint32_t hit = 0xFFFFFFFFu;
+            if (q.rate == 0) {
+                if (seq_cur(q.base, 0, 0, q.interval, P) == t) hit = c;         // the tempo stands still
+            } else if (monotone) {
+                if (!(t >= 0.0f && t < P)) break;                               // fmodf never returns it: stuck forever
+                const double Pd = (double)P;
+                const float x_last = __fdiv_rn((float)(uint32_t)last_tick, q.interval);
+                double k = floor((double)__fdiv_rn((float)(q.base + q.rate * c), q.interval) / Pd) - 1.0;
+                if (k < 0.0) k = 0.0;
+                for (;; k += 1.0) {
+                    const double X = (double)t + k * Pd;                        // fmodf is exact: a hit needs x(c) == X
+                    if (X > (double)x_last) break;
+                    const float Xf = (float)X;
+                    if ((double)Xf != X) continue;                              // not an f32: x(c) can never equal it
+                    uint32_t lo = c, hi = n_calls;                              // first call with x >= Xf
+                    while (lo < hi) {
+                        const uint32_t mid = lo + (hi - lo) / 2;
+                        if (__fdiv_rn((float)(q.base + q.rate * mid), q.interval) >= Xf) hi = mid; else lo = mid + 1;
+                    }
+                    if (lo < n_calls && seq_cur(q.base, q.rate, lo, q.interval, P) == t) { hit = lo; break; }
+                }
+            } else {
+                for (uint32_t cc = c; cc < n_calls; ++cc)
+                    if (seq_cur(q.base, q.rate, cc, q.interval, P) == t) { hit = cc; break; }
+            }
+            if (hit == 0xFFFFFFFFu) break;
+            const uint64_t r = xo_next(q.s0, q.s1);                                // next_i64_range(0, 100): blast_rand.rs:50-59
+            const long long draw = (long long)__umul64hi(r, 100ull);
+            if (draw < f32_as_i64(q.chance[q.idx])) {
+                if (n_ev < (uint32_t)kMaxEvents) ev[n_ev] = hit;
+                n_ev += 1;
+            }
+            q.idx = (q.idx + 1) % q.n_steps;
+            c = hit + 1;
+        }
+        seqs[s_first + si].idx = q.idx;
+        seqs[s_first + si].s0 = q.s0;
+        seqs[s_first + si].s1 = q.s1;
+    }
+    if (n_ev > (uint32_t)kMaxEvents) { atomicOr(err, 2u); n_ev = kMaxEvents; }
+    // sort + de-duplicate (several Seqs of one voice may fire at the same call; the effect is the same reset)
+    for (uint32_t i = 1; i < n_ev; ++i) {
+        const uint32_t x = ev[i];
+        uint32_t j = i;
+        while (j > 0 && ev[j - 1] > x) { ev[j] = ev[j - 1]; --j; }
+        ev[j] = x;
+    }
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < n_ev; ++i)
+        if (m == 0 || ev[m - 1] != ev[i]) ev[m++] = ev[i];
+    nevents[vi] = m;
+}
+
 // ---------------------------------------------------------------- K3
 // One thread per voice.  Builds the segment list for `total = frames * S` advance events, the
 // per-tile records, and writes the position after the render back into the voice.
-__global__ void voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t frames,
-                                    Seg* __restrict__ segs, uint32_t* __restrict__ nsegs,
-                                    TileRec* __restrict__ recs, uint32_t n_tiles, uint32_t* __restrict__ err) {
-    uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (vi >= n_voices) return;
-    VoiceDev v = voices[vi];
-    Seg* sg = segs + (size_t)vi * kMaxSeg;
-    uint32_t n = 0;
-    auto emit = [&](uint32_t step0, float p0, int32_t d, float scale) {
-        if (n < (uint32_t)kMaxSeg) sg[n] = Seg{step0, p0, d, scale};
-        n += 1;
-    };
-    float p = v.pos;
-    const float vel = v.vel;
-    const uint32_t total = v.active ? frames * v.S : 0;
+// Positions of `n_adv` advance events starting from position p: emits arithmetic segments through
+// emit(advance index relative to the start, p0, d, scale) and returns the position after the last advance
+// (the walk stops at a frozen position or a fixed point, which then holds forever).
+template <typename Emit>
+__device__ __forceinline__ float build_epoch(float p, const float vel, const uint32_t end, const uint32_t total, Emit emit) {
     uint32_t s = 0;
-    if (total == 0) emit(0, p, 0, 0.0f);
+    if (total == 0) emit(0u, p, 0, 0.0f);
     while (s < total) {
-        if (f2u_sat(p) >= v.end) { emit(s, p, 0, 0.0f); break; }                 // frozen (engine.rs:407-410)
+        if (f2u_sat(p) >= end) { emit(s, p, 0, 0.0f); break; }                   // frozen (engine.rs:407-410)
         const float p1 = __fadd_rn(p, vel);
         if (__float_as_uint(p1) == __float_as_uint(p)) { emit(s, p, 0, 0.0f); break; }   // fixed point
         const float p2 = __fadd_rn(p1, vel);
@@ -147,8 +230,8 @@ __global__ void voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_vo
                 // growing positive position: stop the run at the first frozen step
                 const int e = (int)(E0 ? E0 : 1) - 150;
                 uint64_t thr;                               // smallest q with q * 2^e >= end
-                if (e >= 0) thr = e >= 32 ? 1ull : (((uint64_t)v.end + (1ull << e) - 1) >> e);
-                else thr = (-e) >= 40 ? ~0ull : ((uint64_t)v.end << (-e));
+                if (e >= 0) thr = e >= 32 ? 1ull : (((uint64_t)end + (1ull << e) - 1) >> e);
+                else thr = (-e) >= 40 ? ~0ull : ((uint64_t)end << (-e));
                 if (thr > (uint64_t)qs) {
                     uint64_t kf = (thr - (uint64_t)qs + (uint64_t)d - 1) / (uint64_t)d;
                     if (kf < (uint64_t)kmax) kmax = (uint32_t)kf;
@@ -172,8 +255,61 @@ __global__ void voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_vo
         p = p1;
         s += 1;
     }
+    return p;
+}
+
+// One thread per voice.  Builds the segment list for `frames * S` steps (advance events, or calls for voices
+// with Seq processes, whose retrigger events start new epochs: processes.rs:82-85), the per-tile records, and
+// writes the position after the render back into the voice.
+__global__ void voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t frames,
+                                    Seg* __restrict__ segs, uint32_t* __restrict__ nsegs,
+                                    TileRec* __restrict__ recs, uint32_t n_tiles, uint32_t* __restrict__ err,
+                                    const uint32_t* __restrict__ events, const uint32_t* __restrict__ nevents) {
+    uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vi >= n_voices) return;
+    VoiceDev v = voices[vi];
+    Seg* sg = segs + (size_t)vi * kMaxSeg;
+    uint32_t n = 0;
+    float p = v.pos;
+    const uint32_t total = v.active ? frames * v.S : 0;
+    if (v.adv == 0 || total == 0) {
+        p = build_epoch(p, v.vel, v.end, total, [&](uint32_t a, float p0, int32_t d, float scale) {
+            if (n < (uint32_t)kMaxSeg) sg[n] = Seg{a, p0, d, scale};
+            n += 1;
+        });
+    } else {
+        // steps are calls; epochs are delimited by the retrigger events found by seq_event_scan
+        const uint32_t* ev = events + (size_t)vi * kMaxEvents;
+        const uint32_t n_ev = nevents[vi];
+        uint32_t cc = 0, e = 0, last0 = 0xFFFFFFFFu;
+        auto put = [&](uint32_t step0, float p0, int32_t d, float scale) {
+            if (step0 == last0 && n > 0) {                                        // same call as the previous segment: replace it
+                if (n <= (uint32_t)kMaxSeg) sg[n - 1] = Seg{step0, p0, d, scale};
+                return;
+            }
+            last0 = step0;
+            if (n < (uint32_t)kMaxSeg) sg[n] = Seg{step0, p0, d, scale};
+            n += 1;
+        };
+        for (;;) {
+            if (e < n_ev && ev[e] == cc) {                                        // retrigger before the read at call cc
+                p = v.vel >= 0.0f ? 0.0f : (float)v.end;                           // processes.rs:82-85
+                e += 1;
+            }
+            const uint32_t stop = (e < n_ev && ev[e] < total) ? ev[e] : total;   // next retrigger (or the end); stop > cc
+            const uint32_t a_cc = adv_count(cc, v.adv);
+            const uint32_t n_adv = adv_count(stop, v.adv) - a_cc;                // advancing calls in [cc, stop)
+            p = build_epoch(p, v.vel, v.end, n_adv, [&](uint32_t a, float p0, int32_t d, float scale) {
+                put(a == 0 ? cc : adv_first_call(a_cc + a, v.adv), p0, d, scale);
+            });
+            // calls between the last advancing call and `stop` read the position after all n_adv advances
+            if (n_adv > 0 && adv_count(stop - 1, v.adv) - a_cc == n_adv) put(adv_first_call(a_cc + n_adv, v.adv), p, 0, 0.0f);
+            cc = stop;
+            if (stop >= total) break;
+        }
+    }
     if (n > (uint32_t)kMaxSeg) {
-        atomicExch(err, 1u);
+        atomicOr(err, 1u);
         n = kMaxSeg;
     }
     nsegs[vi] = n;
@@ -185,12 +321,11 @@ __global__ void voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_vo
         const uint32_t st = t * (uint32_t)kFT * v.S;
         while (j + 1 < n && sg[j + 1].step0 <= st) ++j;
         const Seg g = sg[j];
-        const uint32_t k0 = st - g.step0;
         const uint32_t next = (j + 1 < n) ? sg[j + 1].step0 : 0xFFFFFFFFu;
         uint32_t left = next - st;
         if (left > 0xFFFFFFu) left = 0xFFFFFFu;
         TileRec r;
-        r.p0 = seg_eval(g.p0, g.d, g.scale, k0);
+        r.p0 = seg_pos(g, st, v.adv);
         r.d = g.d;
         r.scale = g.scale;
         r.meta = left | (j << 24);
@@ -205,24 +340,24 @@ struct VoiceS {            // what K4 needs per voice, staged in shared memory
     float vel, gain;
     uint32_t S, nch;
     uint32_t active, nseg;
+    uint32_t adv;
     TileRec rec;
 };
 
 __device__ __forceinline__ float position_eval(bool fast, float p0, int32_t d, float scale, uint32_t recmeta,
                                                const Seg* __restrict__ sg, uint32_t nseg, uint32_t tile_step0,
-                                               uint32_t step_local) {
-    if (fast) return seg_eval(p0, d, scale, step_local);
+                                               uint32_t step_local, uint32_t adv = 0) {
+    if (fast) return seg_eval(p0, d, scale, adv_count(tile_step0 + step_local, adv) - adv_count(tile_step0, adv));
     // the tile straddles a segment boundary: walk the (short) segment list from the tile's segment
     const uint32_t abs_step = tile_step0 + step_local;
     uint32_t j = recmeta >> 24;
     while (j + 1 < nseg && sg[j + 1].step0 <= abs_step) ++j;
-    const Seg g = sg[j];
-    return seg_eval(g.p0, g.d, g.scale, abs_step - g.step0);
+    return seg_pos(sg[j], abs_step, adv);
 }
 
 __device__ __forceinline__ float position_at(const VoiceS& v, const Seg* __restrict__ sg, bool fast,
                                              uint32_t tile_step0, uint32_t step_local) {
-    return position_eval(fast, v.rec.p0, v.rec.d, v.rec.scale, v.rec.meta, sg, v.nseg, tile_step0, step_local);
+    return position_eval(fast, v.rec.p0, v.rec.d, v.rec.scale, v.rec.meta, sg, v.nseg, tile_step0, step_local, v.adv);
 }
 
 // (sample * gain) as i16 for one source channel at position p (engine.rs:429-442)
@@ -263,7 +398,7 @@ voice_render_mix(const VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_
             const VoiceDev v = voices[vb + threadIdx.x];
             VoiceS s;
             s.smp = v.smp; s.end = v.end; s.C = v.C; s.vel = v.vel; s.gain = v.gain; s.S = v.S; s.nch = v.nch;
-            s.active = v.active; s.nseg = nsegs[vb + threadIdx.x];
+            s.active = v.active; s.nseg = nsegs[vb + threadIdx.x]; s.adv = v.adv;
             s.rec = recs[(size_t)tile * n_voices + vb + threadIdx.x];
             sv[threadIdx.x] = s;
         }
@@ -274,7 +409,7 @@ voice_render_mix(const VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_
             const Seg* __restrict__ sg = segs + (size_t)(vb + i) * kMaxSeg;
             const uint32_t tile_step0 = f0 * v.S;
             const bool fast = (v.rec.meta & 0xFFFFFFu) >= (uint32_t)kFT * v.S + 2u || v.S == 0;
-            if (v.C == 2 && v.nch == 2) {
+            if (v.C == 2 && v.nch == 2 && v.adv == 0) {
                 // stereo voice on a >= 2-channel bus: one 32-bit load fetches L and R of a frame
                 const uint32_t* __restrict__ pairs = reinterpret_cast<const uint32_t*>(v.smp);
 #pragma unroll
@@ -321,13 +456,15 @@ voice_render_mix(const VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_
                 for (int j = 0; j < kFPT; ++j) {
                     const uint32_t fl = threadIdx.x + j * kThreads;
                     if (fl < nf) {
-                        const float p = position_at(v, sg, fast, tile_step0, fl * v.S);
-                        const uint32_t idx = f2u_sat(p);
-                        if (idx < v.end) {
-                            const int16_t* sp = v.smp + (size_t)idx * v.C;
+                        float p = position_at(v, sg, fast, tile_step0, fl * v.S);
 #pragma unroll
-                            for (int c = 0; c < OC; ++c)
-                                if ((uint32_t)c < v.nch) acc[j][c] += voice_sample(sp + c, v.C, p, v.vel, v.gain);
+                        for (int c = 0; c < OC; ++c) {
+                            if ((uint32_t)c < v.nch) {
+                                // a retrigger can land between the channels of one frame (processes.rs:82-85)
+                                if (v.adv && c > 0) p = position_at(v, sg, fast, tile_step0, fl * v.S + c);
+                                const uint32_t idx = f2u_sat(p);
+                                if (idx < v.end) acc[j][c] += voice_sample(v.smp + (size_t)idx * v.C + c, v.C, p, v.vel, v.gain);
+                            }
                         }
                     }
                 }
@@ -572,6 +709,7 @@ __device__ __forceinline__ void consume_generic(const StageMeta& m, uint32_t sta
     const uint32_t fa = m.frange & 0xFFFF, span = (m.frange >> 16) - fa;
     const bool slow = (m.mode >> 17) & 1;
     const bool lerp = m.vel != 1.0f;
+    const uint32_t adv = m.a0_off;                  // generic pieces carry the voice's advance map here
     const uint32_t sbase = stage_addr + m.byte_off;
     const uint32_t j_lo = fa / kConsumers, j_hi = (fa + span - 1) / kConsumers;
 #pragma unroll
@@ -582,16 +720,17 @@ __device__ __forceinline__ void consume_generic(const StageMeta& m, uint32_t sta
 #pragma unroll
             for (int c = 0; c < OC; ++c) {
                 if ((uint32_t)c < nch) {
-                    const uint32_t step = (fl - fa) * S + ((C == 1) ? (uint32_t)c : 0u);   // steps since the piece start
+                    // steps since the piece start; voices with Seq processes step per call (adv != 0)
+                    const uint32_t step = (fl - fa) * S + ((C == 1 || adv) ? (uint32_t)c : 0u);
+                    const uint32_t abs0 = (f0 + fa) * S;
                     float p;
                     if (!slow) {
-                        p = seg_eval(m.p0, m.d, m.scale, step);
+                        p = seg_eval(m.p0, m.d, m.scale, adv ? adv_count(abs0 + step, adv) - adv_count(abs0, adv) : step);
                     } else {
-                        const uint32_t abs_step = (f0 + fa) * S + step;
+                        const uint32_t abs_step = abs0 + step;
                         uint32_t k = m.seg_hint;
                         while (k + 1 < m.nseg && m.sg[k + 1].step0 <= abs_step) ++k;
-                        const Seg g = m.sg[k];
-                        p = seg_eval(g.p0, g.d, g.scale, abs_step - g.step0);
+                        p = seg_pos(m.sg[k], abs_step, adv);
                     }
                     const uint32_t idx = f2u_sat(p);
                     if (idx < m.end) {
@@ -678,7 +817,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                 uint32_t bytes = 0;
                 unsigned long long src = 0;
                 bool unit_tile = false;
-                if (first_round && cur < nf && OC == 2 && v.C == 2 && v.nch == 2 && v.vel == 1.0f && r.p0 >= 0.0f) {
+                if (first_round && cur < nf && OC == 2 && v.C == 2 && v.nch == 2 && v.adv == 0 && v.vel == 1.0f && r.p0 >= 0.0f) {
                     // velocity 1.0: while position + frames stays below 2^24 and the start is a multiple of the
                     // coarsest ulp it will meet, every `position += 1.0` is exact, whatever binades it crosses:
                     // the whole tile is one unit-step piece (frame index = floor(p0) + frame).
@@ -703,7 +842,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                         }
                     }
                 }
-                if (first_round && !unit_tile && cur < nf && OC == 2 && v.C == 2 && v.nch == 2 &&
+                if (first_round && !unit_tile && cur < nf && OC == 2 && v.C == 2 && v.nch == 2 && v.adv == 0 &&
                     (r.meta & 0xFFFFFFu) < nf * v.S)
                     hold_multi = true;
                 if (!unit_tile && cur < nf && !hold_multi) {
@@ -723,7 +862,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                         const Seg g = sg[seg_j];
                         const uint32_t seg_end = (seg_j + 1 < nseg) ? sg[seg_j + 1].step0 : 0xFFFFFFFFu;
                         const uint32_t whole = (seg_end - abs0) / v.S;           // frames entirely inside the segment
-                        p_a = seg_eval(g.p0, g.d, g.scale, abs0 - g.step0);
+                        p_a = seg_pos(g, abs0, v.adv);
                         d = g.d; scale = g.scale;
                         if (whole >= 1) {
                             fb = min(nf, cur + whole);
@@ -735,14 +874,15 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                     cur = fb;
                     const uint32_t last_step = v.S ? (fb - fa) * v.S - 1 : 0;
                     float p_last;
-                    if (!slow) {
-                        p_last = seg_eval(p_a, d, scale, last_step);
-                    } else {
-                        const uint32_t abs_last = tile_step0 + fa * v.S + last_step;
-                        uint32_t k = seg_j;
-                        while (k + 1 < nseg && sg[k + 1].step0 <= abs_last) ++k;
-                        const Seg g = sg[k];
-                        p_last = seg_eval(g.p0, g.d, g.scale, abs_last - g.step0);
+                    {
+                        const uint32_t abs_first = tile_step0 + fa * v.S, abs_last = abs_first + last_step;
+                        if (!slow) {
+                            p_last = seg_eval(p_a, d, scale, adv_count(abs_last, v.adv) - adv_count(abs_first, v.adv));
+                        } else {
+                            uint32_t k = seg_j;
+                            while (k + 1 < nseg && sg[k + 1].step0 <= abs_last) ++k;
+                            p_last = seg_pos(sg[k], abs_last, v.adv);
+                        }
                     }
                     const bool weird = (p_a != p_a) || (p_last != p_last) || (v.vel != v.vel);
                     const uint32_t idx_lo = f2u_sat(fminf(p_a, p_last));
@@ -764,7 +904,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                             m.byte_off = (uint32_t)(b0 - a0);
                             // fast consumer paths: one segment, every frame audible, stereo voice on a
                             // stereo bus, positions in [0, 2^24)
-                            if (OC == 2 && v.C == 2 && v.nch == 2 && !slow && idx_hi < v.end && p_a >= 0.0f && p_last >= 0.0f) {
+                            if (OC == 2 && v.C == 2 && v.nch == 2 && v.adv == 0 && !slow && idx_hi < v.end && p_a >= 0.0f && p_last >= 0.0f) {
                                 if (v.vel == 1.0f && __fmul_rn((float)d, scale) == 1.0f) {
                                     path = kPathStereoUnit;
                                     m.a0_off = m.byte_off + (f2u_sat(p_a) - idx_lo - fa) * 4u;
@@ -784,6 +924,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                     }                                     // else: silent piece, nothing to enqueue
                     const bool fullr = (fa == 0 && fb == (uint32_t)kFT);
                     m.mode = mode | (path << 8) | ((fullr ? 1u : 0u) << 16) | ((slow ? 1u : 0u) << 17);
+                    if (path == kPathGeneric) m.a0_off = v.adv;
                     m.gain = v.gain;
                     m.frange = fa | (fb << 16);
                     m.d = d;
@@ -989,18 +1130,163 @@ __global__ void bus_finalize(const int32_t* __restrict__ partial, int16_t* __res
 
 }  // namespace
 
+namespace blast_rdr {
+
+void route_voice(VoiceDev& v, uint32_t oc, bool has_seq) {
+    uint32_t lo = 0, na = 0;
+    if (v.C == 1) {                 // engine.rs:419-422: bus channels 0 and 1 both read (and advance) a mono voice
+        v.nch = oc < 2 ? oc : 2;
+        v.S = v.nch;
+        lo = 0; na = v.nch;
+    } else if (oc >= v.C) {         // engine.rs:425-427, 445-447
+        v.nch = v.C;
+        v.S = 1;
+        lo = v.C - 1; na = 1;
+    } else {                        // ch == C-1 never happens: the voice never advances
+        v.nch = oc;
+        v.S = 0;
+    }
+    v.adv = 0;
+    if (has_seq) {                  // steps become calls: a retrigger can land between two channels of a frame
+        v.adv = oc | (lo << 8) | (na << 16);
+        v.S = oc;
+    }
+}
+
+void free_buffers(RenderBuffers& rb) {
+    if (rb.d_voices) cudaFree(rb.d_voices);
+    if (rb.d_segs) cudaFree(rb.d_segs);
+    if (rb.d_nsegs) cudaFree(rb.d_nsegs);
+    if (rb.d_err) cudaFree(rb.d_err);
+    if (rb.d_recs) cudaFree(rb.d_recs);
+    if (rb.d_seqs) cudaFree(rb.d_seqs);
+    if (rb.d_events) cudaFree(rb.d_events);
+    if (rb.d_nevents) cudaFree(rb.d_nevents);
+    rb = RenderBuffers{};
+}
+
+int reserve_buffers(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t n_seqs) {
+    const size_t nv = n_voices ? n_voices : 1;
+    if (nv > rb.voices_cap) {
+        BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (rb.d_voices) cudaFree(rb.d_voices);
+        if (rb.d_segs) cudaFree(rb.d_segs);
+        if (rb.d_nsegs) cudaFree(rb.d_nsegs);
+        rb.d_voices = nullptr; rb.d_segs = nullptr; rb.d_nsegs = nullptr;
+        rb.voices_cap = 0;
+        BLAST_CUDA_TRY(cudaMalloc(&rb.d_voices, nv * sizeof(VoiceDev)));
+        BLAST_CUDA_TRY(cudaMalloc(&rb.d_segs, nv * kMaxSeg * sizeof(Seg)));
+        BLAST_CUDA_TRY(cudaMalloc(&rb.d_nsegs, nv * sizeof(uint32_t)));
+        rb.voices_cap = nv;
+        if (rb.d_events) {                       // sized by voices: regrown below
+            cudaFree(rb.d_events); cudaFree(rb.d_nevents);
+            rb.d_events = nullptr; rb.d_nevents = nullptr;
+        }
+    }
+    if (!rb.d_err) BLAST_CUDA_TRY(cudaMalloc(&rb.d_err, sizeof(uint32_t)));
+    if (n_seqs > 0) {
+        if (n_seqs > rb.seqs_cap) {
+            BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (rb.d_seqs) cudaFree(rb.d_seqs);
+            rb.d_seqs = nullptr;
+            rb.seqs_cap = 0;
+            BLAST_CUDA_TRY(cudaMalloc(&rb.d_seqs, (size_t)n_seqs * sizeof(SeqDev)));
+            rb.seqs_cap = n_seqs;
+        }
+        if (!rb.d_events) {
+            BLAST_CUDA_TRY(cudaMalloc(&rb.d_events, rb.voices_cap * kMaxEvents * sizeof(uint32_t)));
+            BLAST_CUDA_TRY(cudaMalloc(&rb.d_nevents, rb.voices_cap * sizeof(uint32_t)));
+        }
+    }
+    return BLAST_OK;
+}
+
+int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t n_seqs, uint32_t oc, uint64_t frames,
+                  int32_t* d_partial_bus) {
+    if (frames == 0) return BLAST_OK;
+    if (frames > 0x7FFFFFFFull) return blast::set_error(BLAST_ERR_CAPACITY, "at most 2^31-1 frames per render call");
+    if (n_seqs > 0 && frames * oc > 0x7FFFFFFFull)
+        return blast::set_error(BLAST_ERR_CAPACITY, "at most 2^31-1 calls (frames x channels) per render call with Seq processes");
+    const uint32_t n_tiles = (uint32_t)((frames + kFT - 1) / kFT);
+    const size_t slots = (size_t)frames * oc;
+    if (n_voices == 0) {
+        BLAST_CUDA_TRY(cudaMemsetAsync(d_partial_bus, 0, slots * sizeof(int32_t), ctx->stream));
+        return BLAST_OK;
+    }
+    const size_t need = (size_t)n_tiles * n_voices;
+    if (need > rb.recs_cap) {
+        BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (rb.d_recs) BLAST_CUDA_TRY(cudaFree(rb.d_recs));
+        rb.d_recs = nullptr;
+        rb.recs_cap = 0;
+        BLAST_CUDA_TRY(cudaMalloc(&rb.d_recs, need * sizeof(TileRec)));
+        rb.recs_cap = need;
+    }
+    BLAST_CUDA_TRY(cudaMemsetAsync(rb.d_err, 0, sizeof(uint32_t), ctx->stream));
+    if (n_seqs > 0) {
+        seq_event_scan<<<(n_voices + 31) / 32, 32, 0, ctx->stream>>>(rb.d_voices, n_voices, rb.d_seqs, (uint32_t)(frames * oc),
+                                                                      rb.d_events, rb.d_nevents, rb.d_err);
+        BLAST_CUDA_TRY(cudaGetLastError());
+        ctx->launches += 1;
+    }
+    voice_position_scan<<<(n_voices + 31) / 32, 32, 0, ctx->stream>>>(rb.d_voices, n_voices, (uint32_t)frames, rb.d_segs, rb.d_nsegs,
+                                                                       rb.d_recs, n_tiles, rb.d_err, rb.d_events, rb.d_nevents);
+    BLAST_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+
+    // voice groups: enough CTAs to fill the GPU a few times over, groups of >= 64 voices
+    uint32_t groups = 1;
+    const uint32_t want_ctas = (uint32_t)ctx->sm_count * 16;
+    while (n_tiles * groups < want_ctas && n_voices / (groups * 2) >= 64) groups *= 2;
+    const uint32_t per_group = (n_voices + groups - 1) / groups;
+    groups = (n_voices + per_group - 1) / per_group;
+    const int use_atomic = groups > 1;
+    if (use_atomic) BLAST_CUDA_TRY(cudaMemsetAsync(d_partial_bus, 0, slots * sizeof(int32_t), ctx->stream));
+    dim3 grid(n_tiles, groups);
+    dim3 grid_tma(n_tiles * groups, 1);      // 1-D, decoded tile-major inside the kernel
+    static const bool legacy = getenv("BLAST_RENDER_LEGACY") != nullptr;
+    if (oc <= 2 && !legacy) {
+        // TMA pipeline kernel (one producer warp + eight consumer warps)
+        if (oc == 1) {
+            BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
+            voice_render_mix_tma<1><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(rb.d_voices, n_voices, per_group, groups, rb.d_segs,
+                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic);
+        } else {
+            BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
+            voice_render_mix_tma<2><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(rb.d_voices, n_voices, per_group, groups, rb.d_segs,
+                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic);
+        }
+    } else {
+#define BLAST_LAUNCH_MIX(OCV)                                                                              \
+    voice_render_mix<OCV><<<grid, kThreads, 0, ctx->stream>>>(rb.d_voices, n_voices, per_group, rb.d_segs,  \
+                                                               rb.d_nsegs, rb.d_recs, (uint32_t)frames,      \
+                                                               d_partial_bus, use_atomic)
+        switch (oc) {
+            case 1: BLAST_LAUNCH_MIX(1); break;
+            case 2: BLAST_LAUNCH_MIX(2); break;
+            case 3: BLAST_LAUNCH_MIX(3); break;
+            case 4: BLAST_LAUNCH_MIX(4); break;
+            case 5: BLAST_LAUNCH_MIX(5); break;
+            case 6: BLAST_LAUNCH_MIX(6); break;
+            case 7: BLAST_LAUNCH_MIX(7); break;
+            default: BLAST_LAUNCH_MIX(8); break;
+        }
+#undef BLAST_LAUNCH_MIX
+    }
+    BLAST_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    return BLAST_OK;
+}
+
+}  // namespace blast_rdr
+
 struct blast_scene {
     uint32_t n_voices = 0;
     uint32_t out_channels = 0;
     std::vector<blast_track> tracks;
     std::vector<blast_voice> voices;     // host mirror of the ABI voices (positions refreshed on get)
-    VoiceDev* d_voices = nullptr;
+    RenderBuffers rb;
     VoiceDev* d_voices0 = nullptr;       // the table as last uploaded (blast_scene_restore_dev)
-    Seg* d_segs = nullptr;
-    uint32_t* d_nsegs = nullptr;
-    uint32_t* d_err = nullptr;
-    TileRec* d_recs = nullptr;
-    size_t recs_cap = 0;                 // in records
 };
 
 namespace {
@@ -1021,17 +1307,7 @@ int make_voice_dev(const blast_scene* sc, const blast_voice& in, uint32_t index,
     v.vel = in.velocity;
     v.gain = in.gain;
     v.active = in.active ? 1u : 0u;
-    const uint32_t oc = sc->out_channels;
-    if (v.C == 1) {                 // engine.rs:419-422
-        v.nch = oc < 2 ? oc : 2;
-        v.S = v.nch;
-    } else if (oc >= v.C) {         // engine.rs:425-427, 445-447
-        v.nch = v.C;
-        v.S = 1;
-    } else {                        // ch == C-1 never happens: the voice never advances
-        v.nch = oc;
-        v.S = 0;
-    }
+    route_voice(v, sc->out_channels, false);
     *out = v;
     return BLAST_OK;
 }
@@ -1041,8 +1317,8 @@ int upload_voices(blast_ctx* ctx, blast_scene* sc) {
     for (uint32_t i = 0; i < sc->n_voices; ++i)
         if (int rc = make_voice_dev(sc, sc->voices[i], i, &hv[i])) return rc;
     if (sc->n_voices) {
-        BLAST_CUDA_TRY(cudaMemcpyAsync(sc->d_voices, hv.data(), hv.size() * sizeof(VoiceDev), cudaMemcpyHostToDevice, ctx->stream));
-        BLAST_CUDA_TRY(cudaMemcpyAsync(sc->d_voices0, sc->d_voices, hv.size() * sizeof(VoiceDev), cudaMemcpyDeviceToDevice, ctx->stream));
+        BLAST_CUDA_TRY(cudaMemcpyAsync(sc->rb.d_voices, hv.data(), hv.size() * sizeof(VoiceDev), cudaMemcpyHostToDevice, ctx->stream));
+        BLAST_CUDA_TRY(cudaMemcpyAsync(sc->d_voices0, sc->rb.d_voices, hv.size() * sizeof(VoiceDev), cudaMemcpyDeviceToDevice, ctx->stream));
         BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
     return BLAST_OK;
@@ -1066,11 +1342,8 @@ int blast_scene_create(blast_ctx* ctx, const blast_track* tracks, uint32_t n_tra
     sc->voices.assign(voices, voices + n_voices);
     auto fail = [&](int rc) { blast_scene_destroy(ctx, sc); return rc; };
     const size_t nv = n_voices ? n_voices : 1;
-    if (cudaMalloc(&sc->d_voices, nv * sizeof(VoiceDev)) != cudaSuccess ||
-        cudaMalloc(&sc->d_voices0, nv * sizeof(VoiceDev)) != cudaSuccess ||
-        cudaMalloc(&sc->d_segs, nv * kMaxSeg * sizeof(Seg)) != cudaSuccess ||
-        cudaMalloc(&sc->d_nsegs, nv * sizeof(uint32_t)) != cudaSuccess ||
-        cudaMalloc(&sc->d_err, sizeof(uint32_t)) != cudaSuccess)
+    if (int rc = reserve_buffers(ctx, sc->rb, n_voices, 0)) return fail(rc);
+    if (cudaMalloc(&sc->d_voices0, nv * sizeof(VoiceDev)) != cudaSuccess)
         return fail(blast::set_error(BLAST_ERR_CUDA, "blast_scene_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())));
     if (int rc = upload_voices(ctx, sc)) return fail(rc);
     *out = sc;
@@ -1083,12 +1356,8 @@ void blast_scene_destroy(blast_ctx* ctx, blast_scene* sc) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
     }
-    if (sc->d_voices) cudaFree(sc->d_voices);
+    free_buffers(sc->rb);
     if (sc->d_voices0) cudaFree(sc->d_voices0);
-    if (sc->d_segs) cudaFree(sc->d_segs);
-    if (sc->d_nsegs) cudaFree(sc->d_nsegs);
-    if (sc->d_err) cudaFree(sc->d_err);
-    if (sc->d_recs) cudaFree(sc->d_recs);
     delete sc;
 }
 
@@ -1108,7 +1377,7 @@ int blast_scene_restore_dev(blast_ctx* ctx, blast_scene* sc) {
     if (int rc = blast::bind(ctx)) return rc;
     BLAST_REQUIRE(sc != nullptr, BLAST_ERR_ARG, "blast_scene_restore_dev: null scene");
     if (sc->n_voices)
-        BLAST_CUDA_TRY(cudaMemcpyAsync(sc->d_voices, sc->d_voices0, (size_t)sc->n_voices * sizeof(VoiceDev),
+        BLAST_CUDA_TRY(cudaMemcpyAsync(sc->rb.d_voices, sc->d_voices0, (size_t)sc->n_voices * sizeof(VoiceDev),
                                        cudaMemcpyDeviceToDevice, ctx->stream));
     return BLAST_OK;
 }
@@ -1119,7 +1388,7 @@ int blast_scene_get_voices(blast_ctx* ctx, blast_scene* sc, blast_voice* out, ui
     BLAST_REQUIRE(n_voices == sc->n_voices, BLAST_ERR_ARG, "blast_scene_get_voices: voice count differs from the scene's");
     std::vector<VoiceDev> hv(sc->n_voices);
     if (sc->n_voices) {
-        BLAST_CUDA_TRY(cudaMemcpyAsync(hv.data(), sc->d_voices, hv.size() * sizeof(VoiceDev), cudaMemcpyDeviceToHost, ctx->stream));
+        BLAST_CUDA_TRY(cudaMemcpyAsync(hv.data(), sc->rb.d_voices, hv.size() * sizeof(VoiceDev), cudaMemcpyDeviceToHost, ctx->stream));
         BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
     for (uint32_t i = 0; i < sc->n_voices; ++i) {
@@ -1132,79 +1401,14 @@ int blast_scene_get_voices(blast_ctx* ctx, blast_scene* sc, blast_voice* out, ui
 int blast_scene_render_dev(blast_ctx* ctx, blast_scene* sc, uint64_t frames, int32_t* d_partial_bus) {
     if (int rc = blast::bind(ctx)) return rc;
     BLAST_REQUIRE(sc && (d_partial_bus || frames == 0), BLAST_ERR_ARG, "blast_scene_render_dev: null argument");
-    if (frames == 0) return BLAST_OK;
-    if (frames > 0x7FFFFFFFull) return blast::set_error(BLAST_ERR_CAPACITY, "at most 2^31-1 frames per render call");
-    const uint32_t oc = sc->out_channels;
-    const uint32_t n_tiles = (uint32_t)((frames + kFT - 1) / kFT);
-    const size_t slots = (size_t)frames * oc;
-    if (sc->n_voices == 0) {
-        BLAST_CUDA_TRY(cudaMemsetAsync(d_partial_bus, 0, slots * sizeof(int32_t), ctx->stream));
-        return BLAST_OK;
-    }
-    const size_t need = (size_t)n_tiles * sc->n_voices;
-    if (need > sc->recs_cap) {
-        BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        if (sc->d_recs) BLAST_CUDA_TRY(cudaFree(sc->d_recs));
-        sc->d_recs = nullptr;
-        sc->recs_cap = 0;
-        BLAST_CUDA_TRY(cudaMalloc(&sc->d_recs, need * sizeof(TileRec)));
-        sc->recs_cap = need;
-    }
-    BLAST_CUDA_TRY(cudaMemsetAsync(sc->d_err, 0, sizeof(uint32_t), ctx->stream));
-    voice_position_scan<<<(sc->n_voices + 31) / 32, 32, 0, ctx->stream>>>(
-        sc->d_voices, sc->n_voices, (uint32_t)frames, sc->d_segs, sc->d_nsegs, sc->d_recs, n_tiles, sc->d_err);
-    BLAST_CUDA_TRY(cudaGetLastError());
-    ctx->launches += 1;
-
-    // voice groups: enough CTAs to fill the GPU a few times over, groups of >= 64 voices
-    uint32_t groups = 1;
-    const uint32_t want_ctas = (uint32_t)ctx->sm_count * 16;
-    while (n_tiles * groups < want_ctas && sc->n_voices / (groups * 2) >= 64) groups *= 2;
-    const uint32_t per_group = (sc->n_voices + groups - 1) / groups;
-    groups = (sc->n_voices + per_group - 1) / per_group;
-    const int use_atomic = groups > 1;
-    if (use_atomic) BLAST_CUDA_TRY(cudaMemsetAsync(d_partial_bus, 0, slots * sizeof(int32_t), ctx->stream));
-    dim3 grid(n_tiles, groups);
-    dim3 grid_tma(n_tiles * groups, 1);      // 1-D, decoded tile-major inside the kernel
-    static const bool legacy = getenv("BLAST_RENDER_LEGACY") != nullptr;
-    if (oc <= 2 && !legacy) {
-        // TMA pipeline kernel (one producer warp + eight consumer warps)
-        if (oc == 1) {
-            BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
-            voice_render_mix_tma<1><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(sc->d_voices, sc->n_voices, per_group, groups, sc->d_segs,
-                                                                                  sc->d_nsegs, sc->d_recs, (uint32_t)frames, d_partial_bus, use_atomic);
-        } else {
-            BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
-            voice_render_mix_tma<2><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(sc->d_voices, sc->n_voices, per_group, groups, sc->d_segs,
-                                                                                  sc->d_nsegs, sc->d_recs, (uint32_t)frames, d_partial_bus, use_atomic);
-        }
-    } else {
-#define BLAST_LAUNCH_MIX(OCV)                                                                              \
-    voice_render_mix<OCV><<<grid, kThreads, 0, ctx->stream>>>(sc->d_voices, sc->n_voices, per_group, sc->d_segs, \
-                                                               sc->d_nsegs, sc->d_recs, (uint32_t)frames,       \
-                                                               d_partial_bus, use_atomic)
-        switch (oc) {
-            case 1: BLAST_LAUNCH_MIX(1); break;
-            case 2: BLAST_LAUNCH_MIX(2); break;
-            case 3: BLAST_LAUNCH_MIX(3); break;
-            case 4: BLAST_LAUNCH_MIX(4); break;
-            case 5: BLAST_LAUNCH_MIX(5); break;
-            case 6: BLAST_LAUNCH_MIX(6); break;
-            case 7: BLAST_LAUNCH_MIX(7); break;
-            default: BLAST_LAUNCH_MIX(8); break;
-        }
-#undef BLAST_LAUNCH_MIX
-    }
-    BLAST_CUDA_TRY(cudaGetLastError());
-    ctx->launches += 1;
-    return BLAST_OK;
+    return launch_render(ctx, sc->rb, sc->n_voices, 0, sc->out_channels, frames, d_partial_bus);
 }
 
 int blast_scene_check(blast_ctx* ctx, blast_scene* sc) {
     if (int rc = blast::bind(ctx)) return rc;
     BLAST_REQUIRE(sc != nullptr, BLAST_ERR_ARG, "blast_scene_check: null scene");
     uint32_t e = 0;
-    BLAST_CUDA_TRY(cudaMemcpyAsync(&e, sc->d_err, sizeof(e), cudaMemcpyDeviceToHost, ctx->stream));
+    BLAST_CUDA_TRY(cudaMemcpyAsync(&e, sc->rb.d_err, sizeof(e), cudaMemcpyDeviceToHost, ctx->stream));
     BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (e) return blast::set_error(BLAST_ERR_CAPACITY, "a voice trajectory needed more than %d position segments", kMaxSeg);
     return BLAST_OK;

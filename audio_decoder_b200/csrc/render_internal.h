@@ -1,0 +1,80 @@
+// render_internal.h — structures shared by render.cu (kernels + scene API) and conductor.cu (host state machine)
+#pragma once
+#include "blast_internal.h"
+
+namespace blast_rdr {
+
+constexpr int kMaxSeg = 160;
+constexpr int kFT = 2048;                      // frames per tile
+constexpr int kThreads = 256;
+constexpr int kFPT = kFT / kThreads;           // frames per thread
+constexpr int kVoiceBatch = 64;                // voices staged in shared memory at a time
+constexpr int kMaxOut = 8;
+
+struct VoiceDev {
+    const int16_t* smp;
+    uint32_t end;          // Voice::new: samples.len()/channels - 1 (engine.rs:302)
+    uint32_t C;            // track channels
+    float pos, vel, gain;
+    uint32_t active;
+    uint32_t S;            // advance events per frame for this voice on this bus: 0, 1 or 2
+    uint32_t nch;          // bus channels this voice feeds
+    uint32_t adv;          // 0: every step is an advance event.  Else (voices with Seq processes) steps are
+                           // calls: oc | lo << 8 | na << 16 = calls per frame, first advancing channel, count
+    uint32_t first_seq;    // index of the voice's first SeqDev | n_seqs << 24 (0 seqs for plain voices)
+};
+static_assert(sizeof(VoiceDev) == 48, "VoiceDev layout");
+
+struct Seg {               // positions for steps [step0, next.step0): p0 + (step-step0)*d*scale
+    uint32_t step0;
+    float p0;
+    int32_t d;
+    float scale;
+};
+
+struct TileRec {           // state of one voice at the first step of one tile
+    float p0;
+    int32_t d;
+    float scale;
+    uint32_t meta;         // [23:0] steps this segment still covers (saturating), [31:24] segment index
+};
+
+
+constexpr int kMaxEvents = 256;        // retrigger events per voice per render call
+
+struct SeqDev {            // one Seq process (processes.rs:52-99) flattened for the GPU
+    uint32_t base;         // tempo.current as the Seq sees it at call 0 of this render
+    uint32_t rate;         // ticks of its tempo per call
+    float interval;        // TempoState.interval (samples)
+    float period_f;        // period as f32
+    uint32_t n_steps;
+    uint32_t idx;          // SeqState.idx (in/out)
+    const float* steps;    // device
+    const float* chance;   // device
+    unsigned long long s0, s1;   // X128P state (in/out)
+};
+
+struct RenderBuffers {     // device scratch of one render (owned by a scene or a conductor); grow-only
+    VoiceDev* d_voices = nullptr;
+    Seg* d_segs = nullptr;
+    uint32_t* d_nsegs = nullptr;
+    uint32_t* d_err = nullptr;         // bit 0: a trajectory needed > kMaxSeg segments, bit 1: > kMaxEvents retriggers
+    TileRec* d_recs = nullptr;
+    size_t recs_cap = 0;               // in records
+    size_t voices_cap = 0;
+    SeqDev* d_seqs = nullptr;          // only with Seq processes
+    size_t seqs_cap = 0;
+    uint32_t* d_events = nullptr;      // [voices_cap][kMaxEvents] retrigger call indices
+    uint32_t* d_nevents = nullptr;     // [voices_cap]
+};
+
+int  reserve_buffers(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t n_seqs);
+void free_buffers(RenderBuffers& rb);
+// Seq event scan (when n_seqs > 0) + position scan + render/mix of the first n_voices records of rb.d_voices into
+// the int32 partial bus (overwritten); async on ctx->stream.  Device-side capacity errors land in rb.d_err.
+int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t n_seqs, uint32_t out_channels,
+                  uint64_t frames, int32_t* d_partial_bus);
+// VoiceDev routing fields (S, nch, adv) for a voice with C channels on an out_channels bus
+void route_voice(VoiceDev& v, uint32_t out_channels, bool has_seq);
+
+}  // namespace blast_rdr
