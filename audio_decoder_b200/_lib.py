@@ -53,6 +53,32 @@ class MpegHeader(C.Structure):
                 ("payload_len", C.c_uint32), ("skip", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class TempoRepr(C.Structure):
+    _fields_ = [("idx", C.c_uint64), ("owned", C.c_uint32), ("mode", C.c_uint32), ("unit", C.c_uint32),
+                ("interval", C.c_float)]
+
+
+class Command(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("idx_kind", C.c_uint32), ("idx", C.c_uint64), ("val", C.c_float),
+                ("reserved", C.c_uint32), ("tempo", TempoRepr),
+                ("n_members", C.c_uint32), ("reserved2", C.c_uint32), ("member_voice", C.POINTER(C.c_uint64)),
+                ("member_update_tempo", C.POINTER(C.c_uint8)), ("member_n_procs", C.POINTER(C.c_uint32)),
+                ("member_proc_ids", C.POINTER(C.c_uint64)),
+                ("period", C.c_uint64), ("n_steps", C.c_uint32), ("reserved3", C.c_uint32),
+                ("steps", C.POINTER(C.c_float)), ("chance", C.POINTER(C.c_float)),
+                ("rng_s0", C.c_uint64), ("rng_s1", C.c_uint64)]
+
+
+class TimedCommand(C.Structure):
+    _fields_ = [("frame", C.c_uint64), ("cmd", Command)]
+
+
+class VoiceState(C.Structure):
+    _fields_ = [("active", C.c_uint32), ("position", C.c_float), ("velocity", C.c_float), ("gain", C.c_float),
+                ("end", C.c_uint64), ("channels", C.c_uint32), ("tempo_current", C.c_uint32),
+                ("tempo_active", C.c_uint32), ("n_processes", C.c_uint32)]
+
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
 _vp, _u64, _u32, _sz = C.c_void_p, C.c_uint64, C.c_uint32, C.c_size_t
 SIGNATURES = {
@@ -109,6 +135,21 @@ SIGNATURES = {
     "blast_mpeg_gather_dev": (C.c_int, [_vp, _vp, _u64, _vp, _u64, _vp, _u64, C.POINTER(_u64)]),
     "blast_mpeg_parse": (C.c_int, [_vp, _vp, _u64, C.c_int, _vp, _u64, C.POINTER(_u64), C.POINTER(_u32),
                                    C.POINTER(_u64), _vp, _u64, C.POINTER(_u64)]),
+    "blast_convert_interval": (C.c_float, [_u32, _u32, C.c_float]),
+    "blast_conductor_create": (C.c_int, [_vp, _u32, _u32, C.POINTER(Track), _u32, C.POINTER(_vp)]),
+    "blast_conductor_destroy": (None, [_vp, _vp]),
+    "blast_conductor_apply": (C.c_int, [_vp, _vp, C.POINTER(Command)]),
+    "blast_conductor_set_shard": (C.c_int, [_vp, _u32, _u32]),
+    "blast_conductor_render_dev": (C.c_int, [_vp, _vp, _u64, _vp]),
+    "blast_conductor_coordinate": (C.c_int, [_vp, _vp, _u64, _vp]),
+    "blast_conductor_render_timeline_dev": (C.c_int, [_vp, _vp, C.POINTER(TimedCommand), _u32, _u64, _vp]),
+    "blast_conductor_render_timeline": (C.c_int, [_vp, _vp, C.POINTER(TimedCommand), _u32, _u64, _vp]),
+    "blast_conductor_n_voices": (C.c_int, [_vp, C.c_int]),
+    "blast_conductor_n_groups": (C.c_int, [_vp]),
+    "blast_conductor_get_voice": (C.c_int, [_vp, C.c_int, _u32, C.POINTER(VoiceState)]),
+    "blast_conductor_set_voice": (C.c_int, [_vp, C.c_int, _u32, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                            C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "blast_conductor_clock": (_u64, [_vp]),
     "blast_render": (C.c_int, [_vp, C.POINTER(Track), _u32, C.POINTER(Voice), _u32, _u32, _u64, _vp,
                                C.POINTER(Voice)]),
 }

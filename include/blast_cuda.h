@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BLAST_ABI_VERSION 1
+#define BLAST_ABI_VERSION 2
 
 enum {
     BLAST_OK = 0,
@@ -191,6 +191,104 @@ int  blast_bus_finalize_dev(blast_ctx* ctx, const int32_t* d_partial, int16_t* d
 int  blast_render(blast_ctx* ctx, const blast_track* tracks, uint32_t n_tracks, const blast_voice* voices,
                   uint32_t n_voices, uint32_t out_channels, uint64_t frames, int16_t* host_bus_out,
                   blast_voice* voices_after /* nullable */);
+
+/* ------------------------------------------------------------------ L1b: the Conductor (Command timeline, tempo, Seq)
+ * replaces Conductor::{prepare, apply, coordinate} (blast/src/audio_processing/engine.rs:36-248), Voice /
+ * Group transport (engine.rs:318-384, 477-528), TempoState (blast_time.rs:58-161) and the Seq process
+ * (processes.rs:52-99).  The Command payloads are the reference's (commands.rs:86-234) with names already
+ * resolved to indices, exactly what CmdProcessor hands to the audio thread.  The control state machine runs
+ * on the host (it is a few scalar updates per command); every sample, every position step and every Seq
+ * event / RNG draw is computed on the GPU. */
+enum { BLAST_TM_PROCESS = 0, BLAST_TM_VOICE = 1, BLAST_TM_GROUP = 2, BLAST_TM_CONTEXT = 3, BLAST_TM_TBD = 4 };  /* TempoMode */
+enum { BLAST_TU_SAMPLES = 0, BLAST_TU_MILLIS = 1, BLAST_TU_BPM = 2 };                                          /* TempoUnit */
+enum { BLAST_CMD_LOAD = 0, BLAST_CMD_START, BLAST_CMD_PAUSE, BLAST_CMD_RESUME, BLAST_CMD_STOP, BLAST_CMD_UNLOAD,
+       BLAST_CMD_VELOCITY, BLAST_CMD_GROUP, BLAST_CMD_TC, BLAST_CMD_SEQ, BLAST_CMD_QUIT };                   /* Command */
+enum { BLAST_IDX_TEMPO = 0, BLAST_IDX_VOICE = 1, BLAST_IDX_PROCESS = 2, BLAST_IDX_GROUP = 3 };                 /* Idx */
+
+typedef struct {               /* TempoRepr (commands.rs:187-234) */
+    uint64_t idx;              /* borrowed tempo: index into voices / groups / tempo contexts (by mode) */
+    uint32_t owned;            /* 1: a new TempoState initialised with (mode, unit, interval) */
+    uint32_t mode;             /* BLAST_TM_* */
+    uint32_t unit;             /* BLAST_TU_* */
+    float    interval;         /* in `unit`; converted like convert_interval (blast_time.rs:151-161) */
+} blast_tempo_repr;
+
+typedef struct {               /* Command + its Args struct (commands.rs:86-161), flattened */
+    uint32_t kind;             /* BLAST_CMD_* */
+    uint32_t idx_kind;         /* BLAST_IDX_* for Start / Pause / Resume / Stop / Seq */
+    uint64_t idx;              /* Idx payload; LoadArgs.track_idx; UnloadArgs.idx; VelocityArgs.idx */
+    float    val;              /* VelocityArgs.val */
+    uint32_t reserved;
+    blast_tempo_repr tempo;    /* LoadArgs.tempo_repr / GroupArgs.tempo / TcArgs.tempo / SeqArgs.tempo */
+    /* GroupArgs.vs_fs_ps: member m = (voice index at the time it is removed, update_tempo, process ids) */
+    uint32_t n_members;
+    uint32_t reserved2;
+    const uint64_t* member_voice;
+    const uint8_t*  member_update_tempo;   /* nullable = all false */
+    const uint32_t* member_n_procs;        /* nullable = all 0 */
+    const uint64_t* member_proc_ids;       /* concatenated over members */
+    /* SeqArgs (jit is carried by the reference but never read: processes.rs:61) */
+    uint64_t period;
+    uint32_t n_steps;
+    uint32_t reserved3;
+    const float* steps;
+    const float* chance;       /* n_steps entries, like steps (commands.rs:944-945) */
+    uint64_t rng_s0, rng_s1;   /* SeqArgs.rng state: blast_x128p_seed(seed) replaces fast_seed() (commands.rs:838) */
+} blast_command;
+
+typedef struct {               /* one entry of an offline timeline: `cmd` is applied before frame `frame` is rendered */
+    uint64_t frame;
+    blast_command cmd;
+} blast_timed_command;
+
+typedef struct {               /* VoiceState (engine.rs:279-286) + what Voice::new derives */
+    uint32_t active;
+    float    position;
+    float    velocity;
+    float    gain;
+    uint64_t end;
+    uint32_t channels;
+    uint32_t tempo_current;    /* state.tempo.current */
+    uint32_t tempo_active;
+    uint32_t n_processes;
+} blast_voice_state;
+
+typedef struct blast_conductor blast_conductor;
+/* convert_interval (blast_time.rs:151-161) with sample_rate::get() = sample_rate */
+float blast_convert_interval(uint32_t sample_rate, uint32_t unit, float interval);
+/* Conductor::prepare (engine.rs:36-44) + sample_rate::set (runtime.rs:37).  Tracks stay where they are in HBM;
+ * voices refer to them by index (the reference clones the samples per voice, engine.rs:309). */
+int  blast_conductor_create(blast_ctx* ctx, uint32_t out_channels, uint32_t sample_rate, const blast_track* tracks,
+                            uint32_t n_tracks, blast_conductor** out);
+void blast_conductor_destroy(blast_ctx* ctx, blast_conductor* c);
+/* Conductor::apply (engine.rs:83-248).  Out-of-range indices (the reference `unwrap()`s / indexes: panic) return
+ * BLAST_ERR_REF_PANIC and leave the state untouched.  Quit is accepted and ignored (the reference raises SIGTERM). */
+int  blast_conductor_apply(blast_ctx* ctx, blast_conductor* c, const blast_command* cmd);
+/* Multi-GPU: this rank renders the voices whose load order number is congruent to rank mod world; every rank
+ * applies every command and tracks every tempo.  Partial buses are summed (int32) before finalising. */
+int  blast_conductor_set_shard(blast_conductor* c, uint32_t rank, uint32_t world);
+/* `frames` iterations of coordinate()'s frame loop (engine.rs:46-81) into the int32 partial bus
+ * d_partial_bus[frames * out_channels] (overwritten); voices, Seqs, tempi and the clock advance.  Returns after
+ * the device work has finished (the Seq / position state is read back). BLAST_ERR_REF_PANIC where a Seq would index
+ * an empty step list (processes.rs:79). */
+int  blast_conductor_render_dev(blast_ctx* ctx, blast_conductor* c, uint64_t frames, int32_t* d_partial_bus);
+/* coordinate() with a host bus: interleaved S16_LE like the ALSA area (runtime.rs:272-276) */
+int  blast_conductor_coordinate(blast_ctx* ctx, blast_conductor* c, uint64_t frames, int16_t* host_bus_out);
+/* Offline render of a whole Command timeline (the reference applies queued commands between periods,
+ * runtime.rs:326-328): events sorted by frame, frame <= total_frames.  Commands at frame f take effect before
+ * frame f is rendered. */
+int  blast_conductor_render_timeline_dev(blast_ctx* ctx, blast_conductor* c, const blast_timed_command* events,
+                                         uint32_t n_events, uint64_t total_frames, int32_t* d_partial_bus);
+int  blast_conductor_render_timeline(blast_ctx* ctx, blast_conductor* c, const blast_timed_command* events,
+                                     uint32_t n_events, uint64_t total_frames, int16_t* host_bus_out);
+/* state access: group < 0 addresses Conductor.voices, else Conductor.groups[group].voices */
+int  blast_conductor_n_voices(const blast_conductor* c, int group);       /* -1: no such group */
+int  blast_conductor_n_groups(const blast_conductor* c);
+int  blast_conductor_get_voice(const blast_conductor* c, int group, uint32_t idx, blast_voice_state* out);
+/* VoiceState's fields are pub (engine.rs:279-286); gain in particular has no Command.  Nullable = keep. */
+int  blast_conductor_set_voice(blast_conductor* c, int group, uint32_t idx, const float* position,
+                               const float* velocity, const float* gain, const int* active);
+uint64_t blast_conductor_clock(const blast_conductor* c);                 /* clock::current (blast_time.rs:29-31) */
 
 /* ------------------------------------------------------------------ RNG parameter streams
  * replaces X128P (blast/src/audio_processing/blast_rand.rs:4-60): xoroshiro128+ with the 55/14/36

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
     # and the ctypes table covers the whole header (no unbound entry points)
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert L.blast_abi_version() == 1
+    assert L.blast_abi_version() == 2
 
 
 def test_no_cpu_fallback():
@@ -188,3 +188,28 @@ def test_mpeg_header_info_matches_oracle_exhaustively():
         assert o.frame_len_ok == oh.frame_len_ok, hex(h)
         if oh.frame_len_ok:
             assert o.payload_len == oh.payload_len, hex(h)
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """every ABI struct: sizeof and field offsets of the ctypes mirror == what gcc computes from include/blast_cuda.h"""
+    import ctypes as C
+    import subprocess
+    structs = {"blast_pcm_desc": _lib.PcmDesc, "blast_pcm_job": _lib.PcmJob, "blast_pcm24_job": _lib.Pcm24Job,
+               "blast_track": _lib.Track, "blast_voice": _lib.Voice, "blast_x128p": _lib.X128PState,
+               "blast_mpeg_header": _lib.MpegHeader, "blast_tempo_repr": _lib.TempoRepr, "blast_command": _lib.Command,
+               "blast_timed_command": _lib.TimedCommand, "blast_voice_state": _lib.VoiceState}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "blast_cuda.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for f, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ['return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for f, _ in cls._fields_:
+            assert int(got[f"{cname}.{f}"]) == getattr(cls, f).offset, (cname, f)
