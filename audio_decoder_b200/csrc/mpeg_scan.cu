@@ -10,59 +10,64 @@
 //   :367-496, :154-234, :255-303  parse_header / Header::{format,match_ref,compute_frame_len} with their
 //             quirks (version low bit = protection bit, bitrate column always 4, "CRC" = 20)
 //
-// K7 is a single-pass chained scan, HBM-bound at 1 byte read per input byte (+12 B per candidate).
-// The greedy rule is a 4-state machine (state = header bytes still to skip); a byte range acts on it as
-// a map {0..3} -> {0..3} plus a candidate count per entry state, and maps compose associatively.  Each
-// thread owns 64 consecutive bytes: it builds the 64-bit "raw sync" mask with SWAR byte tests, resolves
-// the greedy selection for the entry states that can differ, and summarises itself as (map, counts).
-// Lanes whose predecessor's map is constant know their entry state at once (the overwhelmingly common
-// case); the rest propagate in a short loop.  Warp summaries are combined by warp 0, tile summaries by
-// decoupled look-back over 32-tile windows, and every thread then emits its candidates at their final,
-// position-ordered indices.
+// K7 reads every input byte exactly once (1 B/byte of HBM traffic + 12 B per candidate, plus 6 B per candidate
+// of temp list written and re-read).  The greedy rule is a 4-state machine (state = header bytes still to
+// skip); a byte range acts on it as a map {0..3} -> {0..3} plus a candidate count per entry state, and maps
+// compose associatively.  Three launches, none of which ever waits for another thread block:
+//   K7a mpeg_walk       one warp per 32 KiB span: finds the span's candidates under entry state 0 and leaves
+//                       them in the span's slot of a temp list, plus a 16-byte record (map, counts per entry
+//                       state, "head-sensitive" flag)
+//   K7b mpeg_span_scan  folds the records (8 MB for 16 GiB of input): true entry state and first global
+//                       candidate index of every span
+//   K7c mpeg_compact    moves the lists to their final, position-ordered place (coalesced)
+// A span's entry state only matters when its very first three bytes hold a raw sync ("head-sensitive",
+// ~0.15 % of spans on random data, every span on 0xFF floods): K7a then also counts it under the other three
+// entry states, and K7c re-walks it with direct emission if its true entry state is not 0 (same for spans
+// whose candidates overflow their slot).
+//
+// The walk.  16 rounds of 2 KiB per span.  The bytes go global -> shared memory by coalesced 16-byte
+// cp.async (LDGSTS: L2 only, no registers), kStages rounds deep, into padded rows from which each lane reads
+// ITS 64 consecutive bytes with conflict-free LDS.128 (the per-lane LDG.128 at a 64-byte lane stride of v2
+// cost 16 L1 wavefronts per instruction).  Per lane: a 5-instruction-per-word SWAR test gives 0x80 flags,
+// two IDP4A per word pair pack them into the 64-bit "raw sync" mask M, and the greedy selection is resolved
+// from the lane's entry state — in the common case (no two raw syncs within 4 bytes, no sync pair straddling
+// a lane boundary) every raw sync is selected and nothing iterates.  Headers are read from the staged rows:
+// no byte is fetched from HBM twice.
+//
+// Measured dead ends, kept for the record (C5, 16 GiB): a single-pass chained scan with decoupled look-back
+// was built first in four variants — v1 16 KiB tiles (0.57 TB/s), v2 256 KiB tiles + two passes over the tile
+// (2.0 TB/s, 10 instructions per byte, headers re-read from HBM), v3 warp-per-tile without barriers (1.1 TB/s:
+// ~3,500 tiles in lock step, look-back chains 8x longer), v3 with a dedicated chaining warp and
+// software-pipelined hand-off (1.8 TB/s).  With the look-back disabled the same walk ran at 4.3 TB/s: all
+// tiles of a wave finish together, so every look-back reaches back a whole wave over loaded-L2 round trips
+// and every CTA advances at the pace of the slowest one.  Hence three independent launches.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "blast_internal.h"
 
 namespace {
 
-constexpr int kScanThreads = 256;
-constexpr int kScanWarps = kScanThreads / 32;
-constexpr int kChunk = 64;                                  // bytes per thread per round
-constexpr int kRounds = 16;                                 // rounds per tile: a warp walks 16 x 2 KiB = 32 KiB
-constexpr int kSpanBytes = kRounds * 32 * kChunk;           // contiguous bytes per warp per tile
-constexpr int kTileBytes = kScanWarps * kSpanBytes;         // 256 KiB
+constexpr int kWalkers = 8;                                 // warps per CTA
+constexpr int kScanThreads = kWalkers * 32;
+constexpr int kCtasPerSm = 3;
+constexpr int kChunk = 64;                                  // bytes per lane per round
+constexpr int kRowBytes = kChunk + 16;                      // staged chunk + padding: conflict-free LDS.128 at 64-byte lane stride
+constexpr int kStageBytes = 32 * kRowBytes;                 // one round of one warp in shared memory
+constexpr int kStages = 3;                                  // staged rounds per warp (cp.async groups)
+constexpr int kRounds = 16;                                 // rounds per span
+constexpr int kRoundBytes = 32 * kChunk;                    // 2 KiB
+constexpr int kSpanBytes = kRounds * kRoundBytes;           // 32 KiB per warp
+constexpr int kCandCap = 256;                               // candidates per span that fit its slot of the temp lists
+constexpr size_t kScanSmem = (size_t)kWalkers * kStages * kStageBytes;
 constexpr uint32_t kIdentityMap = 0xE4;                     // s -> s for s = 0..3, two bits each
-
-struct TileDesc {             // 64 bytes
-    uint32_t flag;            // 0 = nothing, 1 = aggregate valid, 2 = inclusive prefix valid
-    uint32_t map;             // aggregate: exit state per entry state (4 x 2 bits)
-    uint32_t c[4];            // aggregate: candidates per entry state
-    uint32_t state;           // inclusive: exit state of this tile under the true entry state
-    uint32_t pad0;
-    uint32_t cnt_lo, cnt_hi;  // inclusive: candidates in tiles 0..this
-    uint32_t pad[6];
-};
-
 struct ScanCtl {
-    unsigned long long next_tile;
+    unsigned long long next_tile; // span counter of the walk kernel
     unsigned long long total;     // candidates found
     uint32_t panic;               // the reference indexes out of bounds (last byte 0xFF reached with state 0)
     uint32_t pad;
 };
-
-// ---- SWAR byte predicates: 0x80 in every byte that satisfies the test
-__device__ __forceinline__ uint32_t is_ff(uint32_t w) {
-    const uint32_t y = (~w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-    return ~y & w & 0x80808080u;
-}
-__device__ __forceinline__ uint32_t is_e0(uint32_t w) {        // (b & 0xE0) == 0xE0
-    const uint32_t t = (w & 0x60606060u) + 0x20202020u;
-    return t & w & 0x80808080u;
-}
-__device__ __forceinline__ uint32_t nibble_of(uint32_t flags) {  // 0x80 flags of 4 bytes -> 4 bits
-    return ((flags >> 7) * 0x10204080u) >> 28;
-}
 
 // greedy non-overlapping selection on a 64-bit raw mask, skipping the first s_in bytes
 __device__ __forceinline__ unsigned long long resolve(unsigned long long M, uint32_t s_in, uint32_t& s_out) {
@@ -88,323 +93,384 @@ __device__ __forceinline__ uint32_t map_after(uint32_t first, uint32_t then) {  
     for (int s = 0; s < 4; ++s) r |= map_get(then, map_get(first, s)) << (2 * s);
     return r;
 }
-__device__ __forceinline__ bool map_is_const(uint32_t map) {
-    const uint32_t e = map & 3u;
-    return map == e * 0x55u;
-}
-__device__ __forceinline__ uint32_t cnt16(uint32_t c01, uint32_t c23, uint32_t s) {
-    const uint32_t w = (s & 2) ? c23 : c01;
-    return (s & 1) ? (w >> 16) : (w & 0xFFFFu);
-}
-
-template <typename T>
-__device__ __forceinline__ T pick4(T a0, T a1, T a2, T a3, uint32_t i) {       // register-only a[i]
-    return i == 0 ? a0 : i == 1 ? a1 : i == 2 ? a2 : a3;
+// raw sync flags of one word: 0x80 in byte i <=> b[i] == 0xFF && (b[i+1] & 0xE0) == 0xE0, where `next` is
+// the following word.  z = b[i] & (b[i+1] | 0x1F) is 0xFF exactly then; the byte-wise == 0xFF test is
+// carry-free (low 7 bits + 1 reaches bit 7 iff they are all ones).
+__device__ __forceinline__ uint32_t sync_flags(uint32_t w, uint32_t next) {
+    const uint32_t sh = __funnelshift_r(w, next, 8);
+    const uint32_t z = w & (sh | 0x1F1F1F1Fu);
+    const uint32_t t = (z & 0x7F7F7F7Fu) + 0x01010101u;
+    return t & z & 0x80808080u;
 }
 
-struct Agg {
-    uint32_t map;
-    uint32_t c[4];
+enum : int { kModeCompact = 0, kModeCount = 1, kModeEmit = 2 };
+
+struct SpanOut {
+    uint32_t total;        // candidates (uniform)
+    uint32_t exit_state;   // state after the last byte of the tile (uniform)
+    bool sens;             // the first three bytes of the tile hold a raw sync: the entry state matters
 };
-__device__ __forceinline__ Agg agg_then(const Agg& a, const Agg& b) {            // a first, then b
-    Agg r;
-    r.map = map_after(a.map, b.map);
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// One walk over a warp's span with a KNOWN entry state.
+//  kModeCompact: candidates -> shared-memory list (s_off, s_hdr) while it has room (total may exceed kCandCap)
+//  kModeCount:   counts only
+//  kModeEmit:    candidates -> out_pos / out_hdr at index gbase + k
+// The bytes travel global -> shared memory with coalesced 16-byte cp.async (LDGSTS, L2 only, no registers),
+// kStages rounds deep, into rows of 64 + 16 bytes so that every lane then reads ITS 64 consecutive bytes with
+// four conflict-free LDS.128.  NEAR_END instances carry the end-of-buffer handling; interior spans do not.
+template <bool NEAR_END>
+__device__ __noinline__ SpanOut walk_span(const int MODE, const uint8_t* __restrict__ bytes, const unsigned long long n,
+                                          const unsigned long long span0, const uint32_t entry, const uint32_t lane,
+                                          const uint32_t ring,           // shared-memory address of this warp's stage ring
+                                          uint16_t* __restrict__ s_off, uint32_t* __restrict__ s_hdr,
+                                          unsigned long long* __restrict__ out_pos, uint32_t* __restrict__ out_hdr,
+                                          const unsigned long long cap, const unsigned long long gbase,
+                                          ScanCtl* __restrict__ ctl) {
+    SpanOut o;
+    o.total = 0;
+    o.sens = false;
+    uint32_t carry = entry;                                            // entry state of lane 0 this round (uniform)
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint8_t* src = bytes + span0 + 16u * lane;                   // lane's first 16-byte unit of round 0
+    const uint32_t dst = (lane >> 2) * kRowBytes + (lane & 3) * 16;    // unit j = lane + 32 q -> row (j >> 2) = lane/4 + 8 q
+
+    auto issue = [&](int r) {
+        if (r < kRounds) {
+            const uint32_t st = ring + (uint32_t)(r % kStages) * kStageBytes + dst;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) r.c[s] = a.c[s] + pick4(b.c[0], b.c[1], b.c[2], b.c[3], map_get(a.map, s));
-    return r;
-}
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t off = (uint32_t)r * kRoundBytes + 512u * q;
+                if (!NEAR_END || span0 + off + 16ull * lane < n) cp_async16(st + (uint32_t)q * 8u * kRowBytes, src + off);
+            }
+        }
+        cp_async_commit();
+    };
+    // first word after the span: lane 31's look-ahead in the last round
+    uint32_t after_word = 0;
+    if (lane == 31 && span0 + (unsigned long long)kSpanBytes < n)
+        after_word = __ldg(reinterpret_cast<const uint32_t*>(bytes + span0 + kSpanBytes));
 
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__global__ void __launch_bounds__(kScanThreads)
-mpeg_sync_scan(const uint8_t* __restrict__ bytes, unsigned long long n, TileDesc* __restrict__ desc,
-               unsigned long long n_tiles, ScanCtl* __restrict__ ctl, unsigned long long* __restrict__ out_pos,
-               uint32_t* __restrict__ out_hdr, unsigned long long cap) {
-    // per (warp, round, lane): raw-sync mask and the lane's pre-map relative to the warp span's entry state
-    __shared__ unsigned long long s_mask[kScanWarps * kRounds * 32];
-    __shared__ uint8_t s_tpre[kScanWarps * kRounds * 32];
-    __shared__ unsigned long long s_tile;
-    __shared__ uint32_t s_wmap[kScanWarps], s_wc[kScanWarps][4];      // warp-span aggregates
-    __shared__ uint32_t s_wentry[kScanWarps];                          // true entry state of every warp span
-    __shared__ unsigned long long s_wbase[kScanWarps];                 // global candidate index at the span start
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(&ctl->next_tile, 1ull);
-        __syncthreads();
-        const unsigned long long tile = s_tile;
-        if (tile >= n_tiles) return;
-        const unsigned long long span0 = tile * (unsigned long long)kTileBytes + (unsigned long long)warp * kSpanBytes;
-
-        // ================= pass 1: masks + summaries, one warp walks its contiguous 32 KiB span
-        uint32_t wrun = kIdentityMap;          // span entry state -> entry state of the current round (uniform)
-        uint32_t wc01 = 0, wc23 = 0;           // candidates so far per span-entry hypothesis (uniform, 4 x 16 bit)
+#pragma unroll
+    for (int r = 0; r < kStages - 1; ++r) issue(r);
 #pragma unroll 1
-        for (int r = 0; r < kRounds; ++r) {
-            const unsigned long long base = span0 + (unsigned long long)r * (32 * kChunk) + (unsigned long long)lane * kChunk;
-            uint32_t w[17];
-            {
-                const uint4* v = reinterpret_cast<const uint4*>(bytes + base);
+    for (int r = 0; r < kRounds; ++r) {
+        issue(r + kStages - 1);
+        cp_async_wait<kStages - 2>();                                   // rounds r and r + 1 have landed (this lane's part)
+        __syncwarp();                                                   // ... and everybody else's
+        const uint32_t row = ring + (uint32_t)(r % kStages) * kStageBytes + lane * kRowBytes;
+        uint32_t w[17];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint4 x = make_uint4(0, 0, 0, 0);
-                    if (base + 16ull * q < n) x = __ldg(v + q);
-                    w[4 * q] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w;
-                }
-                w[16] = (base + 64 < n) ? __ldg(reinterpret_cast<const uint32_t*>(bytes + base + 64)) : 0u;
-                if (base + 68 > n) {                                     // the buffer ends inside this window
+        for (int q = 0; q < 4; ++q) {
+            const uint4 v = lds128(row + 16u * q);
+            w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+        }
+        {
+            const uint32_t down = __shfl_down_sync(0xFFFFFFFFu, w[0], 1);
+            uint32_t wrap = after_word;
+            if (r + 1 < kRounds) wrap = lds32(ring + (uint32_t)((r + 1) % kStages) * kStageBytes);
+            w[16] = lane == 31 ? wrap : down;
+        }
+        const uint32_t rel = (uint32_t)r * kRoundBytes + lane * kChunk;          // offset of the lane's chunk in the span
+        if (NEAR_END) {
+            const unsigned long long base = span0 + rel;
+            if (base + 68 > n) {                                        // the buffer ends inside this window
 #pragma unroll
-                    for (int k = 0; k < 17; ++k) {
-                        const unsigned long long p = base + 4ull * k;
-                        if (p >= n) w[k] = 0;
-                        else if (p + 4 > n) w[k] &= (1u << (8 * (uint32_t)(n - p))) - 1u;
-                    }
+                for (int k = 0; k < 17; ++k) {
+                    const unsigned long long p = base + 4ull * k;
+                    if (p >= n) w[k] = 0;
+                    else if (p + 4 > n) w[k] &= (1u << (8 * (uint32_t)(n - p))) - 1u;
                 }
             }
-            // raw sync mask: bit i <=> b[i]==0xFF && (b[i+1]&0xE0)==0xE0; two words per multiply
-            uint32_t mlo, mhi;
-            {
-                uint32_t raw[16];
-                uint32_t e_next = is_e0(w[16]);
+        }
+        // ---- raw sync mask M: bit i <=> b[i]==0xFF && (b[i+1]&0xE0)==0xE0
+        uint32_t mlo, mhi;
+        {
+            uint32_t acc[8];
 #pragma unroll
-                for (int k = 15; k >= 0; --k) {
-                    const uint32_t e = is_e0(w[k]);
-                    raw[k] = is_ff(w[k]) & __funnelshift_r(e, e_next, 8);
-                    e_next = e;
-                }
-                uint32_t b8[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) b8[k] = (((raw[2 * k] >> 7) | (raw[2 * k + 1] >> 3)) * 0x01020408u);   // byte 3 = 8 flags
-                mlo = __byte_perm(__byte_perm(b8[0], b8[1], 0x0073), __byte_perm(b8[2], b8[3], 0x0073), 0x5410);
-                mhi = __byte_perm(__byte_perm(b8[4], b8[5], 0x0073), __byte_perm(b8[6], b8[7], 0x0073), 0x5410);
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t f0 = sync_flags(w[2 * k], w[2 * k + 1]);
+                const uint32_t f1 = sync_flags(w[2 * k + 1], w[2 * k + 2]);
+                // flags are 0x80 per byte: the dot products leave (8 mask bits) << 7
+                acc[k] = __dp4a(f1, 0x80402010u, __dp4a(f0, 0x08040201u, 0u));
             }
-            const unsigned long long M = ((unsigned long long)mhi << 32) | mlo;
-            unsigned long long okmask = ~0ull;
+            mlo = (acc[0] >> 7) | (acc[1] << 1) | (acc[2] << 9) | (acc[3] << 17);
+            mhi = (acc[4] >> 7) | (acc[5] << 1) | (acc[6] << 9) | (acc[7] << 17);
+        }
+        const unsigned long long M = ((unsigned long long)mhi << 32) | mlo;
+        if (r == 0) o.sens = __shfl_sync(0xFFFFFFFFu, mlo & 7u, 0) != 0;
+
+        // ---- greedy selection
+        unsigned long long sel = 0;
+        uint32_t e = 0;
+        const uint32_t anym = __ballot_sync(0xFFFFFFFFu, (mlo | mhi) != 0u);
+        if (anym || carry) {
+            // fast path (practically always): no two raw syncs closer than 4 bytes inside a chunk, and no chunk whose
+            // first 3 bytes hold a raw sync right after a chunk whose last 3 bytes do -> every raw sync is selected
+            const uint32_t H = mhi >> 29;
+            uint32_t pH = __shfl_up_sync(0xFFFFFFFFu, H, 1);
+            if (lane == 0) pH = carry;
+            const unsigned long long clash = M & ((M >> 1) | (M >> 2) | (M >> 3));
+            const bool cross = pH != 0 && (mlo & 7u) != 0;
+            uint32_t x;
+            if (!__any_sync(0xFFFFFFFFu, clash != 0ull || cross)) {
+                sel = M;
+                x = H ? 32u - (uint32_t)__clz((int)H) : 0u;              // H in {1, 2, 4}: spill-over of the last header
+                e = lane == 0 ? carry : 0u;                              // (only used by the trailing-0xFF check)
+            } else {
+                x = 0;
+                bool known = lane == 0 || pH == 0 || (mlo & 7u) == 0;
+                e = lane == 0 ? carry : 0u;
+                if (known && M) sel = resolve(M, e, x);
+                while (!__all_sync(0xFFFFFFFFu, known)) {
+                    const uint32_t px = __shfl_up_sync(0xFFFFFFFFu, x, 1);
+                    const bool pk = __shfl_up_sync(0xFFFFFFFFu, (int)known, 1) != 0;
+                    if (!known && pk) { e = px; sel = resolve(M, e, x); known = true; }
+                }
+            }
+            carry = __shfl_sync(0xFFFFFFFFu, x, 31);
+        }
+
+        if (NEAR_END) {
+            const unsigned long long base = span0 + rel;
+            // mpeg.rs:20: `reader[cur + 1]` with cur == n-1 panics when the scan reaches a trailing 0xFF
+            if (MODE != kModeCount && n - 1 >= base && n - 1 < base + kChunk) {
+                const uint32_t il = (uint32_t)(n - 1 - base);
+                if (bytes[n - 1] == 0xFF) {
+                    const unsigned long long before = il ? (sel & ((1ull << il) - 1ull)) : 0ull;
+                    bool skipped = il < e;
+                    if (before) skipped = skipped || (il - (uint32_t)(63 - __clzll((long long)before)) <= 3);
+                    if (!skipped) ctl->panic = 1;
+                }
+            }
+            // a header that would run past the end of the buffer is dropped (mpeg.rs:25-37)
             if (base + 67 >= n) {
                 const unsigned long long lim = n > base + 3 ? n - 3 - base : 0;
-                okmask = lim >= 64 ? ~0ull : ((1ull << lim) - 1ull);
+                sel &= lim >= 64 ? ~0ull : ((1ull << lim) - 1ull);
             }
-            // per-thread summary
-            uint32_t my_map, my_cnt;
-            {
-                uint32_t e0;
-                const unsigned long long sel0 = resolve(M, 0, e0);
-                my_map = e0 * 0x55u;
-                my_cnt = (uint32_t)__popcll(sel0 & okmask) * 0x01010101u;
-                if (M & 7ull) {
-#pragma unroll
-                    for (uint32_t s = 1; s < 4; ++s) {
-                        uint32_t es;
-                        const unsigned long long sel = resolve(M, s, es);
-                        my_map = (my_map & ~(3u << (2 * s))) | (es << (2 * s));
-                        my_cnt = (my_cnt & ~(0xFFu << (8 * s))) | ((uint32_t)__popcll(sel & okmask) << (8 * s));
-                    }
-                }
-            }
-            // lane's pre-map within this round: round entry state -> lane entry state
-            uint32_t pre = kIdentityMap;
-            {
-                bool known = lane == 0;
-                const uint32_t pm = __shfl_up_sync(0xFFFFFFFFu, my_map, 1);
-                if (lane > 0 && map_is_const(pm)) { pre = pm; known = true; }
-                while (!__all_sync(0xFFFFFFFFu, known)) {
-                    const uint32_t ppre = __shfl_up_sync(0xFFFFFFFFu, pre, 1);
-                    const bool pknown = __shfl_up_sync(0xFFFFFFFFu, (int)known, 1) != 0;
-                    if (!known && pknown) { pre = map_after(ppre, pm); known = true; }
-                }
-            }
-            const uint32_t tpre = map_after(wrun, pre);              // span entry -> lane entry
-            const uint32_t slot = (warp * kRounds + r) * 32 + lane;
-            s_mask[slot] = M;
-            s_tpre[slot] = (uint8_t)tpre;
-            {
-                const uint32_t k0 = (my_cnt >> (8 * map_get(tpre, 0))) & 0xFF, k1 = (my_cnt >> (8 * map_get(tpre, 1))) & 0xFF;
-                const uint32_t k2 = (my_cnt >> (8 * map_get(tpre, 2))) & 0xFF, k3 = (my_cnt >> (8 * map_get(tpre, 3))) & 0xFF;
-                wc01 += __reduce_add_sync(0xFFFFFFFFu, k0 | (k1 << 16));
-                wc23 += __reduce_add_sync(0xFFFFFFFFu, k2 | (k3 << 16));
-            }
-            const uint32_t round_map = __shfl_sync(0xFFFFFFFFu, map_after(pre, my_map), 31);
-            wrun = map_after(wrun, round_map);
         }
-        if (lane == 0) {
-            s_wmap[warp] = wrun;
-            s_wc[warp][0] = wc01 & 0xFFFF; s_wc[warp][1] = wc01 >> 16; s_wc[warp][2] = wc23 & 0xFFFF; s_wc[warp][3] = wc23 >> 16;
-        }
-        __syncthreads();
 
-        // ================= warp 0: combine the spans, publish the aggregate, look back, publish inclusive
-        if (warp == 0) {
-            Agg run;
-            run.map = kIdentityMap;
-            run.c[0] = run.c[1] = run.c[2] = run.c[3] = 0;
-            Agg keep = run;                        // prefix before span `lane`
-#pragma unroll
-            for (int k = 0; k < kScanWarps; ++k) {
-                if ((int)lane == k) keep = run;
-                Agg wk;
-                wk.map = s_wmap[k];
-                wk.c[0] = s_wc[k][0]; wk.c[1] = s_wc[k][1]; wk.c[2] = s_wc[k][2]; wk.c[3] = s_wc[k][3];
-                run = agg_then(run, wk);
-            }
-            TileDesc* me = desc + tile;
-            uint32_t entry = 0;
-            unsigned long long cbase = 0;
-            if (tile > 0) {
-                if (lane == 0) {
-                    me->map = run.map;
-                    me->c[0] = run.c[0]; me->c[1] = run.c[1]; me->c[2] = run.c[2]; me->c[3] = run.c[3];
-                    st_release(&me->flag, 1u);
-                }
-                uint32_t fmap = kIdentityMap;
-                unsigned long long fc[4] = {0, 0, 0, 0};
-                long long look = (long long)tile - 1;
-                for (;;) {
-                    const long long t = look - (long long)lane;
-                    uint32_t flag = 2, amap = kIdentityMap, a0 = 0, a1 = 0, a2 = 0, a3 = 0, st = 0, clo = 0, chi = 0;
-                    if (t >= 0) {
-                        const TileDesc* dsc = desc + t;
-                        do { flag = ld_acquire(&dsc->flag); } while (flag == 0);
-                        if (flag == 2) { st = ld_relaxed(&dsc->state); clo = ld_relaxed(&dsc->cnt_lo); chi = ld_relaxed(&dsc->cnt_hi); }
-                        else { amap = ld_relaxed(&dsc->map); a0 = ld_relaxed(&dsc->c[0]); a1 = ld_relaxed(&dsc->c[1]); a2 = ld_relaxed(&dsc->c[2]); a3 = ld_relaxed(&dsc->c[3]); }
-                    }
-                    const uint32_t incm = __ballot_sync(0xFFFFFFFFu, flag == 2);     // lanes past tile 0 count as inclusive(0,0)
-                    const int first = incm ? __ffs(incm) - 1 : 32;
-                    // "simple" aggregate: constant map, count independent of the entry state (practically every tile)
-                    const bool simple = map_is_const(amap) && a0 == a1 && a1 == a2 && a2 == a3;
-                    const uint32_t need = first >= 32 ? 0xFFFFFFFFu : ((1u << first) - 1u);
-                    const uint32_t simple_m = __ballot_sync(0xFFFFFFFFu, simple) & need;
-                    if (simple_m == need) {
-                        if (first > 0) {
-                            const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, (int)lane < first ? a0 : 0u);
-                            const uint32_t e0 = __shfl_sync(0xFFFFFFFFu, amap, 0) & 3u;
-                            const unsigned long long nc = tot + pick4(fc[0], fc[1], fc[2], fc[3], e0);
-                            fc[0] = fc[1] = fc[2] = fc[3] = nc;
-                            fmap = map_get(fmap, e0) * 0x55u;
-                        }
-                    } else {
-                        for (int i = 0; i < first; ++i) {                              // nearest tile first
-                            const uint32_t m_i = __shfl_sync(0xFFFFFFFFu, amap, i);
-                            const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, a0, i), b1 = __shfl_sync(0xFFFFFFFFu, a1, i);
-                            const uint32_t b2 = __shfl_sync(0xFFFFFFFFu, a2, i), b3 = __shfl_sync(0xFFFFFFFFu, a3, i);
-                            unsigned long long nc[4];
-#pragma unroll
-                            for (int s = 0; s < 4; ++s) nc[s] = pick4(b0, b1, b2, b3, (uint32_t)s) + pick4(fc[0], fc[1], fc[2], fc[3], map_get(m_i, s));
-#pragma unroll
-                            for (int s = 0; s < 4; ++s) fc[s] = nc[s];
-                            fmap = map_after(m_i, fmap);
-                        }
-                    }
-                    if (first < 32) {
-                        const uint32_t sigma = __shfl_sync(0xFFFFFFFFu, st, first);
-                        const uint32_t lo = __shfl_sync(0xFFFFFFFFu, clo, first), hi = __shfl_sync(0xFFFFFFFFu, chi, first);
-                        entry = map_get(fmap, sigma);
-                        cbase = (((unsigned long long)hi << 32) | lo) + pick4(fc[0], fc[1], fc[2], fc[3], sigma);
-                        break;
-                    }
-                    look -= 32;
-                }
-            }
-            if (lane == 0) {
-                const unsigned long long cend = cbase + pick4(run.c[0], run.c[1], run.c[2], run.c[3], entry);
-                me->state = map_get(run.map, entry);
-                me->cnt_lo = (uint32_t)cend;
-                me->cnt_hi = (uint32_t)(cend >> 32);
-                st_release(&me->flag, 2u);
-                if (tile + 1 == n_tiles) ctl->total = cend;
-            }
-            if (lane < kScanWarps) {
-                s_wentry[lane] = map_get(keep.map, entry);
-                s_wbase[lane] = cbase + pick4(keep.c[0], keep.c[1], keep.c[2], keep.c[3], entry);
-            }
-        }
-        __syncthreads();
-
-        // ================= pass 2: true entry states are known; emit candidates at their final indices
-        {
-            const uint32_t span_entry = s_wentry[warp];
-            unsigned long long run_base = s_wbase[warp];
-            const bool near_end = span0 + kSpanBytes + 4 > n;       // this span touches the end of the buffer
-#pragma unroll 1
-            for (int r = 0; r < kRounds; ++r) {
-                const unsigned long long base = span0 + (unsigned long long)r * (32 * kChunk) + (unsigned long long)lane * kChunk;
-                const uint32_t slot = (warp * kRounds + r) * 32 + lane;
-                const unsigned long long M = s_mask[slot];
-                const uint32_t my_entry = map_get((uint32_t)s_tpre[slot], span_entry);
-                uint32_t dummy;
-                const unsigned long long sel_all = M ? resolve(M, my_entry, dummy) : 0ull;
-                unsigned long long okmask = ~0ull;
-                if (near_end && base + 67 >= n) {
-                    const unsigned long long lim = n > base + 3 ? n - 3 - base : 0;
-                    okmask = lim >= 64 ? ~0ull : ((1ull << lim) - 1ull);
-                }
-                unsigned long long sel = sel_all & okmask;
-                const uint32_t cnt = (uint32_t)__popcll(sel);
+        // ---- count + sink
+        const uint32_t cnt = (uint32_t)__popcll(sel);
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, cnt != 0);
+        if (bal) {
+            uint32_t pre, round_total;
+            if (__any_sync(0xFFFFFFFFu, cnt > 1)) {
                 uint32_t inc = cnt;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, inc, d);
                     if ((int)lane >= d) inc += a;
                 }
-                unsigned long long idx = run_base + (inc - cnt);
-                run_base += __shfl_sync(0xFFFFFFFFu, inc, 31);
-                // header = 4 bytes at base+i, read as two aligned words (L2 hits: the tile was just scanned).
-                // The first two candidates' loads are issued together; more than two per 64 bytes is rare.
-                const uint32_t* wp = reinterpret_cast<const uint32_t*>(bytes + base);
-                int i0 = -1, i1 = -1;
-                uint32_t a0 = 0, b0 = 0, a1 = 0, b1 = 0;
-                if (sel) { i0 = __ffsll((long long)sel) - 1; sel &= sel - 1; }
-                if (sel) { i1 = __ffsll((long long)sel) - 1; sel &= sel - 1; }
-                if (i0 >= 0) { a0 = __ldg(wp + (i0 >> 2)); if (i0 & 3) b0 = __ldg(wp + (i0 >> 2) + 1); }
-                if (i1 >= 0) { a1 = __ldg(wp + (i1 >> 2)); if (i1 & 3) b1 = __ldg(wp + (i1 >> 2) + 1); }
-                if (i0 >= 0) {
-                    if (idx < cap) {
-                        out_pos[idx] = base + (unsigned long long)i0;
-                        out_hdr[idx] = __byte_perm(__funnelshift_r(a0, b0, 8 * (i0 & 3)), 0, 0x0123);    // big-endian (mpeg.rs:22-38)
+                pre = inc - cnt;
+                round_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            } else {
+                pre = (uint32_t)__popc(bal & lt_mask);
+                round_total = (uint32_t)__popc(bal);
+            }
+            if (MODE != kModeCount && cnt) {
+                uint32_t k = o.total + pre;
+                unsigned long long m = sel;
+                while (m) {
+                    const int i = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    // header = 4 bytes at chunk offset i: two aligned words of the staged row (the 17th is w[16])
+                    const uint32_t a = lds32(row + 4u * (uint32_t)(i >> 2));
+                    const uint32_t b = (i >> 2) == 15 ? w[16] : lds32(row + 4u * (uint32_t)(i >> 2) + 4u);
+                    const uint32_t h = __byte_perm(__funnelshift_r(a, b, 8 * (i & 3)), 0, 0x0123);     // big-endian (mpeg.rs:22-38)
+                    if (MODE == kModeCompact) {
+                        if (k < (uint32_t)kCandCap) {
+                            s_off[k] = (uint16_t)(rel + (uint32_t)i);
+                            s_hdr[k] = h;
+                        }
+                    } else {
+                        const unsigned long long gi = gbase + k;
+                        if (gi < cap) {
+                            out_pos[gi] = span0 + rel + (unsigned long long)i;
+                            out_hdr[gi] = h;
+                        }
                     }
-                    idx += 1;
-                }
-                if (i1 >= 0) {
-                    if (idx < cap) {
-                        out_pos[idx] = base + (unsigned long long)i1;
-                        out_hdr[idx] = __byte_perm(__funnelshift_r(a1, b1, 8 * (i1 & 3)), 0, 0x0123);
-                    }
-                    idx += 1;
-                }
-                while (sel) {
-                    const int i = __ffsll((long long)sel) - 1;
-                    sel &= sel - 1;
-                    if (idx < cap) {
-                        const uint32_t a = __ldg(wp + (i >> 2)), b = (i & 3) ? __ldg(wp + (i >> 2) + 1) : 0u;
-                        out_pos[idx] = base + (unsigned long long)i;
-                        out_hdr[idx] = __byte_perm(__funnelshift_r(a, b, 8 * (i & 3)), 0, 0x0123);
-                    }
-                    idx += 1;
-                }
-                // mpeg.rs:20: `reader[cur + 1]` with cur == n-1 panics when the scan reaches a trailing 0xFF
-                if (near_end && n > 0 && n - 1 >= base && n - 1 < base + kChunk) {
-                    const uint32_t il = (uint32_t)(n - 1 - base);
-                    if (bytes[n - 1] == 0xFF) {
-                        const unsigned long long before = il ? (sel_all & ((1ull << il) - 1ull)) : 0ull;
-                        bool skipped = il < my_entry;
-                        if (before) skipped = skipped || (il - (uint32_t)(63 - __clzll((long long)before)) <= 3);
-                        if (!skipped) ctl->panic = 1;
-                    }
+                    k += 1;
                 }
             }
+            o.total += round_total;
         }
-        __syncthreads();            // shared scratch is reused by the next tile
+        __syncwarp();                              // the stage is refilled by the next iteration's cp.async
+    }
+    cp_async_wait<0>();
+    o.exit_state = carry;
+    return o;
+}
+
+__device__ __forceinline__ SpanOut walk_tile(const int MODE, const uint8_t* __restrict__ bytes, const unsigned long long n,
+                                             const unsigned long long span0, const uint32_t entry, const uint32_t lane,
+                                             const uint32_t ring, uint16_t* __restrict__ s_off, uint32_t* __restrict__ s_hdr,
+                                             unsigned long long* __restrict__ out_pos, uint32_t* __restrict__ out_hdr,
+                                             const unsigned long long cap, const unsigned long long gbase,
+                                             ScanCtl* __restrict__ ctl) {
+    if (span0 + (unsigned long long)kSpanBytes + 80 > n)
+        return walk_span<true>(MODE, bytes, n, span0, entry, lane, ring, s_off, s_hdr, out_pos, out_hdr, cap, gbase, ctl);
+    return walk_span<false>(MODE, bytes, n, span0, entry, lane, ring, s_off, s_hdr, out_pos, out_hdr, cap, gbase, ctl);
+}
+
+// ---------------------------------------------------------------- K7a: walk
+// Every warp takes spans from a global counter (the next id is fetched while the current span is walked) and
+// leaves, per span: its candidates under entry state 0 in the span's slot of the temp lists, and a 16-byte
+// record {map, sens, c0..c3}.  No warp ever waits for another one.
+struct SpanRec {               // 16 bytes
+    uint32_t meta;             // exit-state map (8 bits) | sens << 8
+    uint32_t c01;              // candidates under entry state 0 | 1 << 16
+    uint32_t c23;              // ... 2 | 3 << 16
+    uint32_t pad;
+};
+
+__global__ void __launch_bounds__(kScanThreads, kCtasPerSm)
+mpeg_walk(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long n_spans, ScanCtl* __restrict__ ctl,
+          SpanRec* __restrict__ recs, uint16_t* __restrict__ t_off, uint32_t* __restrict__ t_hdr) {
+    extern __shared__ __align__(128) uint8_t smem_dyn[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ring = smem_addr(smem_dyn) + warp * (uint32_t)(kStages * kStageBytes);
+    unsigned long long span = 0;
+    if (lane == 0) span = atomicAdd(&ctl->next_tile, 1ull);
+    span = __shfl_sync(0xFFFFFFFFu, span, 0);
+    while (span < n_spans) {
+        unsigned long long next = 0;
+        if (lane == 0) next = atomicAdd(&ctl->next_tile, 1ull);       // latency hidden behind the walk
+        const unsigned long long span0 = span * (unsigned long long)kSpanBytes;
+        uint16_t* g_off = t_off + span * (unsigned long long)kCandCap;
+        uint32_t* g_hdr = t_hdr + span * (unsigned long long)kCandCap;
+        const SpanOut w0 = walk_tile(kModeCompact, bytes, n, span0, 0u, lane, ring, g_off, g_hdr, nullptr, nullptr, 0ull, 0ull, ctl);
+        uint32_t amap = w0.exit_state * 0x55u;
+        uint32_t c0 = w0.total, c1 = w0.total, c2 = w0.total, c3 = w0.total;
+        if (w0.sens) {                                   // rare: the span's first 3 bytes hold a raw sync
+            const SpanOut w1 = walk_tile(kModeCount, bytes, n, span0, 1u, lane, ring, g_off, g_hdr, nullptr, nullptr, 0ull, 0ull, ctl);
+            const SpanOut w2 = walk_tile(kModeCount, bytes, n, span0, 2u, lane, ring, g_off, g_hdr, nullptr, nullptr, 0ull, 0ull, ctl);
+            const SpanOut w3 = walk_tile(kModeCount, bytes, n, span0, 3u, lane, ring, g_off, g_hdr, nullptr, nullptr, 0ull, 0ull, ctl);
+            amap = w0.exit_state | (w1.exit_state << 2) | (w2.exit_state << 4) | (w3.exit_state << 6);
+            c1 = w1.total; c2 = w2.total; c3 = w3.total;
+        }
+        if (lane == 0) {
+            SpanRec r;
+            r.meta = amap | (w0.sens ? 0x100u : 0u);
+            r.c01 = c0 | (c1 << 16);
+            r.c23 = c2 | (c3 << 16);
+            r.pad = 0;
+            *reinterpret_cast<uint4*>(recs + span) = *reinterpret_cast<const uint4*>(&r);
+        }
+        span = __shfl_sync(0xFFFFFFFFu, next, 0);
+    }
+}
+
+// ---------------------------------------------------------------- K7b: scan over the span records
+// One CTA: thread t folds a contiguous chunk of records, thread 0 chains the 1,024 chunk aggregates, every
+// thread then replays its chunk with the true entry state and leaves (entry state, first candidate index)
+// per span.  16 GiB of input are 524,288 records = 8 MB.
+constexpr int kSpanScanThreads = 1024;
+__device__ __forceinline__ uint32_t rec_count(const SpanRec& r, uint32_t s) {
+    const uint32_t w = (s & 2) ? r.c23 : r.c01;
+    return (s & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
+__global__ void __launch_bounds__(kSpanScanThreads)
+mpeg_span_scan(const SpanRec* __restrict__ recs, unsigned long long n_spans, uint8_t* __restrict__ span_entry,
+               unsigned long long* __restrict__ span_base, ScanCtl* __restrict__ ctl) {
+    __shared__ uint32_t s_map[kSpanScanThreads];
+    __shared__ unsigned long long s_c[4][kSpanScanThreads];
+    __shared__ uint32_t s_entry[kSpanScanThreads];
+    __shared__ unsigned long long s_base[kSpanScanThreads];
+    const unsigned long long per = (n_spans + kSpanScanThreads - 1) / kSpanScanThreads;
+    const unsigned long long a = threadIdx.x * per, b = min(n_spans, a + per);
+    uint32_t map = kIdentityMap;
+    unsigned long long c[4] = {0, 0, 0, 0};
+    for (unsigned long long i = a; i < b; ++i) {
+        const uint4 v = *reinterpret_cast<const uint4*>(recs + i);
+        SpanRec r;
+        r.meta = v.x; r.c01 = v.y; r.c23 = v.z; r.pad = 0;
+#pragma unroll
+        for (uint32_t s = 0; s < 4; ++s) c[s] += rec_count(r, map_get(map, s));
+        map = map_after(map, r.meta & 0xFFu);
+    }
+    s_map[threadIdx.x] = map;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) s_c[s][threadIdx.x] = c[s];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t state = 0;
+        unsigned long long cnt = 0;
+        for (int t = 0; t < kSpanScanThreads; ++t) {
+            s_entry[t] = state;
+            s_base[t] = cnt;
+            cnt += s_c[state][t];
+            state = map_get(s_map[t], state);
+        }
+        ctl->total = cnt;
+    }
+    __syncthreads();
+    uint32_t state = s_entry[threadIdx.x];
+    unsigned long long cnt = s_base[threadIdx.x];
+    for (unsigned long long i = a; i < b; ++i) {
+        const uint4 v = *reinterpret_cast<const uint4*>(recs + i);
+        SpanRec r;
+        r.meta = v.x; r.c01 = v.y; r.c23 = v.z; r.pad = 0;
+        span_entry[i] = (uint8_t)state;
+        span_base[i] = cnt;
+        cnt += rec_count(r, state);
+        state = map_get(r.meta & 0xFFu, state);
+    }
+}
+
+// ---------------------------------------------------------------- K7c: compact
+// Moves every span's list to its final, position-ordered place.  Spans whose list is not valid for their
+// true entry state (head-sensitive with entry != 0) or did not fit their slot are re-walked with direct
+// emission.
+__global__ void __launch_bounds__(kScanThreads, kCtasPerSm)
+mpeg_compact(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long n_spans, ScanCtl* __restrict__ ctl,
+             const SpanRec* __restrict__ recs, const uint8_t* __restrict__ span_entry,
+             const unsigned long long* __restrict__ span_base, const uint16_t* __restrict__ t_off,
+             const uint32_t* __restrict__ t_hdr, unsigned long long* __restrict__ out_pos, uint32_t* __restrict__ out_hdr,
+             unsigned long long cap) {
+    extern __shared__ __align__(128) uint8_t smem_dyn[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ring = smem_addr(smem_dyn) + warp * (uint32_t)(kStages * kStageBytes);
+    const unsigned long long n_warps = (unsigned long long)gridDim.x * (kScanThreads / 32);
+    for (unsigned long long span = (unsigned long long)blockIdx.x * (kScanThreads / 32) + warp; span < n_spans; span += n_warps) {
+        const uint4 v = *reinterpret_cast<const uint4*>(recs + span);
+        SpanRec r;
+        r.meta = v.x; r.c01 = v.y; r.c23 = v.z; r.pad = 0;
+        const uint32_t entry = span_entry[span];
+        const unsigned long long base = span_base[span];
+        const uint32_t count = rec_count(r, entry);
+        const unsigned long long span0 = span * (unsigned long long)kSpanBytes;
+        const bool sens = (r.meta & 0x100u) != 0;
+        if ((!sens || entry == 0) && count <= (uint32_t)kCandCap) {
+            const uint16_t* g_off = t_off + span * (unsigned long long)kCandCap;
+            const uint32_t* g_hdr = t_hdr + span * (unsigned long long)kCandCap;
+            for (uint32_t k = lane; k < count; k += 32) {
+                const unsigned long long gi = base + k;
+                if (gi < cap) {
+                    out_pos[gi] = span0 + g_off[k];
+                    out_hdr[gi] = g_hdr[k];
+                }
+            }
+        } else {
+            walk_tile(kModeEmit, bytes, n, span0, entry, lane, ring, nullptr, nullptr, out_pos, out_hdr, cap, base, ctl);
+        }
     }
 }
 
@@ -630,21 +696,39 @@ int run_scan(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, uint64_t* d_p
     if (((uintptr_t)d_bytes & 15) != 0) return blast::set_error(BLAST_ERR_ARG, "mpeg scan: d_bytes must be 16-byte aligned");
     *n_out = 0;
     if (len == 0) return BLAST_OK;
-    const unsigned long long n_tiles = (len + kTileBytes - 1) / kTileBytes;
-    // tile descriptors + control block live in context scratch (no cudaMalloc / cudaFree on this path)
-    TileDesc* desc = static_cast<TileDesc*>(blast::scratch(ctx, 0, n_tiles * sizeof(TileDesc) + 256));
-    if (!desc) return BLAST_ERR_CUDA;
-    ScanCtl* ctl = reinterpret_cast<ScanCtl*>(reinterpret_cast<uint8_t*>(desc) + ((n_tiles * sizeof(TileDesc) + 127) & ~127ull));
+    const unsigned long long n_spans = (len + kSpanBytes - 1) / kSpanBytes;
+    // span records, per-span (entry, base) and the control block live in context scratch slot 0, the temp candidate
+    // lists in slot 1 (grow-only: no cudaMalloc / cudaFree on this path after the first call of a given size)
+    const size_t rec_b = (n_spans * sizeof(SpanRec) + 255) & ~255ull, base_b = (n_spans * 8 + 255) & ~255ull;
+    const size_t entry_b = (n_spans + 255) & ~255ull;
+    uint8_t* s0 = static_cast<uint8_t*>(blast::scratch(ctx, 0, rec_b + base_b + entry_b + 256));
+    if (!s0) return BLAST_ERR_CUDA;
+    SpanRec* recs = reinterpret_cast<SpanRec*>(s0);
+    unsigned long long* span_base = reinterpret_cast<unsigned long long*>(s0 + rec_b);
+    uint8_t* span_entry = s0 + rec_b + base_b;
+    ScanCtl* ctl = reinterpret_cast<ScanCtl*>(s0 + rec_b + base_b + entry_b);
+    const size_t hdr_b = (n_spans * kCandCap * sizeof(uint32_t) + 255) & ~255ull;
+    uint8_t* s1 = static_cast<uint8_t*>(blast::scratch(ctx, 1, hdr_b + n_spans * kCandCap * sizeof(uint16_t)));
+    if (!s1) return BLAST_ERR_CUDA;
+    uint32_t* t_hdr = reinterpret_cast<uint32_t*>(s1);
+    uint16_t* t_off = reinterpret_cast<uint16_t*>(s1 + hdr_b);
     ScanCtl* h_ctl = static_cast<ScanCtl*>(blast::mailbox(ctx));
     if (!h_ctl) return BLAST_ERR_CUDA;
-    BLAST_CUDA_TRY(cudaMemsetAsync(desc, 0, ((n_tiles * sizeof(TileDesc) + 127) & ~127ull) + sizeof(ScanCtl), ctx->stream));
+    BLAST_CUDA_TRY(cudaMemsetAsync(ctl, 0, sizeof(ScanCtl), ctx->stream));
     static int per_sm = 0;
-    if (per_sm == 0) BLAST_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpeg_sync_scan, kScanThreads, 0));
-    const unsigned grid = (unsigned)std::min<unsigned long long>(n_tiles, (unsigned long long)ctx->sm_count * std::max(per_sm, 1));
-    mpeg_sync_scan<<<grid, kScanThreads, 0, ctx->stream>>>(d_bytes, len, desc, n_tiles, ctl,
-                                                           reinterpret_cast<unsigned long long*>(d_pos), d_hdr, cap);
+    if (per_sm == 0) {
+        BLAST_CUDA_TRY(cudaFuncSetAttribute(mpeg_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
+        BLAST_CUDA_TRY(cudaFuncSetAttribute(mpeg_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
+        BLAST_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpeg_walk, kScanThreads, kScanSmem));
+    }
+    const unsigned long long want = (n_spans + kWalkers - 1) / kWalkers;
+    const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)ctx->sm_count * std::max(per_sm, 1));
+    mpeg_walk<<<grid, kScanThreads, kScanSmem, ctx->stream>>>(d_bytes, len, n_spans, ctl, recs, t_off, t_hdr);
+    mpeg_span_scan<<<1, kSpanScanThreads, 0, ctx->stream>>>(recs, n_spans, span_entry, span_base, ctl);
+    mpeg_compact<<<grid, kScanThreads, kScanSmem, ctx->stream>>>(d_bytes, len, n_spans, ctl, recs, span_entry, span_base, t_off, t_hdr,
+                                                                reinterpret_cast<unsigned long long*>(d_pos), d_hdr, cap);
     BLAST_CUDA_TRY(cudaGetLastError());
-    ctx->launches += 1;
+    ctx->launches += 3;
     BLAST_CUDA_TRY(cudaMemcpyAsync(h_ctl, ctl, sizeof(ScanCtl), cudaMemcpyDeviceToHost, ctx->stream));
     BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     const ScanCtl h = *h_ctl;

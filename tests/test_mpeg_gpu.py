@@ -65,9 +65,9 @@ def test_scan_random_buffers(ctx, alphabet):
 
 
 def test_scan_boundaries_every_offset(ctx):
-    """a lone header at every offset around the 64-byte chunk, warp (2 KiB) and tile (16 KiB) boundaries,
+    """a lone header at every offset around the 64-byte chunk, warp-round (2 KiB) and tile (32 KiB) boundaries,
     with and without a second sync 1..4 bytes later (the greedy skip)"""
-    for centre in (64, 2048, 16384, 32768):
+    for centre in (64, 2048, 16384, 32768, 65536):
         for off in range(centre - 6, centre + 6):
             for gap in (0, 1, 2, 3, 4):
                 b = np.zeros(centre + 64, dtype=np.uint8)
