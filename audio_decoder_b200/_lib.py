@@ -92,6 +92,7 @@ SIGNATURES = {
     "blast_ctx_device": (C.c_int, [_vp]),
     "blast_ctx_sm_count": (C.c_int, [_vp]),
     "blast_ctx_launch_count": (_u64, [_vp]),
+    "blast_ctx_trim": (C.c_int, [_vp]),
     "blast_dev_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
     "blast_dev_free": (C.c_int, [_vp, _vp]),
     "blast_host_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),

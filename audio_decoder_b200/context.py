@@ -134,6 +134,10 @@ class Context:
     def sync(self):
         check(self.lib.blast_ctx_sync(self.h))
 
+    def trim(self):
+        """release the context's grow-only device scratch"""
+        check(self.lib.blast_ctx_trim(self.h))
+
     @property
     def device(self) -> int:
         return self.lib.blast_ctx_device(self.h)

@@ -135,6 +135,18 @@ void blast_ctx_destroy(blast_ctx* ctx) {
     delete ctx;
 }
 
+int blast_ctx_trim(blast_ctx* ctx) {
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < blast_ctx::kScratch; ++i) {
+        if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+        ctx->scratch[i] = nullptr;
+        ctx->scratch_cap[i] = 0;
+    }
+    blast::release_pipe(ctx);
+    return BLAST_OK;
+}
+
 int blast_ctx_set_stream(blast_ctx* ctx, void* cuda_stream) {
     if (int rc = blast::bind(ctx)) return rc;
     BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));

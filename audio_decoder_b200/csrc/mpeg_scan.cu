@@ -13,12 +13,13 @@
 // K7 reads every input byte exactly once (1 B/byte of HBM traffic + 12 B per candidate, plus 6 B per candidate
 // of temp list written and re-read).  The greedy rule is a 4-state machine (state = header bytes still to
 // skip); a byte range acts on it as a map {0..3} -> {0..3} plus a candidate count per entry state, and maps
-// compose associatively.  Three launches, none of which ever waits for another thread block:
+// compose associatively.  Five launches, none of which ever waits for another thread block:
 //   K7a mpeg_walk       one warp per 32 KiB span: finds the span's candidates under entry state 0 and leaves
 //                       them in the span's slot of a temp list, plus a 16-byte record (map, counts per entry
 //                       state, "head-sensitive" flag)
-//   K7b mpeg_span_scan  folds the records (8 MB for 16 GiB of input): true entry state and first global
-//                       candidate index of every span
+//   K7b mpeg_span_fold / mpeg_block_chain / mpeg_span_fold<APPLY>   an ordinary three-step scan over the
+//                       records (8 MB for 16 GiB of input): true entry state and first global candidate index
+//                       of every span
 //   K7c mpeg_compact    moves the lists to their final, position-ordered place (coalesced)
 // A span's entry state only matters when its very first three bytes hold a raw sync ("head-sensitive",
 // ~0.15 % of spans on random data, every span on 0xFF floods): K7a then also counts it under the other three
@@ -93,6 +94,11 @@ __device__ __forceinline__ uint32_t map_after(uint32_t first, uint32_t then) {  
     for (int s = 0; s < 4; ++s) r |= map_get(then, map_get(first, s)) << (2 * s);
     return r;
 }
+template <typename T>
+__device__ __forceinline__ T pick4(T a0, T a1, T a2, T a3, uint32_t i) {       // register-only a[i]
+    return i == 0 ? a0 : i == 1 ? a1 : i == 2 ? a2 : a3;
+}
+
 // raw sync flags of one word: 0x80 in byte i <=> b[i] == 0xFF && (b[i+1] & 0xE0) == 0xE0, where `next` is
 // the following word.  z = b[i] & (b[i+1] | 0x1F) is 0xFF exactly then; the byte-wise == 0xFF test is
 // carry-free (low 7 bits + 1 reaches bit 7 iff they are all ones).
@@ -379,60 +385,148 @@ mpeg_walk(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long
 }
 
 // ---------------------------------------------------------------- K7b: scan over the span records
-// One CTA: thread t folds a contiguous chunk of records, thread 0 chains the 1,024 chunk aggregates, every
-// thread then replays its chunk with the true entry state and leaves (entry state, first candidate index)
-// per span.  16 GiB of input are 524,288 records = 8 MB.
-constexpr int kSpanScanThreads = 1024;
+// (map, counts) aggregates compose associatively, so this is an ordinary three-step scan: fold blocks of 2,048
+// records (K7b-1), chain the block aggregates (K7b-2, one warp), replay every block with its true entry state
+// (K7b-3 = the same kernel as K7b-1 in APPLY mode) leaving (entry state, first candidate index) per span.
+// 16 GiB of input are 524,288 records = 8 MB.
+struct Agg {
+    uint32_t map;
+    uint32_t c[4];
+};
+__device__ __forceinline__ Agg agg_identity() {
+    Agg r;
+    r.map = kIdentityMap;
+    r.c[0] = r.c[1] = r.c[2] = r.c[3] = 0;
+    return r;
+}
+__device__ __forceinline__ Agg agg_then(const Agg& a, const Agg& b) {            // a first, then b
+    Agg r;
+    r.map = map_after(a.map, b.map);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) r.c[s] = a.c[s] + pick4(b.c[0], b.c[1], b.c[2], b.c[3], map_get(a.map, s));
+    return r;
+}
+__device__ __forceinline__ Agg agg_shfl_up(const Agg& a, int d) {
+    Agg r;
+    r.map = __shfl_up_sync(0xFFFFFFFFu, a.map, d);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) r.c[s] = __shfl_up_sync(0xFFFFFFFFu, a.c[s], d);
+    return r;
+}
 __device__ __forceinline__ uint32_t rec_count(const SpanRec& r, uint32_t s) {
     const uint32_t w = (s & 2) ? r.c23 : r.c01;
     return (s & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
-__global__ void __launch_bounds__(kSpanScanThreads)
-mpeg_span_scan(const SpanRec* __restrict__ recs, unsigned long long n_spans, uint8_t* __restrict__ span_entry,
-               unsigned long long* __restrict__ span_base, ScanCtl* __restrict__ ctl) {
-    __shared__ uint32_t s_map[kSpanScanThreads];
-    __shared__ unsigned long long s_c[4][kSpanScanThreads];
-    __shared__ uint32_t s_entry[kSpanScanThreads];
-    __shared__ unsigned long long s_base[kSpanScanThreads];
-    const unsigned long long per = (n_spans + kSpanScanThreads - 1) / kSpanScanThreads;
-    const unsigned long long a = threadIdx.x * per, b = min(n_spans, a + per);
-    uint32_t map = kIdentityMap;
-    unsigned long long c[4] = {0, 0, 0, 0};
-    for (unsigned long long i = a; i < b; ++i) {
-        const uint4 v = *reinterpret_cast<const uint4*>(recs + i);
-        SpanRec r;
-        r.meta = v.x; r.c01 = v.y; r.c23 = v.z; r.pad = 0;
+__device__ __forceinline__ Agg agg_of(const SpanRec& r) {
+    Agg a;
+    a.map = r.meta & 0xFFu;
+    a.c[0] = r.c01 & 0xFFFFu; a.c[1] = r.c01 >> 16; a.c[2] = r.c23 & 0xFFFFu; a.c[3] = r.c23 >> 16;
+    return a;
+}
+
+constexpr int kFoldThreads = 256;
+constexpr int kFoldPerThread = 8;
+constexpr int kFoldBlock = kFoldThreads * kFoldPerThread;       // records per block
+
+struct BlockAgg {              // 32 bytes
+    uint32_t map, c[4];        // K7b-1: the block's aggregate
+    uint32_t entry;            // K7b-2: entry state of the block
+    unsigned long long base;   // K7b-2: candidates before the block
+};
+
+template <bool APPLY>
+__global__ void __launch_bounds__(kFoldThreads)
+mpeg_span_fold(const SpanRec* __restrict__ recs, unsigned long long n_spans, BlockAgg* __restrict__ blocks,
+               uint8_t* __restrict__ span_entry, unsigned long long* __restrict__ span_base) {
+    __shared__ Agg s_warp[kFoldThreads / 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * kFoldBlock + (unsigned long long)threadIdx.x * kFoldPerThread;
+    SpanRec r[kFoldPerThread];
+    Agg mine = agg_identity();
 #pragma unroll
-        for (uint32_t s = 0; s < 4; ++s) c[s] += rec_count(r, map_get(map, s));
-        map = map_after(map, r.meta & 0xFFu);
-    }
-    s_map[threadIdx.x] = map;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) s_c[s][threadIdx.x] = c[s];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t state = 0;
-        unsigned long long cnt = 0;
-        for (int t = 0; t < kSpanScanThreads; ++t) {
-            s_entry[t] = state;
-            s_base[t] = cnt;
-            cnt += s_c[state][t];
-            state = map_get(s_map[t], state);
+    for (int k = 0; k < kFoldPerThread; ++k) {
+        r[k].meta = kIdentityMap; r[k].c01 = 0; r[k].c23 = 0; r[k].pad = 0;
+        if (i0 + k < n_spans) {
+            const uint4 v = *reinterpret_cast<const uint4*>(recs + i0 + k);
+            r[k].meta = v.x; r[k].c01 = v.y; r[k].c23 = v.z;
         }
-        ctl->total = cnt;
+        mine = agg_then(mine, agg_of(r[k]));
     }
+    // inclusive scan over the warp, then over the warps
+    Agg inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const Agg up = agg_shfl_up(inc, d);
+        if ((int)lane >= d) inc = agg_then(up, inc);
+    }
+    if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    uint32_t state = s_entry[threadIdx.x];
-    unsigned long long cnt = s_base[threadIdx.x];
-    for (unsigned long long i = a; i < b; ++i) {
-        const uint4 v = *reinterpret_cast<const uint4*>(recs + i);
-        SpanRec r;
-        r.meta = v.x; r.c01 = v.y; r.c23 = v.z; r.pad = 0;
-        span_entry[i] = (uint8_t)state;
-        span_base[i] = cnt;
-        cnt += rec_count(r, state);
-        state = map_get(r.meta & 0xFFu, state);
+    Agg before = agg_identity();                   // everything in the block before this warp
+    Agg total = agg_identity();
+#pragma unroll
+    for (int w = 0; w < kFoldThreads / 32; ++w) {
+        if (w == (int)warp) before = total;
+        total = agg_then(total, s_warp[w]);
     }
+    if (!APPLY) {
+        if (threadIdx.x == 0) {
+            BlockAgg b;
+            b.map = total.map;
+            b.c[0] = total.c[0]; b.c[1] = total.c[1]; b.c[2] = total.c[2]; b.c[3] = total.c[3];
+            b.entry = 0; b.base = 0;
+            blocks[blockIdx.x] = b;
+        }
+        return;
+    }
+    // exclusive prefix of this thread inside the block
+    Agg ex = agg_shfl_up(inc, 1);
+    if (lane == 0) ex = agg_identity();
+    ex = agg_then(before, ex);
+    const uint32_t b_entry = blocks[blockIdx.x].entry;
+    uint32_t state = map_get(ex.map, b_entry);
+    unsigned long long cnt = blocks[blockIdx.x].base + pick4(ex.c[0], ex.c[1], ex.c[2], ex.c[3], b_entry);
+#pragma unroll
+    for (int k = 0; k < kFoldPerThread; ++k) {
+        if (i0 + k < n_spans) {
+            span_entry[i0 + k] = (uint8_t)state;
+            span_base[i0 + k] = cnt;
+            cnt += rec_count(r[k], state);
+            state = map_get(r[k].meta & 0xFFu, state);
+        }
+    }
+}
+
+// K7b-2: one warp chains the block aggregates, 32 at a time
+__global__ void mpeg_block_chain(BlockAgg* __restrict__ blocks, unsigned long long n_blocks, ScanCtl* __restrict__ ctl) {
+    const uint32_t lane = threadIdx.x;
+    uint32_t state = 0;
+    unsigned long long cnt = 0;
+    for (unsigned long long b0 = 0; b0 < n_blocks; b0 += 32) {
+        const unsigned long long b = b0 + lane;
+        Agg mine = agg_identity();
+        if (b < n_blocks) {
+            mine.map = blocks[b].map;
+            mine.c[0] = blocks[b].c[0]; mine.c[1] = blocks[b].c[1]; mine.c[2] = blocks[b].c[2]; mine.c[3] = blocks[b].c[3];
+        }
+        Agg inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const Agg up = agg_shfl_up(inc, d);
+            if ((int)lane >= d) inc = agg_then(up, inc);
+        }
+        Agg ex = agg_shfl_up(inc, 1);
+        if (lane == 0) ex = agg_identity();
+        if (b < n_blocks) {
+            blocks[b].entry = map_get(ex.map, state);
+            blocks[b].base = cnt + pick4(ex.c[0], ex.c[1], ex.c[2], ex.c[3], state);
+        }
+        const uint32_t lmap = __shfl_sync(0xFFFFFFFFu, inc.map, 31);
+        const uint32_t l0 = __shfl_sync(0xFFFFFFFFu, inc.c[0], 31), l1 = __shfl_sync(0xFFFFFFFFu, inc.c[1], 31);
+        const uint32_t l2 = __shfl_sync(0xFFFFFFFFu, inc.c[2], 31), l3 = __shfl_sync(0xFFFFFFFFu, inc.c[3], 31);
+        cnt += pick4(l0, l1, l2, l3, state);
+        state = map_get(lmap, state);
+    }
+    if (lane == 0) ctl->total = cnt;
 }
 
 // ---------------------------------------------------------------- K7c: compact
@@ -564,7 +658,11 @@ __global__ void mpeg_first_index(const uint32_t* __restrict__ hdr, unsigned long
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint32_t h = hdr[i];
         uint32_t pl, sk;
-        if (cand_valid(h, ref, pl, sk)) atomicMin(first + (h & (kHdrBins - 1)), i);
+        if (cand_valid(h, ref, pl, sk)) {
+            // the dominant header is shared by most candidates: look before the atomic (the table only ever decreases)
+            unsigned long long* slot = first + (h & (kHdrBins - 1));
+            if (*reinterpret_cast<volatile unsigned long long*>(slot) > i) atomicMin(slot, i);
+        }
     }
 }
 
@@ -701,12 +799,15 @@ int run_scan(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, uint64_t* d_p
     // lists in slot 1 (grow-only: no cudaMalloc / cudaFree on this path after the first call of a given size)
     const size_t rec_b = (n_spans * sizeof(SpanRec) + 255) & ~255ull, base_b = (n_spans * 8 + 255) & ~255ull;
     const size_t entry_b = (n_spans + 255) & ~255ull;
-    uint8_t* s0 = static_cast<uint8_t*>(blast::scratch(ctx, 0, rec_b + base_b + entry_b + 256));
+    const unsigned long long n_blocks = (n_spans + kFoldBlock - 1) / kFoldBlock;
+    const size_t blk_b = (n_blocks * sizeof(BlockAgg) + 255) & ~255ull;
+    uint8_t* s0 = static_cast<uint8_t*>(blast::scratch(ctx, 0, rec_b + base_b + entry_b + blk_b + 256));
     if (!s0) return BLAST_ERR_CUDA;
     SpanRec* recs = reinterpret_cast<SpanRec*>(s0);
     unsigned long long* span_base = reinterpret_cast<unsigned long long*>(s0 + rec_b);
     uint8_t* span_entry = s0 + rec_b + base_b;
-    ScanCtl* ctl = reinterpret_cast<ScanCtl*>(s0 + rec_b + base_b + entry_b);
+    BlockAgg* blocks = reinterpret_cast<BlockAgg*>(s0 + rec_b + base_b + entry_b);
+    ScanCtl* ctl = reinterpret_cast<ScanCtl*>(s0 + rec_b + base_b + entry_b + blk_b);
     const size_t hdr_b = (n_spans * kCandCap * sizeof(uint32_t) + 255) & ~255ull;
     uint8_t* s1 = static_cast<uint8_t*>(blast::scratch(ctx, 1, hdr_b + n_spans * kCandCap * sizeof(uint16_t)));
     if (!s1) return BLAST_ERR_CUDA;
@@ -724,11 +825,13 @@ int run_scan(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, uint64_t* d_p
     const unsigned long long want = (n_spans + kWalkers - 1) / kWalkers;
     const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)ctx->sm_count * std::max(per_sm, 1));
     mpeg_walk<<<grid, kScanThreads, kScanSmem, ctx->stream>>>(d_bytes, len, n_spans, ctl, recs, t_off, t_hdr);
-    mpeg_span_scan<<<1, kSpanScanThreads, 0, ctx->stream>>>(recs, n_spans, span_entry, span_base, ctl);
+    mpeg_span_fold<false><<<(unsigned)n_blocks, kFoldThreads, 0, ctx->stream>>>(recs, n_spans, blocks, span_entry, span_base);
+    mpeg_block_chain<<<1, 32, 0, ctx->stream>>>(blocks, n_blocks, ctl);
+    mpeg_span_fold<true><<<(unsigned)n_blocks, kFoldThreads, 0, ctx->stream>>>(recs, n_spans, blocks, span_entry, span_base);
     mpeg_compact<<<grid, kScanThreads, kScanSmem, ctx->stream>>>(d_bytes, len, n_spans, ctl, recs, span_entry, span_base, t_off, t_hdr,
                                                                 reinterpret_cast<unsigned long long*>(d_pos), d_hdr, cap);
     BLAST_CUDA_TRY(cudaGetLastError());
-    ctx->launches += 3;
+    ctx->launches += 5;
     BLAST_CUDA_TRY(cudaMemcpyAsync(h_ctl, ctl, sizeof(ScanCtl), cudaMemcpyDeviceToHost, ctx->stream));
     BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     const ScanCtl h = *h_ctl;
@@ -787,18 +890,21 @@ int blast_mpeg_index_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, i
     BLAST_REQUIRE(n_offsets_out && (d_bytes || len == 0), BLAST_ERR_ARG, "blast_mpeg_index_dev: null argument");
     *n_offsets_out = 0;
     if (n_candidates_out) *n_candidates_out = 0;
-    DevFree mem;
-    // candidates: one pass with a guessed capacity (an MP3 stream has one sync per ~400 bytes, random
-    // bytes one per 2,048); an exact second pass only if the guess was too small
-    uint64_t n_cand = 0, guess = len / 32 + 4096;
+    // candidates: one pass with a guessed capacity (an MP3 stream has one sync per ~400 bytes, random bytes one
+    // per 2,048); an exact second pass only if the guess was too small.  All buffers are context scratch
+    // (grow-only): a second call of the same size allocates nothing.
+    uint64_t n_cand = 0, guess = len / 128 + 4096;
+    auto cand_buffers = [&](uint64_t count, unsigned long long** pos, uint32_t** hdr) -> bool {
+        *pos = static_cast<unsigned long long*>(blast::scratch(ctx, 2, count * 8));
+        *hdr = static_cast<uint32_t*>(blast::scratch(ctx, 3, count * 4));
+        return *pos && *hdr;
+    };
     unsigned long long* d_pos = nullptr;
     uint32_t* d_hdr = nullptr;
-    BLAST_CUDA_TRY(mem.alloc(&d_pos, guess * 8));
-    BLAST_CUDA_TRY(mem.alloc(&d_hdr, guess * 4));
+    if (!cand_buffers(guess, &d_pos, &d_hdr)) return BLAST_ERR_CUDA;
     int rc = run_scan(ctx, d_bytes, len, reinterpret_cast<uint64_t*>(d_pos), d_hdr, guess, &n_cand);
     if (rc == BLAST_ERR_CAPACITY) {
-        BLAST_CUDA_TRY(mem.alloc(&d_pos, n_cand * 8));
-        BLAST_CUDA_TRY(mem.alloc(&d_hdr, n_cand * 4));
+        if (!cand_buffers(n_cand, &d_pos, &d_hdr)) return BLAST_ERR_CUDA;
         uint64_t n2 = 0;
         rc = run_scan(ctx, d_bytes, len, reinterpret_cast<uint64_t*>(d_pos), d_hdr, n_cand, &n2);
     }
@@ -806,33 +912,35 @@ int blast_mpeg_index_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, i
     if (n_candidates_out) *n_candidates_out = n_cand;
     if (n_cand == 0) return blast::set_error(BLAST_ERR_REF_PANIC, "no sync candidates: the reference indexes an empty list (mpeg.rs:64)");
 
-    uint32_t* d_hist = nullptr;
-    unsigned long long *d_best = nullptr, *d_first = nullptr, *d_bc = nullptr, *d_bb = nullptr, *d_total = nullptr;
-    uint32_t* d_err = nullptr;
     const unsigned long long n_blocks = (n_cand + kClsBlock - 1) / kClsBlock;
-    BLAST_CUDA_TRY(mem.alloc(&d_hist, kHdrBins * sizeof(uint32_t)));
-    BLAST_CUDA_TRY(mem.alloc(&d_best, 8));
-    BLAST_CUDA_TRY(mem.alloc(&d_first, (size_t)kHdrBins * 8));
-    BLAST_CUDA_TRY(mem.alloc(&d_bc, n_blocks * 8));
-    BLAST_CUDA_TRY(mem.alloc(&d_bb, n_blocks * 8));
-    BLAST_CUDA_TRY(mem.alloc(&d_total, 8));
-    BLAST_CUDA_TRY(mem.alloc(&d_err, 4));
-    BLAST_CUDA_TRY(cudaMemsetAsync(d_hist, 0, kHdrBins * sizeof(uint32_t), ctx->stream));
-    BLAST_CUDA_TRY(cudaMemsetAsync(d_best, 0, 8, ctx->stream));
-    BLAST_CUDA_TRY(cudaMemsetAsync(d_first, 0xFF, (size_t)kHdrBins * 8, ctx->stream));
-    BLAST_CUDA_TRY(cudaMemsetAsync(d_err, 0, 4, ctx->stream));
+    const size_t hist_b = kHdrBins * sizeof(uint32_t), first_b = (size_t)kHdrBins * 8, bc_b = (n_blocks * 8 + 255) & ~255ull;
+    uint8_t* s4 = static_cast<uint8_t*>(blast::scratch(ctx, 4, hist_b + first_b + 2 * bc_b + 256));
+    if (!s4) return BLAST_ERR_CUDA;
+    uint32_t* d_hist = reinterpret_cast<uint32_t*>(s4);
+    unsigned long long* d_first = reinterpret_cast<unsigned long long*>(s4 + hist_b);
+    unsigned long long* d_bc = reinterpret_cast<unsigned long long*>(s4 + hist_b + first_b);
+    unsigned long long* d_bb = reinterpret_cast<unsigned long long*>(s4 + hist_b + first_b + bc_b);
+    unsigned long long* d_best = reinterpret_cast<unsigned long long*>(s4 + hist_b + first_b + 2 * bc_b);
+    unsigned long long* d_total = d_best + 1;
+    uint32_t* d_err = reinterpret_cast<uint32_t*>(d_best + 2);
+    unsigned long long* h_box = static_cast<unsigned long long*>(blast::mailbox(ctx));
+    if (!h_box) return BLAST_ERR_CUDA;
+    h_box += 64;                                          // the first 512 bytes of the mailbox belong to run_scan
+    BLAST_CUDA_TRY(cudaMemsetAsync(d_hist, 0, hist_b, ctx->stream));
+    BLAST_CUDA_TRY(cudaMemsetAsync(d_best, 0, 24, ctx->stream));
     const unsigned g = (unsigned)std::min<unsigned long long>((n_cand + 255) / 256, (unsigned long long)ctx->sm_count * 16);
     mpeg_hist<<<g, 256, 0, ctx->stream>>>(d_hdr, n_cand, d_hist);
     mpeg_pick_ref<<<kHdrBins / 256, 256, 0, ctx->stream>>>(d_hist, d_best);
     BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 2;
-    unsigned long long best = 0;
-    BLAST_CUDA_TRY(cudaMemcpyAsync(&best, d_best, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    BLAST_CUDA_TRY(cudaMemcpyAsync(h_box, d_best, 8, cudaMemcpyDeviceToHost, ctx->stream));
     BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long best = h_box[0];
     if (best == 0) return blast::set_error(BLAST_ERR_REF_PANIC, "no parsable header: the reference indexes past its candidate list (mpeg.rs:64)");
     const uint32_t ref_header = 0xFFE00000u | (kHdrBins - 1 - (uint32_t)(best & (kHdrBins - 1)));
     if (ref_header_out) *ref_header_out = ref_header;
     if (reference_compat) {
+        BLAST_CUDA_TRY(cudaMemsetAsync(d_first, 0xFF, first_b, ctx->stream));
         mpeg_first_index<<<g, 256, 0, ctx->stream>>>(d_hdr, n_cand, ref_header, d_first);
         ctx->launches += 1;
     }
@@ -841,11 +949,10 @@ int blast_mpeg_index_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, i
     mpeg_scan_blocks<<<1, 1024, 0, ctx->stream>>>(d_bc, d_bb, n_blocks, d_total);
     BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 2;
-    unsigned long long total = 0;
-    uint32_t err = 0;
-    BLAST_CUDA_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    BLAST_CUDA_TRY(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BLAST_CUDA_TRY(cudaMemcpyAsync(h_box, d_best, 24, cudaMemcpyDeviceToHost, ctx->stream));
     BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long total = h_box[1];
+    const uint32_t err = (uint32_t)h_box[2];
     *n_offsets_out = total;
     if (err && reference_compat)
         return blast::set_error(BLAST_ERR_REF_PANIC, "a frame payload extends past the end of the file (mpeg.rs:96 indexes out of bounds)");

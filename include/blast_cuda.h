@@ -66,6 +66,9 @@ void* blast_ctx_stream(blast_ctx* ctx);
 int  blast_ctx_sync(blast_ctx* ctx);
 int  blast_ctx_device(const blast_ctx* ctx);
 int  blast_ctx_sm_count(const blast_ctx* ctx);
+/* Releases the context's grow-only device scratch (staging slabs, candidate lists, tile tables).  The hot entry
+ * points never cudaMalloc / cudaFree once warm; this gives the memory back between workloads. */
+int  blast_ctx_trim(blast_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t blast_ctx_launch_count(const blast_ctx* ctx);
 
