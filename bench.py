@@ -11,8 +11,9 @@ pass over the whole batch.  At N > 1 every rank owns its own 1,024-file shard (w
 no data-path collective for decode).
 
 The JSON line follows the driver contract; `value` is device-resident throughput (CUDA events on the
-launching stream), `e2e` the same metric through the host-buffer C-ABI call (pinned host file images in,
-host AudioFile.samples out, copies inside the timed region).
+launching stream), `e2e` the same metric through the host-buffer C-ABI call (pinned host file images in, S16
+bus out, copies inside the timed region; decoded tracks stay in HBM), `e2e_parse_dropin` the variant that also
+returns every AudioFile.samples Vec to the host like a literal aiff::parse() drop-in.
 """
 from __future__ import annotations
 
@@ -231,7 +232,7 @@ def run_ours(args):
     ctx.sync()
     barrier(dist, local)
     launches = ctx.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
     ms_decode = sum(e[0].elapsed_ms(e[1]) for e in evs) / args.steps
     ms_mix = sum(e[1].elapsed_ms(e[2]) for e in evs) / args.steps if mix else 0.0
     ms_total = max_over_ranks(dist, local, ms_total)
@@ -262,9 +263,12 @@ def run_ours(args):
                         "frac": round(ach / peak, 4), "algorithmic_bytes_per_step": alg_bytes_mix,
                         "ms_per_step": round(ms_mix, 4), "traffic": traffic.get("voice_render_mix_tma_c2")}
 
-    # ---- e2e: host file images (pinned) -> blast_pcm_decode_batch (host AudioFile.samples out, tracks stay in
-    #      HBM) -> render of the decoded tracks -> S16 bus copied back to the host
-    e2e = None
+    # ---- e2e: the same step through the host-buffer C ABI.  Pinned host file images -> blast_pcm_decode_batch
+    #      (H2D inside) -> render of the decoded tracks -> S16 bus copied back to the host.
+    #      "e2e":        AudioFile.samples stay in HBM (their only consumer is the render kernel; SURVEY §8 b)
+    #      "e2e_parse_dropin": additionally every AudioFile.samples Vec is delivered to the host, as a literal
+    #                    aiff::parse() drop-in must (doubles the PCIe traffic)
+    e2e = e2e_dropin = None
     if not args.no_e2e:
         h_out = ctx.pinned(n_files * words_per_file * 2)
         h_bus = ctx.pinned(2 * frames_per_file * 2) if mix else None
@@ -273,9 +277,13 @@ def run_ours(args):
         dd = (_lib.PcmDesc * n_files)(*descs)
         host_out = (C.c_void_p * n_files)(*[h_out.ptr + i * words_per_file * 2 for i in range(n_files)])
         dev_out = (C.c_void_p * n_files)(*[d_out.ptr + i * words_per_file * 2 for i in range(n_files)])
+        pcie = {}
+        pp = os.path.join(ROOT, "profiles", "r01_pcie_probe.json")
+        if os.path.exists(pp):
+            pcie = json.load(open(pp))
 
-        def e2e_step():
-            rc = L.blast_pcm_decode_batch(ctx.h, n_files, files, lens, dd, host_out, dev_out)
+        def e2e_step(to_host):
+            rc = L.blast_pcm_decode_batch(ctx.h, n_files, files, lens, dd, host_out if to_host else None, dev_out)
             if rc != 0:
                 raise RuntimeError(L.blast_last_error().decode())
             if mix:
@@ -287,24 +295,37 @@ def run_ours(args):
                 L.blast_memcpy_d2h(ctx.h, h_bus.ptr, d_bus.ptr, 2 * n_slots)
                 ctx.sync()
 
-        for _ in range(2):
-            e2e_step()
-        barrier(dist, local)
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        ctx.sync()
-        dt = (time.perf_counter() - t0) / args.e2e_steps
-        dt = max_over_ranks(dist, local, dt)
+        def e2e_run(to_host):
+            for _ in range(2):
+                e2e_step(to_host)
+            barrier(dist, local)
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                e2e_step(to_host)
+            ctx.sync()
+            dt = (time.perf_counter() - t0) / args.e2e_steps
+            dt = max_over_ranks(dist, local, dt)
+            h2d = n_files * data_len
+            d2h = (n_files * words_per_file * 2 if to_host else 0) + (2 * n_slots if mix else 0)
+            r = {"value": round(world * samples_per_step / dt / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                 "d2h_bytes_per_step": d2h, "ms_per_step": round(dt * 1e3, 3),
+                 "pcie_GBps": round(max(h2d, d2h) / dt / 1e9, 2)}
+            if pcie:
+                r["pcie_peak_GBps"] = pcie.get("bidir_each_GBps" if to_host else "h2d_GBps")
+                r["pcie_frac"] = round(r["pcie_GBps"] / r["pcie_peak_GBps"], 3)
+                r["pcie_peak_source"] = "tools/pcie_probe.py on this pool's B200 box (profiles/r01_pcie_probe.json)"
+            return r
+
+        e2e = e2e_run(False)
+        e2e["api"] = ("blast_pcm_decode_batch (pinned host file images in, decoded tracks kept in HBM)" +
+                      (" + blast_scene_render_dev + blast_bus_finalize_dev + S16 bus D2H" if mix else ""))
+        e2e_dropin = e2e_run(True)
+        e2e_dropin["api"] = e2e["api"].replace("decoded tracks kept in HBM", "host AudioFile.samples out AND tracks kept in HBM")
         # spot-check the e2e result against numpy (not timed)
         got = h_out.view(np.int16, words_per_file, 0)
         assert np.array_equal(got, view[0, off:off + data_len].view(">i2").astype(np.int16)), "e2e output mismatch"
-        e2e = {"value": round(world * samples_per_step / dt / 1e9, 3), "unit": UNIT,
-               "h2d_bytes_per_step": n_files * data_len,
-               "d2h_bytes_per_step": n_files * words_per_file * 2 + (2 * n_slots if mix else 0),
-               "ms_per_step": round(dt * 1e3, 3),
-               "api": "blast_pcm_decode_batch (pinned host images in, host AudioFile.samples out, tracks kept in HBM)"
-                      + (" + blast_scene_render_dev + blast_bus_finalize_dev + bus D2H" if mix else "")}
+    if rank == 0:
+        clocks = sampler.stop()
 
     workload = (f"C2: batch decode {n_files} x 24-bit BE 48 kHz stereo AIFF ({data_len} payload B each), reference-exact "
                 "byte-pair decode to i16" + (f", then mix of the {n_files} decoded tracks (stereo voices, velocity 1, "
@@ -322,7 +343,7 @@ def run_ours(args):
                                   ("; one int32 all-reduce of the partial bus per step (NCCL)" if world > 1 and mix else "; no collective")},
         "roofline": roofline, "roofline_mix": roofline_mix,
         "kernel_ms": {"decode": round(ms_decode, 4), "mix": round(ms_mix, 4)},
-        "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
+        "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "e2e_parse_dropin": e2e_dropin,
     }
     if rank == 0 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(view, image_len, n_files, threads=1, budget_s=args.cpu_seconds, mix=mix)

@@ -13,6 +13,7 @@ pub const BLAST_ERR_REF_PANIC: c_int = 5;
 #[repr(C)] pub struct blast_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct blast_scene { _p: [u8; 0] }
 #[repr(C)] pub struct blast_pcm_plan { _p: [u8; 0] }
+#[repr(C)] pub struct blast_conductor { _p: [u8; 0] }
 
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct blast_pcm_desc {
@@ -27,6 +28,54 @@ pub struct blast_track { pub d_samples: *const i16, pub n_samples: u64, pub num_
 pub struct blast_voice { pub track: u32, pub active: u32, pub position: f32, pub velocity: f32, pub gain: f32, pub reserved: u32 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct blast_x128p { pub s0: u64, pub s1: u64 }
+
+// ---- Conductor (engine.rs:36-248, commands.rs:86-234): TempoMode / TempoUnit / Command / Idx discriminants
+pub const BLAST_TM_PROCESS: u32 = 0; pub const BLAST_TM_VOICE: u32 = 1; pub const BLAST_TM_GROUP: u32 = 2;
+pub const BLAST_TM_CONTEXT: u32 = 3; pub const BLAST_TM_TBD: u32 = 4;
+pub const BLAST_TU_SAMPLES: u32 = 0; pub const BLAST_TU_MILLIS: u32 = 1; pub const BLAST_TU_BPM: u32 = 2;
+pub const BLAST_CMD_LOAD: u32 = 0; pub const BLAST_CMD_START: u32 = 1; pub const BLAST_CMD_PAUSE: u32 = 2;
+pub const BLAST_CMD_RESUME: u32 = 3; pub const BLAST_CMD_STOP: u32 = 4; pub const BLAST_CMD_UNLOAD: u32 = 5;
+pub const BLAST_CMD_VELOCITY: u32 = 6; pub const BLAST_CMD_GROUP: u32 = 7; pub const BLAST_CMD_TC: u32 = 8;
+pub const BLAST_CMD_SEQ: u32 = 9; pub const BLAST_CMD_QUIT: u32 = 10;
+pub const BLAST_IDX_TEMPO: u32 = 0; pub const BLAST_IDX_VOICE: u32 = 1; pub const BLAST_IDX_PROCESS: u32 = 2;
+pub const BLAST_IDX_GROUP: u32 = 3;
+
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct blast_tempo_repr { pub idx: u64, pub owned: u32, pub mode: u32, pub unit: u32, pub interval: f32 }
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct blast_command {
+    pub kind: u32, pub idx_kind: u32, pub idx: u64, pub val: f32, pub reserved: u32,
+    pub tempo: blast_tempo_repr,
+    pub n_members: u32, pub reserved2: u32,
+    pub member_voice: *const u64, pub member_update_tempo: *const u8, pub member_n_procs: *const u32,
+    pub member_proc_ids: *const u64,
+    pub period: u64, pub n_steps: u32, pub reserved3: u32, pub steps: *const f32, pub chance: *const f32,
+    pub rng_s0: u64, pub rng_s1: u64,
+}
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct blast_timed_command { pub frame: u64, pub cmd: blast_command }
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct blast_voice_state {
+    pub active: u32, pub position: f32, pub velocity: f32, pub gain: f32, pub end: u64, pub channels: u32,
+    pub tempo_current: u32, pub tempo_active: u32, pub n_processes: u32,
+}
+
+extern "C" {
+    pub fn blast_conductor_create(ctx: *mut blast_ctx, out_channels: u32, sample_rate: u32, tracks: *const blast_track,
+                                  n_tracks: u32, out: *mut *mut blast_conductor) -> c_int;
+    pub fn blast_conductor_destroy(ctx: *mut blast_ctx, c: *mut blast_conductor);
+    pub fn blast_conductor_apply(ctx: *mut blast_ctx, c: *mut blast_conductor, cmd: *const blast_command) -> c_int;
+    pub fn blast_conductor_set_shard(c: *mut blast_conductor, rank: u32, world: u32) -> c_int;
+    pub fn blast_conductor_render_dev(ctx: *mut blast_ctx, c: *mut blast_conductor, frames: u64, d_partial_bus: *mut i32) -> c_int;
+    pub fn blast_conductor_coordinate(ctx: *mut blast_ctx, c: *mut blast_conductor, frames: u64, host_bus_out: *mut i16) -> c_int;
+    pub fn blast_conductor_render_timeline(ctx: *mut blast_ctx, c: *mut blast_conductor, events: *const blast_timed_command,
+                                           n_events: u32, total_frames: u64, host_bus_out: *mut i16) -> c_int;
+    pub fn blast_conductor_get_voice(c: *const blast_conductor, group: c_int, idx: u32, out: *mut blast_voice_state) -> c_int;
+    pub fn blast_conductor_set_voice(c: *mut blast_conductor, group: c_int, idx: u32, position: *const f32,
+                                     velocity: *const f32, gain: *const f32, active: *const c_int) -> c_int;
+    pub fn blast_conductor_clock(c: *const blast_conductor) -> u64;
+    pub fn blast_convert_interval(sample_rate: u32, unit: u32, interval: f32) -> f32;
+}
 
 extern "C" {
     pub fn blast_last_error() -> *const c_char;
