@@ -262,8 +262,7 @@ __device__ __forceinline__ float build_epoch(float p, const float vel, const uin
 // with Seq processes, whose retrigger events start new epochs: processes.rs:82-85), the per-tile records, and
 // writes the position after the render back into the voice.
 __global__ void voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t frames,
-                                    Seg* __restrict__ segs, uint32_t* __restrict__ nsegs,
-                                    TileRec* __restrict__ recs, uint32_t n_tiles, uint32_t* __restrict__ err,
+                                    Seg* __restrict__ segs, uint32_t* __restrict__ nsegs, uint32_t* __restrict__ err,
                                     const uint32_t* __restrict__ events, const uint32_t* __restrict__ nevents) {
     uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x;
     if (vi >= n_voices) return;
@@ -315,22 +314,37 @@ __global__ void voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_vo
     nsegs[vi] = n;
     voices[vi].pos = p;
 
-    // per-tile records, layout [tile][voice] so that K4's staging loads are coalesced
-    uint32_t j = 0;
-    for (uint32_t t = 0; t < n_tiles; ++t) {
-        const uint32_t st = t * (uint32_t)kFT * v.S;
-        while (j + 1 < n && sg[j + 1].step0 <= st) ++j;
-        const Seg g = sg[j];
-        const uint32_t next = (j + 1 < n) ? sg[j + 1].step0 : 0xFFFFFFFFu;
-        uint32_t left = next - st;
-        if (left > 0xFFFFFFu) left = 0xFFFFFFu;
-        TileRec r;
-        r.p0 = seg_pos(g, st, v.adv);
-        r.d = g.d;
-        r.scale = g.scale;
-        r.meta = left | (j << 24);
-        recs[(size_t)t * n_voices + vi] = r;
+}
+
+// K3b: one thread per (tile, voice): the state of the voice at the first step of the tile, found by bisection in the
+// voice's segment list.  Layout [tile][voice] so that K4's staging loads are coalesced.  (As a loop at the end of
+// K3 this was 131 us of serial work for C2's 1,024 voices x 352 tiles: 18 % of the whole mix.)
+__global__ void voice_tile_records(const VoiceDev* __restrict__ voices, uint32_t n_voices, const Seg* __restrict__ segs,
+                                   const uint32_t* __restrict__ nsegs, TileRec* __restrict__ recs, uint32_t n_tiles) {
+    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned long long)n_tiles * n_voices) return;
+    const uint32_t t = (uint32_t)(idx / n_voices), vi = (uint32_t)(idx - (unsigned long long)t * n_voices);
+    const uint32_t active = voices[vi].active, S = voices[vi].S, adv = voices[vi].adv;
+    if (!active) return;                                        // K4 never reads the records of an inactive voice
+    const Seg* __restrict__ sg = segs + (size_t)vi * kMaxSeg;
+    const uint32_t n = nsegs[vi];
+    const uint32_t st = t * (uint32_t)kFT * S;
+    uint32_t lo = 0, hi = n;                                    // last j with sg[j].step0 <= st (sg[0].step0 == 0)
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sg[mid].step0 <= st) lo = mid; else hi = mid;
     }
+    const uint32_t j = lo;
+    const Seg g = sg[j];
+    const uint32_t next = (j + 1 < n) ? sg[j + 1].step0 : 0xFFFFFFFFu;
+    uint32_t left = next - st;
+    if (left > 0xFFFFFFu) left = 0xFFFFFFu;
+    TileRec r;
+    r.p0 = seg_pos(g, st, adv);
+    r.d = g.d;
+    r.scale = g.scale;
+    r.meta = left | (j << 24);
+    recs[idx] = r;
 }
 
 // ---------------------------------------------------------------- K4
@@ -1230,9 +1244,11 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         ctx->launches += 1;
     }
     voice_position_scan<<<(n_voices + 31) / 32, 32, 0, ctx->stream>>>(rb.d_voices, n_voices, (uint32_t)frames, rb.d_segs, rb.d_nsegs,
-                                                                       rb.d_recs, n_tiles, rb.d_err, rb.d_events, rb.d_nevents);
+                                                                       rb.d_err, rb.d_events, rb.d_nevents);
+    voice_tile_records<<<(unsigned)((need + 255) / 256), 256, 0, ctx->stream>>>(rb.d_voices, n_voices, rb.d_segs, rb.d_nsegs,
+                                                                                rb.d_recs, n_tiles);
     BLAST_CUDA_TRY(cudaGetLastError());
-    ctx->launches += 1;
+    ctx->launches += 2;
 
     // voice groups: enough CTAs to fill the GPU a few times over, groups of >= 64 voices
     uint32_t groups = 1;

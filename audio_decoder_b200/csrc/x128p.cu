@@ -104,15 +104,60 @@ __global__ void x128p_jump_states(const uint4* __restrict__ mats, int n_mats, ui
     out[s] = U128{lo, hi};
 }
 
+// Sub-stream start states: sub k of stream s starts at J^k * state_s, J = T^(draws / split).  mats = J^(2^b).
+__global__ void x128p_split_states(const uint4* __restrict__ mats, int n_mats, const U128* __restrict__ states,
+                                   uint64_t n_streams, uint32_t split, U128* __restrict__ out) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_streams * split) return;
+    const uint64_t s = t / split;
+    const uint32_t k = (uint32_t)(t - s * split);
+    uint64_t lo = states[s].lo, hi = states[s].hi;
+    for (int b = 0; b < n_mats; ++b) {
+        if (!((k >> b) & 1)) continue;
+        const uint4* __restrict__ m = mats + (size_t)b * 128;
+        uint64_t alo = 0, ahi = 0;
+#pragma unroll 4
+        for (int i = 0; i < 64; ++i) {
+            const uint4 c0 = __ldg(m + i), c1 = __ldg(m + 64 + i);
+            const uint64_t m0 = 0 - ((lo >> i) & 1), m1 = 0 - ((hi >> i) & 1);
+            alo ^= (((uint64_t)c0.y << 32) | c0.x) & m0;
+            ahi ^= (((uint64_t)c0.w << 32) | c0.z) & m0;
+            alo ^= (((uint64_t)c1.y << 32) | c1.x) & m1;
+            ahi ^= (((uint64_t)c1.w << 32) | c1.z) & m1;
+        }
+        lo = alo;
+        hi = ahi;
+    }
+    out[t] = U128{lo, hi};
+}
+
+// after the fill: stream state = state of its last sub-stream; checks = xor / wrapping sum over the sub-streams
+__global__ void x128p_merge_split(const U128* __restrict__ sub_states, const uint64_t* __restrict__ sub_checks,
+                                  uint64_t n_streams, uint32_t split, U128* __restrict__ states,
+                                  uint64_t* __restrict__ checks) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    states[s] = sub_states[s * split + split - 1];
+    if (checks) {
+        uint64_t xr = 0, sr = 0, xg = 0, sg = 0;
+        for (uint32_t k = 0; k < split; ++k) {
+            const uint64_t* c = sub_checks + (s * split + k) * 4;
+            xr ^= c[0]; sr += c[1]; xg ^= c[2]; sg += c[3];
+        }
+        uint64_t* o = checks + s * 4;
+        o[0] = xr; o[1] = sr; o[2] = xg; o[3] = sg;
+    }
+}
+
 constexpr int kWarps = 8;
-constexpr int kRound = 16;                 // draws staged per stream per round (one 128-byte row)
+constexpr int kRound = 32;                 // draws staged per stream per round (one 256-byte row)
 constexpr int kPitch = kRound + 1;         // u64 row pitch: conflict-free column writes
 
 template <bool kRaw, bool kRanged, bool kChecks>
 __global__ void __launch_bounds__(kWarps * 32)
 x128p_streams(U128* __restrict__ states, uint64_t n_streams, uint64_t draws, int64_t lo, uint64_t range,
               uint64_t* __restrict__ raw, int64_t* __restrict__ ranged, uint64_t* __restrict__ checks) {
-    extern __shared__ uint64_t tile_all[];
+    extern __shared__ __align__(16) uint64_t tile_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t* tile_raw = tile_all + (size_t)warp * 32 * kPitch * ((kRaw ? 1 : 0) + (kRanged ? 1 : 0));
     uint64_t* tile_rng = tile_raw + (kRaw ? 32 * kPitch : 0);
@@ -124,6 +169,8 @@ x128p_streams(U128* __restrict__ states, uint64_t n_streams, uint64_t draws, int
     if (live) { const U128 st = states[stream]; s0 = st.lo; s1 = st.hi; }
     uint64_t xr = 0, sr = 0, xg = 0, sg = 0;
     const uint32_t rows = (uint32_t)min((uint64_t)32, n_streams - stream0);
+    // 16-byte stores need 16-byte aligned rows in memory: row start = (stream * draws + j0) * 8
+    const bool vec_ok = (draws % 2 == 0) && (((uintptr_t)raw | (uintptr_t)ranged) & 15) == 0;
 
     for (uint64_t j0 = 0; j0 < draws; j0 += kRound) {
         const int nj = (int)min((uint64_t)kRound, draws - j0);
@@ -137,15 +184,33 @@ x128p_streams(U128* __restrict__ states, uint64_t n_streams, uint64_t draws, int
         }
         if (kRaw || kRanged) {
             __syncwarp();
-            // row `q` of the tile = nj consecutive draws of stream stream0+q: 128 contiguous bytes in
-            // memory; each store instruction writes two rows (lanes 0-15 / 16-31)
-            const uint32_t jl = lane & 15;
-            for (uint32_t q2 = 0; q2 < rows; q2 += 2) {
-                const uint32_t q = q2 + (lane >> 4);
-                if (q < rows && (int)jl < nj) {
-                    const size_t base = (size_t)(stream0 + q) * draws + j0;
-                    if (kRaw) raw[base + jl] = tile_raw[q * kPitch + jl];
-                    if (kRanged) ranged[base + jl] = (int64_t)tile_rng[q * kPitch + jl];
+            // row `q` of the tile = nj consecutive draws of stream stream0+q: 256 contiguous bytes in memory
+            if (vec_ok && nj == kRound) {
+                // 16 lanes x 16 bytes per row, two rows per store instruction
+                const uint32_t jl = (lane & 15) * 2;
+                for (uint32_t q2 = 0; q2 < rows; q2 += 2) {
+                    const uint32_t q = q2 + (lane >> 4);
+                    if (q < rows) {
+                        const size_t base = (size_t)(stream0 + q) * draws + j0 + jl;
+                        if (kRaw) {
+                            const uint64_t a = tile_raw[q * kPitch + jl], b = tile_raw[q * kPitch + jl + 1];
+                            blast::st_stream(reinterpret_cast<uint4*>(raw + base),
+                                             make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32)));
+                        }
+                        if (kRanged) {
+                            const uint64_t a = tile_rng[q * kPitch + jl], b = tile_rng[q * kPitch + jl + 1];
+                            blast::st_stream(reinterpret_cast<uint4*>(ranged + base),
+                                             make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32)));
+                        }
+                    }
+                }
+            } else {
+                for (uint32_t q = 0; q < rows; ++q) {
+                    if (lane < nj) {
+                        const size_t base = (size_t)(stream0 + q) * draws + j0;
+                        if (kRaw) raw[base + lane] = tile_raw[q * kPitch + lane];
+                        if (kRanged) ranged[base + lane] = (int64_t)tile_rng[q * kPitch + lane];
+                    }
                 }
             }
             __syncwarp();
@@ -219,24 +284,19 @@ int blast_x128p_jump_dev(blast_ctx* ctx, const blast_x128p* base, uint64_t strid
     return BLAST_OK;
 }
 
-int blast_x128p_fill_dev(blast_ctx* ctx, blast_x128p* d_states, uint64_t n_streams, uint64_t draws_per_stream,
-                         int64_t lower, int64_t upper, uint64_t* d_raw, int64_t* d_ranged, uint64_t* d_checks) {
-    if (int rc = blast::bind(ctx)) return rc;
-    BLAST_REQUIRE(d_states || n_streams == 0, BLAST_ERR_ARG, "blast_x128p_fill_dev: null states");
-    if (n_streams == 0 || draws_per_stream == 0) return BLAST_OK;
-    // blast_rand.rs:52-55: range = |upper - lower|
-    const uint64_t range = upper > lower ? (uint64_t)upper - (uint64_t)lower : (uint64_t)lower - (uint64_t)upper;
+namespace {
+
+int launch_fill(blast_ctx* ctx, U128* st, uint64_t n_streams, uint64_t draws, int64_t lower, uint64_t range, uint64_t* d_raw,
+                int64_t* d_ranged, uint64_t* d_checks) {
     const unsigned blocks = (unsigned)((n_streams + kWarps * 32 - 1) / (kWarps * 32));
     const int sel = (d_raw ? 1 : 0) | (d_ranged ? 2 : 0) | (d_checks ? 4 : 0);
     const size_t smem = (size_t)kWarps * 32 * kPitch * sizeof(uint64_t) * ((d_raw ? 1 : 0) + (d_ranged ? 1 : 0));
-    U128* st = reinterpret_cast<U128*>(d_states);
 #define BLAST_FILL(R, G, K)                                                                                  \
     do {                                                                                                     \
         auto kern = x128p_streams<R, G, K>;                                                                  \
         if (smem > 48 * 1024)                                                                                \
             BLAST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kern<<<blocks, kWarps * 32, smem, ctx->stream>>>(st, n_streams, draws_per_stream, lower, range, d_raw,  \
-                                                         d_ranged, d_checks);                                \
+        kern<<<blocks, kWarps * 32, smem, ctx->stream>>>(st, n_streams, draws, lower, range, d_raw, d_ranged, d_checks); \
     } while (0)
     switch (sel) {
         case 0: BLAST_FILL(false, false, false); break;     // advance only
@@ -249,6 +309,65 @@ int blast_x128p_fill_dev(blast_ctx* ctx, blast_x128p* d_states, uint64_t n_strea
         default: BLAST_FILL(true, true, true); break;
     }
 #undef BLAST_FILL
+    BLAST_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    return BLAST_OK;
+}
+
+}  // namespace
+
+int blast_x128p_fill_dev(blast_ctx* ctx, blast_x128p* d_states, uint64_t n_streams, uint64_t draws_per_stream,
+                         int64_t lower, int64_t upper, uint64_t* d_raw, int64_t* d_ranged, uint64_t* d_checks) {
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_REQUIRE(d_states || n_streams == 0, BLAST_ERR_ARG, "blast_x128p_fill_dev: null states");
+    if (n_streams == 0 || draws_per_stream == 0) return BLAST_OK;
+    // blast_rand.rs:52-55: range = |upper - lower|
+    const uint64_t range = upper > lower ? (uint64_t)upper - (uint64_t)lower : (uint64_t)lower - (uint64_t)upper;
+    U128* st = reinterpret_cast<U128*>(d_states);
+
+    // One thread per stream leaves most of the machine idle when there are few, long streams (C4: 65,536 streams are
+    // 22 % of the resident threads, each a serial chain of 65,536 draws).  The generator is GF(2)-linear, so a stream
+    // can be cut into `split` sub-streams that start at J^k * state (J = T^(draws/split)); draw j of sub-stream k is
+    // draw k*draws/split + j of the stream and lands at the same address.
+    uint32_t split = 1;
+    const uint64_t want_threads = (uint64_t)ctx->sm_count * 1536;
+    while (split < 64 && n_streams * split < want_threads && draws_per_stream % (2ull * split) == 0 &&
+           draws_per_stream / (2ull * split) >= 1024)
+        split *= 2;
+    if (split == 1) return launch_fill(ctx, st, n_streams, draws_per_stream, lower, range, d_raw, d_ranged, d_checks);
+
+    const uint64_t sub = draws_per_stream / split, n_sub = n_streams * split;
+    int n_mats = 0;
+    while ((1u << n_mats) < split) ++n_mats;
+    const size_t mats_b = (size_t)n_mats * 128 * sizeof(uint4), st_b = (n_sub * sizeof(U128) + 255) & ~255ull;
+    uint8_t* sc = static_cast<uint8_t*>(blast::scratch(ctx, 5, mats_b + st_b + (d_checks ? n_sub * 32 : 0)));
+    if (!sc) return BLAST_ERR_CUDA;
+    uint4* d_mats = reinterpret_cast<uint4*>(sc);
+    U128* d_sub = reinterpret_cast<U128*>(sc + mats_b);
+    uint64_t* d_subchecks = d_checks ? reinterpret_cast<uint64_t*>(sc + mats_b + st_b) : nullptr;
+    // J^(2^b): cached per (sub, n_mats) — squaring 128x128 bit matrices costs about a millisecond on the host
+    static uint64_t cached_sub = 0;
+    static int cached_mats = 0;
+    static void* cached_ptr = nullptr;
+    static std::vector<uint4> h;
+    if (cached_sub != sub || cached_mats != n_mats || cached_ptr != d_mats) {
+        BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));             // `h` may still be in flight
+        h.assign((size_t)n_mats * 128, make_uint4(0, 0, 0, 0));
+        Mat j = mat_pow(transition(), sub);
+        for (int b = 0; b < n_mats; ++b) {
+            for (int i = 0; i < 128; ++i)
+                h[(size_t)b * 128 + i] = make_uint4((uint32_t)j[i].lo, (uint32_t)(j[i].lo >> 32), (uint32_t)j[i].hi,
+                                                    (uint32_t)(j[i].hi >> 32));
+            if (b + 1 < n_mats) j = mat_mul(j, j);
+        }
+        BLAST_CUDA_TRY(cudaMemcpyAsync(d_mats, h.data(), mats_b, cudaMemcpyHostToDevice, ctx->stream));
+        cached_sub = sub; cached_mats = n_mats; cached_ptr = d_mats;
+    }
+    x128p_split_states<<<(unsigned)((n_sub + 127) / 128), 128, 0, ctx->stream>>>(d_mats, n_mats, st, n_streams, split, d_sub);
+    BLAST_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    if (int rc = launch_fill(ctx, d_sub, n_sub, sub, lower, range, d_raw, d_ranged, d_subchecks)) return rc;
+    x128p_merge_split<<<(unsigned)((n_streams + 127) / 128), 128, 0, ctx->stream>>>(d_sub, d_subchecks, n_streams, split, st, d_checks);
     BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
     return BLAST_OK;
