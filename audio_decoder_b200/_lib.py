@@ -79,6 +79,10 @@ class VoiceState(C.Structure):
                 ("tempo_active", C.c_uint32), ("n_processes", C.c_uint32)]
 
 
+class MpegShardAgg(C.Structure):
+    _fields_ = [("exit_state", C.c_uint32 * 4), ("count", C.c_uint64 * 4)]
+
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
 _vp, _u64, _u32, _sz = C.c_void_p, C.c_uint64, C.c_uint32, C.c_size_t
 SIGNATURES = {
@@ -108,6 +112,7 @@ SIGNATURES = {
     "blast_aiff_probe": (C.c_int, [_vp, _sz, C.POINTER(PcmDesc)]),
     "blast_pcm_out_len": (_sz, [C.POINTER(PcmDesc)]),
     "blast_file_name": (C.c_int, [C.c_char_p, C.c_char_p, _sz]),
+    "blast_asset_consensus": (C.c_int, [C.POINTER(PcmDesc), _u32, C.POINTER(_u32), C.POINTER(_u32)]),
     "blast_pcm_plan_create": (C.c_int, [_vp, C.POINTER(PcmJob), _u32, C.POINTER(_vp)]),
     "blast_pcm_plan_run_dev": (C.c_int, [_vp, _vp]),
     "blast_pcm_plan_destroy": (None, [_vp, _vp]),
@@ -133,6 +138,12 @@ SIGNATURES = {
     "blast_mpeg_scan_dev": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _u64, C.POINTER(_u64)]),
     "blast_mpeg_index_dev": (C.c_int, [_vp, _vp, _u64, C.c_int, _vp, _u64, C.POINTER(_u64), C.POINTER(_u32),
                                        C.POINTER(_u64)]),
+    "blast_mpeg_hist_dev": (C.c_int, [_vp, _vp, _u64, _vp]),
+    "blast_mpeg_pick_ref_dev": (C.c_int, [_vp, _vp, C.POINTER(_u32)]),
+    "blast_mpeg_first_pos_dev": (C.c_int, [_vp, _vp, _vp, _u64, _u32, _vp]),
+    "blast_mpeg_classify_dev": (C.c_int, [_vp, _vp, _vp, _u64, _u32, _vp, _u64, _vp, _u64, C.POINTER(_u64)]),
+    "blast_mpeg_shard_walk_dev": (C.c_int, [_vp, _vp, _u64, _u64, C.POINTER(MpegShardAgg)]),
+    "blast_mpeg_shard_emit_dev": (C.c_int, [_vp, _vp, _u64, _u64, _u32, _u64, _vp, _vp, _u64, C.POINTER(_u64)]),
     "blast_mpeg_gather_dev": (C.c_int, [_vp, _vp, _u64, _vp, _u64, _vp, _u64, C.POINTER(_u64)]),
     "blast_mpeg_parse": (C.c_int, [_vp, _vp, _u64, C.c_int, _vp, _u64, C.POINTER(_u64), C.POINTER(_u32),
                                    C.POINTER(_u64), _vp, _u64, C.POINTER(_u64)]),

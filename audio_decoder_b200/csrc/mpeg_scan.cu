@@ -65,7 +65,9 @@ constexpr size_t kScanSmem = (size_t)kWalkers * kStages * kStageBytes;
 constexpr uint32_t kIdentityMap = 0xE4;                     // s -> s for s = 0..3, two bits each
 struct ScanCtl {
     unsigned long long next_tile; // span counter of the walk kernel
-    unsigned long long total;     // candidates found
+    unsigned long long total;     // candidates found (under the entry state of the last chain)
+    unsigned long long count[4];  // candidates under entry state s (sharded scans: the range's aggregate)
+    uint32_t exit_state[4];       // state after the last byte under entry state s
     uint32_t panic;               // the reference indexes out of bounds (last byte 0xFF reached with state 0)
     uint32_t pad;
 };
@@ -149,7 +151,7 @@ __device__ __noinline__ SpanOut walk_span(const int MODE, const uint8_t* __restr
                                           uint16_t* __restrict__ s_off, uint32_t* __restrict__ s_hdr,
                                           unsigned long long* __restrict__ out_pos, uint32_t* __restrict__ out_hdr,
                                           const unsigned long long cap, const unsigned long long gbase,
-                                          ScanCtl* __restrict__ ctl) {
+                                          const unsigned long long pos_offset, ScanCtl* __restrict__ ctl) {
     SpanOut o;
     o.total = 0;
     o.sens = false;
@@ -309,7 +311,7 @@ __device__ __noinline__ SpanOut walk_span(const int MODE, const uint8_t* __restr
                     } else {
                         const unsigned long long gi = gbase + k;
                         if (gi < cap) {
-                            out_pos[gi] = span0 + rel + (unsigned long long)i;
+                            out_pos[gi] = pos_offset + span0 + rel + (unsigned long long)i;
                             out_hdr[gi] = h;
                         }
                     }
@@ -330,10 +332,10 @@ __device__ __forceinline__ SpanOut walk_tile(const int MODE, const uint8_t* __re
                                              const uint32_t ring, uint16_t* __restrict__ s_off, uint32_t* __restrict__ s_hdr,
                                              unsigned long long* __restrict__ out_pos, uint32_t* __restrict__ out_hdr,
                                              const unsigned long long cap, const unsigned long long gbase,
-                                             ScanCtl* __restrict__ ctl) {
+                                             const unsigned long long pos_offset, ScanCtl* __restrict__ ctl) {
     if (span0 + (unsigned long long)kSpanBytes + 80 > n)
-        return walk_span<true>(MODE, bytes, n, span0, entry, lane, ring, s_off, s_hdr, out_pos, out_hdr, cap, gbase, ctl);
-    return walk_span<false>(MODE, bytes, n, span0, entry, lane, ring, s_off, s_hdr, out_pos, out_hdr, cap, gbase, ctl);
+        return walk_span<true>(MODE, bytes, n, span0, entry, lane, ring, s_off, s_hdr, out_pos, out_hdr, cap, gbase, pos_offset, ctl);
+    return walk_span<false>(MODE, bytes, n, span0, entry, lane, ring, s_off, s_hdr, out_pos, out_hdr, cap, gbase, pos_offset, ctl);
 }
 
 // ---------------------------------------------------------------- K7a: walk
@@ -362,13 +364,13 @@ mpeg_walk(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long
         const unsigned long long span0 = span * (unsigned long long)kSpanBytes;
         uint16_t* g_off = t_off + span * (unsigned long long)kCandCap;
         uint32_t* g_hdr = t_hdr + span * (unsigned long long)kCandCap;
-        const SpanOut w0 = walk_tile(kModeCompact, bytes, n, span0, 0u, lane, ring, g_off, g_hdr, nullptr, nullptr, 0ull, 0ull, ctl);
+        const SpanOut w0 = walk_tile(kModeCompact, bytes, n, span0, 0u, lane, ring, g_off, g_hdr, nullptr, nullptr, 0ull, 0ull, 0ull, ctl);
         uint32_t amap = w0.exit_state * 0x55u;
         uint32_t c0 = w0.total, c1 = w0.total, c2 = w0.total, c3 = w0.total;
         if (w0.sens) {                                   // rare: the span's first 3 bytes hold a raw sync
-            const SpanOut w1 = walk_tile(kModeCount, bytes, n, span0, 1u, lane, ring, g_off, g_hdr, nullptr, nullptr, 0ull, 0ull, ctl);
-            const SpanOut w2 = walk_tile(kModeCount, bytes, n, span0, 2u, lane, ring, g_off, g_hdr, nullptr, nullptr, 0ull, 0ull, ctl);
-            const SpanOut w3 = walk_tile(kModeCount, bytes, n, span0, 3u, lane, ring, g_off, g_hdr, nullptr, nullptr, 0ull, 0ull, ctl);
+            const SpanOut w1 = walk_tile(kModeCount, bytes, n, span0, 1u, lane, ring, g_off, g_hdr, nullptr, nullptr, 0ull, 0ull, 0ull, ctl);
+            const SpanOut w2 = walk_tile(kModeCount, bytes, n, span0, 2u, lane, ring, g_off, g_hdr, nullptr, nullptr, 0ull, 0ull, 0ull, ctl);
+            const SpanOut w3 = walk_tile(kModeCount, bytes, n, span0, 3u, lane, ring, g_off, g_hdr, nullptr, nullptr, 0ull, 0ull, 0ull, ctl);
             amap = w0.exit_state | (w1.exit_state << 2) | (w2.exit_state << 4) | (w3.exit_state << 6);
             c1 = w1.total; c2 = w2.total; c3 = w3.total;
         }
@@ -497,9 +499,10 @@ mpeg_span_fold(const SpanRec* __restrict__ recs, unsigned long long n_spans, Blo
 }
 
 // K7b-2: one warp chains the block aggregates, 32 at a time
-__global__ void mpeg_block_chain(BlockAgg* __restrict__ blocks, unsigned long long n_blocks, ScanCtl* __restrict__ ctl) {
+__global__ void mpeg_block_chain(BlockAgg* __restrict__ blocks, unsigned long long n_blocks, ScanCtl* __restrict__ ctl,
+                                 uint32_t entry) {
     const uint32_t lane = threadIdx.x;
-    uint32_t state = 0;
+    uint32_t state = entry;
     unsigned long long cnt = 0;
     for (unsigned long long b0 = 0; b0 < n_blocks; b0 += 32) {
         const unsigned long long b = b0 + lane;
@@ -526,7 +529,11 @@ __global__ void mpeg_block_chain(BlockAgg* __restrict__ blocks, unsigned long lo
         cnt += pick4(l0, l1, l2, l3, state);
         state = map_get(lmap, state);
     }
-    if (lane == 0) ctl->total = cnt;
+    if (lane == 0) {
+        ctl->total = cnt;
+        ctl->count[entry] = cnt;
+        ctl->exit_state[entry] = state;
+    }
 }
 
 // ---------------------------------------------------------------- K7c: compact
@@ -538,7 +545,7 @@ mpeg_compact(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned l
              const SpanRec* __restrict__ recs, const uint8_t* __restrict__ span_entry,
              const unsigned long long* __restrict__ span_base, const uint16_t* __restrict__ t_off,
              const uint32_t* __restrict__ t_hdr, unsigned long long* __restrict__ out_pos, uint32_t* __restrict__ out_hdr,
-             unsigned long long cap) {
+             unsigned long long cap, unsigned long long pos_offset) {
     extern __shared__ __align__(128) uint8_t smem_dyn[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t ring = smem_addr(smem_dyn) + warp * (uint32_t)(kStages * kStageBytes);
@@ -558,12 +565,12 @@ mpeg_compact(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned l
             for (uint32_t k = lane; k < count; k += 32) {
                 const unsigned long long gi = base + k;
                 if (gi < cap) {
-                    out_pos[gi] = span0 + g_off[k];
+                    out_pos[gi] = pos_offset + span0 + g_off[k];
                     out_hdr[gi] = g_hdr[k];
                 }
             }
         } else {
-            walk_tile(kModeEmit, bytes, n, span0, entry, lane, ring, nullptr, nullptr, out_pos, out_hdr, cap, base, ctl);
+            walk_tile(kModeEmit, bytes, n, span0, entry, lane, ring, nullptr, nullptr, out_pos, out_hdr, cap, base, pos_offset, ctl);
         }
     }
 }
@@ -650,8 +657,10 @@ __device__ __forceinline__ bool cand_valid(uint32_t h, const HdrInfo& ref, uint3
     return frame_len_bits(o, payload, skip);
 }
 
-__global__ void mpeg_first_index(const uint32_t* __restrict__ hdr, unsigned long long n, uint32_t ref_header,
-                                 unsigned long long* __restrict__ first) {
+// first file position of every valid header value (the duplicate-first quirk, mpeg.rs:39); positions rather than
+// candidate indices so that the table can be min-reduced across GPUs
+__global__ void mpeg_first_pos(const unsigned long long* __restrict__ pos, const uint32_t* __restrict__ hdr, unsigned long long n,
+                               uint32_t ref_header, unsigned long long* __restrict__ first) {
     HdrInfo ref;
     parse_header_bits(ref_header, ref);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -661,7 +670,8 @@ __global__ void mpeg_first_index(const uint32_t* __restrict__ hdr, unsigned long
         if (cand_valid(h, ref, pl, sk)) {
             // the dominant header is shared by most candidates: look before the atomic (the table only ever decreases)
             unsigned long long* slot = first + (h & (kHdrBins - 1));
-            if (*reinterpret_cast<volatile unsigned long long*>(slot) > i) atomicMin(slot, i);
+            const unsigned long long p = pos[i];
+            if (*reinterpret_cast<volatile unsigned long long*>(slot) > p) atomicMin(slot, p);
         }
     }
 }
@@ -690,8 +700,9 @@ mpeg_classify(const unsigned long long* __restrict__ pos, const uint32_t* __rest
             const uint32_t h = hdr[i];
             uint32_t pl, sk;
             if (cand_valid(h, ref, pl, sk)) {
-                cnt[k] = 1 + ((compat && first[h & (kHdrBins - 1)] == i) ? 1u : 0u);
-                if (pos[i] + sk + pl > file_len) atomicExch(err, 1u);       // mpeg.rs:95-97 indexes past EOF
+                const unsigned long long p = pos[i];
+                cnt[k] = 1 + ((compat && first[h & (kHdrBins - 1)] == p) ? 1u : 0u);
+                if (p + sk + pl > file_len) atomicExch(err, 1u);            // mpeg.rs:95-97 indexes past EOF
             }
         }
         mine += cnt[k];
@@ -789,50 +800,72 @@ struct DevFree {
     }
 };
 
-int run_scan(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, uint64_t* d_pos, uint32_t* d_hdr, uint64_t cap,
-             uint64_t* n_out) {
-    if (((uintptr_t)d_bytes & 15) != 0) return blast::set_error(BLAST_ERR_ARG, "mpeg scan: d_bytes must be 16-byte aligned");
-    *n_out = 0;
-    if (len == 0) return BLAST_OK;
-    const unsigned long long n_spans = (len + kSpanBytes - 1) / kSpanBytes;
-    // span records, per-span (entry, base) and the control block live in context scratch slot 0, the temp candidate
-    // lists in slot 1 (grow-only: no cudaMalloc / cudaFree on this path after the first call of a given size)
-    const size_t rec_b = (n_spans * sizeof(SpanRec) + 255) & ~255ull, base_b = (n_spans * 8 + 255) & ~255ull;
-    const size_t entry_b = (n_spans + 255) & ~255ull;
-    const unsigned long long n_blocks = (n_spans + kFoldBlock - 1) / kFoldBlock;
-    const size_t blk_b = (n_blocks * sizeof(BlockAgg) + 255) & ~255ull;
+struct ScanBufs {
+    unsigned long long n_spans = 0, n_blocks = 0;
+    SpanRec* recs = nullptr;
+    unsigned long long* span_base = nullptr;
+    uint8_t* span_entry = nullptr;
+    BlockAgg* blocks = nullptr;
+    ScanCtl* ctl = nullptr;
+    uint32_t* t_hdr = nullptr;
+    uint16_t* t_off = nullptr;
+    unsigned grid = 0;
+};
+
+// span records, per-span (entry, base), block aggregates and the control block live in context scratch slot 0, the
+// temp candidate lists in slot 1 (grow-only: no cudaMalloc / cudaFree on this path after the first call of a size)
+int scan_buffers(blast_ctx* ctx, uint64_t own_len, ScanBufs& sb) {
+    sb.n_spans = (own_len + kSpanBytes - 1) / kSpanBytes;
+    sb.n_blocks = (sb.n_spans + kFoldBlock - 1) / kFoldBlock;
+    const size_t rec_b = (sb.n_spans * sizeof(SpanRec) + 255) & ~255ull, base_b = (sb.n_spans * 8 + 255) & ~255ull;
+    const size_t entry_b = (sb.n_spans + 255) & ~255ull, blk_b = (sb.n_blocks * sizeof(BlockAgg) + 255) & ~255ull;
     uint8_t* s0 = static_cast<uint8_t*>(blast::scratch(ctx, 0, rec_b + base_b + entry_b + blk_b + 256));
     if (!s0) return BLAST_ERR_CUDA;
-    SpanRec* recs = reinterpret_cast<SpanRec*>(s0);
-    unsigned long long* span_base = reinterpret_cast<unsigned long long*>(s0 + rec_b);
-    uint8_t* span_entry = s0 + rec_b + base_b;
-    BlockAgg* blocks = reinterpret_cast<BlockAgg*>(s0 + rec_b + base_b + entry_b);
-    ScanCtl* ctl = reinterpret_cast<ScanCtl*>(s0 + rec_b + base_b + entry_b + blk_b);
-    const size_t hdr_b = (n_spans * kCandCap * sizeof(uint32_t) + 255) & ~255ull;
-    uint8_t* s1 = static_cast<uint8_t*>(blast::scratch(ctx, 1, hdr_b + n_spans * kCandCap * sizeof(uint16_t)));
+    sb.recs = reinterpret_cast<SpanRec*>(s0);
+    sb.span_base = reinterpret_cast<unsigned long long*>(s0 + rec_b);
+    sb.span_entry = s0 + rec_b + base_b;
+    sb.blocks = reinterpret_cast<BlockAgg*>(s0 + rec_b + base_b + entry_b);
+    sb.ctl = reinterpret_cast<ScanCtl*>(s0 + rec_b + base_b + entry_b + blk_b);
+    const size_t hdr_b = (sb.n_spans * kCandCap * sizeof(uint32_t) + 255) & ~255ull;
+    uint8_t* s1 = static_cast<uint8_t*>(blast::scratch(ctx, 1, hdr_b + sb.n_spans * kCandCap * sizeof(uint16_t)));
     if (!s1) return BLAST_ERR_CUDA;
-    uint32_t* t_hdr = reinterpret_cast<uint32_t*>(s1);
-    uint16_t* t_off = reinterpret_cast<uint16_t*>(s1 + hdr_b);
-    ScanCtl* h_ctl = static_cast<ScanCtl*>(blast::mailbox(ctx));
-    if (!h_ctl) return BLAST_ERR_CUDA;
-    BLAST_CUDA_TRY(cudaMemsetAsync(ctl, 0, sizeof(ScanCtl), ctx->stream));
+    sb.t_hdr = reinterpret_cast<uint32_t*>(s1);
+    sb.t_off = reinterpret_cast<uint16_t*>(s1 + hdr_b);
     static int per_sm = 0;
     if (per_sm == 0) {
         BLAST_CUDA_TRY(cudaFuncSetAttribute(mpeg_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
         BLAST_CUDA_TRY(cudaFuncSetAttribute(mpeg_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
         BLAST_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpeg_walk, kScanThreads, kScanSmem));
     }
-    const unsigned long long want = (n_spans + kWalkers - 1) / kWalkers;
-    const unsigned grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)ctx->sm_count * std::max(per_sm, 1));
-    mpeg_walk<<<grid, kScanThreads, kScanSmem, ctx->stream>>>(d_bytes, len, n_spans, ctl, recs, t_off, t_hdr);
-    mpeg_span_fold<false><<<(unsigned)n_blocks, kFoldThreads, 0, ctx->stream>>>(recs, n_spans, blocks, span_entry, span_base);
-    mpeg_block_chain<<<1, 32, 0, ctx->stream>>>(blocks, n_blocks, ctl);
-    mpeg_span_fold<true><<<(unsigned)n_blocks, kFoldThreads, 0, ctx->stream>>>(recs, n_spans, blocks, span_entry, span_base);
-    mpeg_compact<<<grid, kScanThreads, kScanSmem, ctx->stream>>>(d_bytes, len, n_spans, ctl, recs, span_entry, span_base, t_off, t_hdr,
-                                                                reinterpret_cast<unsigned long long*>(d_pos), d_hdr, cap);
+    const unsigned long long want = (sb.n_spans + kWalkers - 1) / kWalkers;
+    sb.grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)ctx->sm_count * std::max(per_sm, 1));
+    return BLAST_OK;
+}
+
+// phase 1: walk the own spans (`readable` >= own_len bytes may be read: a following range's first bytes are real data)
+// and fold the records into block aggregates
+int scan_walk(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t readable, const ScanBufs& sb) {
+    BLAST_CUDA_TRY(cudaMemsetAsync(sb.ctl, 0, sizeof(ScanCtl), ctx->stream));
+    mpeg_walk<<<sb.grid, kScanThreads, kScanSmem, ctx->stream>>>(d_bytes, readable, sb.n_spans, sb.ctl, sb.recs, sb.t_off, sb.t_hdr);
+    mpeg_span_fold<false><<<(unsigned)sb.n_blocks, kFoldThreads, 0, ctx->stream>>>(sb.recs, sb.n_spans, sb.blocks, sb.span_entry, sb.span_base);
     BLAST_CUDA_TRY(cudaGetLastError());
-    ctx->launches += 5;
-    BLAST_CUDA_TRY(cudaMemcpyAsync(h_ctl, ctl, sizeof(ScanCtl), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->launches += 2;
+    return BLAST_OK;
+}
+
+// phase 2: chain the blocks from a known entry state, give every span its (entry, base), move the lists out
+int scan_emit(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t readable, const ScanBufs& sb, uint32_t entry, uint64_t pos_offset,
+              uint64_t* d_pos, uint32_t* d_hdr, uint64_t cap, uint64_t* n_out) {
+    ScanCtl* h_ctl = static_cast<ScanCtl*>(blast::mailbox(ctx));
+    if (!h_ctl) return BLAST_ERR_CUDA;
+    mpeg_block_chain<<<1, 32, 0, ctx->stream>>>(sb.blocks, sb.n_blocks, sb.ctl, entry);
+    mpeg_span_fold<true><<<(unsigned)sb.n_blocks, kFoldThreads, 0, ctx->stream>>>(sb.recs, sb.n_spans, sb.blocks, sb.span_entry, sb.span_base);
+    mpeg_compact<<<sb.grid, kScanThreads, kScanSmem, ctx->stream>>>(d_bytes, readable, sb.n_spans, sb.ctl, sb.recs, sb.span_entry, sb.span_base,
+                                                                   sb.t_off, sb.t_hdr, reinterpret_cast<unsigned long long*>(d_pos), d_hdr,
+                                                                   cap, pos_offset);
+    BLAST_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 3;
+    BLAST_CUDA_TRY(cudaMemcpyAsync(h_ctl, sb.ctl, sizeof(ScanCtl), cudaMemcpyDeviceToHost, ctx->stream));
     BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     const ScanCtl h = *h_ctl;
     *n_out = h.total;
@@ -840,6 +873,17 @@ int run_scan(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, uint64_t* d_p
     if (h.total > cap) return blast::set_error(BLAST_ERR_CAPACITY, "mpeg scan: %llu candidates, capacity %llu",
                                                (unsigned long long)h.total, (unsigned long long)cap);
     return BLAST_OK;
+}
+
+int run_scan(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, uint64_t* d_pos, uint32_t* d_hdr, uint64_t cap,
+             uint64_t* n_out) {
+    if (((uintptr_t)d_bytes & 15) != 0) return blast::set_error(BLAST_ERR_ARG, "mpeg scan: d_bytes must be 16-byte aligned");
+    *n_out = 0;
+    if (len == 0) return BLAST_OK;
+    ScanBufs sb;
+    if (int rc = scan_buffers(ctx, len, sb)) return rc;
+    if (int rc = scan_walk(ctx, d_bytes, len, sb)) return rc;
+    return scan_emit(ctx, d_bytes, len, sb, 0u, 0ull, d_pos, d_hdr, cap, n_out);
 }
 
 }  // namespace
@@ -894,73 +938,159 @@ int blast_mpeg_index_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, i
     // per 2,048); an exact second pass only if the guess was too small.  All buffers are context scratch
     // (grow-only): a second call of the same size allocates nothing.
     uint64_t n_cand = 0, guess = len / 128 + 4096;
-    auto cand_buffers = [&](uint64_t count, unsigned long long** pos, uint32_t** hdr) -> bool {
-        *pos = static_cast<unsigned long long*>(blast::scratch(ctx, 2, count * 8));
+    auto cand_buffers = [&](uint64_t count, uint64_t** pos, uint32_t** hdr) -> bool {
+        *pos = static_cast<uint64_t*>(blast::scratch(ctx, 2, count * 8));
         *hdr = static_cast<uint32_t*>(blast::scratch(ctx, 3, count * 4));
         return *pos && *hdr;
     };
-    unsigned long long* d_pos = nullptr;
+    uint64_t* d_pos = nullptr;
     uint32_t* d_hdr = nullptr;
     if (!cand_buffers(guess, &d_pos, &d_hdr)) return BLAST_ERR_CUDA;
-    int rc = run_scan(ctx, d_bytes, len, reinterpret_cast<uint64_t*>(d_pos), d_hdr, guess, &n_cand);
+    int rc = run_scan(ctx, d_bytes, len, d_pos, d_hdr, guess, &n_cand);
     if (rc == BLAST_ERR_CAPACITY) {
         if (!cand_buffers(n_cand, &d_pos, &d_hdr)) return BLAST_ERR_CUDA;
         uint64_t n2 = 0;
-        rc = run_scan(ctx, d_bytes, len, reinterpret_cast<uint64_t*>(d_pos), d_hdr, n_cand, &n2);
+        rc = run_scan(ctx, d_bytes, len, d_pos, d_hdr, n_cand, &n2);
     }
     if (rc != BLAST_OK) return rc;
     if (n_candidates_out) *n_candidates_out = n_cand;
     if (n_cand == 0) return blast::set_error(BLAST_ERR_REF_PANIC, "no sync candidates: the reference indexes an empty list (mpeg.rs:64)");
 
-    const unsigned long long n_blocks = (n_cand + kClsBlock - 1) / kClsBlock;
-    const size_t hist_b = kHdrBins * sizeof(uint32_t), first_b = (size_t)kHdrBins * 8, bc_b = (n_blocks * 8 + 255) & ~255ull;
-    uint8_t* s4 = static_cast<uint8_t*>(blast::scratch(ctx, 4, hist_b + first_b + 2 * bc_b + 256));
+    const size_t hist_b = kHdrBins * sizeof(uint32_t), first_b = (size_t)kHdrBins * 8;
+    uint8_t* s4 = static_cast<uint8_t*>(blast::scratch(ctx, 4, hist_b + first_b));
     if (!s4) return BLAST_ERR_CUDA;
     uint32_t* d_hist = reinterpret_cast<uint32_t*>(s4);
-    unsigned long long* d_first = reinterpret_cast<unsigned long long*>(s4 + hist_b);
-    unsigned long long* d_bc = reinterpret_cast<unsigned long long*>(s4 + hist_b + first_b);
-    unsigned long long* d_bb = reinterpret_cast<unsigned long long*>(s4 + hist_b + first_b + bc_b);
-    unsigned long long* d_best = reinterpret_cast<unsigned long long*>(s4 + hist_b + first_b + 2 * bc_b);
-    unsigned long long* d_total = d_best + 1;
-    uint32_t* d_err = reinterpret_cast<uint32_t*>(d_best + 2);
-    unsigned long long* h_box = static_cast<unsigned long long*>(blast::mailbox(ctx));
-    if (!h_box) return BLAST_ERR_CUDA;
-    h_box += 64;                                          // the first 512 bytes of the mailbox belong to run_scan
+    uint64_t* d_first = reinterpret_cast<uint64_t*>(s4 + hist_b);
     BLAST_CUDA_TRY(cudaMemsetAsync(d_hist, 0, hist_b, ctx->stream));
-    BLAST_CUDA_TRY(cudaMemsetAsync(d_best, 0, 24, ctx->stream));
-    const unsigned g = (unsigned)std::min<unsigned long long>((n_cand + 255) / 256, (unsigned long long)ctx->sm_count * 16);
-    mpeg_hist<<<g, 256, 0, ctx->stream>>>(d_hdr, n_cand, d_hist);
-    mpeg_pick_ref<<<kHdrBins / 256, 256, 0, ctx->stream>>>(d_hist, d_best);
-    BLAST_CUDA_TRY(cudaGetLastError());
-    ctx->launches += 2;
-    BLAST_CUDA_TRY(cudaMemcpyAsync(h_box, d_best, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    const unsigned long long best = h_box[0];
-    if (best == 0) return blast::set_error(BLAST_ERR_REF_PANIC, "no parsable header: the reference indexes past its candidate list (mpeg.rs:64)");
-    const uint32_t ref_header = 0xFFE00000u | (kHdrBins - 1 - (uint32_t)(best & (kHdrBins - 1)));
+    if ((rc = blast_mpeg_hist_dev(ctx, d_hdr, n_cand, d_hist)) != BLAST_OK) return rc;
+    uint32_t ref_header = 0;
+    if ((rc = blast_mpeg_pick_ref_dev(ctx, d_hist, &ref_header)) != BLAST_OK) return rc;
     if (ref_header_out) *ref_header_out = ref_header;
     if (reference_compat) {
         BLAST_CUDA_TRY(cudaMemsetAsync(d_first, 0xFF, first_b, ctx->stream));
-        mpeg_first_index<<<g, 256, 0, ctx->stream>>>(d_hdr, n_cand, ref_header, d_first);
-        ctx->launches += 1;
+        if ((rc = blast_mpeg_first_pos_dev(ctx, d_pos, d_hdr, n_cand, ref_header, d_first)) != BLAST_OK) return rc;
     }
-    mpeg_classify<<<(unsigned)n_blocks, kClsThreads, 0, ctx->stream>>>(d_pos, d_hdr, n_cand, ref_header, d_first, reference_compat,
-                                                                     len, d_bc, nullptr, 0, nullptr, 0, d_err);
+    return blast_mpeg_classify_dev(ctx, d_pos, d_hdr, n_cand, ref_header, reference_compat ? d_first : nullptr, len, d_offsets_out, cap,
+                                   n_offsets_out);
+}
+
+// ---- sharded scan (SURVEY §8 e): one contiguous byte range per GPU, one small exchange between the two phases
+int blast_mpeg_shard_walk_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t own_len, uint64_t halo_len,
+                              blast_mpeg_shard_agg* agg_out) {
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_REQUIRE(agg_out && (d_bytes || own_len == 0), BLAST_ERR_ARG, "blast_mpeg_shard_walk_dev: null argument");
+    if (((uintptr_t)d_bytes & 15) != 0) return blast::set_error(BLAST_ERR_ARG, "mpeg scan: d_bytes must be 16-byte aligned");
+    if (halo_len != 0 && (own_len % kSpanBytes != 0 || halo_len < 16))
+        return blast::set_error(BLAST_ERR_ARG, "a range that is followed by another one must be a multiple of %d bytes and carry >= 16 halo bytes", kSpanBytes);
+    for (int s = 0; s < 4; ++s) { agg_out->exit_state[s] = (uint32_t)s; agg_out->count[s] = 0; }
+    if (own_len == 0) return BLAST_OK;
+    ScanBufs sb;
+    if (int rc = scan_buffers(ctx, own_len, sb)) return rc;
+    if (int rc = scan_walk(ctx, d_bytes, own_len + halo_len, sb)) return rc;
+    for (uint32_t s = 0; s < 4; ++s) mpeg_block_chain<<<1, 32, 0, ctx->stream>>>(sb.blocks, sb.n_blocks, sb.ctl, s);
+    BLAST_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 4;
+    ScanCtl* h_ctl = static_cast<ScanCtl*>(blast::mailbox(ctx));
+    if (!h_ctl) return BLAST_ERR_CUDA;
+    BLAST_CUDA_TRY(cudaMemcpyAsync(h_ctl, sb.ctl, sizeof(ScanCtl), cudaMemcpyDeviceToHost, ctx->stream));
+    BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < 4; ++s) { agg_out->exit_state[s] = h_ctl->exit_state[s]; agg_out->count[s] = h_ctl->count[s]; }
+    return BLAST_OK;
+}
+
+int blast_mpeg_shard_emit_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t own_len, uint64_t halo_len, uint32_t entry_state,
+                              uint64_t pos_offset, uint64_t* d_pos_out, uint32_t* d_hdr_out, uint64_t cap, uint64_t* n_out) {
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_REQUIRE(n_out && (d_bytes || own_len == 0) && ((d_pos_out && d_hdr_out) || cap == 0), BLAST_ERR_ARG,
+                  "blast_mpeg_shard_emit_dev: null argument");
+    BLAST_REQUIRE(entry_state < 4, BLAST_ERR_ARG, "blast_mpeg_shard_emit_dev: entry_state must be 0..3");
+    *n_out = 0;
+    if (own_len == 0) return BLAST_OK;
+    ScanBufs sb;
+    if (int rc = scan_buffers(ctx, own_len, sb)) return rc;           // same sizes as the walk: the same scratch, untouched
+    return scan_emit(ctx, d_bytes, own_len + halo_len, sb, entry_state, pos_offset, d_pos_out, d_hdr_out, cap, n_out);
+}
+
+// ---- the header vote and the frame filter as separate steps (blast_mpeg_index_dev = these four in sequence)
+int blast_mpeg_hist_dev(blast_ctx* ctx, const uint32_t* d_hdr, uint64_t n, uint32_t* d_hist) {
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_REQUIRE(d_hist && (d_hdr || n == 0), BLAST_ERR_ARG, "blast_mpeg_hist_dev: null argument");
+    if (n == 0) return BLAST_OK;
+    const unsigned g = (unsigned)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)ctx->sm_count * 16);
+    mpeg_hist<<<g, 256, 0, ctx->stream>>>(d_hdr, n, d_hist);
+    BLAST_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    return BLAST_OK;
+}
+
+int blast_mpeg_pick_ref_dev(blast_ctx* ctx, const uint32_t* d_hist, uint32_t* ref_header_out) {
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_REQUIRE(d_hist && ref_header_out, BLAST_ERR_ARG, "blast_mpeg_pick_ref_dev: null argument");
+    unsigned long long* d_best = static_cast<unsigned long long*>(blast::scratch(ctx, 6, 256));
+    unsigned long long* h_box = static_cast<unsigned long long*>(blast::mailbox(ctx));
+    if (!d_best || !h_box) return BLAST_ERR_CUDA;
+    h_box += 64;
+    BLAST_CUDA_TRY(cudaMemsetAsync(d_best, 0, 8, ctx->stream));
+    mpeg_pick_ref<<<kHdrBins / 256, 256, 0, ctx->stream>>>(d_hist, d_best);
+    BLAST_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    BLAST_CUDA_TRY(cudaMemcpyAsync(h_box, d_best, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h_box[0] == 0) return blast::set_error(BLAST_ERR_REF_PANIC, "no parsable header: the reference indexes past its candidate list (mpeg.rs:64)");
+    *ref_header_out = 0xFFE00000u | (kHdrBins - 1 - (uint32_t)(h_box[0] & (kHdrBins - 1)));
+    return BLAST_OK;
+}
+
+int blast_mpeg_first_pos_dev(blast_ctx* ctx, const uint64_t* d_pos, const uint32_t* d_hdr, uint64_t n, uint32_t ref_header,
+                             uint64_t* d_first) {
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_REQUIRE(d_first && ((d_pos && d_hdr) || n == 0), BLAST_ERR_ARG, "blast_mpeg_first_pos_dev: null argument");
+    if (n == 0) return BLAST_OK;
+    const unsigned g = (unsigned)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)ctx->sm_count * 16);
+    mpeg_first_pos<<<g, 256, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long*>(d_pos), d_hdr, n, ref_header,
+                                               reinterpret_cast<unsigned long long*>(d_first));
+    BLAST_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    return BLAST_OK;
+}
+
+int blast_mpeg_classify_dev(blast_ctx* ctx, const uint64_t* d_pos, const uint32_t* d_hdr, uint64_t n, uint32_t ref_header,
+                            const uint64_t* d_first, uint64_t stream_len, uint64_t* d_offsets_out, uint64_t cap,
+                            uint64_t* n_offsets_out) {
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_REQUIRE(n_offsets_out && ((d_pos && d_hdr) || n == 0), BLAST_ERR_ARG, "blast_mpeg_classify_dev: null argument");
+    *n_offsets_out = 0;
+    if (n == 0) return BLAST_OK;
+    const int compat = d_first != nullptr;
+    const unsigned long long n_blocks = (n + kClsBlock - 1) / kClsBlock;
+    const size_t bc_b = (n_blocks * 8 + 255) & ~255ull;
+    uint8_t* s7 = static_cast<uint8_t*>(blast::scratch(ctx, 7, 2 * bc_b + 256));
+    unsigned long long* h_box = static_cast<unsigned long long*>(blast::mailbox(ctx));
+    if (!s7 || !h_box) return BLAST_ERR_CUDA;
+    h_box += 64;
+    unsigned long long* d_bc = reinterpret_cast<unsigned long long*>(s7);
+    unsigned long long* d_bb = reinterpret_cast<unsigned long long*>(s7 + bc_b);
+    unsigned long long* d_total = reinterpret_cast<unsigned long long*>(s7 + 2 * bc_b);
+    uint32_t* d_err = reinterpret_cast<uint32_t*>(d_total + 1);
+    BLAST_CUDA_TRY(cudaMemsetAsync(d_total, 0, 16, ctx->stream));
+    const unsigned long long* pos = reinterpret_cast<const unsigned long long*>(d_pos);
+    const unsigned long long* first = reinterpret_cast<const unsigned long long*>(d_first);
+    mpeg_classify<<<(unsigned)n_blocks, kClsThreads, 0, ctx->stream>>>(pos, d_hdr, n, ref_header, first, compat, stream_len, d_bc, nullptr, 0,
+                                                                     nullptr, 0, d_err);
     mpeg_scan_blocks<<<1, 1024, 0, ctx->stream>>>(d_bc, d_bb, n_blocks, d_total);
     BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 2;
-    BLAST_CUDA_TRY(cudaMemcpyAsync(h_box, d_best, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    BLAST_CUDA_TRY(cudaMemcpyAsync(h_box, d_total, 16, cudaMemcpyDeviceToHost, ctx->stream));
     BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    const unsigned long long total = h_box[1];
-    const uint32_t err = (uint32_t)h_box[2];
+    const unsigned long long total = h_box[0];
+    const uint32_t err = (uint32_t)h_box[1];
     *n_offsets_out = total;
-    if (err && reference_compat)
+    if (err && compat)
         return blast::set_error(BLAST_ERR_REF_PANIC, "a frame payload extends past the end of the file (mpeg.rs:96 indexes out of bounds)");
     if (d_offsets_out) {
         if (total > cap) return blast::set_error(BLAST_ERR_CAPACITY, "mpeg index: %llu offsets, capacity %llu", total, (unsigned long long)cap);
-        mpeg_classify<<<(unsigned)n_blocks, kClsThreads, 0, ctx->stream>>>(d_pos, d_hdr, n_cand, ref_header, d_first, reference_compat,
-                                                                         len, d_bc, d_bb, 1, reinterpret_cast<unsigned long long*>(d_offsets_out),
-                                                                         cap, d_err);
+        mpeg_classify<<<(unsigned)n_blocks, kClsThreads, 0, ctx->stream>>>(pos, d_hdr, n, ref_header, first, compat, stream_len, d_bc, d_bb, 1,
+                                                                         reinterpret_cast<unsigned long long*>(d_offsets_out), cap, d_err);
         BLAST_CUDA_TRY(cudaGetLastError());
         ctx->launches += 1;
         BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));

@@ -187,4 +187,24 @@ int blast_file_name(const char* path, char* out, size_t cap) {
     return BLAST_OK;
 }
 
+// main.rs:79-120: the engine runs at the most frequent sample rate of the decoded assets and with the largest
+// channel count.  Ties between rates follow HashMap iteration order in the reference (nondeterministic); here the
+// smallest rate wins.  No assets: 44100 Hz / 2 channels, as the reference's fall-backs.
+int blast_asset_consensus(const blast_pcm_desc* descs, uint32_t n, uint32_t* sample_rate_out, uint32_t* num_channels_out) {
+    BLAST_REQUIRE((descs || n == 0) && sample_rate_out && num_channels_out, BLAST_ERR_ARG, "blast_asset_consensus: null argument");
+    uint32_t best_rate = 44100, best_count = 0, channels = n ? 0 : 2;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t count = 0;
+        for (uint32_t k = 0; k < n; ++k) count += descs[k].sample_rate == descs[i].sample_rate;
+        if (count > best_count || (count == best_count && descs[i].sample_rate < best_rate)) {
+            best_count = count;
+            best_rate = descs[i].sample_rate;
+        }
+        channels = descs[i].num_channels > channels ? descs[i].num_channels : channels;
+    }
+    *sample_rate_out = best_rate;
+    *num_channels_out = channels;
+    return BLAST_OK;
+}
+
 }  // extern "C"

@@ -67,3 +67,100 @@ class ShardedScene:
         ap.finalize_bus(self.ctx, part.data_ptr(), bus.data_ptr(), n)
         self.scene.check()
         return bus
+
+
+# ---------------------------------------------------------------------------------- MPEG scan over byte ranges
+MPEG_RANGE_ALIGN = 32768          # every range but the last is a multiple of the scan's span size
+MPEG_HALO = 16                    # bytes of the following range a rank must also hold (look-ahead + header bytes)
+MPEG_HDR_BINS = 1 << 21
+
+
+def mpeg_plan_ranges(total_len: int, world: int):
+    """-> [(start, own_len, halo_len)] per rank: contiguous ranges, all but the last a multiple of 32 KiB"""
+    spans = (total_len + MPEG_RANGE_ALIGN - 1) // MPEG_RANGE_ALIGN
+    per = (spans + world - 1) // world
+    out = []
+    for r in range(world):
+        a = min(total_len, r * per * MPEG_RANGE_ALIGN)
+        b = min(total_len, (r + 1) * per * MPEG_RANGE_ALIGN)
+        halo = min(MPEG_HALO, total_len - b)
+        # a range that ends the stream carries no halo; ranges after it are empty
+        out.append((a, b - a, halo if b < total_len else 0))
+    return out
+
+
+def mpeg_fold_aggs(aggs):
+    """aggs[r] = (exit_state[4], count[4]) of range r -> [(entry_state, candidates_before)] per rank, total.
+    The greedy scan is a 4-state machine (header bytes still to skip); range 0 starts in state 0."""
+    state, before, out = 0, 0, []
+    for exit_state, count in aggs:
+        out.append((state, before))
+        before += int(count[state])
+        state = int(exit_state[state])
+    return out, before
+
+
+def mpeg_exchange_aggs(agg, group=None, device=None):
+    """all-gather of the 8 numbers of every rank's range aggregate (the scan's one exchange step)"""
+    import torch
+    import torch.distributed as dist
+    mine = torch.tensor(list(agg[0]) + list(agg[1]), dtype=torch.int64, device=device)
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return [agg]
+    world = dist.get_world_size(group)
+    got = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(got, mine, group=group)
+    return [([int(x) for x in g[:4].tolist()], [int(x) for x in g[4:].tolist()]) for g in got]
+
+
+class ShardedMpegIndex:
+    """mpeg::parse's frame-offset index for ONE stream cut into byte ranges over the ranks of a process group.
+
+    Every rank holds its range (+ 16 halo bytes) in HBM.  Collectives: one all-gather of 8 int64 per rank (range
+    aggregates), one all-reduce(sum) of the 2^21-bin header histogram (8 MB, int32), and with reference_compat one
+    all-reduce(min) of the first-position table (16 MB, int64).  The index stays sharded: each rank returns the
+    offsets that fall into its range (they are global file positions, already in order across ranks).
+    """
+
+    def __init__(self, ctx, rank: int, world: int, group=None):
+        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+
+    def run(self, d_bytes: int, total_len: int, reference_compat: bool = True):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import file_parsing as fp
+        from .errors import check
+        ctx = self.ctx
+        dev = torch.device("cuda", ctx.device)
+        start, own, halo = mpeg_plan_ranges(total_len, self.world)[self.rank]
+        agg = fp.mpeg.shard_walk_dev(ctx, d_bytes, own, halo)
+        aggs = mpeg_exchange_aggs(agg, self.group, dev)
+        folded, n_cand_total = mpeg_fold_aggs(aggs)
+        entry, _before = folded[self.rank]
+        count = agg[1][entry]
+        d_pos, d_hdr = fp.mpeg.shard_emit_dev(ctx, d_bytes, own, halo, entry, start, count)
+        hist = torch.zeros(MPEG_HDR_BINS, dtype=torch.int32, device=dev)
+        check(ctx.lib.blast_mpeg_hist_dev(ctx.h, d_hdr.ptr, count, hist.data_ptr()))
+        multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
+        if multi:
+            dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
+        ref = C.c_uint32()
+        check(ctx.lib.blast_mpeg_pick_ref_dev(ctx.h, hist.data_ptr(), C.byref(ref)))
+        first_ptr = None
+        if reference_compat:
+            # all-ones = "no position yet"; int64 max is the same bit pattern minus the sign bit, so min() over
+            # int64 needs non-negative values: use 2^63-1 as the sentinel (positions are far below it)
+            first = torch.full((MPEG_HDR_BINS,), (1 << 63) - 1, dtype=torch.int64, device=dev)
+            check(ctx.lib.blast_mpeg_first_pos_dev(ctx.h, d_pos.ptr, d_hdr.ptr, count, ref.value, first.data_ptr()))
+            if multi:
+                dist.all_reduce(first, op=dist.ReduceOp.MIN, group=self.group)
+            first_ptr = first.data_ptr()
+        n = C.c_uint64()
+        check(ctx.lib.blast_mpeg_classify_dev(ctx.h, d_pos.ptr, d_hdr.ptr, count, ref.value, first_ptr, total_len, None, 0,
+                                              C.byref(n)))
+        d_off = ctx.alloc(max(16, 8 * n.value))
+        check(ctx.lib.blast_mpeg_classify_dev(ctx.h, d_pos.ptr, d_hdr.ptr, count, ref.value, first_ptr, total_len,
+                                              d_off.ptr, n.value, C.byref(n)))
+        return dict(d_offsets=d_off, n_offsets=n.value, ref_header=ref.value, n_candidates=n_cand_total,
+                    n_candidates_local=count, range=(start, own, halo), d_pos=d_pos, d_hdr=d_hdr)

@@ -66,6 +66,14 @@ def file_name(path: str) -> str:
     return buf.value.decode()
 
 
+def asset_consensus(descs) -> tuple[int, int]:
+    """(mutual sample rate, channel count) of an asset set: main.rs:79-120"""
+    arr = (_lib.PcmDesc * max(1, len(descs)))(*descs)
+    rate, ch = C.c_uint32(), C.c_uint32()
+    check(_lib.load().blast_asset_consensus(arr, len(descs), C.byref(rate), C.byref(ch)))
+    return rate.value, ch.value
+
+
 def decode_batch(ctx: Context, images, descs, *, to_host=True, keep_on_device=False):
     """blast_pcm_decode_batch over host file images.
 
@@ -194,6 +202,24 @@ class _Mpeg:
                                            C.byref(n), C.byref(ref), C.byref(ncand)))
         return dict(offsets=d_off.download(np.uint64, n.value), ref_header=ref.value, n_candidates=ncand.value,
                     d_offsets=d_off)
+
+    @staticmethod
+    def shard_walk_dev(ctx: Context, d_bytes: int, own_len: int, halo_len: int):
+        """phase 1 of the sharded scan -> (exit_state[4], count[4]) of this byte range"""
+        agg = _lib.MpegShardAgg()
+        check(ctx.lib.blast_mpeg_shard_walk_dev(ctx.h, d_bytes, own_len, halo_len, C.byref(agg)))
+        return [int(x) for x in agg.exit_state], [int(x) for x in agg.count]
+
+    @staticmethod
+    def shard_emit_dev(ctx: Context, d_bytes: int, own_len: int, halo_len: int, entry_state: int, pos_offset: int,
+                       count: int):
+        """phase 2 -> device buffers (positions uint64 with pos_offset added, headers uint32) of `count` candidates"""
+        d_pos, d_hdr = ctx.alloc(max(16, 8 * count)), ctx.alloc(max(16, 4 * count))
+        n = C.c_uint64()
+        check(ctx.lib.blast_mpeg_shard_emit_dev(ctx.h, d_bytes, own_len, halo_len, entry_state, pos_offset, d_pos.ptr,
+                                                d_hdr.ptr, count, C.byref(n)))
+        assert n.value == count, (n.value, count)
+        return d_pos, d_hdr
 
     @staticmethod
     def gather_dev(ctx: Context, d_bytes: int, length: int, d_offsets: int, n_offsets: int) -> np.ndarray:

@@ -110,6 +110,11 @@ size_t blast_pcm_out_len(const blast_pcm_desc* desc);   /* ceil(data_len / 2) i1
 /* file-name rule applied after decoding (wav.rs:156-164, aiff.rs:172-180) */
 int    blast_file_name(const char* path, char* out, size_t cap);
 
+/* Asset-set consensus of main() (blast/src/main.rs:79-120): the most frequent sample rate (ties: the smallest; the
+ * reference follows HashMap order) and the largest channel count of the successfully decoded files; 44100 / 2
+ * when there are none.  These are what run_blast() opens the output device with. */
+int    blast_asset_consensus(const blast_pcm_desc* descs, uint32_t n, uint32_t* sample_rate_out, uint32_t* num_channels_out);
+
 /* One decode job on device-resident bytes: n_words byte pairs at d_src (ANY byte
  * alignment) -> int16 at d_dst (2-byte aligned).  d_src must be readable up to the next
  * 16-byte boundary past its last byte (true for blast_dev_alloc / cudaMalloc buffers). */
@@ -348,6 +353,34 @@ int  blast_mpeg_scan_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, u
 int  blast_mpeg_index_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, int reference_compat,
                           uint64_t* d_offsets_out, uint64_t cap, uint64_t* n_offsets_out, uint32_t* ref_header_out,
                           uint64_t* n_candidates_out);
+/* The same in separate steps (blast_mpeg_index_dev = scan + these four).  The histogram has BLAST_MPEG_HDR_BINS
+ * uint32 bins indexed by the low 21 header bits (the 11 sync bits are fixed) and is ACCUMULATED into; the
+ * first-position table has BLAST_MPEG_HDR_BINS uint64 entries, initialised by the caller to all-ones, and is
+ * min-reduced into.  Both may be summed / min-reduced across GPUs between the steps (one NCCL all-reduce each). */
+#define BLAST_MPEG_HDR_BINS (1u << 21)
+int  blast_mpeg_hist_dev(blast_ctx* ctx, const uint32_t* d_hdr, uint64_t n, uint32_t* d_hist);                  /* async */
+int  blast_mpeg_pick_ref_dev(blast_ctx* ctx, const uint32_t* d_hist, uint32_t* ref_header_out);                 /* mpeg.rs:53-73 */
+int  blast_mpeg_first_pos_dev(blast_ctx* ctx, const uint64_t* d_pos, const uint32_t* d_hdr, uint64_t n, uint32_t ref_header,
+                              uint64_t* d_first);                                                               /* async */
+/* d_first nullable = no duplicate-first quirk; stream_len = length of the WHOLE stream (payload-past-EOF check) */
+int  blast_mpeg_classify_dev(blast_ctx* ctx, const uint64_t* d_pos, const uint32_t* d_hdr, uint64_t n, uint32_t ref_header,
+                             const uint64_t* d_first, uint64_t stream_len, uint64_t* d_offsets_out, uint64_t cap,
+                             uint64_t* n_offsets_out);
+
+/* Sharded scan (multi-GPU, SURVEY.md §8 e): one logical stream cut into contiguous byte ranges, one per GPU.  Every
+ * range but the last must be a multiple of 32,768 bytes and is followed in d_bytes by halo_len >= 16 bytes of the next
+ * range; the last range has halo_len 0.  Phase 1 returns the range's action on the greedy scan's 4-state machine:
+ * exit state and candidate count for each of the 4 possible entry states.  The host folds the ranges in order
+ * (entry state of range r = exit state of range r-1 under ITS entry state; range 0 enters in state 0) — an exchange
+ * of 48 bytes per GPU — and phase 2 emits the range's candidates (positions + pos_offset) for its true entry state.
+ * The two calls must follow each other on the same context (the walk's intermediate lists stay in its scratch). */
+typedef struct { uint32_t exit_state[4]; uint64_t count[4]; } blast_mpeg_shard_agg;
+int  blast_mpeg_shard_walk_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t own_len, uint64_t halo_len,
+                               blast_mpeg_shard_agg* agg_out);
+int  blast_mpeg_shard_emit_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t own_len, uint64_t halo_len,
+                               uint32_t entry_state, uint64_t pos_offset, uint64_t* d_pos_out, uint32_t* d_hdr_out,
+                               uint64_t cap, uint64_t* n_out);
+
 /* Payload gather (mpeg.rs:86-121): concatenated b[pos+skip .. pos+skip+len] of the indexed frames.
  * d_payload_out nullable (size only). */
 int  blast_mpeg_gather_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, const uint64_t* d_offsets,

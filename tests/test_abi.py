@@ -197,7 +197,7 @@ def test_struct_layouts_match_the_header(tmp_path):
     structs = {"blast_pcm_desc": _lib.PcmDesc, "blast_pcm_job": _lib.PcmJob, "blast_pcm24_job": _lib.Pcm24Job,
                "blast_track": _lib.Track, "blast_voice": _lib.Voice, "blast_x128p": _lib.X128PState,
                "blast_mpeg_header": _lib.MpegHeader, "blast_tempo_repr": _lib.TempoRepr, "blast_command": _lib.Command,
-               "blast_timed_command": _lib.TimedCommand, "blast_voice_state": _lib.VoiceState}
+               "blast_timed_command": _lib.TimedCommand, "blast_voice_state": _lib.VoiceState, "blast_mpeg_shard_agg": _lib.MpegShardAgg}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "blast_cuda.h"', 'int main(void) {']
     for cname, cls in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
@@ -213,3 +213,13 @@ def test_struct_layouts_match_the_header(tmp_path):
         assert int(got[cname]) == C.sizeof(cls), cname
         for f, _ in cls._fields_:
             assert int(got[f"{cname}.{f}"]) == getattr(cls, f).offset, (cname, f)
+
+
+def test_asset_consensus():
+    """main.rs:79-120: most frequent rate, largest channel count; 44100 / 2 without assets"""
+    def d(rate, ch):
+        return _lib.PcmDesc(rate, ch, 16, 0, 44, 100)
+    assert fp.asset_consensus([]) == (44100, 2)
+    assert fp.asset_consensus([d(48000, 1)]) == (48000, 1)
+    assert fp.asset_consensus([d(48000, 2), d(44100, 1), d(44100, 6), d(22050, 2)]) == (44100, 6)
+    assert fp.asset_consensus([d(48000, 2), d(44100, 2)]) == (44100, 2)          # tie: smallest (reference: HashMap order)

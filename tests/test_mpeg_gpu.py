@@ -135,3 +135,53 @@ def test_c5_scaled_properties(ctx):
     assert np.all(np.diff(idx["offsets"].astype(np.int64)) >= 0)
     again = fp.mpeg.index_dev(ctx, d.ptr, buf.size, reference_compat=True)
     assert np.array_equal(again["offsets"], idx["offsets"])
+
+
+def _sharded_scan_one_gpu(ctx, b, world):
+    """every range gets its own device buffer (range + 16 halo bytes), as on `world` GPUs; the two phases run per range"""
+    from audio_decoder_b200 import distributed as bd
+    ranges = bd.mpeg_plan_ranges(b.size, world)
+    bufs = [ctx.to_device(b[a:a + own + halo]) if own else None for a, own, halo in ranges]
+    aggs = [fp.mpeg.shard_walk_dev(ctx, d.ptr, own, halo) if own else ([0, 1, 2, 3], [0, 0, 0, 0])
+            for d, (a, own, halo) in zip(bufs, ranges)]
+    folded, total = bd.mpeg_fold_aggs(aggs)
+    pos, hdr = [], []
+    for d, (a, own, halo), agg, (entry, before) in zip(bufs, ranges, aggs, folded):
+        if not own:
+            continue
+        assert fp.mpeg.shard_walk_dev(ctx, d.ptr, own, halo) == agg          # phase 1 again: the scratch is shared here
+        d_pos, d_hdr = fp.mpeg.shard_emit_dev(ctx, d.ptr, own, halo, entry, a, agg[1][entry])
+        pos.append(d_pos.download(np.uint64, agg[1][entry]))
+        hdr.append(d_hdr.download(np.uint32, agg[1][entry]))
+    return np.concatenate(pos), np.concatenate(hdr), total
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_scan_equals_whole_scan(ctx, world):
+    rng = np.random.default_rng(40 + world)
+    cases = [synth.mp3_like(9, 700),                                                       # ~290 KB of frames
+             np.concatenate([np.zeros(2, np.uint8), np.full(5 * 32768 + 11, 0xFF, np.uint8), np.zeros(9, np.uint8)]),   # flood
+             np.concatenate([rng.choice(np.array([0xFF, 0xFF, 0xE0, 0xFB, 0x00, 0x90], dtype=np.uint8), size=4 * 32768 + 5000),
+                             np.zeros(4, np.uint8)])]
+    # a sync straddling every range boundary by 1..3 bytes
+    edge = np.zeros(9 * 32768, dtype=np.uint8)
+    for k in range(1, 9):
+        off = k * 32768 - (k % 4)
+        edge[off:off + 4] = [0xFF, 0xFB, 0x90, 0x64]
+    cases.append(edge)
+    for b in cases:
+        epos, ehdr = oracle.mpeg_sync_scan(b)
+        pos, hdr, total = _sharded_scan_one_gpu(ctx, b, world)
+        assert total == len(epos)
+        assert np.array_equal(pos, epos) and np.array_equal(hdr, ehdr)
+
+
+def test_sharded_index_world1_equals_index(ctx):
+    from audio_decoder_b200 import distributed as bd
+    buf = synth.mp3_like(0xC5, 30000)
+    d = ctx.to_device(buf)
+    for compat in (True, False):
+        exp = oracle.mpeg_parse(buf, reference_compat=compat, want_payload=False)
+        got = bd.ShardedMpegIndex(ctx, 0, 1).run(d.ptr, buf.size, reference_compat=compat)
+        assert got["ref_header"] == exp["ref_header"] and got["n_candidates"] == exp["n_candidates"]
+        assert np.array_equal(got["d_offsets"].download(np.uint64, got["n_offsets"]), exp["offsets"])
