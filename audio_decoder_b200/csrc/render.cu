@@ -1252,7 +1252,8 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
 
     // voice groups: enough CTAs to fill the GPU a few times over, groups of >= 64 voices
     uint32_t groups = 1;
-    const uint32_t want_ctas = (uint32_t)ctx->sm_count * 16;
+    static const uint32_t ctas_per_sm = getenv("BLAST_RENDER_CTAS_PER_SM") ? (uint32_t)atoi(getenv("BLAST_RENDER_CTAS_PER_SM")) : 32u;
+    const uint32_t want_ctas = (uint32_t)ctx->sm_count * ctas_per_sm;
     while (n_tiles * groups < want_ctas && n_voices / (groups * 2) >= 64) groups *= 2;
     const uint32_t per_group = (n_voices + groups - 1) / groups;
     groups = (n_voices + per_group - 1) / per_group;
