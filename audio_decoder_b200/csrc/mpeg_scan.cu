@@ -157,17 +157,22 @@ __device__ __noinline__ SpanOut walk_span(const int MODE, const uint8_t* __restr
     o.sens = false;
     uint32_t carry = entry;                                            // entry state of lane 0 this round (uniform)
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint8_t* src = bytes + span0 + 16u * lane;                   // lane's first 16-byte unit of round 0
+    const uint8_t* src = bytes + span0 + 16u * lane;                   // lane's first 16-byte unit of the next round to fetch
     const uint32_t dst = (lane >> 2) * kRowBytes + (lane & 3) * 16;    // unit j = lane + 32 q -> row (j >> 2) = lane/4 + 8 q
+    const uint32_t ring_end = ring + (uint32_t)(kStages * kStageBytes);
+    uint32_t st_fill = ring;                                           // stage the next fetched round goes to
+    unsigned long long fetched = span0 + 16ull * lane;                 // position of `src` (end-of-buffer test only)
 
-    auto issue = [&](int r) {
-        if (r < kRounds) {
-            const uint32_t st = ring + (uint32_t)(r % kStages) * kStageBytes + dst;
+    auto issue = [&](bool any) {
+        if (any) {
+            const uint32_t st = st_fill + dst;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t off = (uint32_t)r * kRoundBytes + 512u * q;
-                if (!NEAR_END || span0 + off + 16ull * lane < n) cp_async16(st + (uint32_t)q * 8u * kRowBytes, src + off);
-            }
+            for (int q = 0; q < 4; ++q)
+                if (!NEAR_END || fetched + 512ull * q < n) cp_async16(st + (uint32_t)q * 8u * kRowBytes, src + 512 * q);
+            src += kRoundBytes;
+            if (NEAR_END) fetched += kRoundBytes;
+            st_fill += kStageBytes;
+            if (st_fill == ring_end) st_fill = ring;
         }
         cp_async_commit();
     };
@@ -177,13 +182,16 @@ __device__ __noinline__ SpanOut walk_span(const int MODE, const uint8_t* __restr
         after_word = __ldg(reinterpret_cast<const uint32_t*>(bytes + span0 + kSpanBytes));
 
 #pragma unroll
-    for (int r = 0; r < kStages - 1; ++r) issue(r);
+    for (int r = 0; r < kStages - 1; ++r) issue(true);
+    uint32_t st_cur = ring;                                            // stage of the round being processed
 #pragma unroll 1
     for (int r = 0; r < kRounds; ++r) {
-        issue(r + kStages - 1);
+        issue(r + kStages - 1 < kRounds);
         cp_async_wait<kStages - 2>();                                   // rounds r and r + 1 have landed (this lane's part)
         __syncwarp();                                                   // ... and everybody else's
-        const uint32_t row = ring + (uint32_t)(r % kStages) * kStageBytes + lane * kRowBytes;
+        const uint32_t row = st_cur + lane * kRowBytes;
+        uint32_t st_next = st_cur + kStageBytes;
+        if (st_next == ring_end) st_next = ring;
         uint32_t w[17];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -193,7 +201,7 @@ __device__ __noinline__ SpanOut walk_span(const int MODE, const uint8_t* __restr
         {
             const uint32_t down = __shfl_down_sync(0xFFFFFFFFu, w[0], 1);
             uint32_t wrap = after_word;
-            if (r + 1 < kRounds) wrap = lds32(ring + (uint32_t)((r + 1) % kStages) * kStageBytes);
+            if (r + 1 < kRounds) wrap = lds32(st_next);
             w[16] = lane == 31 ? wrap : down;
         }
         const uint32_t rel = (uint32_t)r * kRoundBytes + lane * kChunk;          // offset of the lane's chunk in the span
@@ -295,10 +303,12 @@ __device__ __noinline__ SpanOut walk_span(const int MODE, const uint8_t* __restr
             }
             if (MODE != kModeCount && cnt) {
                 uint32_t k = o.total + pre;
-                unsigned long long m = sel;
-                while (m) {
-                    const int i = __ffsll((long long)m) - 1;
-                    m &= m - 1;
+                uint32_t slo = (uint32_t)sel, shi = (uint32_t)(sel >> 32);
+                do {
+                    // lowest selected bit (one candidate per lane is the rule: no 64-bit loop bookkeeping for it)
+                    int i;
+                    if (slo) { i = __ffs((int)slo) - 1; slo &= slo - 1; }
+                    else { i = 32 + __ffs((int)shi) - 1; shi &= shi - 1; }
                     // header = 4 bytes at chunk offset i: two aligned words of the staged row (the 17th is w[16])
                     const uint32_t a = lds32(row + 4u * (uint32_t)(i >> 2));
                     const uint32_t b = (i >> 2) == 15 ? w[16] : lds32(row + 4u * (uint32_t)(i >> 2) + 4u);
@@ -316,11 +326,12 @@ __device__ __noinline__ SpanOut walk_span(const int MODE, const uint8_t* __restr
                         }
                     }
                     k += 1;
-                }
+                } while (slo | shi);
             }
             o.total += round_total;
         }
         __syncwarp();                              // the stage is refilled by the next iteration's cp.async
+        st_cur = st_next;
     }
     cp_async_wait<0>();
     o.exit_state = carry;
