@@ -25,6 +25,7 @@
 // the chunk is re-run at half the length from the (host-authoritative) state, nothing is committed on overflow.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <memory>
 #include <numeric>
 #include <unordered_map>
@@ -438,6 +439,8 @@ int render_span(blast_ctx* ctx, blast_conductor* c, uint64_t frames, int32_t* d_
     const uint32_t oc = c->out_channels;
     uint64_t done = 0;
     uint64_t chunk = frames;
+    static const bool debug = getenv("BLAST_CONDUCTOR_DEBUG") != nullptr;
+    uint32_t n_ok = 0, n_retry = 0;
     while (done < frames) {
         Flat f;
         if (int rc = flatten(c, f)) return rc;
@@ -450,6 +453,7 @@ int render_span(blast_ctx* ctx, blast_conductor* c, uint64_t frames, int32_t* d_
         bool overflow = false;
         if (int rc = render_chunk(ctx, c, f, n, d_partial + done * oc, &overflow)) return rc;
         if (overflow) {
+            n_retry += 1;
             if (n == 1) return blast::set_error(BLAST_ERR_CAPACITY, "a single frame needs more than %d position segments / %d retriggers", kMaxSeg, kMaxEvents);
             chunk = std::max<uint64_t>(1, n / 2);
             continue;
@@ -459,7 +463,10 @@ int render_span(blast_ctx* ctx, blast_conductor* c, uint64_t frames, int32_t* d_
         for (auto& kv : f.ticks) kv.first->current += (uint32_t)((uint64_t)kv.second * calls);
         c->clock += n;                                                               // clock::advance(1) per frame
         done += n;
+        n_ok += 1;
     }
+    if (debug) fprintf(stderr, "[blast conductor] span of %llu frames: %u chunk(s), %u overflow retr%s, last chunk %llu frames\n",
+                       (unsigned long long)frames, n_ok, n_retry, n_retry == 1 ? "y" : "ies", (unsigned long long)chunk);
     return BLAST_OK;
 }
 

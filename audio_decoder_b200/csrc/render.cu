@@ -263,17 +263,18 @@ __device__ __forceinline__ float build_epoch(float p, const float vel, const uin
 // writes the position after the render back into the voice.
 __global__ void voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t frames,
                                     Seg* __restrict__ segs, uint32_t* __restrict__ nsegs, uint32_t* __restrict__ err,
-                                    const uint32_t* __restrict__ events, const uint32_t* __restrict__ nevents) {
+                                    const uint32_t* __restrict__ events, const uint32_t* __restrict__ nevents,
+                                    const uint32_t seg_cap) {
     uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x;
     if (vi >= n_voices) return;
     VoiceDev v = voices[vi];
-    Seg* sg = segs + (size_t)vi * kMaxSeg;
+    Seg* sg = segs + (size_t)vi * seg_cap;
     uint32_t n = 0;
     float p = v.pos;
     const uint32_t total = v.active ? frames * v.S : 0;
     if (v.adv == 0 || total == 0) {
         p = build_epoch(p, v.vel, v.end, total, [&](uint32_t a, float p0, int32_t d, float scale) {
-            if (n < (uint32_t)kMaxSeg) sg[n] = Seg{a, p0, d, scale};
+            if (n < seg_cap) sg[n] = Seg{a, p0, d, scale};
             n += 1;
         });
     } else {
@@ -283,11 +284,11 @@ __global__ void voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_vo
         uint32_t cc = 0, e = 0, last0 = 0xFFFFFFFFu;
         auto put = [&](uint32_t step0, float p0, int32_t d, float scale) {
             if (step0 == last0 && n > 0) {                                        // same call as the previous segment: replace it
-                if (n <= (uint32_t)kMaxSeg) sg[n - 1] = Seg{step0, p0, d, scale};
+                if (n <= seg_cap) sg[n - 1] = Seg{step0, p0, d, scale};
                 return;
             }
             last0 = step0;
-            if (n < (uint32_t)kMaxSeg) sg[n] = Seg{step0, p0, d, scale};
+            if (n < seg_cap) sg[n] = Seg{step0, p0, d, scale};
             n += 1;
         };
         for (;;) {
@@ -307,9 +308,9 @@ __global__ void voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_vo
             if (stop >= total) break;
         }
     }
-    if (n > (uint32_t)kMaxSeg) {
+    if (n > seg_cap) {
         atomicOr(err, 1u);
-        n = kMaxSeg;
+        n = seg_cap;
     }
     nsegs[vi] = n;
     voices[vi].pos = p;
@@ -320,13 +321,15 @@ __global__ void voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_vo
 // voice's segment list.  Layout [tile][voice] so that K4's staging loads are coalesced.  (As a loop at the end of
 // K3 this was 131 us of serial work for C2's 1,024 voices x 352 tiles: 18 % of the whole mix.)
 __global__ void voice_tile_records(const VoiceDev* __restrict__ voices, uint32_t n_voices, const Seg* __restrict__ segs,
-                                   const uint32_t* __restrict__ nsegs, TileRec* __restrict__ recs, uint32_t n_tiles) {
+                                   const uint32_t* __restrict__ nsegs, TileRec* __restrict__ recs, uint32_t n_tiles,
+                                   const uint32_t* __restrict__ err, const uint32_t seg_cap) {
+    if (*err) return;                                           // a segment / event list overflowed: this render is void
     const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (unsigned long long)n_tiles * n_voices) return;
     const uint32_t t = (uint32_t)(idx / n_voices), vi = (uint32_t)(idx - (unsigned long long)t * n_voices);
     const uint32_t active = voices[vi].active, S = voices[vi].S, adv = voices[vi].adv;
     if (!active) return;                                        // K4 never reads the records of an inactive voice
-    const Seg* __restrict__ sg = segs + (size_t)vi * kMaxSeg;
+    const Seg* __restrict__ sg = segs + (size_t)vi * seg_cap;
     const uint32_t n = nsegs[vi];
     const uint32_t st = t * (uint32_t)kFT * S;
     uint32_t lo = 0, hi = n;                                    // last j with sg[j].step0 <= st (sg[0].step0 == 0)
@@ -338,12 +341,12 @@ __global__ void voice_tile_records(const VoiceDev* __restrict__ voices, uint32_t
     const Seg g = sg[j];
     const uint32_t next = (j + 1 < n) ? sg[j + 1].step0 : 0xFFFFFFFFu;
     uint32_t left = next - st;
-    if (left > 0xFFFFFFu) left = 0xFFFFFFu;
+    if (left > 0xFFFFu) left = 0xFFFFu;                      // only compared with kFT * S + 2 <= 16,386
     TileRec r;
     r.p0 = seg_pos(g, st, adv);
     r.d = g.d;
     r.scale = g.scale;
-    r.meta = left | (j << 24);
+    r.meta = left | (j << 16);
     recs[idx] = r;
 }
 
@@ -364,7 +367,7 @@ __device__ __forceinline__ float position_eval(bool fast, float p0, int32_t d, f
     if (fast) return seg_eval(p0, d, scale, adv_count(tile_step0 + step_local, adv) - adv_count(tile_step0, adv));
     // the tile straddles a segment boundary: walk the (short) segment list from the tile's segment
     const uint32_t abs_step = tile_step0 + step_local;
-    uint32_t j = recmeta >> 24;
+    uint32_t j = recmeta >> 16;
     while (j + 1 < nseg && sg[j + 1].step0 <= abs_step) ++j;
     return seg_pos(sg[j], abs_step, adv);
 }
@@ -391,8 +394,10 @@ template <int OC>
 __global__ void __launch_bounds__(kThreads)
 voice_render_mix(const VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t voices_per_group,
                  const Seg* __restrict__ segs, const uint32_t* __restrict__ nsegs,
-                 const TileRec* __restrict__ recs, uint32_t frames, int32_t* __restrict__ bus, int use_atomic) {
+                 const TileRec* __restrict__ recs, uint32_t frames, int32_t* __restrict__ bus, int use_atomic,
+                 const uint32_t* __restrict__ err, const uint32_t seg_cap) {
     __shared__ VoiceS sv[kVoiceBatch];
+    if (*err) return;                                           // truncated trajectories must not be rendered
     const uint32_t tile = blockIdx.x;
     const uint32_t f0 = tile * (uint32_t)kFT;
     const uint32_t nf = min((uint32_t)kFT, frames - f0);
@@ -420,9 +425,9 @@ voice_render_mix(const VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_
         for (uint32_t i = 0; i < nb; ++i) {
             const VoiceS& v = sv[i];
             if (!v.active) continue;
-            const Seg* __restrict__ sg = segs + (size_t)(vb + i) * kMaxSeg;
+            const Seg* __restrict__ sg = segs + (size_t)(vb + i) * seg_cap;
             const uint32_t tile_step0 = f0 * v.S;
-            const bool fast = (v.rec.meta & 0xFFFFFFu) >= (uint32_t)kFT * v.S + 2u || v.S == 0;
+            const bool fast = (v.rec.meta & 0xFFFFu) >= (uint32_t)kFT * v.S + 2u || v.S == 0;
             if (v.C == 2 && v.nch == 2 && v.adv == 0) {
                 // stereo voice on a >= 2-channel bus: one 32-bit load fetches L and R of a frame
                 const uint32_t* __restrict__ pairs = reinterpret_cast<const uint32_t*>(v.smp);
@@ -776,8 +781,10 @@ template <int OC>
 __global__ void __launch_bounds__(kTmaThreads)
 voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t voices_per_group,
                      uint32_t n_groups, const Seg* __restrict__ segs, const uint32_t* __restrict__ nsegs,
-                     const TileRec* __restrict__ recs, uint32_t frames, int32_t* __restrict__ bus, int use_atomic) {
+                     const TileRec* __restrict__ recs, uint32_t frames, int32_t* __restrict__ bus, int use_atomic,
+                     const uint32_t* __restrict__ err, const uint32_t seg_cap) {
     extern __shared__ __align__(128) uint8_t smem[];
+    if (*err) return;                                           // truncated trajectories must not be rendered (uniform exit)
     uint8_t* stages = smem;
     uint8_t* meta_base = smem + (size_t)kStages * kStageBytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(meta_base + kStages * kMetaStride);
@@ -817,9 +824,9 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                 v = voices[vi];
                 if (v.active) {
                     r = recs[(size_t)tile * n_voices + vi];
-                    sg = segs + (size_t)vi * kMaxSeg;
+                    sg = segs + (size_t)vi * seg_cap;
                     nseg = nsegs[vi];
-                    seg_j = r.meta >> 24;
+                    seg_j = r.meta >> 16;
                     cur = 0;
                 }
             }
@@ -831,7 +838,10 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                 uint32_t bytes = 0;
                 unsigned long long src = 0;
                 bool unit_tile = false;
-                if (first_round && cur < nf && OC == 2 && v.C == 2 && v.nch == 2 && v.adv == 0 && v.vel == 1.0f && r.p0 >= 0.0f) {
+                // (voices with Seq processes step per call and their segments also end at retriggers: for them the
+                // tile must lie inside ONE segment; a stereo voice on a stereo bus advances once per frame either way)
+                if (first_round && cur < nf && OC == 2 && v.C == 2 && v.nch == 2 && v.vel == 1.0f && r.p0 >= 0.0f &&
+                    (v.adv == 0 || (r.meta & 0xFFFFu) >= nf * v.S)) {
                     // velocity 1.0: while position + frames stays below 2^24 and the start is a multiple of the
                     // coarsest ulp it will meet, every `position += 1.0` is exact, whatever binades it crosses:
                     // the whole tile is one unit-step piece (frame index = floor(p0) + frame).
@@ -857,7 +867,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                     }
                 }
                 if (first_round && !unit_tile && cur < nf && OC == 2 && v.C == 2 && v.nch == 2 && v.adv == 0 &&
-                    (r.meta & 0xFFFFFFu) < nf * v.S)
+                    (r.meta & 0xFFFFu) < nf * v.S)
                     hold_multi = true;
                 if (!unit_tile && cur < nf && !hold_multi) {
                     uint32_t fa = cur, fb;
@@ -868,7 +878,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                     const uint32_t tile_step0 = f0 * v.S;
                     if (v.S == 0) {
                         fb = nf; p_a = r.p0; d = 0; scale = 0.0f;
-                    } else if (cur == 0 && (r.meta & 0xFFFFFFu) >= nf * v.S) {
+                    } else if (cur == 0 && (r.meta & 0xFFFFu) >= nf * v.S) {
                         fb = nf; p_a = r.p0; d = r.d; scale = r.scale;           // the common case: one piece
                     } else {
                         const uint32_t abs0 = tile_step0 + cur * v.S;
@@ -918,7 +928,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                             m.byte_off = (uint32_t)(b0 - a0);
                             // fast consumer paths: one segment, every frame audible, stereo voice on a
                             // stereo bus, positions in [0, 2^24)
-                            if (OC == 2 && v.C == 2 && v.nch == 2 && v.adv == 0 && !slow && idx_hi < v.end && p_a >= 0.0f && p_last >= 0.0f) {
+                            if (OC == 2 && v.C == 2 && v.nch == 2 && !slow && idx_hi < v.end && p_a >= 0.0f && p_last >= 0.0f) {
                                 if (v.vel == 1.0f && __fmul_rn((float)d, scale) == 1.0f) {
                                     path = kPathStereoUnit;
                                     m.a0_off = m.byte_off + (f2u_sat(p_a) - idx_lo - fa) * 4u;
@@ -1181,7 +1191,9 @@ void free_buffers(RenderBuffers& rb) {
 
 int reserve_buffers(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t n_seqs) {
     const size_t nv = n_voices ? n_voices : 1;
-    if (nv > rb.voices_cap) {
+    // voices with Seq processes start a new run of ~20 segments at every retrigger: give them room for ~50 of them
+    const uint32_t seg_cap = n_seqs ? (uint32_t)kMaxSegSeq : (uint32_t)kMaxSeg;
+    if (nv > rb.voices_cap || seg_cap > rb.seg_cap) {
         BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         if (rb.d_voices) cudaFree(rb.d_voices);
         if (rb.d_segs) cudaFree(rb.d_segs);
@@ -1189,9 +1201,10 @@ int reserve_buffers(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32
         rb.d_voices = nullptr; rb.d_segs = nullptr; rb.d_nsegs = nullptr;
         rb.voices_cap = 0;
         BLAST_CUDA_TRY(cudaMalloc(&rb.d_voices, nv * sizeof(VoiceDev)));
-        BLAST_CUDA_TRY(cudaMalloc(&rb.d_segs, nv * kMaxSeg * sizeof(Seg)));
+        rb.seg_cap = std::max(rb.seg_cap, seg_cap);
+        BLAST_CUDA_TRY(cudaMalloc(&rb.d_segs, nv * rb.seg_cap * sizeof(Seg)));
         BLAST_CUDA_TRY(cudaMalloc(&rb.d_nsegs, nv * sizeof(uint32_t)));
-        rb.voices_cap = nv;
+        rb.voices_cap = std::max(nv, rb.voices_cap);
         if (rb.d_events) {                       // sized by voices: regrown below
             cudaFree(rb.d_events); cudaFree(rb.d_nevents);
             rb.d_events = nullptr; rb.d_nevents = nullptr;
@@ -1244,9 +1257,9 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         ctx->launches += 1;
     }
     voice_position_scan<<<(n_voices + 31) / 32, 32, 0, ctx->stream>>>(rb.d_voices, n_voices, (uint32_t)frames, rb.d_segs, rb.d_nsegs,
-                                                                       rb.d_err, rb.d_events, rb.d_nevents);
+                                                                       rb.d_err, rb.d_events, rb.d_nevents, rb.seg_cap);
     voice_tile_records<<<(unsigned)((need + 255) / 256), 256, 0, ctx->stream>>>(rb.d_voices, n_voices, rb.d_segs, rb.d_nsegs,
-                                                                                rb.d_recs, n_tiles);
+                                                                                rb.d_recs, n_tiles, rb.d_err, rb.seg_cap);
     BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 2;
 
@@ -1267,17 +1280,17 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         if (oc == 1) {
             BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
             voice_render_mix_tma<1><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(rb.d_voices, n_voices, per_group, groups, rb.d_segs,
-                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic);
+                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, rb.d_err, rb.seg_cap);
         } else {
             BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
             voice_render_mix_tma<2><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(rb.d_voices, n_voices, per_group, groups, rb.d_segs,
-                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic);
+                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, rb.d_err, rb.seg_cap);
         }
     } else {
 #define BLAST_LAUNCH_MIX(OCV)                                                                              \
     voice_render_mix<OCV><<<grid, kThreads, 0, ctx->stream>>>(rb.d_voices, n_voices, per_group, rb.d_segs,  \
                                                                rb.d_nsegs, rb.d_recs, (uint32_t)frames,      \
-                                                               d_partial_bus, use_atomic)
+                                                               d_partial_bus, use_atomic, rb.d_err, rb.seg_cap)
         switch (oc) {
             case 1: BLAST_LAUNCH_MIX(1); break;
             case 2: BLAST_LAUNCH_MIX(2); break;

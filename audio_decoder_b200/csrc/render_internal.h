@@ -4,7 +4,8 @@
 
 namespace blast_rdr {
 
-constexpr int kMaxSeg = 160;
+constexpr int kMaxSeg = 160;                   // position segments per voice per render (plain voices: <= ~45 are ever needed)
+constexpr int kMaxSegSeq = 1024;               // ... when Seq processes retrigger voices
 constexpr int kFT = 2048;                      // frames per tile
 constexpr int kThreads = 256;
 constexpr int kFPT = kFT / kThreads;           // frames per thread
@@ -36,7 +37,7 @@ struct TileRec {           // state of one voice at the first step of one tile
     float p0;
     int32_t d;
     float scale;
-    uint32_t meta;         // [23:0] steps this segment still covers (saturating), [31:24] segment index
+    uint32_t meta;         // [15:0] steps this segment still covers (saturating), [31:16] segment index
 };
 
 
@@ -62,6 +63,7 @@ struct RenderBuffers {     // device scratch of one render (owned by a scene or 
     TileRec* d_recs = nullptr;
     size_t recs_cap = 0;               // in records
     size_t voices_cap = 0;
+    uint32_t seg_cap = 0;              // segments per voice in d_segs
     SeqDev* d_seqs = nullptr;          // only with Seq processes
     size_t seqs_cap = 0;
     uint32_t* d_events = nullptr;      // [voices_cap][kMaxEvents] retrigger call indices

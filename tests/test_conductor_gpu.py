@@ -326,7 +326,10 @@ def test_sharded_partials_sum_to_the_whole(ctx):
     assert np.array_equal(o.coordinate(frames), whole)
 
 
-@pytest.mark.parametrize("seed", range(6))
+import os as _os
+
+
+@pytest.mark.parametrize("seed", range(int(_os.environ.get("BLAST_FUZZ_SEEDS", "6"))))
 def test_random_command_streams(ctx, seed):
     """fuzz: random commands (valid and invalid indices), random spans, everything compared after every span"""
     r = np.random.default_rng(1000 + seed)
@@ -373,3 +376,17 @@ def test_random_command_streams(ctx, seed):
         else:
             p.coordinate(int(r.choice([1, 7, 300, 2048, 2500, 5000])))
     p.coordinate(3000)
+
+
+def test_long_span_many_epochs_overflow_path(ctx):
+    """one coordinate() call that needs hundreds of position segments per voice: the first attempts overflow the segment
+    list on the device (K4 must then skip the void render instead of walking truncated trajectories), the span is
+    re-run in halves until it fits"""
+    p = Pair(ctx, 2, make_tracks(12, [(400000, 2)] * 3 + [(400000, 1)]))
+    for t in range(4):
+        p.both("load", t, T(mode=ap.TM_VOICE, interval=float(1500 + 100 * t)))
+        p.both("seq", t, T(owned=False, mode=ap.TM_VOICE, idx=t), 4, [0.0, 1.0, 2.0, 3.0], [50.0, 100.0, 25.0, 75.0], rng_state(90 + t))
+        p.both("velocity", t, [1.0, 0.77, 1.31, 1.0][t])
+        p.both("start", t)
+    p.coordinate(300000)
+    p.coordinate(50000)
