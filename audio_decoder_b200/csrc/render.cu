@@ -264,7 +264,8 @@ __device__ __forceinline__ float build_epoch(float p, const float vel, const uin
 __global__ void voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t frames,
                                     Seg* __restrict__ segs, uint32_t* __restrict__ nsegs, uint32_t* __restrict__ err,
                                     const uint32_t* __restrict__ events, const uint32_t* __restrict__ nevents,
-                                    const uint32_t seg_cap) {
+                                    const uint32_t seg_cap, const uint32_t oc, Split* __restrict__ splits,
+                                    uint32_t* __restrict__ nsplits) {
     uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x;
     if (vi >= n_voices) return;
     VoiceDev v = voices[vi];
@@ -272,11 +273,92 @@ __global__ void voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_vo
     uint32_t n = 0;
     float p = v.pos;
     const uint32_t total = v.active ? frames * v.S : 0;
-    if (v.adv == 0 || total == 0) {
+    const uint32_t n_seq = v.first_seq >> 24;
+    if (nsplits) nsplits[vi] = 0;
+    if (n_seq == 0 || total == 0) {
         p = build_epoch(p, v.vel, v.end, total, [&](uint32_t a, float p0, int32_t d, float scale) {
             if (n < seg_cap) sg[n] = Seg{a, p0, d, scale};
             n += 1;
         });
+    } else if (v.adv == 0) {
+        // Voice with Seq processes that advances (S >= 1): steps stay advance events, exactly as for a plain voice.
+        // A retrigger before the read of call c = f * oc + k (processes.rs:82-85) starts a new epoch at home position
+        // at step A(c) = advance events before call c.  For a C >= 2 voice hit at 0 < k < C the channels < k of frame
+        // f have already read the OLD position of step f: that is recorded as a split and patched by K4b.
+        const uint32_t* ev = events + (size_t)vi * kMaxEvents;
+        const uint32_t n_ev = nevents[vi];
+        const float home = v.vel >= 0.0f ? 0.0f : (float)v.end;
+        Split* sp = splits + (size_t)vi * kMaxEvents;
+        uint32_t n_sp = 0, cur = 0, last0 = 0xFFFFFFFFu;
+        auto put = [&](uint32_t step0, float p0, int32_t d, float scale) {
+            if (step0 == last0 && n > 0) {                                        // an epoch of zero steps: replaced by its successor
+                if (n <= seg_cap) sg[n - 1] = Seg{step0, p0, d, scale};
+                return;
+            }
+            last0 = step0;
+            if (n < seg_cap) sg[n] = Seg{step0, p0, d, scale};
+            n += 1;
+        };
+        // Every epoch after a retrigger starts at `home` with the same velocity, so its segment sequence is the same
+        // every time up to where it is cut off: it is built once, as a template at the tail of the voice's segment
+        // area, and instantiated per epoch by shifting step0 (the closed form per segment is exact, so the position
+        // at the cut is too).  Only the first epoch (carried-in position) is built directly.
+        constexpr uint32_t kTpl = 64;
+        const bool use_tpl = n_ev > 0 && seg_cap > 4 * kTpl;
+        const uint32_t cap_eff = use_tpl ? seg_cap - kTpl : seg_cap;            // segments the voice itself may use
+        Seg* tpl = sg + cap_eff;
+        uint32_t n_tpl = 0;
+        bool tpl_ok = false;
+        if (use_tpl) {
+            build_epoch(home, v.vel, v.end, total, [&](uint32_t rel, float p0, int32_t d, float scale) {
+                if (n_tpl < kTpl) tpl[n_tpl] = Seg{rel, p0, d, scale};
+                n_tpl += 1;
+            });
+            tpl_ok = n_tpl <= kTpl;
+        }
+        auto put_capped = [&](uint32_t step0, float p0, int32_t d, float scale) {
+            if (step0 == last0 && n > 0) {
+                if (n <= cap_eff) sg[n - 1] = Seg{step0, p0, d, scale};
+                return;
+            }
+            last0 = step0;
+            if (n < cap_eff) sg[n] = Seg{step0, p0, d, scale};
+            n += 1;
+        };
+        bool at_home = false;                                                    // the current epoch starts at `home`
+        for (uint32_t e = 0; e <= n_ev; ++e) {
+            uint32_t a = total, f = 0, k = 0;
+            if (e < n_ev) {
+                const uint32_t c = ev[e];
+                f = c / oc;
+                k = c - f * oc;
+                a = v.C == 1 ? f * v.S + min(k, v.nch) : f + (k >= v.C ? 1u : 0u);
+                if (a > total) a = total;
+            }
+            const uint32_t base_step = cur, n_adv = a - cur;
+            if (at_home && tpl_ok) {
+                uint32_t t = 0;
+                for (; t < n_tpl && (t == 0 || tpl[t].step0 < n_adv); ++t) put_capped(base_step + tpl[t].step0, tpl[t].p0, tpl[t].d, tpl[t].scale);
+                // position after n_adv advances = position of step n_adv: in the last template segment that starts at or
+                // before it (a segment's closed form is only valid up to its own last step)
+                const Seg g = (t < n_tpl && tpl[t].step0 <= n_adv) ? tpl[t] : tpl[t - 1];
+                p = seg_eval(g.p0, g.d, g.scale, n_adv - g.step0);
+            } else {
+                p = build_epoch(p, v.vel, v.end, n_adv, [&](uint32_t rel, float p0, int32_t d, float scale) {
+                    put_capped(base_step + rel, p0, d, scale);
+                });
+            }
+            if (e == n_ev) break;
+            if (v.C >= 2 && k > 0 && k < v.C && k < oc) {                         // channels < k of frame f read the old position
+                if (n_sp < (uint32_t)kMaxEvents) sp[n_sp] = Split{f, k, p, 0u};
+                n_sp += 1;
+            }
+            p = home;
+            cur = a;
+            at_home = true;
+        }
+        if (n > cap_eff) n = seg_cap + 1;                                        // reported as an overflow below
+        nsplits[vi] = min(n_sp, (uint32_t)kMaxEvents);
     } else {
         // steps are calls; epochs are delimited by the retrigger events found by seq_event_scan
         const uint32_t* ev = events + (size_t)vi * kMaxEvents;
@@ -841,7 +923,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                 // (voices with Seq processes step per call and their segments also end at retriggers: for them the
                 // tile must lie inside ONE segment; a stereo voice on a stereo bus advances once per frame either way)
                 if (first_round && cur < nf && OC == 2 && v.C == 2 && v.nch == 2 && v.vel == 1.0f && r.p0 >= 0.0f &&
-                    (v.adv == 0 || (r.meta & 0xFFFFu) >= nf * v.S)) {
+                    ((v.first_seq >> 24) == 0 || (r.meta & 0xFFFFu) >= nf * v.S)) {
                     // velocity 1.0: while position + frames stays below 2^24 and the start is a multiple of the
                     // coarsest ulp it will meet, every `position += 1.0` is exact, whatever binades it crosses:
                     // the whole tile is one unit-step piece (frame index = floor(p0) + frame).
@@ -1031,34 +1113,58 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                             }
                         }
                         const bool all_ok = __all_sync(0xFFFFFFFFu, ok) && !overflow;
-                        const uint32_t lo_all = __reduce_min_sync(0xFFFFFFFFu, idx_lo);
-                        const uint32_t hi_all = __reduce_max_sync(0xFFFFFFFFu, (ex && !silent) ? idx_hi : 0u);
-                        const bool audible = lo_all != 0xFFFFFFFFu;
-                        const unsigned long long b0 = smp_i + (unsigned long long)lo_all * 4ull;
-                        const unsigned long long b1 = smp_i + ((unsigned long long)hi_all + 2ull) * 4ull;
-                        const unsigned long long a0 = b0 & ~15ull, a1 = (b1 + 15ull) & ~15ull;
-                        if (all_ok && (!audible || a1 - a0 <= (unsigned long long)kStageBytes)) {
-                            if (audible) {
-                                const uint32_t st = o % kStages, round = o / kStages;
-                                if (lane == 0 && round > 0) mbar_wait(empty + st, (round - 1) & 1);
-                                __syncwarp();
-                                if (ex) ptabs[st * kMaxPieces + lane] = make_uint4(fa | (fe << 16), (uint32_t)q0v, (uint32_t)g.d, shv | (silent ? 0x100u : 0u));
-                                if (lane == 0) {
-                                    StageMeta mm{};
-                                    mm.mode = kModeStaged | (kPathStereoMulti << 8);
-                                    mm.gain = gain_i;
-                                    mm.a0_off = (uint32_t)__popc(exm);
-                                    mm.frange = (vel_i != 1.0f) ? 1u : 0u;
-                                    mm.base_idx = lo_all;
-                                    mm.byte_off = (uint32_t)(b0 - a0);
-                                    *reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride) = mm;
+                        // every audible piece must fit a stage on its own; then the pieces are packed, in order, into as few
+                        // staged items as possible (normally one; two when a retrigger jumps to a far-away source region)
+                        auto span_fits = [&](uint32_t lo, uint32_t hi) -> bool {
+                            const unsigned long long b0 = smp_i + (unsigned long long)lo * 4ull;
+                            const unsigned long long b1 = smp_i + ((unsigned long long)hi + 2ull) * 4ull;
+                            return ((b1 + 15ull) & ~15ull) - (b0 & ~15ull) <= (unsigned long long)kStageBytes;
+                        };
+                        const bool own_fits = !ex || silent || span_fits(idx_lo, idx_hi);
+                        if (all_ok && __all_sync(0xFFFFFFFFu, own_fits)) {
+                            const uint32_t n_ex = (uint32_t)__popc(exm);            // segments j0 .. j0 + n_ex - 1 (a contiguous run of lanes)
+                            uint32_t g0 = 0;
+                            while (g0 < n_ex) {
+                                // running min / max of the source range over lanes g0 .. lane
+                                uint32_t lo_run = (lane >= g0 && ex) ? idx_lo : 0xFFFFFFFFu;
+                                uint32_t hi_run = (lane >= g0 && ex && !silent) ? idx_hi : 0u;
+#pragma unroll
+                                for (int d = 1; d < 32; d <<= 1) {
+                                    const uint32_t ul = __shfl_up_sync(0xFFFFFFFFu, lo_run, d), uh = __shfl_up_sync(0xFFFFFFFFu, hi_run, d);
+                                    if (lane >= g0 + (uint32_t)d) { lo_run = min(lo_run, ul); hi_run = max(hi_run, uh); }
                                 }
-                                __syncwarp();
-                                if (lane == 0) {
-                                    mbar_arrive_expect_tx(full + st, (uint32_t)(a1 - a0));
-                                    bulk_g2s(stages + (size_t)st * kStageBytes, reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0), full + st);
+                                const bool fit = lane >= g0 && lane < n_ex && (lo_run == 0xFFFFFFFFu || span_fits(lo_run, hi_run));
+                                const uint32_t fitm = __ballot_sync(0xFFFFFFFFu, fit) >> g0;
+                                const uint32_t cnt = fitm == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~fitm) - 1u;   // >= 1: every piece fits on its own
+                                const uint32_t L = g0 + cnt - 1u;
+                                const uint32_t lo_g = __shfl_sync(0xFFFFFFFFu, lo_run, L), hi_g = __shfl_sync(0xFFFFFFFFu, hi_run, L);
+                                if (lo_g != 0xFFFFFFFFu) {                                          // something audible in this group
+                                    const unsigned long long b0 = smp_i + (unsigned long long)lo_g * 4ull;
+                                    const unsigned long long b1 = smp_i + ((unsigned long long)hi_g + 2ull) * 4ull;
+                                    const unsigned long long a0 = b0 & ~15ull, a1 = (b1 + 15ull) & ~15ull;
+                                    const uint32_t st = o % kStages, round = o / kStages;
+                                    if (lane == 0 && round > 0) mbar_wait(empty + st, (round - 1) & 1);
+                                    __syncwarp();
+                                    if (ex && lane >= g0 && lane <= L)
+                                        ptabs[st * kMaxPieces + lane - g0] = make_uint4(fa | (fe << 16), (uint32_t)q0v, (uint32_t)g.d, shv | (silent ? 0x100u : 0u));
+                                    if (lane == 0) {
+                                        StageMeta mm{};
+                                        mm.mode = kModeStaged | (kPathStereoMulti << 8);
+                                        mm.gain = gain_i;
+                                        mm.a0_off = cnt;
+                                        mm.frange = (vel_i != 1.0f) ? 1u : 0u;
+                                        mm.base_idx = lo_g;
+                                        mm.byte_off = (uint32_t)(b0 - a0);
+                                        *reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride) = mm;
+                                    }
+                                    __syncwarp();
+                                    if (lane == 0) {
+                                        mbar_arrive_expect_tx(full + st, (uint32_t)(a1 - a0));
+                                        bulk_g2s(stages + (size_t)st * kStageBytes, reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0), full + st);
+                                    }
+                                    o += 1;
                                 }
-                                o += 1;
+                                g0 = L + 1u;
                             }
                             if (lane == i) cur = nf;
                         }
@@ -1131,6 +1237,29 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
     }
 }
 
+// ---------------------------------------------------------------- K4b
+// Split frames of voices with Seq processes: a retrigger that landed between the channels of frame f.  K4 rendered
+// every channel of that frame from the NEW epoch (home position); the channels before the hit must carry the old
+// position's sample instead: add (old - new) for them.  One thread per (voice, split).
+__global__ void voice_split_fixup(const VoiceDev* __restrict__ voices, uint32_t n_voices, const Split* __restrict__ splits,
+                                  const uint32_t* __restrict__ nsplits, uint32_t oc, int32_t* __restrict__ bus,
+                                  const uint32_t* __restrict__ err) {
+    if (*err) return;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t vi = idx / (uint32_t)kMaxEvents, si = idx % (uint32_t)kMaxEvents;
+    if (vi >= n_voices || si >= nsplits[vi]) return;
+    const VoiceDev v = voices[vi];
+    const Split s = splits[(size_t)vi * kMaxEvents + si];
+    const float home = v.vel >= 0.0f ? 0.0f : (float)v.end;
+    const uint32_t i_old = f2u_sat(s.p_old), i_new = f2u_sat(home);
+    for (uint32_t ch = 0; ch < s.k && ch < v.nch; ++ch) {
+        int32_t delta = 0;
+        if (i_old < v.end) delta += voice_sample(v.smp + (size_t)i_old * v.C + ch, v.C, s.p_old, v.vel, v.gain);
+        if (i_new < v.end) delta -= voice_sample(v.smp + (size_t)i_new * v.C + ch, v.C, home, v.vel, v.gain);
+        if (delta) atomicAdd(bus + (size_t)s.frame * oc + ch, delta);
+    }
+}
+
 // ---------------------------------------------------------------- K5
 // i16 wrapping accumulate == int32 sum mod 2^16 (engine.rs:441, release semantics)
 __global__ void bus_finalize(const int32_t* __restrict__ partial, int16_t* __restrict__ bus, uint64_t n) {
@@ -1171,7 +1300,7 @@ void route_voice(VoiceDev& v, uint32_t oc, bool has_seq) {
         v.S = 0;
     }
     v.adv = 0;
-    if (has_seq) {                  // steps become calls: a retrigger can land between two channels of a frame
+    if (has_seq && v.S == 0) {      // a voice that never advances but can be retriggered: steps become calls
         v.adv = oc | (lo << 8) | (na << 16);
         v.S = oc;
     }
@@ -1186,6 +1315,8 @@ void free_buffers(RenderBuffers& rb) {
     if (rb.d_seqs) cudaFree(rb.d_seqs);
     if (rb.d_events) cudaFree(rb.d_events);
     if (rb.d_nevents) cudaFree(rb.d_nevents);
+    if (rb.d_splits) cudaFree(rb.d_splits);
+    if (rb.d_nsplits) cudaFree(rb.d_nsplits);
     rb = RenderBuffers{};
 }
 
@@ -1206,8 +1337,8 @@ int reserve_buffers(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32
         BLAST_CUDA_TRY(cudaMalloc(&rb.d_nsegs, nv * sizeof(uint32_t)));
         rb.voices_cap = std::max(nv, rb.voices_cap);
         if (rb.d_events) {                       // sized by voices: regrown below
-            cudaFree(rb.d_events); cudaFree(rb.d_nevents);
-            rb.d_events = nullptr; rb.d_nevents = nullptr;
+            cudaFree(rb.d_events); cudaFree(rb.d_nevents); cudaFree(rb.d_splits); cudaFree(rb.d_nsplits);
+            rb.d_events = nullptr; rb.d_nevents = nullptr; rb.d_splits = nullptr; rb.d_nsplits = nullptr;
         }
     }
     if (!rb.d_err) BLAST_CUDA_TRY(cudaMalloc(&rb.d_err, sizeof(uint32_t)));
@@ -1223,6 +1354,8 @@ int reserve_buffers(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32
         if (!rb.d_events) {
             BLAST_CUDA_TRY(cudaMalloc(&rb.d_events, rb.voices_cap * kMaxEvents * sizeof(uint32_t)));
             BLAST_CUDA_TRY(cudaMalloc(&rb.d_nevents, rb.voices_cap * sizeof(uint32_t)));
+            BLAST_CUDA_TRY(cudaMalloc(&rb.d_splits, rb.voices_cap * kMaxEvents * sizeof(Split)));
+            BLAST_CUDA_TRY(cudaMalloc(&rb.d_nsplits, rb.voices_cap * sizeof(uint32_t)));
         }
     }
     return BLAST_OK;
@@ -1257,7 +1390,7 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         ctx->launches += 1;
     }
     voice_position_scan<<<(n_voices + 31) / 32, 32, 0, ctx->stream>>>(rb.d_voices, n_voices, (uint32_t)frames, rb.d_segs, rb.d_nsegs,
-                                                                       rb.d_err, rb.d_events, rb.d_nevents, rb.seg_cap);
+                                                                       rb.d_err, rb.d_events, rb.d_nevents, rb.seg_cap, oc, rb.d_splits, rb.d_nsplits);
     voice_tile_records<<<(unsigned)((need + 255) / 256), 256, 0, ctx->stream>>>(rb.d_voices, n_voices, rb.d_segs, rb.d_nsegs,
                                                                                 rb.d_recs, n_tiles, rb.d_err, rb.seg_cap);
     BLAST_CUDA_TRY(cudaGetLastError());
@@ -1305,6 +1438,12 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
     }
     BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
+    if (n_seqs > 0) {
+        voice_split_fixup<<<(n_voices * (uint32_t)kMaxEvents + 255) / 256, 256, 0, ctx->stream>>>(rb.d_voices, n_voices, rb.d_splits,
+                                                                                              rb.d_nsplits, oc, d_partial_bus, rb.d_err);
+        BLAST_CUDA_TRY(cudaGetLastError());
+        ctx->launches += 1;
+    }
     return BLAST_OK;
 }
 

@@ -5,7 +5,7 @@
 namespace blast_rdr {
 
 constexpr int kMaxSeg = 160;                   // position segments per voice per render (plain voices: <= ~45 are ever needed)
-constexpr int kMaxSegSeq = 1024;               // ... when Seq processes retrigger voices
+constexpr int kMaxSegSeq = 2048;               // ... when Seq processes retrigger voices
 constexpr int kFT = 2048;                      // frames per tile
 constexpr int kThreads = 256;
 constexpr int kFPT = kFT / kThreads;           // frames per thread
@@ -43,6 +43,13 @@ struct TileRec {           // state of one voice at the first step of one tile
 
 constexpr int kMaxEvents = 256;        // retrigger events per voice per render call
 
+struct Split {             // a retrigger between the channels of one frame (C >= 2 voices): channels < k keep the old sample
+    uint32_t frame;
+    uint32_t k;
+    float p_old;           // position of the trajectory the channels < k have read
+    uint32_t pad;
+};
+
 struct SeqDev {            // one Seq process (processes.rs:52-99) flattened for the GPU
     uint32_t base;         // tempo.current as the Seq sees it at call 0 of this render
     uint32_t rate;         // ticks of its tempo per call
@@ -68,6 +75,8 @@ struct RenderBuffers {     // device scratch of one render (owned by a scene or 
     size_t seqs_cap = 0;
     uint32_t* d_events = nullptr;      // [voices_cap][kMaxEvents] retrigger call indices
     uint32_t* d_nevents = nullptr;     // [voices_cap]
+    Split* d_splits = nullptr;         // [voices_cap][kMaxEvents]
+    uint32_t* d_nsplits = nullptr;     // [voices_cap]
 };
 
 int  reserve_buffers(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t n_seqs);

@@ -95,6 +95,7 @@ def c3_seq(ctx, voices, frames, iters):
             c.velocity(v, vel)
             c.start(v)
             c.set_voice(v, gain=float(np.float32(u) * np.float32(2.0 ** -7)))
+        c.render_partial_dev(4096, part.ptr)           # warm-up span: the conductor's buffers are allocated here
         ctx.sync()
         e0 = ctx.event().record()
         c.render_partial_dev(frames, part.ptr)
