@@ -375,6 +375,22 @@ int blast_pcm_decode_batch(blast_ctx* ctx, uint32_t n, const uint8_t* const* fil
     uint32_t chunk_index = 0;
     int rc = BLAST_OK;
 
+    // Host copies are coalesced: consecutive pieces whose source bytes are (almost) adjacent in host memory — the next
+    // piece of the same file, or the next file when the two images are back to back (the bytes in between are then
+    // that file's own header) — travel in ONE cudaMemcpyAsync, and so do results whose host and device destinations
+    // are both adjacent.  An asset directory read into one buffer is 2 copies per 32 MiB chunk instead of 2 per file.
+    constexpr uint64_t kMaxGap = 4096;
+    auto src_of = [&](const Piece& p) { return files[p.file] + descs[p.file].data_off + 2 * p.word0; };
+    auto adjacent = [&](const Piece& a, const Piece& b, uint64_t* gap) -> bool {
+        const uint8_t* end_a = src_of(a) + 2 * a.words;
+        const uint8_t* beg_b = src_of(b);
+        const bool same_file = a.file == b.file && b.word0 == a.word0 + a.words;
+        const bool back_to_back = b.file == a.file + 1 && files[a.file] + lens[a.file] == files[b.file];
+        if (!(same_file || back_to_back) || beg_b < end_a || (uint64_t)(beg_b - end_a) > kMaxGap) return false;
+        *gap = (uint64_t)(beg_b - end_a);
+        return true;
+    };
+
     auto flush = [&]() -> int {
         if (pieces.empty()) return BLAST_OK;
         blast_ctx::Lane& lane = ctx->lane[chunk_index % blast_ctx::kPipe];
@@ -383,11 +399,23 @@ int blast_pcm_decode_batch(blast_ctx* ctx, uint32_t n, const uint8_t* const* fil
         BLAST_CUDA_TRY(cudaStreamSynchronize(st));          // lane buffers are free again
         jobs.clear();
         ht.clear();
+        struct Run { const uint8_t* src; uint64_t dev_off, bytes; };
+        std::vector<Run> runs;
         uint64_t in_off = 0, out_off = 0;
-        for (const Piece& p : pieces) {
+        for (size_t k = 0; k < pieces.size(); ++k) {
+            const Piece& p = pieces[k];
+            uint64_t gap = 0;
+            if (k > 0 && adjacent(pieces[k - 1], p, &gap)) {
+                Run& r = runs.back();                        // device layout mirrors the host layout inside a run
+                in_off = r.dev_off + r.bytes + gap;
+                r.bytes += gap + 2 * p.words;
+            } else {
+                in_off = (in_off + 15) & ~15ull;
+                runs.push_back(Run{src_of(p), in_off, 2 * p.words});
+            }
             int16_t* dst = (d_out && d_out[p.file]) ? d_out[p.file] + p.word0 : (int16_t*)lane.d_tmp + out_off;
             jobs.push_back(blast_pcm_job{lane.d_in + in_off, dst, p.words, descs[p.file].big_endian, 0});
-            in_off += (2 * p.words + 15) & ~15ull;
+            in_off += 2 * p.words;
             out_off += (p.words + 7) & ~7ull;
         }
         uint64_t words = 0;
@@ -395,21 +423,34 @@ int blast_pcm_decode_batch(blast_ctx* ctx, uint32_t n, const uint8_t* const* fil
         std::memcpy(lane.h_tiles, ht.data(), ht.size() * sizeof(TileRef));
         BLAST_CUDA_TRY(cudaMemcpyAsync(lane.d_jobs, lane.h_jobs, jobs.size() * sizeof(JobDev), cudaMemcpyHostToDevice, st));
         BLAST_CUDA_TRY(cudaMemcpyAsync(lane.d_tiles, lane.h_tiles, ht.size() * sizeof(TileRef), cudaMemcpyHostToDevice, st));
-        for (size_t k = 0; k < pieces.size(); ++k) {
-            const Piece& p = pieces[k];
-            const uint8_t* src = files[p.file] + descs[p.file].data_off + 2 * p.word0;
-            BLAST_CUDA_TRY(cudaMemcpyAsync((void*)jobs[k].d_src, src, 2 * p.words, cudaMemcpyHostToDevice, st));
-        }
+        for (const Run& r : runs)
+            BLAST_CUDA_TRY(cudaMemcpyAsync(lane.d_in + r.dev_off, r.src, r.bytes, cudaMemcpyHostToDevice, st));
         int grid = (int)std::min<uint64_t>(ht.size(), (uint64_t)ctx->sm_count * kCtasPerSm);
         pcm16_decode_batch<<<grid, kThreads, 0, st>>>((const JobDev*)lane.d_jobs, (const TileRef*)lane.d_tiles, (uint32_t)ht.size());
         BLAST_CUDA_TRY(cudaGetLastError());
         ctx->launches += 1;
         if (host_out) {
+            int16_t* h_run = nullptr;
+            const int16_t* d_run = nullptr;
+            uint64_t run_words = 0;
+            auto send = [&]() -> int {
+                if (run_words) BLAST_CUDA_TRY(cudaMemcpyAsync(h_run, d_run, 2 * run_words, cudaMemcpyDeviceToHost, st));
+                run_words = 0;
+                return BLAST_OK;
+            };
             for (size_t k = 0; k < pieces.size(); ++k) {
                 const Piece& p = pieces[k];
-                if (host_out[p.file])
-                    BLAST_CUDA_TRY(cudaMemcpyAsync(host_out[p.file] + p.word0, jobs[k].d_dst, 2 * p.words, cudaMemcpyDeviceToHost, st));
+                if (!host_out[p.file]) continue;
+                int16_t* h = host_out[p.file] + p.word0;
+                const int16_t* d = jobs[k].d_dst;
+                if (run_words && h == h_run + run_words && d == d_run + run_words) {
+                    run_words += p.words;
+                } else {
+                    if (int r = send()) return r;
+                    h_run = h; d_run = d; run_words = p.words;
+                }
             }
+            if (int r = send()) return r;
         }
         pieces.clear();
         chunk_bytes = 0;
@@ -420,7 +461,7 @@ int blast_pcm_decode_batch(blast_ctx* ctx, uint32_t n, const uint8_t* const* fil
         uint64_t total = (descs[i].data_len + 1) / 2;
         for (uint64_t w0 = 0; w0 < total && rc == BLAST_OK; w0 += kPieceWords) {
             uint64_t w = std::min(kPieceWords, total - w0);
-            uint64_t slot = (2 * w + 15) & ~15ull;
+            uint64_t slot = ((2 * w + 15) & ~15ull) + kMaxGap;     // room for a coalesced gap in front of the piece
             if (!pieces.empty() && (chunk_bytes + slot > kChunkBytes || pieces.size() >= kChunkPieces)) rc = flush();
             pieces.push_back(Piece{i, w0, w});
             chunk_bytes += slot;

@@ -145,17 +145,19 @@ def run_ours(args):
     words_per_file = (data_len + 1) // 2
     frames_per_file = words_per_file // 2                      # stereo
 
-    # ---- synthetic file images: pinned host slab (e2e input) + HBM slab (device-resident input)
-    h_in = ctx.pinned(n_files * slot)
+    # ---- synthetic file images: pinned host slab (e2e input; the images lie back to back like an asset directory
+    #      read into one buffer) + HBM slab (device-resident input, one 256-byte aligned slot per file)
+    h_in = ctx.pinned(n_files * image_len)
     rng = np.random.default_rng(0xC20000 + rank)
-    view = h_in.u8.reshape(n_files, slot)
+    view = h_in.u8.reshape(n_files, image_len)
     view[:, :len(hdr)] = hdr
     chunk = 64
     for i in range(0, n_files, chunk):
         view[i:i + chunk, len(hdr):image_len] = rng.integers(0, 256, size=(min(chunk, n_files - i), data_len), dtype=np.uint8)
     d_in = ctx.alloc(n_files * slot)
     d_out = ctx.alloc(n_files * words_per_file * 2)
-    L.blast_memcpy_h2d(ctx.h, d_in.ptr, h_in.ptr, n_files * slot)
+    for i in range(n_files):
+        L.blast_memcpy_h2d(ctx.h, d_in.ptr + i * slot, h_in.ptr + i * image_len, image_len)
     ctx.sync()
     descs = [fp.probe("aiff", view[0, :image_len])] * n_files
     off = descs[0].data_off
@@ -163,7 +165,7 @@ def run_ours(args):
         # payload-only layout: what blast_pcm_decode_batch stages (16-byte aligned payloads)
         d_pay = ctx.alloc(n_files * slot)
         for i in range(n_files):
-            L.blast_memcpy_h2d(ctx.h, d_pay.ptr + i * slot, h_in.ptr + i * slot + off, data_len)
+            L.blast_memcpy_h2d(ctx.h, d_pay.ptr + i * slot, h_in.ptr + i * image_len + off, data_len)
         ctx.sync()
         d_src_base, src_extra = d_pay.ptr, 0
     else:
@@ -272,7 +274,7 @@ def run_ours(args):
     if not args.no_e2e:
         h_out = ctx.pinned(n_files * words_per_file * 2)
         h_bus = ctx.pinned(2 * frames_per_file * 2) if mix else None
-        files = (C.c_void_p * n_files)(*[h_in.ptr + i * slot for i in range(n_files)])
+        files = (C.c_void_p * n_files)(*[h_in.ptr + i * image_len for i in range(n_files)])
         lens = (C.c_size_t * n_files)(*([image_len] * n_files))
         dd = (_lib.PcmDesc * n_files)(*descs)
         host_out = (C.c_void_p * n_files)(*[h_out.ptr + i * words_per_file * 2 for i in range(n_files)])

@@ -172,3 +172,30 @@ def test_pcm24_extension(ctx, be, kind):
     for b, exp in zip(bufs, expect):
         got = b.download(np.int32 if kind == 0 else np.int16, len(exp))
         assert np.array_equal(got, exp)
+
+
+def test_back_to_back_images_are_coalesced_and_still_exact(ctx):
+    """an asset directory read into ONE host buffer: consecutive images are adjacent, so their copies travel
+    coalesced (payload + the next file's header bytes in one cudaMemcpyAsync); separate buffers in between"""
+    rng = np.random.default_rng(99)
+    kinds, images = [], []
+    for k in range(9):
+        kind = "wav" if k % 3 == 0 else "aiff"
+        n = int(rng.choice([0, 2, 777, 4096, 100001, 300000]))
+        img = synth.wav_image(500 + k, n) if kind == "wav" else synth.aiff_image(500 + k, n)
+        if n % 2:
+            img = np.concatenate([img, np.array([0x3C], np.uint8)])          # the byte the odd payload reads past its chunk
+        kinds.append(kind)
+        images.append(img)
+    slab = np.concatenate(images[:6])                                        # files 0..5 back to back
+    views, off = [], 0
+    for img in images[:6]:
+        views.append(slab[off:off + img.size])
+        off += img.size
+    views += images[6:]                                                      # files 6..8 in buffers of their own
+    descs = [fp.probe(k, im) for k, im in zip(kinds, views)]
+    outs, tracks = fp.decode_batch(ctx, views, descs, keep_on_device=True)
+    for k, im, o, t in zip(kinds, views, outs, tracks):
+        _, exp = (oracle.wav_parse if k == "wav" else oracle.aiff_parse)(im)
+        assert np.array_equal(o, exp), k
+        assert np.array_equal(t.download(np.int16, exp.size) if exp.size else exp, exp), k
