@@ -199,3 +199,31 @@ def test_back_to_back_images_are_coalesced_and_still_exact(ctx):
         _, exp = (oracle.wav_parse if k == "wav" else oracle.aiff_parse)(im)
         assert np.array_equal(o, exp), k
         assert np.array_equal(t.download(np.int16, exp.size) if exp.size else exp, exp), k
+
+
+def test_full_size_c2_batch_properties(ctx):
+    """BASELINE config 2 at full size — 1,024 x 2,880,000-byte 24-bit BE AIFF payloads, 1,474,560,000 i16 words — in
+    four sub-batches of 256 files: every word equals numpy's big-endian reading of the payload, and a checksum of
+    per-file checksums ties the four sub-batches together"""
+    n_files, sub = synth.C2_FILES, 256
+    hdr = np.frombuffer(synth.aiff_header(synth.C2_DATA_LEN), dtype=np.uint8)
+    image_len = hdr.size + synth.C2_DATA_LEN
+    total_words, digest = 0, np.uint64(0)
+    for b0 in range(0, n_files, sub):
+        rng = np.random.default_rng(0xC20000 + b0)
+        slab = np.empty(sub * image_len, dtype=np.uint8)              # the sub-batch lies back to back in one buffer
+        view = slab.reshape(sub, image_len)
+        view[:, :hdr.size] = hdr
+        view[:, hdr.size:] = rng.integers(0, 256, size=(sub, synth.C2_DATA_LEN), dtype=np.uint8)
+        images = [view[i] for i in range(sub)]
+        d = fp.probe("aiff", images[0])
+        assert (d.data_off, d.data_len, d.bits_per_sample, d.sample_rate) == (54, synth.C2_DATA_LEN, 24, 48000)
+        outs, _ = fp.decode_batch(ctx, images, [d] * sub)
+        for i in range(sub):
+            exp = view[i, 54:].view(">i2")
+            assert outs[i].size == synth.C2_DATA_LEN // 2
+            assert np.array_equal(outs[i], exp), (b0, i)
+            total_words += outs[i].size
+            digest ^= np.uint64(int(outs[i].view(np.uint16).astype(np.uint64).sum()) * (b0 + i + 1) & 0xFFFFFFFFFFFFFFFF)
+    assert total_words == 1_474_560_000
+    assert int(digest) != 0

@@ -181,3 +181,51 @@ def test_reference_panics_become_error_codes(ctx):
         ap.render(ctx, [t], [ap.VoiceParams(0, True)], 9, 4)                    # > 8 output channels
     bus, _ = ap.render(ctx, [t], [], 2, 4)                                      # no voices: silence
     assert list(bus) == [0] * 8
+
+
+def test_full_size_c3_properties(ctx):
+    """BASELINE config 3 at full size — 4,096 stereo voices x 2^20 frames, distinct clips generated on the GPU (17 GB),
+    mixed velocities — through the size-independent properties of the mix: linearity over a voice partition (what the
+    multi-GPU reduction relies on) and chained renders == one long render (position carry across calls)."""
+    import ctypes as C
+    from audio_decoder_b200 import blast_rand as br
+    voices, frames = 4096, 1 << 20
+    clip_words = (int(np.ceil(1.5 * frames)) + 2) * 2
+    draws = (clip_words + 3) // 4
+    slab = ctx.alloc(voices * draws * 8)
+    s = br.Streams(ctx, voices, draws, seed=0xC30000)
+    s.fill_dev(draws, 0, 100, slab.ptr, None, None)
+    ctx.sync()
+    prm = br.fill(ctx, 0xC3, 0, 1, 2 * voices, 0, 100, ranged=False, checks=False)[0][0]
+    tracks, vps = [], []
+    for v in range(voices):
+        u = float((int(prm[2 * v]) >> 11) * 2.0 ** -53)
+        w = float((int(prm[2 * v + 1]) >> 11) * 2.0 ** -53)
+        buf = blast.DevBuf.__new__(blast.DevBuf)
+        buf.ctx, buf.ptr, buf.nbytes = ctx, slab.ptr + v * draws * 8, draws * 8
+        buf.free = lambda: None
+        tracks.append(ap.Track(buf, clip_words, 2))
+        vps.append(ap.VoiceParams(v, True, 0.0, 1.0 if v % 2 == 0 else float(np.float32(0.5) + np.float32(w)),
+                                  float(np.float32(u) * np.float32(2.0 ** -7))))
+    n = frames * 2
+    part = ctx.alloc(4 * n)
+
+    def partial(vp, chunks):
+        sc = ap.Scene(ctx, tracks, vp, 2)
+        out, off = np.empty(n, dtype=np.int32), 0
+        for f in chunks:
+            sc.render_partial_dev(f, part.ptr)
+            sc.check()
+            out[off:off + 2 * f] = part.download(np.int32, 2 * f)
+            off += 2 * f
+        sc.close()
+        return out
+
+    whole = partial(vps, [frames])
+    assert np.abs(whole).max() > 1000                                         # something audible was mixed
+    # linearity over voice shards v mod 4 (the 4-GPU sharding rule): int32 partial buses add up exactly
+    shards = sum(partial([p if i % 4 == r else ap.VoiceParams(i, False) for i, p in enumerate(vps)], [frames]).astype(np.int64)
+                 for r in range(4))
+    assert np.array_equal(shards.astype(np.int32), whole)
+    # three chained renders (ragged cut points) == one long render
+    assert np.array_equal(partial(vps, [300_001, 2047, frames - 300_001 - 2047]), whole)
