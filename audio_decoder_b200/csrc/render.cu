@@ -310,7 +310,8 @@ __global__ void voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_vo
         uint32_t n_tpl = 0;
         bool tpl_ok = false;
         if (use_tpl) {
-            build_epoch(home, v.vel, v.end, total, [&](uint32_t rel, float p0, int32_t d, float scale) {
+            // total + 1 steps: the position AFTER the last advance of an epoch (step n_adv <= total) must be covered too
+            build_epoch(home, v.vel, v.end, total + 1u, [&](uint32_t rel, float p0, int32_t d, float scale) {
                 if (n_tpl < kTpl) tpl[n_tpl] = Seg{rel, p0, d, scale};
                 n_tpl += 1;
             });

@@ -390,3 +390,55 @@ def test_long_span_many_epochs_overflow_path(ctx):
         p.both("start", t)
     p.coordinate(300000)
     p.coordinate(50000)
+
+
+@pytest.mark.parametrize("seed", range(int(_os.environ.get("BLAST_FUZZ_SEEDS", "6"))))
+def test_random_degenerate_tempi_and_seqs(ctx, seed):
+    """fuzz over the corners of TempoState / Seq arithmetic: zero, negative, tiny, infinite and NaN intervals (via every
+    unit), period 0, steps that are negative / fractional / -0.0 / beyond the period, chances outside [0, 100] and NaN
+    (`chance as i64` saturates, NaN -> 0), tempi ticked by nobody or by several voices"""
+    r = np.random.default_rng(5000 + seed)
+    oc = int(r.choice([1, 2, 2, 4]))
+    tracks = make_tracks(300 + seed, [(int(r.integers(50, 3000)), int(r.choice([1, 2, 2, 3]))) for _ in range(3)])
+    p = Pair(ctx, oc, tracks)
+    weird_iv = [0.0, -5.0, 1e-3, 0.5, 1.0, 2.0, 7.5, float("inf"), float("nan"), 1e30, 3.0]
+    weird_steps = [0.0, -0.0, 1.0, 0.5, -1.0, 2.0, 3.0, 7.0, float("nan"), 0.25]
+    weird_chance = [0.0, 100.0, 50.0, -5.0, 100.5, float("nan"), 1e30, 99.99]
+    p.both("tc", T(mode=ap.TM_CONTEXT, unit=int(r.integers(0, 3)), interval=float(r.choice(weird_iv))))
+    for t in range(3):
+        owned = bool(r.random() < 0.7) or t == 0
+        p.both("load", t, T(idx=0, owned=owned, mode=ap.TM_VOICE if owned else int(r.choice([ap.TM_VOICE, ap.TM_CONTEXT])),
+                            unit=int(r.integers(0, 3)), interval=float(r.choice(weird_iv))))
+    for _ in range(int(r.integers(2, 7))):
+        n = int(r.integers(1, 4))
+        mode = int(r.choice([ap.TM_VOICE, ap.TM_PROCESS, ap.TM_CONTEXT]))
+        owned = mode == ap.TM_PROCESS or bool(r.random() < 0.3)
+        p.both("seq", int(r.integers(0, 3)), T(idx=int(r.integers(0, 3)) if mode == ap.TM_VOICE else 0, owned=owned, mode=mode,
+                                               unit=int(r.integers(0, 3)), interval=float(r.choice(weird_iv))),
+               int(r.choice([0, 1, 2, 4, 4, 16])), [float(x) for x in r.choice(weird_steps, size=n)],
+               [float(x) for x in r.choice(weird_chance, size=n)], rng_state(int(r.integers(0, 1 << 30))))
+    for v in range(3):
+        p.both("velocity", v, float(r.choice([1.0, 0.5, 1.25, -1.0, 0.0, 3.0])))
+        p.both("start", v)
+    if r.random() < 0.5:
+        p.both("start", 0, ap.IDX_TEMPO)
+    for _ in range(4):
+        p.coordinate(int(r.choice([1, 3, 64, 300, 1500])))
+        if r.random() < 0.3:
+            p.both(str(r.choice(["stop", "start", "pause", "resume"])), int(r.integers(0, 3)))
+
+
+def test_retrigger_on_every_call(ctx):
+    """a context tempo nobody ticks stays at 0, so a Seq with step -0.0 fires on EVERY call: the voice is reset before
+    each channel's read and still advances once per frame (position 1.0 after every frame).  Regression: the epoch
+    template must also cover the position after an epoch's last advance."""
+    p = Pair(ctx, 2, make_tracks(13, [(500, 2), (400, 1)]))
+    p.both("tc", T(mode=ap.TM_CONTEXT, interval=2.0))
+    p.both("start", 0, ap.IDX_TEMPO)
+    for t in range(2):
+        p.both("load", t)
+        p.both("seq", t, T(owned=False, mode=ap.TM_CONTEXT, idx=0), 4, [-0.0], [100.0], rng_state(70 + t))
+        p.both("start", t)
+    for frames in (1, 1, 3, 64, 300):
+        p.coordinate(frames)
+    assert p.g.get_voice(0).position == 1.0 and p.g.get_voice(1).position == 1.0
