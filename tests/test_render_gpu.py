@@ -229,3 +229,31 @@ def test_full_size_c3_properties(ctx):
     assert np.array_equal(shards.astype(np.int32), whole)
     # three chained renders (ragged cut points) == one long render
     assert np.array_equal(partial(vps, [300_001, 2047, frames - 300_001 - 2047]), whole)
+
+
+import os as _os
+
+
+@pytest.mark.parametrize("seed", range(int(_os.environ.get("BLAST_FUZZ_SEEDS", "8"))))
+def test_random_scenes_with_weird_floats(ctx, seed):
+    """fuzz over the f32 corners of Voice::process: NaN / inf / denormal / negative / huge velocities, positions and
+    gains, tiny clips, every channel routing; bus and final positions bit-identical to the oracle"""
+    r = np.random.default_rng(9000 + seed)
+    oc = int(r.choice([1, 2, 2, 3, 4]))
+    frames = int(r.choice([1, 7, 2047, 2048, 2049, 5000]))
+    vels = [1.0, 1.0, 0.5, 2.0 ** -20, 1e-39, 3.7, 1000.5, -0.5, float("nan"), float("inf"), float("-inf"), 0.0, -0.0, 0.9999999]
+    gains = [1.0, 0.0, -1.0, 1e30, -1e30, float("nan"), float("inf"), 2.0 ** -30, 1.6384, 0.5]
+    voices = []
+    for _ in range(int(r.integers(1, 7))):
+        ch = int(r.choice([1, 2, 2, 3]))
+        nfr = int(r.choice([1, 2, 3, 100, 2500, 6000]))
+        pos = [0.0, 0.999, 5.5, -1.0, -0.0, 1e8, float("nan"), 16777215.0, 16777216.0, float(nfr - 1), float(nfr), float(nfr + 100),
+               float(nfr) - 1.5]
+        voices.append(V(r.integers(-32768, 32768, size=nfr * ch).astype(np.int16), ch, float(r.choice(vels)), float(r.choice(gains)),
+                        float(r.choice(pos)), bool(r.random() < 0.9)))
+    with np.errstate(all="ignore"):
+        exp, epos = oracle_render(voices, oc, frames)
+        got, gpos = gpu_render(ctx, voices, oc, frames)
+    assert np.array_equal(got, exp), (seed, oc, frames)
+    for a, b in zip(gpos, epos):
+        assert same_pos(a, b), (seed, a, b)
