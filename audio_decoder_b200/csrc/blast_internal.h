@@ -36,6 +36,11 @@ struct blast_ctx {
     void* scratch[kScratch] = {nullptr};
     size_t scratch_cap[kScratch] = {0};
     void* mailbox = nullptr;          // 4 KiB pinned host memory for small read-backs
+    // per-context (= per-device) caches: function attributes are per device, scratch contents per context
+    int mpeg_ctas_per_sm = 0;         // occupancy of mpeg_walk once its dynamic shared-memory limit has been raised
+    uint64_t x128p_split_sub = 0;     // the sub-stream jump matrices J^(2^b) held in scratch slot 5
+    int x128p_split_mats = 0;
+    void* x128p_split_ptr = nullptr;
 };
 
 struct blast_event {

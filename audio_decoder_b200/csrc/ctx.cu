@@ -143,6 +143,7 @@ int blast_ctx_trim(blast_ctx* ctx) {
         ctx->scratch[i] = nullptr;
         ctx->scratch_cap[i] = 0;
     }
+    ctx->x128p_split_ptr = nullptr;                 // the cached jump matrices lived in scratch
     blast::release_pipe(ctx);
     return BLAST_OK;
 }

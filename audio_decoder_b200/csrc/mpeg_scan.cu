@@ -842,12 +842,14 @@ int scan_buffers(blast_ctx* ctx, uint64_t own_len, ScanBufs& sb) {
     if (!s1) return BLAST_ERR_CUDA;
     sb.t_hdr = reinterpret_cast<uint32_t*>(s1);
     sb.t_off = reinterpret_cast<uint16_t*>(s1 + hdr_b);
-    static int per_sm = 0;
-    if (per_sm == 0) {
+    if (ctx->mpeg_ctas_per_sm == 0) {                      // function attributes are per device: cached per context
+        int per_sm = 0;
         BLAST_CUDA_TRY(cudaFuncSetAttribute(mpeg_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
         BLAST_CUDA_TRY(cudaFuncSetAttribute(mpeg_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
         BLAST_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpeg_walk, kScanThreads, kScanSmem));
+        ctx->mpeg_ctas_per_sm = std::max(per_sm, 1);
     }
+    const int per_sm = ctx->mpeg_ctas_per_sm;
     const unsigned long long want = (sb.n_spans + kWalkers - 1) / kWalkers;
     sb.grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)ctx->sm_count * std::max(per_sm, 1));
     return BLAST_OK;

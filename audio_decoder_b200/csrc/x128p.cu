@@ -346,13 +346,8 @@ int blast_x128p_fill_dev(blast_ctx* ctx, blast_x128p* d_states, uint64_t n_strea
     U128* d_sub = reinterpret_cast<U128*>(sc + mats_b);
     uint64_t* d_subchecks = d_checks ? reinterpret_cast<uint64_t*>(sc + mats_b + st_b) : nullptr;
     // J^(2^b): cached per (sub, n_mats) — squaring 128x128 bit matrices costs about a millisecond on the host
-    static uint64_t cached_sub = 0;
-    static int cached_mats = 0;
-    static void* cached_ptr = nullptr;
-    static std::vector<uint4> h;
-    if (cached_sub != sub || cached_mats != n_mats || cached_ptr != d_mats) {
-        BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));             // `h` may still be in flight
-        h.assign((size_t)n_mats * 128, make_uint4(0, 0, 0, 0));
+    if (ctx->x128p_split_sub != sub || ctx->x128p_split_mats != n_mats || ctx->x128p_split_ptr != d_mats) {
+        std::vector<uint4> h((size_t)n_mats * 128, make_uint4(0, 0, 0, 0));
         Mat j = mat_pow(transition(), sub);
         for (int b = 0; b < n_mats; ++b) {
             for (int i = 0; i < 128; ++i)
@@ -361,7 +356,8 @@ int blast_x128p_fill_dev(blast_ctx* ctx, blast_x128p* d_states, uint64_t n_strea
             if (b + 1 < n_mats) j = mat_mul(j, j);
         }
         BLAST_CUDA_TRY(cudaMemcpyAsync(d_mats, h.data(), mats_b, cudaMemcpyHostToDevice, ctx->stream));
-        cached_sub = sub; cached_mats = n_mats; cached_ptr = d_mats;
+        BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));            // `h` is pageable and dies here
+        ctx->x128p_split_sub = sub; ctx->x128p_split_mats = n_mats; ctx->x128p_split_ptr = d_mats;
     }
     x128p_split_states<<<(unsigned)((n_sub + 127) / 128), 128, 0, ctx->stream>>>(d_mats, n_mats, st, n_streams, split, d_sub);
     BLAST_CUDA_TRY(cudaGetLastError());

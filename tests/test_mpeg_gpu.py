@@ -49,9 +49,10 @@ def test_scan_examples(ctx):
 @pytest.mark.parametrize("alphabet", ["dense", "random", "ffrun"])
 def test_scan_random_buffers(ctx, alphabet):
     rng = np.random.default_rng({"dense": 1, "random": 2, "ffrun": 3}[alphabet])
-    for trial in range(40):
+    import os
+    for trial in range(int(os.environ.get("BLAST_FUZZ_TRIALS", "40"))):
         n = int(rng.choice([1, 2, 3, 4, 5, 63, 64, 65, 127, 128, 129, 2047, 2048, 2049, 16383, 16384, 16385, 16387,
-                            32768 + 61, 70001, 300007]))
+                            32767, 32768, 32769, 32768 + 61, 65535, 65536, 65537, 70001, 300007]))
         if alphabet == "dense":
             b = rng.choice(np.array([0xFF, 0xFF, 0xE0, 0xFB, 0x00, 0x90, 0xF3], dtype=np.uint8), size=n)
         elif alphabet == "random":
