@@ -41,6 +41,7 @@ struct blast_ctx {
     uint64_t x128p_split_sub = 0;     // the sub-stream jump matrices J^(2^b) held in scratch slot 5
     int x128p_split_mats = 0;
     void* x128p_split_ptr = nullptr;
+    bool peer_count_zeroed = false;   // scratch slot 8: block counter of bus_reduce_peers
 };
 
 struct blast_event {

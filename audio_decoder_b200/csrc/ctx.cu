@@ -1,4 +1,6 @@
 // ctx.cu — context lifecycle, memory helpers, event timing for libblast_cuda.so
+#include <cstring>
+
 #include "blast_internal.h"
 
 namespace blast {
@@ -212,6 +214,32 @@ int blast_memcpy_d2h(blast_ctx* ctx, void* dst, const void* d_src, size_t bytes)
 int blast_memset_dev(blast_ctx* ctx, void* d_dst, int value, size_t bytes) {
     if (int rc = blast::bind(ctx)) return rc;
     if (bytes) BLAST_CUDA_TRY(cudaMemsetAsync(d_dst, value, bytes, ctx->stream));
+    return BLAST_OK;
+}
+
+// ---- peer memory between the one-process-per-GPU ranks of a box (CUDA IPC over NVLink / NVSwitch)
+int blast_ipc_export(blast_ctx* ctx, void* d_ptr, uint8_t handle_out[64]) {
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_REQUIRE(d_ptr && handle_out, BLAST_ERR_ARG, "blast_ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    BLAST_CUDA_TRY(cudaIpcGetMemHandle(&h, d_ptr));
+    std::memcpy(handle_out, &h, 64);
+    return BLAST_OK;
+}
+
+int blast_ipc_open(blast_ctx* ctx, const uint8_t handle[64], void** d_ptr_out) {
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_REQUIRE(handle && d_ptr_out, BLAST_ERR_ARG, "blast_ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    BLAST_CUDA_TRY(cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return BLAST_OK;
+}
+
+int blast_ipc_close(blast_ctx* ctx, void* d_ptr) {
+    if (int rc = blast::bind(ctx)) return rc;
+    if (d_ptr) BLAST_CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
     return BLAST_OK;
 }
 

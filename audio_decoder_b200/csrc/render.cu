@@ -1282,6 +1282,77 @@ __global__ void bus_finalize(const int32_t* __restrict__ partial, int16_t* __res
     }
 }
 
+// ---------------------------------------------------------------- K5p: the mix reduction over peer memory
+// One process per GPU; every rank's int32 partial bus is mapped into the root's address space (CUDA IPC over
+// NVLink / NVSwitch).  A rank publishes "my partial bus of step s is complete" with one system-scope store into
+// the root's flag array; the root's kernel waits for all flags, pulls the peers' buses with 128-bit loads, adds its
+// own, wraps to S16 (K5) and acknowledges to every peer — reduction and finalize in ONE kernel, no NCCL call, no
+// intermediate int32 bus.  Exact for the same reason as the all-reduce: i16 wrapping addition is addition mod 2^16.
+__global__ void peer_signal(uint32_t* flag, uint32_t value) {
+    __threadfence_system();                         // everything this stream wrote before is visible before the flag
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+
+__global__ void peer_wait(const uint32_t* flag, uint32_t value) {
+    uint32_t v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - value) < 0) __nanosleep(200);
+    } while ((int32_t)(v - value) < 0);
+}
+
+constexpr int kMaxPeers = 16;
+struct PeerPtrs {
+    const int32_t* part[kMaxPeers];                 // part[0] = own partial bus, the rest = peers' (IPC-mapped)
+    uint32_t* ack[kMaxPeers];                       // peers' ack flags (IPC-mapped); ack[0] unused
+};
+
+__global__ void __launch_bounds__(256)
+bus_reduce_peers(PeerPtrs pp, uint32_t n_parts, const uint32_t* __restrict__ ready, uint32_t step, int16_t* __restrict__ bus,
+                 uint64_t n, uint32_t* __restrict__ done_count) {
+    // every thread block waits for every peer's flag (they all become visible within a microsecond of each other)
+    if (threadIdx.x < n_parts && threadIdx.x > 0) {
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ready + threadIdx.x) : "memory");
+            if ((int32_t)(v - step) < 0) __nanosleep(100);
+        } while ((int32_t)(v - step) < 0);
+    }
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n4 = n / 4;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += stride) {
+        int4 acc = reinterpret_cast<const int4*>(pp.part[0])[k];
+        for (uint32_t r = 1; r < n_parts; ++r) {
+            uint4 v;                                                     // NVLink read, system-coherent (never the .nc path)
+            asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(reinterpret_cast<const uint4*>(pp.part[r]) + k) : "memory");
+            acc.x += (int32_t)v.x; acc.y += (int32_t)v.y; acc.z += (int32_t)v.z; acc.w += (int32_t)v.w;
+        }
+        uint2 o;
+        o.x = ((uint32_t)acc.x & 0xFFFF) | ((uint32_t)acc.y << 16);
+        o.y = ((uint32_t)acc.z & 0xFFFF) | ((uint32_t)acc.w << 16);
+        reinterpret_cast<uint2*>(bus)[k] = o;
+    }
+    for (uint64_t k = n4 * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        int32_t acc = pp.part[0][k];
+        for (uint32_t r = 1; r < n_parts; ++r) acc += *reinterpret_cast<const volatile int32_t*>(pp.part[r] + k);
+        bus[k] = (int16_t)acc;
+    }
+    // the last block to finish acknowledges: the peers may overwrite their partial buses again
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t prev = atomicAdd(done_count, 1u);
+        if (prev + 1 == gridDim.x) {
+            *done_count = 0;
+            __threadfence_system();
+            for (uint32_t r = 1; r < n_parts; ++r)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pp.ack[r]), "r"(step) : "memory");
+        }
+    }
+}
+
 }  // namespace
 
 namespace blast_rdr {
@@ -1591,6 +1662,52 @@ int blast_bus_finalize_dev(blast_ctx* ctx, const int32_t* d_partial, int16_t* d_
     uint64_t blocks = (n_slots / 4 + 255) / 256;
     int grid = (int)std::min<uint64_t>(std::max<uint64_t>(blocks, 1), (uint64_t)ctx->sm_count * 8);
     bus_finalize<<<grid, 256, 0, ctx->stream>>>(d_partial, d_bus, n_slots);
+    BLAST_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    return BLAST_OK;
+}
+
+int blast_peer_signal_dev(blast_ctx* ctx, uint32_t* d_flag, uint32_t value) {
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_REQUIRE(d_flag != nullptr, BLAST_ERR_ARG, "blast_peer_signal_dev: null flag");
+    peer_signal<<<1, 1, 0, ctx->stream>>>(d_flag, value);
+    BLAST_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    return BLAST_OK;
+}
+
+int blast_peer_wait_dev(blast_ctx* ctx, const uint32_t* d_flag, uint32_t value) {
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_REQUIRE(d_flag != nullptr, BLAST_ERR_ARG, "blast_peer_wait_dev: null flag");
+    peer_wait<<<1, 1, 0, ctx->stream>>>(d_flag, value);
+    BLAST_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    return BLAST_OK;
+}
+
+int blast_bus_reduce_peers_dev(blast_ctx* ctx, const int32_t* const* d_parts, uint32_t* const* d_peer_acks, uint32_t n_parts,
+                               const uint32_t* d_ready, uint32_t step, int16_t* d_bus, uint64_t n_slots) {
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_REQUIRE(d_parts && d_bus && n_parts >= 1 && (n_parts == 1 || (d_peer_acks && d_ready)), BLAST_ERR_ARG,
+                  "blast_bus_reduce_peers_dev: null argument");
+    if (n_parts > (uint32_t)kMaxPeers) return blast::set_error(BLAST_ERR_CAPACITY, "at most %d partial buses", kMaxPeers);
+    if (n_slots == 0) return BLAST_OK;
+    PeerPtrs pp{};
+    for (uint32_t r = 0; r < n_parts; ++r) {
+        BLAST_REQUIRE(d_parts[r] != nullptr && ((uintptr_t)d_parts[r] & 15) == 0, BLAST_ERR_ARG, "partial buses must be 16-byte aligned");
+        pp.part[r] = d_parts[r];
+        pp.ack[r] = r ? d_peer_acks[r] : nullptr;
+    }
+    BLAST_REQUIRE(((uintptr_t)d_bus & 7) == 0, BLAST_ERR_ARG, "the bus must be 8-byte aligned");
+    uint32_t* d_count = static_cast<uint32_t*>(blast::scratch(ctx, 8, 256));
+    if (!d_count) return BLAST_ERR_CUDA;
+    if (!ctx->peer_count_zeroed) {
+        BLAST_CUDA_TRY(cudaMemsetAsync(d_count, 0, 256, ctx->stream));
+        ctx->peer_count_zeroed = true;
+    }
+    const uint64_t blocks = (n_slots / 4 + 255) / 256;
+    const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(blocks, 1), (uint64_t)ctx->sm_count * 4);   // all resident: they spin
+    bus_reduce_peers<<<grid, 256, 0, ctx->stream>>>(pp, n_parts, d_ready, step, d_bus, n_slots, d_count);
     BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
     return BLAST_OK;

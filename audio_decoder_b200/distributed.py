@@ -164,3 +164,81 @@ class ShardedMpegIndex:
                                               d_off.ptr, n.value, C.byref(n)))
         return dict(d_offsets=d_off, n_offsets=n.value, ref_header=ref.value, n_candidates=n_cand_total,
                     n_candidates_local=count, range=(start, own, halo), d_pos=d_pos, d_hdr=d_hdr)
+
+
+# ---------------------------------------------------------------------------------- the mix reduction over peer memory
+class PeerBus:
+    """The render's one exchange step without a collective library: every rank's int32 partial bus is mapped into the
+    root rank's address space (CUDA IPC over NVLink / NVSwitch) and the root reduces + finalizes in ONE kernel
+    (blast_bus_reduce_peers_dev).  torch.distributed only carries the 64-byte IPC handles at set-up time.
+
+    Per step, on every rank:      bus.wait_ack(); <render into bus.part.ptr>; bus.reduce(d_bus_i16_on_root)
+    """
+    ACK_OFF = 256                  # byte offset of a rank's own ack flag inside its flag block
+
+    def __init__(self, ctx, n_slots: int, rank: int, world: int, group=None, root: int = 0):
+        import ctypes as C
+        import torch.distributed as dist
+        from .errors import check
+        self.ctx, self.rank, self.world, self.root, self.n_slots = ctx, rank, world, root, n_slots
+        self.part = ctx.alloc(max(256, 4 * n_slots))
+        self.flags = ctx.alloc(512)           # [0, 4*world): ready flags (used on the root), [256, 260): own ack flag
+        self.flags.zero()
+        self.part.zero()
+        ctx.sync()
+        self.step = 0
+        self._opened = []
+        if world == 1:
+            return
+
+        def export(ptr):
+            h = (C.c_uint8 * 64)()
+            check(ctx.lib.blast_ipc_export(ctx.h, ptr, h))
+            return bytes(h)
+
+        def open_(handle):
+            p = C.c_void_p()
+            check(ctx.lib.blast_ipc_open(ctx.h, (C.c_uint8 * 64).from_buffer_copy(handle), C.byref(p)))
+            self._opened.append(p.value)
+            return p.value
+
+        mine = (export(self.part.ptr), export(self.flags.ptr))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine, group=group)
+        if rank == root:
+            self.parts = [self.part.ptr] + [open_(everyone[r][0]) for r in range(world) if r != root]
+            self.acks = [0] + [open_(everyone[r][1]) + self.ACK_OFF for r in range(world) if r != root]
+            self.slot_of = {r: i + 1 for i, r in enumerate(r for r in range(world) if r != root)}
+        else:
+            self.root_flags = open_(everyone[root][1])
+            # my ready flag on the root: entry = my position among the non-root ranks, + 1
+            self.my_slot = 1 + sum(1 for r in range(rank) if r != root)
+        dist.barrier(group=group)
+
+    def wait_ack(self):
+        """before overwriting the partial bus again: the stream waits until the root has consumed the previous step"""
+        from .errors import check
+        if self.world > 1 and self.rank != self.root and self.step > 0:
+            check(self.ctx.lib.blast_peer_wait_dev(self.ctx.h, self.flags.ptr + self.ACK_OFF, self.step))
+
+    def reduce(self, d_bus: int):
+        """after the render: non-root ranks publish their partial bus, the root reduces + wraps into d_bus (S16)"""
+        import ctypes as C
+        from .errors import check
+        self.step += 1
+        L, ctx = self.ctx.lib, self.ctx
+        if self.world == 1:
+            check(L.blast_bus_finalize_dev(ctx.h, self.part.ptr, d_bus, self.n_slots))
+        elif self.rank != self.root:
+            check(L.blast_peer_signal_dev(ctx.h, self.root_flags + 4 * self.my_slot, self.step))
+        else:
+            n = len(self.parts)
+            parts = (C.c_void_p * n)(*self.parts)
+            acks = (C.c_void_p * n)(*self.acks)
+            check(L.blast_bus_reduce_peers_dev(ctx.h, parts, acks, n, self.flags.ptr, self.step, d_bus, self.n_slots))
+
+    def close(self):
+        self.ctx.sync()
+        for p in self._opened:
+            self.ctx.lib.blast_ipc_close(self.ctx.h, p)
+        self._opened = []

@@ -190,7 +190,13 @@ def run_ours(args):
             voices.append(ap.VoiceParams(i, True, 0.0, 1.0, gain))
         scene = ap.Scene(ctx, tracks, voices, 2)
         n_slots = frames_per_file * 2
-        if world > 1:
+        peer = None
+        if world > 1 and args.reduce == "p2p":
+            # the one exchange step over peer memory: partial buses mapped into rank 0, ONE reduce + finalize kernel
+            from audio_decoder_b200 import distributed as bd
+            peer = bd.PeerBus(ctx, n_slots, rank, world)
+            part_ptr = peer.part.ptr
+        elif world > 1:
             t_part = torch.empty(n_slots, dtype=torch.int32, device=f"cuda:{local}")
             part_ptr = t_part.data_ptr()
         else:
@@ -200,6 +206,19 @@ def run_ours(args):
         alg_bytes_mix = 4 * (frames_per_file - 1) * n_files + 2 * n_slots   # source frames touched + S16 bus
     n_ev = 3 if mix else 2
 
+    def mix_step():
+        if peer is not None:
+            peer.wait_ack()                                        # rank 0 has consumed the previous partial bus
+            scene.restore_dev()
+            scene.render_partial_dev(frames_per_file, part_ptr)
+            peer.reduce(d_bus.ptr)                                 # signal (ranks > 0) / wait + reduce + finalize (rank 0)
+            return
+        scene.restore_dev()
+        scene.render_partial_dev(frames_per_file, part_ptr)
+        if world > 1:
+            dist.all_reduce(t_part, op=dist.ReduceOp.SUM)          # NCCL variant: int32 partial buses
+        ap.finalize_bus(ctx, part_ptr, d_bus.ptr, n_slots)
+
     def step(evs=None):
         if evs:
             evs[0].record()
@@ -207,11 +226,7 @@ def run_ours(args):
         if evs:
             evs[1].record()
         if mix:
-            scene.restore_dev()
-            scene.render_partial_dev(frames_per_file, part_ptr)
-            if world > 1:
-                dist.all_reduce(t_part, op=dist.ReduceOp.SUM)      # the one collective: int32 partial buses
-            ap.finalize_bus(ctx, part_ptr, d_bus.ptr, n_slots)
+            mix_step()
             if evs:
                 evs[2].record()
 
@@ -259,8 +274,9 @@ def run_ours(args):
     roofline_mix = None
     if mix:
         ach = alg_bytes_mix / (ms_mix * 1e-3) / 1e9
-        roofline_mix = {"kernel": "voice_position_scan + voice_render_mix_tma + bus_finalize" +
-                                  (" + NCCL all-reduce(int32)" if world > 1 else ""),
+        roofline_mix = {"kernel": "voice_position_scan + voice_tile_records + voice_render_mix_tma + " +
+                                  ("bus_finalize" if world == 1 else "bus_reduce_peers (peer memory)" if peer is not None
+                                   else "NCCL all-reduce(int32) + bus_finalize"),
                         "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                         "frac": round(ach / peak, 4), "algorithmic_bytes_per_step": alg_bytes_mix,
                         "ms_per_step": round(ms_mix, 4), "traffic": traffic.get("voice_render_mix_tma_c2")}
@@ -289,12 +305,9 @@ def run_ours(args):
             if rc != 0:
                 raise RuntimeError(L.blast_last_error().decode())
             if mix:
-                scene.restore_dev()
-                scene.render_partial_dev(frames_per_file, part_ptr)
-                if world > 1:
-                    dist.all_reduce(t_part, op=dist.ReduceOp.SUM)
-                ap.finalize_bus(ctx, part_ptr, d_bus.ptr, n_slots)
-                L.blast_memcpy_d2h(ctx.h, h_bus.ptr, d_bus.ptr, 2 * n_slots)
+                mix_step()
+                if peer is None or rank == 0:                      # over peer memory the bus exists on rank 0 only
+                    L.blast_memcpy_d2h(ctx.h, h_bus.ptr, d_bus.ptr, 2 * n_slots)
                 ctx.sync()
 
         def e2e_run(to_host):
@@ -342,7 +355,8 @@ def run_ours(args):
                    "l2": f"per step {n_files * data_len / 1e6:.0f} MB of file images are read and {samples_per_step * 2 / 1e6:.0f} MB of "
                          "samples written then re-read: far larger than the 126 MB L2 (no flush needed)",
                    "parallelism": f"files / voices sharded over {world} rank(s)" +
-                                  ("; one int32 all-reduce of the partial bus per step (NCCL)" if world > 1 and mix else "; no collective")},
+                                  (("; partial buses reduced + finalized by ONE kernel on rank 0 over peer memory (CUDA IPC / NVLink), no collective library"
+                                    if peer is not None else "; one int32 all-reduce of the partial bus per step (NCCL)") if world > 1 and mix else "; no collective")},
         "roofline": roofline, "roofline_mix": roofline_mix,
         "kernel_ms": {"decode": round(ms_decode, 4), "mix": round(ms_mix, 4)},
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "e2e_parse_dropin": e2e_dropin,
@@ -353,6 +367,9 @@ def run_ours(args):
         print(json.dumps(out))
     plan.close()
     if mix:
+        if peer is not None:
+            barrier(dist, local)
+            peer.close()
         scene.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -468,6 +485,8 @@ def main():
     ap.add_argument("--no-mix", action="store_true", help="decode only (no render/mix of the decoded tracks)")
     ap.add_argument("--ref-files-per-thread", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: the mix reduction over peer memory (one fused kernel on rank 0) or as an NCCL all-reduce")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

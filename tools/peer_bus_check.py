@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Run under torchrun: the mix reduction over peer memory (distributed.PeerBus, one fused reduce + finalize kernel on
+rank 0) against (a) the NCCL all-reduce + finalize path and (b) a single-GPU render of the whole scene on rank 0, over
+several steps with changing gains (exercises the ready / ack flag protocol); then timings of both paths."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import audio_decoder_b200 as blast  # noqa: E402
+from audio_decoder_b200 import audio_processing as ap, distributed as bd  # noqa: E402
+
+if __name__ == "__main__":
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = blast.Context(local, stream=torch.cuda.current_stream().cuda_stream)
+    rng = np.random.default_rng(7)                                   # the same scene on every rank
+    n_voices, frames = 64, 200_003
+    clips = [rng.integers(-32768, 32768, size=(frames * 2 + 8) * 2).astype(np.int16) for _ in range(n_voices)]
+    tracks = [ap.Track.from_host(ctx, c, 2) for c in clips]
+    n = frames * 2
+    peer = bd.PeerBus(ctx, n, rank, world)
+    d_bus = ctx.alloc(2 * n)
+    t_part = torch.empty(n, dtype=torch.int32, device=f"cuda:{local}")
+    d_bus2 = ctx.alloc(2 * n)
+    ok = True
+    for step in range(5):
+        vps = [ap.VoiceParams(v, True, 0.0, 1.0 if v % 3 else 0.77, float(np.float32(0.3 + 0.1 * step + 0.01 * v))) for v in range(n_voices)]
+        mine = [p if v % world == rank else ap.VoiceParams(v, False) for v, p in enumerate(vps)]
+        sc = ap.Scene(ctx, tracks, mine, 2)
+        peer.wait_ack()
+        sc.render_partial_dev(frames, peer.part.ptr)
+        peer.reduce(d_bus.ptr)
+        sc.set_voices(mine)
+        sc.render_partial_dev(frames, t_part.data_ptr())
+        dist.all_reduce(t_part, op=dist.ReduceOp.SUM)
+        ap.finalize_bus(ctx, t_part.data_ptr(), d_bus2.ptr, n)
+        ctx.sync()
+        sc.close()
+        if rank == 0:
+            a, b = d_bus.download(np.int16, n), d_bus2.download(np.int16, n)
+            whole, _ = ap.render(ctx, tracks, vps, 2, frames)
+            ok = ok and np.array_equal(a, b) and np.array_equal(a, whole)
+            assert ok, f"step {step}: peer-memory bus differs"
+    # ---- timing of the exchange alone (partial buses already rendered): C3-sized bus (2^20 frames x 2)
+    n = 1 << 21
+    peer2 = bd.PeerBus(ctx, n, rank, world)
+    d_b = ctx.alloc(2 * n)
+    t_p = torch.zeros(n, dtype=torch.int32, device=f"cuda:{local}")
+    res = {"world": world, "parity": bool(ok)}
+    for name in ("p2p", "nccl"):
+        times = []
+        for it in range(12):
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if name == "p2p":
+                peer2.wait_ack()
+                peer2.reduce(d_b.ptr)
+            else:
+                dist.all_reduce(t_p, op=dist.ReduceOp.SUM)
+                ap.finalize_bus(ctx, t_p.data_ptr(), d_b.ptr, n)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            if it >= 2:
+                times.append(float(ms))
+        res[name + "_us"] = round(1e3 * float(np.median(times)), 1)
+    dist.barrier()
+    peer.close()
+    peer2.close()
+    if rank == 0:
+        print(json.dumps(res))
+    dist.destroy_process_group()
