@@ -165,9 +165,9 @@ SIGNATURES = {
     "blast_ipc_export": (C.c_int, [_vp, _vp, _vp]),
     "blast_ipc_open": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "blast_ipc_close": (C.c_int, [_vp, _vp]),
-    "blast_peer_signal_dev": (C.c_int, [_vp, _vp, _u32]),
-    "blast_peer_wait_dev": (C.c_int, [_vp, _vp, _u32]),
-    "blast_bus_reduce_peers_dev": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _u32, _vp, _u32, _vp, _u64]),
+    "blast_peer_signal_dev": (C.c_int, [_vp, C.POINTER(_vp), _u32, _u32]),
+    "blast_peer_wait_dev": (C.c_int, [_vp, _vp, _u32, _u32]),
+    "blast_bus_reduce_peers_dev": (C.c_int, [_vp, C.POINTER(_vp), _u32, _vp, _u32, _u32, _vp, _u64, _u64, C.POINTER(_vp), _u32]),
     "blast_render": (C.c_int, [_vp, C.POINTER(Track), _u32, C.POINTER(Voice), _u32, _u32, _u64, _vp,
                                C.POINTER(Voice)]),
 }

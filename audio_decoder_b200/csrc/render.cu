@@ -1283,72 +1283,85 @@ __global__ void bus_finalize(const int32_t* __restrict__ partial, int16_t* __res
 }
 
 // ---------------------------------------------------------------- K5p: the mix reduction over peer memory
-// One process per GPU; every rank's int32 partial bus is mapped into the root's address space (CUDA IPC over
-// NVLink / NVSwitch).  A rank publishes "my partial bus of step s is complete" with one system-scope store into
-// the root's flag array; the root's kernel waits for all flags, pulls the peers' buses with 128-bit loads, adds its
-// own, wraps to S16 (K5) and acknowledges to every peer — reduction and finalize in ONE kernel, no NCCL call, no
-// intermediate int32 bus.  Exact for the same reason as the all-reduce: i16 wrapping addition is addition mod 2^16.
-__global__ void peer_signal(uint32_t* flag, uint32_t value) {
-    __threadfence_system();                         // everything this stream wrote before is visible before the flag
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
-}
-
-__global__ void peer_wait(const uint32_t* flag, uint32_t value) {
-    uint32_t v;
-    do {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if ((int32_t)(v - value) < 0) __nanosleep(200);
-    } while ((int32_t)(v - value) < 0);
-}
-
+// One process per GPU; every rank's int32 partial bus (and a small block of step-counter flags) is mapped into its
+// peers' address spaces (CUDA IPC over NVLink / NVSwitch).  Per step every rank (1) publishes "my partial bus of step
+// s is complete" with one system-scope store per peer, (2) runs ONE kernel that waits for all ready flags, pulls ITS
+// slice of every peer's bus with 128-bit loads, adds its own, wraps to S16 (K5) and stores the slice straight into
+// the root's bus, then (3) tells every peer "I am done with your bus" and the root "slice s is in place".
+// Reduce-scatter, finalize and gather-to-root in one kernel, no collective library, no intermediate int32 bus, and
+// 1/N of the bus crosses each GPU's links.  Exact for the same reason as the all-reduce: i16 wrapping addition is
+// addition mod 2^16.
 constexpr int kMaxPeers = 16;
-struct PeerPtrs {
+struct FlagList {
+    uint32_t* p[2 * kMaxPeers];
+};
+struct PartList {
     const int32_t* part[kMaxPeers];                 // part[0] = own partial bus, the rest = peers' (IPC-mapped)
-    uint32_t* ack[kMaxPeers];                       // peers' ack flags (IPC-mapped); ack[0] unused
 };
 
-__global__ void __launch_bounds__(256)
-bus_reduce_peers(PeerPtrs pp, uint32_t n_parts, const uint32_t* __restrict__ ready, uint32_t step, int16_t* __restrict__ bus,
-                 uint64_t n, uint32_t* __restrict__ done_count) {
-    // every thread block waits for every peer's flag (they all become visible within a microsecond of each other)
-    if (threadIdx.x < n_parts && threadIdx.x > 0) {
-        uint32_t v;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ready + threadIdx.x) : "memory");
-            if ((int32_t)(v - step) < 0) __nanosleep(100);
-        } while ((int32_t)(v - step) < 0);
+__global__ void peer_signal(FlagList fl, uint32_t n, uint32_t value) {
+    __threadfence_system();                         // everything this stream wrote before is visible before the flags
+    if (threadIdx.x < n) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(fl.p[threadIdx.x]), "r"(value) : "memory");
+}
+
+__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t value) {
+    uint32_t v;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - value) >= 0) break;       // step counters, compared with wrap-around
+        __nanosleep(100);
     }
+}
+
+__global__ void peer_wait(const uint32_t* flags, uint32_t n, uint32_t value) {
+    if (threadIdx.x < n) wait_flag(flags + threadIdx.x, value);
+}
+
+__global__ void __launch_bounds__(256)
+bus_reduce_peers(PartList pp, uint32_t n_parts, const uint32_t* __restrict__ ready, uint32_t n_ready, uint32_t step,
+                 int16_t* __restrict__ bus, uint64_t slot0, uint64_t n, FlagList after, uint32_t n_after,
+                 uint32_t* __restrict__ done_count) {
+    // every thread block waits for every ready flag (they all become visible within a microsecond of each other)
+    if (threadIdx.x < n_ready) wait_flag(ready + threadIdx.x, step);
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t n4 = n / 4;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += stride) {
-        int4 acc = reinterpret_cast<const int4*>(pp.part[0])[k];
-        for (uint32_t r = 1; r < n_parts; ++r) {
-            uint4 v;                                                     // NVLink read, system-coherent (never the .nc path)
-            asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(reinterpret_cast<const uint4*>(pp.part[r]) + k) : "memory");
-            acc.x += (int32_t)v.x; acc.y += (int32_t)v.y; acc.z += (int32_t)v.z; acc.w += (int32_t)v.w;
+        // all remote loads of this vector are issued before the first add: an NVLink round trip is microseconds
+        uint4 v[kMaxPeers - 1];
+#pragma unroll
+        for (int r = 1; r < kMaxPeers; ++r) {
+            v[r - 1] = make_uint4(0, 0, 0, 0);
+            if ((uint32_t)r < n_parts)                                   // system-coherent loads (never the .nc path)
+                asm("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                    : "=r"(v[r - 1].x), "=r"(v[r - 1].y), "=r"(v[r - 1].z), "=r"(v[r - 1].w)
+                    : "l"(reinterpret_cast<const uint4*>(pp.part[r] + slot0) + k));
+        }
+        int4 acc = reinterpret_cast<const int4*>(pp.part[0] + slot0)[k];
+#pragma unroll
+        for (int r = 1; r < kMaxPeers; ++r) {
+            acc.x += (int32_t)v[r - 1].x; acc.y += (int32_t)v[r - 1].y; acc.z += (int32_t)v[r - 1].z; acc.w += (int32_t)v[r - 1].w;
         }
         uint2 o;
         o.x = ((uint32_t)acc.x & 0xFFFF) | ((uint32_t)acc.y << 16);
         o.y = ((uint32_t)acc.z & 0xFFFF) | ((uint32_t)acc.w << 16);
-        reinterpret_cast<uint2*>(bus)[k] = o;
+        reinterpret_cast<uint2*>(bus + slot0)[k] = o;                    // local on the root, an NVLink store elsewhere
     }
     for (uint64_t k = n4 * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
-        int32_t acc = pp.part[0][k];
-        for (uint32_t r = 1; r < n_parts; ++r) acc += *reinterpret_cast<const volatile int32_t*>(pp.part[r] + k);
-        bus[k] = (int16_t)acc;
+        int32_t acc = pp.part[0][slot0 + k];
+        for (uint32_t r = 1; r < n_parts; ++r) acc += *reinterpret_cast<const volatile int32_t*>(pp.part[r] + slot0 + k);
+        bus[slot0 + k] = (int16_t)acc;
     }
-    // the last block to finish acknowledges: the peers may overwrite their partial buses again
+    // the last block to finish publishes: peers may overwrite their partial buses, the root's slice is in place
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        __threadfence_system();
         const uint32_t prev = atomicAdd(done_count, 1u);
         if (prev + 1 == gridDim.x) {
             *done_count = 0;
             __threadfence_system();
-            for (uint32_t r = 1; r < n_parts; ++r)
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pp.ack[r]), "r"(step) : "memory");
+            for (uint32_t i = 0; i < n_after; ++i)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(after.p[i]), "r"(step) : "memory");
         }
     }
 }
@@ -1667,38 +1680,47 @@ int blast_bus_finalize_dev(blast_ctx* ctx, const int32_t* d_partial, int16_t* d_
     return BLAST_OK;
 }
 
-int blast_peer_signal_dev(blast_ctx* ctx, uint32_t* d_flag, uint32_t value) {
+int blast_peer_signal_dev(blast_ctx* ctx, uint32_t* const* d_flags, uint32_t n_flags, uint32_t value) {
     if (int rc = blast::bind(ctx)) return rc;
-    BLAST_REQUIRE(d_flag != nullptr, BLAST_ERR_ARG, "blast_peer_signal_dev: null flag");
-    peer_signal<<<1, 1, 0, ctx->stream>>>(d_flag, value);
+    BLAST_REQUIRE(d_flags != nullptr || n_flags == 0, BLAST_ERR_ARG, "blast_peer_signal_dev: null flags");
+    if (n_flags > 2u * kMaxPeers) return blast::set_error(BLAST_ERR_CAPACITY, "at most %d flags per signal", 2 * kMaxPeers);
+    if (n_flags == 0) return BLAST_OK;
+    FlagList fl{};
+    for (uint32_t i = 0; i < n_flags; ++i) fl.p[i] = d_flags[i];
+    peer_signal<<<1, 32, 0, ctx->stream>>>(fl, n_flags, value);
     BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
     return BLAST_OK;
 }
 
-int blast_peer_wait_dev(blast_ctx* ctx, const uint32_t* d_flag, uint32_t value) {
+int blast_peer_wait_dev(blast_ctx* ctx, const uint32_t* d_flags, uint32_t n_flags, uint32_t value) {
     if (int rc = blast::bind(ctx)) return rc;
-    BLAST_REQUIRE(d_flag != nullptr, BLAST_ERR_ARG, "blast_peer_wait_dev: null flag");
-    peer_wait<<<1, 1, 0, ctx->stream>>>(d_flag, value);
+    BLAST_REQUIRE(d_flags != nullptr || n_flags == 0, BLAST_ERR_ARG, "blast_peer_wait_dev: null flags");
+    if (n_flags > 32) return blast::set_error(BLAST_ERR_CAPACITY, "at most 32 flags per wait");
+    if (n_flags == 0) return BLAST_OK;
+    peer_wait<<<1, 32, 0, ctx->stream>>>(d_flags, n_flags, value);
     BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
     return BLAST_OK;
 }
 
-int blast_bus_reduce_peers_dev(blast_ctx* ctx, const int32_t* const* d_parts, uint32_t* const* d_peer_acks, uint32_t n_parts,
-                               const uint32_t* d_ready, uint32_t step, int16_t* d_bus, uint64_t n_slots) {
+int blast_bus_reduce_peers_dev(blast_ctx* ctx, const int32_t* const* d_parts, uint32_t n_parts, const uint32_t* d_ready,
+                               uint32_t n_ready, uint32_t step, int16_t* d_bus, uint64_t slot0, uint64_t n_slots,
+                               uint32_t* const* d_signal, uint32_t n_signal) {
     if (int rc = blast::bind(ctx)) return rc;
-    BLAST_REQUIRE(d_parts && d_bus && n_parts >= 1 && (n_parts == 1 || (d_peer_acks && d_ready)), BLAST_ERR_ARG,
+    BLAST_REQUIRE(d_parts && d_bus && n_parts >= 1 && (d_ready || n_ready == 0) && (d_signal || n_signal == 0), BLAST_ERR_ARG,
                   "blast_bus_reduce_peers_dev: null argument");
-    if (n_parts > (uint32_t)kMaxPeers) return blast::set_error(BLAST_ERR_CAPACITY, "at most %d partial buses", kMaxPeers);
-    if (n_slots == 0) return BLAST_OK;
-    PeerPtrs pp{};
+    if (n_parts > (uint32_t)kMaxPeers || n_ready > 32 || n_signal > 2u * kMaxPeers)
+        return blast::set_error(BLAST_ERR_CAPACITY, "at most %d partial buses / 32 ready flags / %d signals", kMaxPeers, 2 * kMaxPeers);
+    BLAST_REQUIRE((slot0 & 3) == 0, BLAST_ERR_ARG, "slot0 must be a multiple of 4");
+    PartList pp{};
     for (uint32_t r = 0; r < n_parts; ++r) {
         BLAST_REQUIRE(d_parts[r] != nullptr && ((uintptr_t)d_parts[r] & 15) == 0, BLAST_ERR_ARG, "partial buses must be 16-byte aligned");
         pp.part[r] = d_parts[r];
-        pp.ack[r] = r ? d_peer_acks[r] : nullptr;
     }
     BLAST_REQUIRE(((uintptr_t)d_bus & 7) == 0, BLAST_ERR_ARG, "the bus must be 8-byte aligned");
+    FlagList after{};
+    for (uint32_t i = 0; i < n_signal; ++i) after.p[i] = d_signal[i];
     uint32_t* d_count = static_cast<uint32_t*>(blast::scratch(ctx, 8, 256));
     if (!d_count) return BLAST_ERR_CUDA;
     if (!ctx->peer_count_zeroed) {
@@ -1707,7 +1729,7 @@ int blast_bus_reduce_peers_dev(blast_ctx* ctx, const int32_t* const* d_parts, ui
     }
     const uint64_t blocks = (n_slots / 4 + 255) / 256;
     const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(blocks, 1), (uint64_t)ctx->sm_count * 4);   // all resident: they spin
-    bus_reduce_peers<<<grid, 256, 0, ctx->stream>>>(pp, n_parts, d_ready, step, d_bus, n_slots, d_count);
+    bus_reduce_peers<<<grid, 256, 0, ctx->stream>>>(pp, n_parts, d_ready, n_ready, step, d_bus, slot0, n_slots, after, n_signal, d_count);
     BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
     return BLAST_OK;

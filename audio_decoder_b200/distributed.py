@@ -168,27 +168,41 @@ class ShardedMpegIndex:
 
 # ---------------------------------------------------------------------------------- the mix reduction over peer memory
 class PeerBus:
-    """The render's one exchange step without a collective library: every rank's int32 partial bus is mapped into the
-    root rank's address space (CUDA IPC over NVLink / NVSwitch) and the root reduces + finalizes in ONE kernel
+    """The render's one exchange step without a collective library: every rank's int32 partial bus and flag block are
+    mapped into every peer's address space (CUDA IPC over NVLink / NVSwitch); each rank reduces ITS 1/N slice of all
+    buses, wraps it to S16 and stores it straight into the root's bus — one kernel per rank
     (blast_bus_reduce_peers_dev).  torch.distributed only carries the 64-byte IPC handles at set-up time.
 
-    Per step, on every rank:      bus.wait_ack(); <render into bus.part.ptr>; bus.reduce(d_bus_i16_on_root)
+    Per step, on every rank:      pb.wait_ack(); <render into pb.part.ptr>; pb.reduce()      (the bus: pb.bus on the root)
+    Flag block of a rank (uint32 step counters): ready[w] at byte 0, ack[w] at byte 256, done[w] at byte 512.
     """
-    ACK_OFF = 256                  # byte offset of a rank's own ack flag inside its flag block
+    READY, ACK, DONE = 0, 256, 512
 
-    def __init__(self, ctx, n_slots: int, rank: int, world: int, group=None, root: int = 0):
+    def __init__(self, ctx, n_slots: int, rank: int, world: int, group=None, root: int = 0, mode: str = "root"):
+        """mode "root":    the root pulls and reduces the whole of every peer's bus (the other ranks only signal and
+                           never wait for each other: no lock step; the root's NVLink ingress carries N-1 buses);
+           mode "scatter": every rank reduces its 1/N slice and stores it into the root's bus (1/N of the traffic per
+                           GPU, but every rank waits for every other one each step)."""
         import ctypes as C
         import torch.distributed as dist
         from .errors import check
+        assert world <= 16 and mode in ("root", "scatter")
+        self.mode = mode
         self.ctx, self.rank, self.world, self.root, self.n_slots = ctx, rank, world, root, n_slots
         self.part = ctx.alloc(max(256, 4 * n_slots))
-        self.flags = ctx.alloc(512)           # [0, 4*world): ready flags (used on the root), [256, 260): own ack flag
+        self.bus = ctx.alloc(max(256, 2 * n_slots))          # the S16 bus (complete on the root only)
+        self.flags = ctx.alloc(1024)
         self.flags.zero()
         self.part.zero()
         ctx.sync()
         self.step = 0
         self._opened = []
+        # my slice of the bus: multiples of 8 slots so that int32 / int16 vector accesses stay aligned
+        per = ((n_slots + world - 1) // world + 7) // 8 * 8
+        self.slot0 = min(n_slots, rank * per)
+        self.slice_len = min(n_slots, (rank + 1) * per) - self.slot0
         if world == 1:
+            self.peer_parts, self.peer_flags, self.root_bus = [], [], self.bus.ptr
             return
 
         def export(ptr):
@@ -202,40 +216,57 @@ class PeerBus:
             self._opened.append(p.value)
             return p.value
 
-        mine = (export(self.part.ptr), export(self.flags.ptr))
+        mine = (export(self.part.ptr), export(self.flags.ptr), export(self.bus.ptr))
         everyone = [None] * world
         dist.all_gather_object(everyone, mine, group=group)
-        if rank == root:
-            self.parts = [self.part.ptr] + [open_(everyone[r][0]) for r in range(world) if r != root]
-            self.acks = [0] + [open_(everyone[r][1]) + self.ACK_OFF for r in range(world) if r != root]
-            self.slot_of = {r: i + 1 for i, r in enumerate(r for r in range(world) if r != root)}
-        else:
-            self.root_flags = open_(everyone[root][1])
-            # my ready flag on the root: entry = my position among the non-root ranks, + 1
-            self.my_slot = 1 + sum(1 for r in range(rank) if r != root)
+        self.peers = [r for r in range(world) if r != rank]
+        self.peer_parts = [open_(everyone[r][0]) for r in self.peers]
+        self.peer_flags = [open_(everyone[r][1]) for r in self.peers]
+        self.root_bus = self.bus.ptr if rank == root else open_(everyone[root][2])
+        self.root_flags = self.flags.ptr if rank == root else self.peer_flags[self.peers.index(root)]
         dist.barrier(group=group)
 
-    def wait_ack(self):
-        """before overwriting the partial bus again: the stream waits until the root has consumed the previous step"""
-        from .errors import check
-        if self.world > 1 and self.rank != self.root and self.step > 0:
-            check(self.ctx.lib.blast_peer_wait_dev(self.ctx.h, self.flags.ptr + self.ACK_OFF, self.step))
-
-    def reduce(self, d_bus: int):
-        """after the render: non-root ranks publish their partial bus, the root reduces + wraps into d_bus (S16)"""
+    def _ptrs(self, values):
         import ctypes as C
+        return (C.c_void_p * max(1, len(values)))(*values), len(values)
+
+    def wait_ack(self):
+        """before overwriting the partial bus again: the stream waits until every rank is done reading the previous one"""
+        from .errors import check
+        if self.world > 1 and self.step > 0:
+            if self.mode == "scatter":
+                check(self.ctx.lib.blast_peer_wait_dev(self.ctx.h, self.flags.ptr + self.ACK, self.world, self.step))
+            elif self.rank != self.root:
+                check(self.ctx.lib.blast_peer_wait_dev(self.ctx.h, self.flags.ptr + self.ACK + 4 * self.root, 1, self.step))
+
+    def reduce(self):
+        """after the render: publish the partial bus, reduce + wrap this rank's slice into the root's bus; on the root the
+        stream then waits until every slice is in place (the bus is complete for whatever is enqueued next)"""
         from .errors import check
         self.step += 1
-        L, ctx = self.ctx.lib, self.ctx
-        if self.world == 1:
-            check(L.blast_bus_finalize_dev(ctx.h, self.part.ptr, d_bus, self.n_slots))
-        elif self.rank != self.root:
-            check(L.blast_peer_signal_dev(ctx.h, self.root_flags + 4 * self.my_slot, self.step))
-        else:
-            n = len(self.parts)
-            parts = (C.c_void_p * n)(*self.parts)
-            acks = (C.c_void_p * n)(*self.acks)
-            check(L.blast_bus_reduce_peers_dev(ctx.h, parts, acks, n, self.flags.ptr, self.step, d_bus, self.n_slots))
+        L, ctx, w = self.ctx.lib, self.ctx, self.world
+        if w == 1:
+            check(L.blast_bus_finalize_dev(ctx.h, self.part.ptr, self.bus.ptr, self.n_slots))
+            return
+        me = 4 * self.rank
+        if self.mode == "root":
+            mine, n = self._ptrs([self.root_flags + self.READY + me])
+            check(L.blast_peer_signal_dev(ctx.h, mine, n, self.step))
+            if self.rank == self.root:
+                parts, n_parts = self._ptrs([self.part.ptr] + self.peer_parts)
+                after, n_after = self._ptrs([f + self.ACK + me for f in self.peer_flags])
+                check(L.blast_bus_reduce_peers_dev(ctx.h, parts, n_parts, self.flags.ptr + self.READY, w, self.step,
+                                                   self.bus.ptr, 0, self.n_slots, after, n_after))
+            return
+        ready, n = self._ptrs([f + self.READY + me for f in self.peer_flags] + [self.flags.ptr + self.READY + me])
+        check(L.blast_peer_signal_dev(ctx.h, ready, n, self.step))
+        parts, n_parts = self._ptrs([self.part.ptr] + self.peer_parts)
+        after, n_after = self._ptrs([f + self.ACK + me for f in self.peer_flags] + [self.flags.ptr + self.ACK + me,
+                                                                                  self.root_flags + self.DONE + me])
+        check(L.blast_bus_reduce_peers_dev(ctx.h, parts, n_parts, self.flags.ptr + self.READY, w, self.step, self.root_bus,
+                                           self.slot0, self.slice_len, after, n_after))
+        if self.rank == self.root:
+            check(L.blast_peer_wait_dev(ctx.h, self.flags.ptr + self.DONE, w, self.step))
 
     def close(self):
         self.ctx.sync()

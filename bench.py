@@ -194,7 +194,7 @@ def run_ours(args):
         if world > 1 and args.reduce == "p2p":
             # the one exchange step over peer memory: partial buses mapped into rank 0, ONE reduce + finalize kernel
             from audio_decoder_b200 import distributed as bd
-            peer = bd.PeerBus(ctx, n_slots, rank, world)
+            peer = bd.PeerBus(ctx, n_slots, rank, world, mode=args.peer_mode)
             part_ptr = peer.part.ptr
         elif world > 1:
             t_part = torch.empty(n_slots, dtype=torch.int32, device=f"cuda:{local}")
@@ -202,7 +202,7 @@ def run_ours(args):
         else:
             d_part = ctx.alloc(4 * n_slots)
             part_ptr = d_part.ptr
-        d_bus = ctx.alloc(2 * n_slots)
+        d_bus = peer.bus if peer is not None else ctx.alloc(2 * n_slots)
         alg_bytes_mix = 4 * (frames_per_file - 1) * n_files + 2 * n_slots   # source frames touched + S16 bus
     n_ev = 3 if mix else 2
 
@@ -211,7 +211,7 @@ def run_ours(args):
             peer.wait_ack()                                        # rank 0 has consumed the previous partial bus
             scene.restore_dev()
             scene.render_partial_dev(frames_per_file, part_ptr)
-            peer.reduce(d_bus.ptr)                                 # signal (ranks > 0) / wait + reduce + finalize (rank 0)
+            peer.reduce()                                          # signal, then ONE kernel: wait + reduce my slice + wrap + store to rank 0
             return
         scene.restore_dev()
         scene.render_partial_dev(frames_per_file, part_ptr)
@@ -355,7 +355,7 @@ def run_ours(args):
                    "l2": f"per step {n_files * data_len / 1e6:.0f} MB of file images are read and {samples_per_step * 2 / 1e6:.0f} MB of "
                          "samples written then re-read: far larger than the 126 MB L2 (no flush needed)",
                    "parallelism": f"files / voices sharded over {world} rank(s)" +
-                                  (("; partial buses reduced + finalized by ONE kernel on rank 0 over peer memory (CUDA IPC / NVLink), no collective library"
+                                  ((f"; partial buses reduced + finalized over peer memory (CUDA IPC / NVLink, mode {args.peer_mode}: one fused kernel), no collective library"
                                     if peer is not None else "; one int32 all-reduce of the partial bus per step (NCCL)") if world > 1 and mix else "; no collective")},
         "roofline": roofline, "roofline_mix": roofline_mix,
         "kernel_ms": {"decode": round(ms_decode, 4), "mix": round(ms_mix, 4)},
@@ -485,6 +485,8 @@ def main():
     ap.add_argument("--no-mix", action="store_true", help="decode only (no render/mix of the decoded tracks)")
     ap.add_argument("--ref-files-per-thread", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--peer-mode", default="root", choices=["root", "scatter"],
+                    help="p2p reduction: the root pulls every bus (no lock step) / every rank reduces its 1/N slice")
     ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: the mix reduction over peer memory (one fused kernel on rank 0) or as an NCCL all-reduce")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -195,21 +195,26 @@ int  blast_scene_render_dev(blast_ctx* ctx, blast_scene* scene, uint64_t frames,
 int  blast_scene_check(blast_ctx* ctx, blast_scene* scene);
 /* S16 bus = low 16 bits of the int32 partial sums (== i16 wrapping accumulate, engine.rs:441) */
 int  blast_bus_finalize_dev(blast_ctx* ctx, const int32_t* d_partial, int16_t* d_bus, uint64_t n_slots);
-/* The same reduction + finalize across the GPUs of one box WITHOUT a collective library: every rank renders its
- * voices into its own int32 partial bus; the buses are mapped into the root rank's address space (blast_ipc_*:
- * CUDA IPC over NVLink / NVSwitch); a rank announces "step s is complete" with blast_peer_signal_dev on the root's
- * ready flag r; the root's ONE kernel waits for all flags, pulls and sums the peers' buses, wraps to S16 and writes
- * step s into every peer's ack flag (peers blast_peer_wait_dev on it before they overwrite their bus again).
- *   d_parts[0] = the root's own partial bus, d_parts[1..] = peers' (16-byte aligned, IPC-mapped);
- *   d_peer_acks[r] = ack flag in rank r's memory (IPC-mapped; entry 0 ignored); d_ready = flag array in the ROOT's memory.
- * Flags are uint32 step counters compared with wrap-around. */
+/* The same reduction + finalize across the GPUs of one box WITHOUT a collective library.  Every rank renders its
+ * voices into its own int32 partial bus; buses and a block of uint32 step-counter flags per rank are mapped into the
+ * peers' address spaces (blast_ipc_*: CUDA IPC over NVLink / NVSwitch).  Per step s every rank
+ *   1. blast_peer_signal_dev: stores s into its entry of every rank's "ready" flags (after its render, stream-ordered);
+ *   2. blast_bus_reduce_peers_dev: ONE kernel waits until all n_ready flags at d_ready have reached s, sums slots
+ *      [slot0, slot0 + n_slots) of all n_parts buses (d_parts[0] = its own), wraps to S16 and stores them into d_bus —
+ *      the ROOT's bus, local or IPC-mapped — and then stores s into the n_signal flags of d_signal (every peer's "ack"
+ *      entry for this rank: "I am done with your bus", and the root's "done" entry: "my slice is in place");
+ *   3. blast_peer_wait_dev on its own ack flags before it overwrites its partial bus again; the root also on its
+ *      done flags before it uses the bus.
+ * Reduce-scatter + finalize + gather-to-root in one kernel; 1/N of the bus crosses each GPU's links.
+ * audio_decoder_b200/distributed.py: PeerBus is the host-side choreography. Flags compare with wrap-around. */
 int  blast_ipc_export(blast_ctx* ctx, void* d_ptr, uint8_t handle_out[64]);
 int  blast_ipc_open(blast_ctx* ctx, const uint8_t handle[64], void** d_ptr_out);
 int  blast_ipc_close(blast_ctx* ctx, void* d_ptr);
-int  blast_peer_signal_dev(blast_ctx* ctx, uint32_t* d_flag, uint32_t value);          /* async, after all prior stream work */
-int  blast_peer_wait_dev(blast_ctx* ctx, const uint32_t* d_flag, uint32_t value);      /* async: the stream waits on device */
-int  blast_bus_reduce_peers_dev(blast_ctx* ctx, const int32_t* const* d_parts, uint32_t* const* d_peer_acks, uint32_t n_parts,
-                                const uint32_t* d_ready, uint32_t step, int16_t* d_bus, uint64_t n_slots);
+int  blast_peer_signal_dev(blast_ctx* ctx, uint32_t* const* d_flags, uint32_t n_flags, uint32_t value);   /* async, after all prior stream work */
+int  blast_peer_wait_dev(blast_ctx* ctx, const uint32_t* d_flags, uint32_t n_flags, uint32_t value);      /* async: the stream waits on device */
+int  blast_bus_reduce_peers_dev(blast_ctx* ctx, const int32_t* const* d_parts, uint32_t n_parts, const uint32_t* d_ready,
+                                uint32_t n_ready, uint32_t step, int16_t* d_bus, uint64_t slot0, uint64_t n_slots,
+                                uint32_t* const* d_signal, uint32_t n_signal);
 /* one-shot with a host bus (interleaved S16_LE like the ALSA area, runtime.rs:272-276) */
 int  blast_render(blast_ctx* ctx, const blast_track* tracks, uint32_t n_tracks, const blast_voice* voices,
                   uint32_t n_voices, uint32_t out_channels, uint64_t frames, int16_t* host_bus_out,

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Run under torchrun: the mix reduction over peer memory (distributed.PeerBus, one fused reduce + finalize kernel on
-rank 0) against (a) the NCCL all-reduce + finalize path and (b) a single-GPU render of the whole scene on rank 0, over
-several steps with changing gains (exercises the ready / ack flag protocol); then timings of both paths."""
+"""Run under torchrun: the mix reduction over peer memory (distributed.PeerBus, both modes) against (a) the NCCL
+all-reduce + finalize path and (b) a single-GPU render of the whole scene on rank 0, over several steps with changing
+gains (exercises the ready / ack / done flag protocol); then timings of the exchange alone."""
 import json
 import os
 import sys
@@ -24,45 +24,49 @@ if __name__ == "__main__":
     clips = [rng.integers(-32768, 32768, size=(frames * 2 + 8) * 2).astype(np.int16) for _ in range(n_voices)]
     tracks = [ap.Track.from_host(ctx, c, 2) for c in clips]
     n = frames * 2
-    peer = bd.PeerBus(ctx, n, rank, world)
-    d_bus = ctx.alloc(2 * n)
     t_part = torch.empty(n, dtype=torch.int32, device=f"cuda:{local}")
     d_bus2 = ctx.alloc(2 * n)
-    ok = True
-    for step in range(5):
-        vps = [ap.VoiceParams(v, True, 0.0, 1.0 if v % 3 else 0.77, float(np.float32(0.3 + 0.1 * step + 0.01 * v))) for v in range(n_voices)]
-        mine = [p if v % world == rank else ap.VoiceParams(v, False) for v, p in enumerate(vps)]
-        sc = ap.Scene(ctx, tracks, mine, 2)
-        peer.wait_ack()
-        sc.render_partial_dev(frames, peer.part.ptr)
-        peer.reduce(d_bus.ptr)
-        sc.set_voices(mine)
-        sc.render_partial_dev(frames, t_part.data_ptr())
-        dist.all_reduce(t_part, op=dist.ReduceOp.SUM)
-        ap.finalize_bus(ctx, t_part.data_ptr(), d_bus2.ptr, n)
-        ctx.sync()
-        sc.close()
-        if rank == 0:
-            a, b = d_bus.download(np.int16, n), d_bus2.download(np.int16, n)
-            whole, _ = ap.render(ctx, tracks, vps, 2, frames)
-            ok = ok and np.array_equal(a, b) and np.array_equal(a, whole)
-            assert ok, f"step {step}: peer-memory bus differs"
+    res = {"world": world}
+    for mode in ("root", "scatter"):
+        peer = bd.PeerBus(ctx, n, rank, world, mode=mode)
+        ok = True
+        for step in range(5):
+            vps = [ap.VoiceParams(v, True, 0.0, 1.0 if v % 3 else 0.77, float(np.float32(0.3 + 0.1 * step + 0.01 * v)))
+                   for v in range(n_voices)]
+            mine = [p if v % world == rank else ap.VoiceParams(v, False) for v, p in enumerate(vps)]
+            sc = ap.Scene(ctx, tracks, mine, 2)
+            peer.wait_ack()
+            sc.render_partial_dev(frames, peer.part.ptr)
+            peer.reduce()
+            sc.set_voices(mine)
+            sc.render_partial_dev(frames, t_part.data_ptr())
+            dist.all_reduce(t_part, op=dist.ReduceOp.SUM)
+            ap.finalize_bus(ctx, t_part.data_ptr(), d_bus2.ptr, n)
+            ctx.sync()
+            sc.close()
+            if rank == 0:
+                a, b = peer.bus.download(np.int16, n), d_bus2.download(np.int16, n)
+                whole, _ = ap.render(ctx, tracks, vps, 2, frames)
+                ok = ok and np.array_equal(a, b) and np.array_equal(a, whole)
+                assert ok, f"mode {mode} step {step}: peer-memory bus differs"
+        res["parity_" + mode] = bool(ok)
+        dist.barrier()
+        peer.close()
     # ---- timing of the exchange alone (partial buses already rendered): C3-sized bus (2^20 frames x 2)
     n = 1 << 21
-    peer2 = bd.PeerBus(ctx, n, rank, world)
     d_b = ctx.alloc(2 * n)
     t_p = torch.zeros(n, dtype=torch.int32, device=f"cuda:{local}")
-    res = {"world": world, "parity": bool(ok)}
-    for name in ("p2p", "nccl"):
+    for name in ("root", "scatter", "nccl"):
+        peer2 = bd.PeerBus(ctx, n, rank, world, mode=name) if name != "nccl" else None
         times = []
         for it in range(12):
             dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            if name == "p2p":
+            if peer2 is not None:
                 peer2.wait_ack()
-                peer2.reduce(d_b.ptr)
+                peer2.reduce()
             else:
                 dist.all_reduce(t_p, op=dist.ReduceOp.SUM)
                 ap.finalize_bus(ctx, t_p.data_ptr(), d_b.ptr, n)
@@ -73,9 +77,9 @@ if __name__ == "__main__":
             if it >= 2:
                 times.append(float(ms))
         res[name + "_us"] = round(1e3 * float(np.median(times)), 1)
-    dist.barrier()
-    peer.close()
-    peer2.close()
+        dist.barrier()
+        if peer2 is not None:
+            peer2.close()
     if rank == 0:
         print(json.dumps(res))
     dist.destroy_process_group()
