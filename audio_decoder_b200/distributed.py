@@ -216,15 +216,34 @@ class PeerBus:
             self._opened.append(p.value)
             return p.value
 
-        mine = (export(self.part.ptr), export(self.flags.ptr), export(self.bus.ptr))
+        # every rank reaches every collective below even if its own IPC calls fail, and all ranks then agree on the
+        # outcome: either everybody has the mapping or everybody raises (the caller may then choose the NCCL variant)
+        err = None
+        try:
+            mine = (export(self.part.ptr), export(self.flags.ptr), export(self.bus.ptr))
+        except Exception as e:                                         # noqa: BLE001
+            mine, err = None, f"rank {rank}: {e}"
         everyone = [None] * world
         dist.all_gather_object(everyone, mine, group=group)
         self.peers = [r for r in range(world) if r != rank]
-        self.peer_parts = [open_(everyone[r][0]) for r in self.peers]
-        self.peer_flags = [open_(everyone[r][1]) for r in self.peers]
-        self.root_bus = self.bus.ptr if rank == root else open_(everyone[root][2])
-        self.root_flags = self.flags.ptr if rank == root else self.peer_flags[self.peers.index(root)]
-        dist.barrier(group=group)
+        if err is None and all(x is not None for x in everyone):
+            try:
+                self.peer_parts = [open_(everyone[r][0]) for r in self.peers]
+                self.peer_flags = [open_(everyone[r][1]) for r in self.peers]
+                self.root_bus = self.bus.ptr if rank == root else open_(everyone[root][2])
+                self.root_flags = self.flags.ptr if rank == root else self.peer_flags[self.peers.index(root)]
+            except Exception as e:                                     # noqa: BLE001
+                err = f"rank {rank}: {e}"
+        elif err is None:
+            err = "a peer could not export its buffers"
+        errs = [None] * world
+        dist.all_gather_object(errs, err, group=group)
+        bad = [e for e in errs if e]
+        if bad:
+            for p in self._opened:
+                ctx.lib.blast_ipc_close(ctx.h, p)
+            self._opened = []
+            raise RuntimeError("peer memory (CUDA IPC) is not available on this box: " + "; ".join(bad))
 
     def _ptrs(self, values):
         import ctypes as C

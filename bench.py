@@ -194,12 +194,18 @@ def run_ours(args):
         if world > 1 and args.reduce == "p2p":
             # the one exchange step over peer memory: partial buses mapped into rank 0, ONE reduce + finalize kernel
             from audio_decoder_b200 import distributed as bd
-            peer = bd.PeerBus(ctx, n_slots, rank, world, mode=args.peer_mode)
-            part_ptr = peer.part.ptr
-        elif world > 1:
+            try:
+                peer = bd.PeerBus(ctx, n_slots, rank, world, mode=args.peer_mode)
+                part_ptr = peer.part.ptr
+            except RuntimeError as e:                              # raised on EVERY rank or on none
+                if rank == 0:
+                    print(f"bench.py: {e}; using the NCCL all-reduce instead", file=sys.stderr)
+                peer = None
+                args.reduce = "nccl"
+        if world > 1 and peer is None:
             t_part = torch.empty(n_slots, dtype=torch.int32, device=f"cuda:{local}")
             part_ptr = t_part.data_ptr()
-        else:
+        elif peer is None:
             d_part = ctx.alloc(4 * n_slots)
             part_ptr = d_part.ptr
         d_bus = peer.bus if peer is not None else ctx.alloc(2 * n_slots)
