@@ -1426,7 +1426,10 @@ int reserve_buffers(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32
             rb.d_events = nullptr; rb.d_nevents = nullptr; rb.d_splits = nullptr; rb.d_nsplits = nullptr;
         }
     }
-    if (!rb.d_err) BLAST_CUDA_TRY(cudaMalloc(&rb.d_err, sizeof(uint32_t)));
+    if (!rb.d_err) {
+        BLAST_CUDA_TRY(cudaMalloc(&rb.d_err, sizeof(uint32_t)));
+        BLAST_CUDA_TRY(cudaMemsetAsync(rb.d_err, 0, sizeof(uint32_t), ctx->stream));
+    }
     if (n_seqs > 0) {
         if (n_seqs > rb.seqs_cap) {
             BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1456,6 +1459,7 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
     const size_t slots = (size_t)frames * oc;
     if (n_voices == 0) {
         BLAST_CUDA_TRY(cudaMemsetAsync(d_partial_bus, 0, slots * sizeof(int32_t), ctx->stream));
+        BLAST_CUDA_TRY(cudaMemsetAsync(rb.d_err, 0, sizeof(uint32_t), ctx->stream));       // nothing can overflow
         return BLAST_OK;
     }
     const size_t need = (size_t)n_tiles * n_voices;
