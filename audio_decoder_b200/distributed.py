@@ -292,3 +292,41 @@ class PeerBus:
         for p in self._opened:
             self.ctx.lib.blast_ipc_close(self.ctx.h, p)
         self._opened = []
+
+
+class ShardedConductor:
+    """The Command-driven Conductor (engine.rs:36-248) over the ranks of a process group: every rank applies every
+    command and tracks every tempo, renders the voices whose load number is congruent to its rank, and the partial
+    buses are reduced + finalized over peer memory (PeerBus).  coordinate() returns the S16 bus on the root rank
+    (None elsewhere).  max_frames = the longest coordinate() span that will be asked for."""
+
+    def __init__(self, ctx, out_channels: int, sample_rate: int, tracks, max_frames: int, rank: int, world: int,
+                 group=None, root: int = 0, mode: str = "root"):
+        from . import audio_processing as ap
+        self.ctx, self.rank, self.world, self.root = ctx, rank, world, root
+        self.out_channels, self.max_frames = out_channels, max_frames
+        self.conductor = ap.Conductor(ctx, out_channels, sample_rate, tracks)
+        self.conductor.set_shard(rank, world)
+        self.peer = PeerBus(ctx, max_frames * out_channels, rank, world, group=group, root=root, mode=mode)
+
+    def __getattr__(self, name):                      # load / start / stop / velocity / seq / group / tc / apply / set_voice ...
+        return getattr(self.conductor, name)
+
+    def coordinate(self, frames: int):
+        assert frames <= self.max_frames
+        n = frames * self.out_channels
+        self.peer.wait_ack()
+        # the reduction always covers the whole mapped bus: clear the tail this span does not write
+        if n < self.peer.n_slots:
+            from .errors import check
+            check(self.ctx.lib.blast_memset_dev(self.ctx.h, self.peer.part.ptr + 4 * n, 0, 4 * (self.peer.n_slots - n)))
+        self.conductor.render_partial_dev(frames, self.peer.part.ptr)
+        self.peer.reduce()
+        if self.rank == self.root:
+            return self.peer.bus.download(np.int16, n)
+        self.ctx.sync()
+        return None
+
+    def close(self):
+        self.peer.close()
+        self.conductor.close()

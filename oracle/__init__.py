@@ -301,9 +301,12 @@ class Conductor:
         self.h = lib().orc_conductor_new(out_channels, sample_rate, arr, len(tracks))
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().orc_conductor_free(self.h)
-            self.h = None
+        try:
+            if getattr(self, "h", None):
+                lib().orc_conductor_free(self.h)
+                self.h = None
+        except Exception:                    # interpreter shutdown
+            pass
 
     def apply(self, cmd: Command):
         _check(lib().orc_conductor_apply(self.h, C.byref(cmd)))

@@ -52,6 +52,39 @@ if __name__ == "__main__":
         res["parity_" + mode] = bool(ok)
         dist.barrier()
         peer.close()
+    # ---- the Command-driven Conductor over the ranks (ShardedConductor) against the CPU oracle on rank 0
+    sc = bd.ShardedConductor(ctx, 2, 48000, tracks[:6], 60_000, rank, world)
+    if rank == 0:
+        import oracle
+        oc = oracle.Conductor(2, 48000, [(c, 2, 48000) for c in clips[:6]])
+        seed_state = oracle.Rng(11).state
+    else:
+        oc, seed_state = None, None
+    box = [seed_state]
+    dist.broadcast_object_list(box, src=0)
+    seed_state = box[0]
+    ok = True
+    for c, mod in ((sc, ap), (oc, None)):
+        if c is None:
+            continue
+        m = ap if mod is ap else __import__("oracle")
+        for t in range(6):
+            c.load(t, m.tempo_repr(mode=m.TM_VOICE, interval=float(300 + 37 * t)))
+            c.seq(t, m.tempo_repr(owned=False, mode=m.TM_VOICE, idx=t), 4, [0.0, 2.0], [100.0, 60.0], seed_state)
+            c.velocity(t, [1.0, 0.8, 1.3, 1.0, 0.5, 1.0][t])
+            c.start(t)
+    for frames, cmd in ((20_000, None), (1, ("velocity", 2, 0.9)), (33_333, ("stop", 4)), (60_000, None)):
+        got = sc.coordinate(frames)
+        if rank == 0:
+            ok = ok and np.array_equal(got, oc.coordinate(frames))
+            assert ok, "sharded conductor differs from the oracle"
+        if cmd:
+            getattr(sc, cmd[0])(*cmd[1:])
+            if rank == 0:
+                getattr(oc, cmd[0])(*cmd[1:])
+    res["parity_sharded_conductor"] = bool(ok)
+    dist.barrier()
+    sc.close()
     # ---- timing of the exchange alone (partial buses already rendered): C3-sized bus (2^20 frames x 2)
     n = 1 << 21
     d_b = ctx.alloc(2 * n)
