@@ -28,6 +28,8 @@ pub struct blast_track { pub d_samples: *const i16, pub n_samples: u64, pub num_
 pub struct blast_voice { pub track: u32, pub active: u32, pub position: f32, pub velocity: f32, pub gain: f32, pub reserved: u32 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct blast_x128p { pub s0: u64, pub s1: u64 }
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct blast_mpeg_shard_agg { pub exit_state: [u32; 4], pub count: [u64; 4] }
 
 // ---- Conductor (engine.rs:36-248, commands.rs:86-234): TempoMode / TempoUnit / Command / Idx discriminants
 pub const BLAST_TM_PROCESS: u32 = 0; pub const BLAST_TM_VOICE: u32 = 1; pub const BLAST_TM_GROUP: u32 = 2;
@@ -111,6 +113,38 @@ extern "C" {
     pub fn blast_x128p_advance(state: *const blast_x128p, n_draws: u64, out: *mut blast_x128p) -> c_int;
     pub fn blast_x128p_fill(ctx: *mut blast_ctx, seed: u64, stride: u64, n_streams: u64, draws_per_stream: u64,
                             lower: i64, upper: i64, raw_out: *mut u64, ranged_out: *mut i64, checks_out: *mut u64) -> c_int;
+
+    pub fn blast_asset_consensus(descs: *const blast_pcm_desc, n: u32, sample_rate_out: *mut u32, num_channels_out: *mut u32) -> c_int;
+    pub fn blast_ctx_trim(ctx: *mut blast_ctx) -> c_int;
+
+    // MPEG in steps / over several GPUs (device pointers)
+    pub fn blast_mpeg_scan_dev(ctx: *mut blast_ctx, d_bytes: *const u8, len: u64, d_pos_out: *mut u64, d_hdr_out: *mut u32,
+                               cap: u64, n_out: *mut u64) -> c_int;
+    pub fn blast_mpeg_index_dev(ctx: *mut blast_ctx, d_bytes: *const u8, len: u64, reference_compat: c_int, d_offsets_out: *mut u64,
+                                cap: u64, n_offsets_out: *mut u64, ref_header_out: *mut u32, n_candidates_out: *mut u64) -> c_int;
+    pub fn blast_mpeg_gather_dev(ctx: *mut blast_ctx, d_bytes: *const u8, len: u64, d_offsets: *const u64, n_offsets: u64,
+                                 d_payload_out: *mut u8, cap: u64, payload_len_out: *mut u64) -> c_int;
+    pub fn blast_mpeg_hist_dev(ctx: *mut blast_ctx, d_hdr: *const u32, n: u64, d_hist: *mut u32) -> c_int;
+    pub fn blast_mpeg_pick_ref_dev(ctx: *mut blast_ctx, d_hist: *const u32, ref_header_out: *mut u32) -> c_int;
+    pub fn blast_mpeg_first_pos_dev(ctx: *mut blast_ctx, d_pos: *const u64, d_hdr: *const u32, n: u64, ref_header: u32,
+                                    d_first: *mut u64) -> c_int;
+    pub fn blast_mpeg_classify_dev(ctx: *mut blast_ctx, d_pos: *const u64, d_hdr: *const u32, n: u64, ref_header: u32,
+                                   d_first: *const u64, stream_len: u64, d_offsets_out: *mut u64, cap: u64,
+                                   n_offsets_out: *mut u64) -> c_int;
+    pub fn blast_mpeg_shard_walk_dev(ctx: *mut blast_ctx, d_bytes: *const u8, own_len: u64, halo_len: u64,
+                                     agg_out: *mut blast_mpeg_shard_agg) -> c_int;
+    pub fn blast_mpeg_shard_emit_dev(ctx: *mut blast_ctx, d_bytes: *const u8, own_len: u64, halo_len: u64, entry_state: u32,
+                                     pos_offset: u64, d_pos_out: *mut u64, d_hdr_out: *mut u32, cap: u64, n_out: *mut u64) -> c_int;
+
+    // the mix reduction over peer memory (one process per GPU)
+    pub fn blast_ipc_export(ctx: *mut blast_ctx, d_ptr: *mut c_void, handle_out: *mut u8) -> c_int;
+    pub fn blast_ipc_open(ctx: *mut blast_ctx, handle: *const u8, d_ptr_out: *mut *mut c_void) -> c_int;
+    pub fn blast_ipc_close(ctx: *mut blast_ctx, d_ptr: *mut c_void) -> c_int;
+    pub fn blast_peer_signal_dev(ctx: *mut blast_ctx, d_flags: *const *mut u32, n_flags: u32, value: u32) -> c_int;
+    pub fn blast_peer_wait_dev(ctx: *mut blast_ctx, d_flags: *const u32, n_flags: u32, value: u32) -> c_int;
+    pub fn blast_bus_reduce_peers_dev(ctx: *mut blast_ctx, d_parts: *const *const i32, n_parts: u32, d_ready: *const u32,
+                                      n_ready: u32, step: u32, d_bus: *mut i16, slot0: u64, n_slots: u64,
+                                      d_signal: *const *mut u32, n_signal: u32) -> c_int;
 
     pub fn blast_mpeg_parse(ctx: *mut blast_ctx, bytes: *const u8, len: u64, reference_compat: c_int,
                             offsets_out: *mut u64, offsets_cap: u64, n_offsets_out: *mut u64, ref_header_out: *mut u32,
