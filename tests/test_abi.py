@@ -223,3 +223,15 @@ def test_asset_consensus():
     assert fp.asset_consensus([d(48000, 1)]) == (48000, 1)
     assert fp.asset_consensus([d(48000, 2), d(44100, 1), d(44100, 6), d(22050, 2)]) == (44100, 6)
     assert fp.asset_consensus([d(48000, 2), d(44100, 2)]) == (44100, 2)          # tie: smallest (reference: HashMap order)
+
+
+def test_rust_sys_crate_names_exist_in_the_header():
+    """rust/blast-cuda-sys cannot be compiled here (no rustc): at least every symbol it binds must be declared by the
+    header, and the entry points a BLAST maintainer needs must be bound"""
+    rs = open(os.path.join(ROOT, "rust", "blast-cuda-sys", "src", "lib.rs")).read()
+    bound = set(re.findall(r"pub fn (blast_[a-z0-9_]+)\s*\(", rs))
+    declared = _declared_symbols()
+    assert bound and bound <= declared, sorted(bound - declared)
+    for need in ("blast_wav_probe", "blast_aiff_probe", "blast_pcm_decode_batch", "blast_file_name", "blast_conductor_apply",
+                 "blast_conductor_coordinate", "blast_render", "blast_x128p_seed", "blast_mpeg_parse", "blast_asset_consensus"):
+        assert need in bound, need
