@@ -683,22 +683,30 @@ __device__ __forceinline__ void unpack_pair(uint32_t w, float& l, float& r) {
     r = __fsub_rn(__uint_as_float(__byte_perm(x, 0x4B400000u, 0x7632)), 12615680.0f);
 }
 
-// velocity == 1.0 inside a unit-step run: frame index advances by one per frame, no interpolation
-template <bool kFull>
+// velocity == 1.0 inside a unit-step run: frame index advances by one per frame, no interpolation.
+// kGainOne: gain == 1.0 — the reference's only value unless the host sets the field (no Command changes it,
+// engine.rs:304): (sample as f32 * 1.0) as i16 == sample, so the mix is two sign extensions and two integer adds.
+template <bool kFull, bool kGainOne>
 __device__ __forceinline__ void consume_stereo_unit(uint32_t stage_addr, uint32_t a0_off, float gain, uint32_t frange,
                                                     int32_t (&acc)[kFPT][2]) {
     const uint32_t a0 = stage_addr + a0_off + threadIdx.x * 4u;
+    auto add = [&](uint32_t w, int32_t& al, int32_t& ar) {
+        if (kGainOne) {
+            al += (int32_t)(int16_t)(w & 0xFFFFu);
+            ar += (int32_t)w >> 16;
+        } else {
+            float l, r;
+            unpack_pair(w, l, r);
+            al += f2i16_sat(__fmul_rn(l, gain));
+            ar += f2i16_sat(__fmul_rn(r, gain));
+        }
+    };
     if (kFull) {
         uint32_t w[kFPT];
 #pragma unroll
         for (int j = 0; j < kFPT; ++j) w[j] = lds_u32(a0 + (uint32_t)j * kConsumers * 4u);
 #pragma unroll
-        for (int j = 0; j < kFPT; ++j) {
-            float l, r;
-            unpack_pair(w[j], l, r);
-            acc[j][0] += f2i16_sat(__fmul_rn(l, gain));
-            acc[j][1] += f2i16_sat(__fmul_rn(r, gain));
-        }
+        for (int j = 0; j < kFPT; ++j) add(w[j], acc[j][0], acc[j][1]);
     } else {
         // partial piece: only the 256-frame slabs it touches are visited (uniform skip), lanes predicated
         const uint32_t fa = frange & 0xFFFF, fb = frange >> 16, span = fb - fa;
@@ -706,12 +714,7 @@ __device__ __forceinline__ void consume_stereo_unit(uint32_t stage_addr, uint32_
 #pragma unroll
         for (int j = 0; j < kFPT; ++j) {
             if ((uint32_t)j < j_lo || (uint32_t)j > j_hi) continue;
-            if ((threadIdx.x + j * kConsumers - fa) < span) {
-                float l, r;
-                unpack_pair(lds_u32(a0 + (uint32_t)j * kConsumers * 4u), l, r);
-                acc[j][0] += f2i16_sat(__fmul_rn(l, gain));
-                acc[j][1] += f2i16_sat(__fmul_rn(r, gain));
-            }
+            if ((threadIdx.x + j * kConsumers - fa) < span) add(lds_u32(a0 + (uint32_t)j * kConsumers * 4u), acc[j][0], acc[j][1]);
         }
     }
 }
@@ -1204,8 +1207,9 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
         const bool fullr = (mode >> 16) & 1;
         if (OC == 2 && path == kPathStereoUnit) {
             auto& a2 = reinterpret_cast<int32_t (&)[kFPT][2]>(acc);
-            if (fullr) consume_stereo_unit<true>(stage_addr, a0_off, gain, frange, a2);
-            else consume_stereo_unit<false>(stage_addr, a0_off, gain, frange, a2);
+            const bool g1 = gain == 1.0f;
+            if (fullr) { if (g1) consume_stereo_unit<true, true>(stage_addr, a0_off, gain, frange, a2); else consume_stereo_unit<true, false>(stage_addr, a0_off, gain, frange, a2); }
+            else { if (g1) consume_stereo_unit<false, true>(stage_addr, a0_off, gain, frange, a2); else consume_stereo_unit<false, false>(stage_addr, a0_off, gain, frange, a2); }
         } else if (OC == 2 && path == kPathStereoLerp) {
             auto& a2 = reinterpret_cast<int32_t (&)[kFPT][2]>(acc);
             if (fullr) consume_stereo_lerp<true>(stage_addr, *mp, a2);

@@ -14,7 +14,7 @@ import audio_decoder_b200 as blast  # noqa: E402
 from audio_decoder_b200 import _lib, audio_processing as ap, blast_rand as br  # noqa: E402
 
 
-def c3(ctx, voices, frames, iters, all_unit):
+def c3(ctx, voices, frames, iters, all_unit, gain_one=False):
     L = ctx.lib
     clip_frames = int(np.ceil(1.5 * frames)) + 2
     clip_words = clip_frames * 2
@@ -29,7 +29,7 @@ def c3(ctx, voices, frames, iters, all_unit):
     for v in range(voices):
         u = float((int(prm[2 * v]) >> 11) * 2.0 ** -53)
         w = float((int(prm[2 * v + 1]) >> 11) * 2.0 ** -53)
-        gain = float(np.float32(u) * np.float32(2.0 ** -7))
+        gain = 1.0 if gain_one else float(np.float32(u) * np.float32(2.0 ** -7))
         vel = 1.0 if (v % 2 == 0 or all_unit) else float(np.float32(0.5) + np.float32(w))
         buf = blast.DevBuf.__new__(blast.DevBuf)
         buf.ctx, buf.ptr, buf.nbytes = ctx, slab.ptr + v * draws * 8, draws * 8
@@ -55,7 +55,8 @@ def c3(ctx, voices, frames, iters, all_unit):
     src_bytes = sum(4.0 * frames * v.velocity for v in vps)
     alg = src_bytes + frames * 2 * 2
     host_bus = bus.download(np.int16, frames * 2)
-    res = {"workload": f"C3 {voices} voices x {frames} frames, stereo, {'v=1' if all_unit else 'mixed velocities'}",
+    res = {"workload": f"C3 {voices} voices x {frames} frames, stereo, {'v=1' if all_unit else 'mixed velocities'}" +
+                       (", gain 1.0 (the reference's default: integer mix)" if gain_one else ""),
            "ms": round(ms, 4), "gsamples_per_s": round(voices * frames * 2 / ms / 1e6, 1),
            "alg_GB": round(alg / 1e9, 3), "GBps": round(alg / ms / 1e6, 1), "mean_velocity": round(mean_vel, 4),
            "bus_crc": int(np.bitwise_xor.reduce(host_bus.view(np.uint16).astype(np.uint32) * np.arange(1, frames * 2 + 1, dtype=np.uint32)))}
@@ -147,6 +148,7 @@ if __name__ == "__main__":
             res["c3_seq"] = c3_seq(ctx, args.voices, args.frames, 2)
         elif not args.skip_c3:
             res["c3_unit"] = c3(ctx, args.voices, args.frames, args.iters, True)
+            res["c3_unit_gain1"] = c3(ctx, args.voices, args.frames, args.iters, True, gain_one=True)
             res["c3_mixed"] = c3(ctx, args.voices, args.frames, args.iters, False)
             res["c3_seq"] = c3_seq(ctx, args.voices, args.frames, 2)
         if not args.skip_c4:
