@@ -1027,6 +1027,13 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                                         m.q0 = qa - (int32_t)fa * d;
                                     }
                                 }
+                            } else if (OC == 2 && v.C == 1 && v.nch == 2 && v.adv == 0 && !slow && idx_hi < v.end && p_a >= 0.0f &&
+                                       v.vel == 1.0f && __fmul_rn((float)d, scale) == 1.0f && (idx_lo & 1u) == 0) {
+                                // a mono voice at velocity 1.0 on a stereo bus advances on both channels (engine.rs:419-422,
+                                // 445-447): L reads sample i0 + 2f, R reads i0 + 2f + 1 — with i0 even that is exactly a packed
+                                // (L, R) pair per frame, i.e. the stereo unit path on the same bytes
+                                path = kPathStereoUnit;
+                                m.a0_off = m.byte_off - fa * 4u;
                             }
                         } else {
                             mode = kModeDirect;

@@ -257,3 +257,18 @@ def test_random_scenes_with_weird_floats(ctx, seed):
     assert np.array_equal(got, exp), (seed, oc, frames)
     for a, b in zip(gpos, epos):
         assert same_pos(a, b), (seed, a, b)
+
+
+def test_mono_unit_velocity_on_stereo_bus(ctx):
+    """a mono voice at velocity 1.0 advances on both channels (L = s[i0 + 2f], R = s[i0 + 2f + 1]): even start positions
+    take the packed-pair fast path, odd ones the generic one; gains 1.0 (integer mix) and != 1.0; clips that end inside"""
+    rng = np.random.default_rng(77)
+    long_ = rng.integers(-32768, 32768, size=40000).astype(np.int16)
+    short = rng.integers(-32768, 32768, size=9001).astype(np.int16)
+    for frames in (5000, 9000):
+        voices = [V(long_, 1, 1.0, 1.0, 0.0), V(long_, 1, 1.0, 0.37, 1.0), V(long_, 1, 1.0, 1.0, 7.0), V(long_, 1, 1.0, 2.5, 4096.0),
+                  V(short, 1, 1.0, 1.0, 0.0), V(short, 1, 1.0, 0.9, 3.0)]
+        exp, epos = oracle_render(voices, 2, frames)
+        got, gpos = gpu_render(ctx, voices, 2, frames)
+        assert np.array_equal(got, exp), frames
+        assert all(same_pos(a, b) for a, b in zip(gpos, epos))
