@@ -13,14 +13,15 @@
 // K7 reads every input byte exactly once (1 B/byte of HBM traffic + 12 B per candidate, plus 6 B per candidate
 // of temp list written and re-read).  The greedy rule is a 4-state machine (state = header bytes still to
 // skip); a byte range acts on it as a map {0..3} -> {0..3} plus a candidate count per entry state, and maps
-// compose associatively.  Five launches, none of which ever waits for another thread block:
+// compose associatively.  Six launches, none of which ever waits for another thread block:
 //   K7a mpeg_walk       one warp per 32 KiB span: finds the span's candidates under entry state 0 and leaves
 //                       them in the span's slot of a temp list, plus a 16-byte record (map, counts per entry
 //                       state, "head-sensitive" flag)
 //   K7b mpeg_span_fold / mpeg_block_chain / mpeg_span_fold<APPLY>   an ordinary three-step scan over the
 //                       records (8 MB for 16 GiB of input): true entry state and first global candidate index
 //                       of every span
-//   K7c mpeg_compact    moves the lists to their final, position-ordered place (coalesced)
+//   K7c mpeg_compact    moves the lists to their final, position-ordered place (coalesced); K7d mpeg_redo re-walks
+//                       the few spans whose list does not apply (see below)
 // A span's entry state only matters when its very first three bytes hold a raw sync ("head-sensitive",
 // ~0.15 % of spans on random data, every span on 0xFF floods): K7a then also counts it under the other three
 // entry states, and K7c re-walks it with direct emission if its true entry state is not 0 (same for spans
@@ -548,41 +549,57 @@ __global__ void mpeg_block_chain(BlockAgg* __restrict__ blocks, unsigned long lo
 }
 
 // ---------------------------------------------------------------- K7c: compact
-// Moves every span's list to its final, position-ordered place.  Spans whose list is not valid for their
-// true entry state (head-sensitive with entry != 0) or did not fit their slot are re-walked with direct
-// emission.
-__global__ void __launch_bounds__(kScanThreads, kCtasPerSm)
-mpeg_compact(const uint8_t* __restrict__ bytes, unsigned long long n, unsigned long long n_spans, ScanCtl* __restrict__ ctl,
-             const SpanRec* __restrict__ recs, const uint8_t* __restrict__ span_entry,
+// Moves every span's list to its final, position-ordered place: one warp per span, no shared memory, so the SMs
+// hold enough warps to hide the dependent loads (record -> base -> list).  Spans whose list is not valid for their
+// true entry state (head-sensitive with entry != 0) or did not fit their slot go to a redo list.
+constexpr int kCompactThreads = 256;
+__global__ void __launch_bounds__(kCompactThreads)
+mpeg_compact(unsigned long long n_spans, const SpanRec* __restrict__ recs, const uint8_t* __restrict__ span_entry,
              const unsigned long long* __restrict__ span_base, const uint16_t* __restrict__ t_off,
              const uint32_t* __restrict__ t_hdr, unsigned long long* __restrict__ out_pos, uint32_t* __restrict__ out_hdr,
-             unsigned long long cap, unsigned long long pos_offset) {
-    extern __shared__ __align__(128) uint8_t smem_dyn[];
+             unsigned long long cap, unsigned long long pos_offset, uint32_t* __restrict__ redo_list,
+             uint32_t* __restrict__ redo_count) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t ring = smem_addr(smem_dyn) + warp * (uint32_t)(kStages * kStageBytes);
-    const unsigned long long n_warps = (unsigned long long)gridDim.x * (kScanThreads / 32);
-    for (unsigned long long span = (unsigned long long)blockIdx.x * (kScanThreads / 32) + warp; span < n_spans; span += n_warps) {
+    const unsigned long long n_warps = (unsigned long long)gridDim.x * (kCompactThreads / 32);
+    for (unsigned long long span = (unsigned long long)blockIdx.x * (kCompactThreads / 32) + warp; span < n_spans; span += n_warps) {
         const uint4 v = *reinterpret_cast<const uint4*>(recs + span);
         SpanRec r;
         r.meta = v.x; r.c01 = v.y; r.c23 = v.z; r.pad = 0;
         const uint32_t entry = span_entry[span];
         const unsigned long long base = span_base[span];
         const uint32_t count = rec_count(r, entry);
-        const unsigned long long span0 = span * (unsigned long long)kSpanBytes;
         const bool sens = (r.meta & 0x100u) != 0;
         if ((!sens || entry == 0) && count <= (uint32_t)kCandCap) {
+            const unsigned long long span0 = pos_offset + span * (unsigned long long)kSpanBytes;
             const uint16_t* g_off = t_off + span * (unsigned long long)kCandCap;
             const uint32_t* g_hdr = t_hdr + span * (unsigned long long)kCandCap;
             for (uint32_t k = lane; k < count; k += 32) {
                 const unsigned long long gi = base + k;
                 if (gi < cap) {
-                    out_pos[gi] = pos_offset + span0 + g_off[k];
+                    out_pos[gi] = span0 + g_off[k];
                     out_hdr[gi] = g_hdr[k];
                 }
             }
-        } else {
-            walk_tile(kModeEmit, bytes, n, span0, entry, lane, ring, nullptr, nullptr, out_pos, out_hdr, cap, base, pos_offset, ctl);
+        } else if (lane == 0) {
+            redo_list[atomicAdd(redo_count, 1u)] = (uint32_t)span;
         }
+    }
+}
+
+// K7d: the spans of the redo list are walked again with their true entry state and emit directly
+__global__ void __launch_bounds__(kScanThreads, kCtasPerSm)
+mpeg_redo(const uint8_t* __restrict__ bytes, unsigned long long n, ScanCtl* __restrict__ ctl, const uint8_t* __restrict__ span_entry,
+          const unsigned long long* __restrict__ span_base, const uint32_t* __restrict__ redo_list,
+          const uint32_t* __restrict__ redo_count, unsigned long long* __restrict__ out_pos, uint32_t* __restrict__ out_hdr,
+          unsigned long long cap, unsigned long long pos_offset) {
+    extern __shared__ __align__(128) uint8_t smem_dyn[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ring = smem_addr(smem_dyn) + warp * (uint32_t)(kStages * kStageBytes);
+    const uint32_t n_redo = *redo_count, n_warps = gridDim.x * (kScanThreads / 32);
+    for (uint32_t i = blockIdx.x * (kScanThreads / 32) + warp; i < n_redo; i += n_warps) {
+        const unsigned long long span = redo_list[i];
+        walk_tile(kModeEmit, bytes, n, span * (unsigned long long)kSpanBytes, span_entry[span], lane, ring, nullptr, nullptr, out_pos,
+                  out_hdr, cap, span_base[span], pos_offset, ctl);
     }
 }
 
@@ -817,6 +834,8 @@ struct ScanBufs {
     unsigned long long* span_base = nullptr;
     uint8_t* span_entry = nullptr;
     BlockAgg* blocks = nullptr;
+    uint32_t* redo_list = nullptr;     // spans that must be re-walked (n_spans entries at most)
+    uint32_t* redo_count = nullptr;
     ScanCtl* ctl = nullptr;
     uint32_t* t_hdr = nullptr;
     uint16_t* t_off = nullptr;
@@ -830,13 +849,16 @@ int scan_buffers(blast_ctx* ctx, uint64_t own_len, ScanBufs& sb) {
     sb.n_blocks = (sb.n_spans + kFoldBlock - 1) / kFoldBlock;
     const size_t rec_b = (sb.n_spans * sizeof(SpanRec) + 255) & ~255ull, base_b = (sb.n_spans * 8 + 255) & ~255ull;
     const size_t entry_b = (sb.n_spans + 255) & ~255ull, blk_b = (sb.n_blocks * sizeof(BlockAgg) + 255) & ~255ull;
-    uint8_t* s0 = static_cast<uint8_t*>(blast::scratch(ctx, 0, rec_b + base_b + entry_b + blk_b + 256));
+    const size_t redo_b = (sb.n_spans * sizeof(uint32_t) + 255) & ~255ull;
+    uint8_t* s0 = static_cast<uint8_t*>(blast::scratch(ctx, 0, rec_b + base_b + entry_b + blk_b + redo_b + 512));
     if (!s0) return BLAST_ERR_CUDA;
     sb.recs = reinterpret_cast<SpanRec*>(s0);
     sb.span_base = reinterpret_cast<unsigned long long*>(s0 + rec_b);
     sb.span_entry = s0 + rec_b + base_b;
     sb.blocks = reinterpret_cast<BlockAgg*>(s0 + rec_b + base_b + entry_b);
-    sb.ctl = reinterpret_cast<ScanCtl*>(s0 + rec_b + base_b + entry_b + blk_b);
+    sb.redo_list = reinterpret_cast<uint32_t*>(s0 + rec_b + base_b + entry_b + blk_b);
+    sb.redo_count = reinterpret_cast<uint32_t*>(s0 + rec_b + base_b + entry_b + blk_b + redo_b);
+    sb.ctl = reinterpret_cast<ScanCtl*>(s0 + rec_b + base_b + entry_b + blk_b + redo_b + 256);
     const size_t hdr_b = (sb.n_spans * kCandCap * sizeof(uint32_t) + 255) & ~255ull;
     uint8_t* s1 = static_cast<uint8_t*>(blast::scratch(ctx, 1, hdr_b + sb.n_spans * kCandCap * sizeof(uint16_t)));
     if (!s1) return BLAST_ERR_CUDA;
@@ -845,7 +867,7 @@ int scan_buffers(blast_ctx* ctx, uint64_t own_len, ScanBufs& sb) {
     if (ctx->mpeg_ctas_per_sm == 0) {                      // function attributes are per device: cached per context
         int per_sm = 0;
         BLAST_CUDA_TRY(cudaFuncSetAttribute(mpeg_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
-        BLAST_CUDA_TRY(cudaFuncSetAttribute(mpeg_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
+        BLAST_CUDA_TRY(cudaFuncSetAttribute(mpeg_redo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
         BLAST_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mpeg_walk, kScanThreads, kScanSmem));
         ctx->mpeg_ctas_per_sm = std::max(per_sm, 1);
     }
@@ -873,11 +895,16 @@ int scan_emit(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t readable, const S
     if (!h_ctl) return BLAST_ERR_CUDA;
     mpeg_block_chain<<<1, 32, 0, ctx->stream>>>(sb.blocks, sb.n_blocks, sb.ctl, entry);
     mpeg_span_fold<true><<<(unsigned)sb.n_blocks, kFoldThreads, 0, ctx->stream>>>(sb.recs, sb.n_spans, sb.blocks, sb.span_entry, sb.span_base);
-    mpeg_compact<<<sb.grid, kScanThreads, kScanSmem, ctx->stream>>>(d_bytes, readable, sb.n_spans, sb.ctl, sb.recs, sb.span_entry, sb.span_base,
-                                                                   sb.t_off, sb.t_hdr, reinterpret_cast<unsigned long long*>(d_pos), d_hdr,
-                                                                   cap, pos_offset);
+    BLAST_CUDA_TRY(cudaMemsetAsync(sb.redo_count, 0, sizeof(uint32_t), ctx->stream));
+    const unsigned cgrid = (unsigned)std::min<unsigned long long>((sb.n_spans + 7) / 8, (unsigned long long)ctx->sm_count * 8);
+    mpeg_compact<<<cgrid, kCompactThreads, 0, ctx->stream>>>(sb.n_spans, sb.recs, sb.span_entry, sb.span_base, sb.t_off, sb.t_hdr,
+                                                             reinterpret_cast<unsigned long long*>(d_pos), d_hdr, cap, pos_offset,
+                                                             sb.redo_list, sb.redo_count);
+    mpeg_redo<<<sb.grid, kScanThreads, kScanSmem, ctx->stream>>>(d_bytes, readable, sb.ctl, sb.span_entry, sb.span_base, sb.redo_list,
+                                                                sb.redo_count, reinterpret_cast<unsigned long long*>(d_pos), d_hdr, cap,
+                                                                pos_offset);
     BLAST_CUDA_TRY(cudaGetLastError());
-    ctx->launches += 3;
+    ctx->launches += 4;
     BLAST_CUDA_TRY(cudaMemcpyAsync(h_ctl, sb.ctl, sizeof(ScanCtl), cudaMemcpyDeviceToHost, ctx->stream));
     BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     const ScanCtl h = *h_ctl;
