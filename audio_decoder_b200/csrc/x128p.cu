@@ -184,7 +184,9 @@ x128p_streams(U128* __restrict__ states, uint64_t n_streams, uint64_t draws, int
         }
         if (kRaw || kRanged) {
             __syncwarp();
-            // row `q` of the tile = nj consecutive draws of stream stream0+q: 256 contiguous bytes in memory
+            // row `q` of the tile = nj consecutive draws of stream stream0+q: 256 contiguous bytes in memory.
+            // (Measured alternative: every lane storing its own draws straight from registers, 32 bytes at a time,
+            // trusting the L2 to assemble lines — 19.0 ms instead of 8.2 ms for the raw C4 fill.)
             if (vec_ok && nj == kRound) {
                 // 16 lanes x 16 bytes per row, two rows per store instruction
                 const uint32_t jl = (lane & 15) * 2;
