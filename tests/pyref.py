@@ -336,3 +336,279 @@ def mpeg_header(h: int):
     payload = None if fl < 20.0 else int(fl) - (20 if prot else 4) + padded
     return dict(version={0: 2.5, 2: 2.0, 3: 1.0}[version], layer=lay, protected=prot, bitrate=bitrate, sr=sr,
                 padded=padded, channel_mode=b3 >> 6, payload=payload, skip=6 if prot else 4, fl=fl)
+
+
+# ---------------- engine.rs:26-248, 318-384, 451-542; blast_time.rs:58-161; processes.rs:52-99 ----------------
+# The Command-driven Conductor, written from the Rust sources (not from oracle/blast_oracle.cpp).  Objects and
+# method names follow the reference; `Rc<RefCell<TempoState>>` sharing is plain Python object identity.
+TM_PROCESS, TM_VOICE, TM_GROUP, TM_CONTEXT, TM_TBD = range(5)
+TU_SAMPLES, TU_MILLIS, TU_BPM = range(3)
+M32 = (1 << 32) - 1
+
+
+class RefPanic(Exception):
+    """the reference would panic here (unwrap on None / index out of bounds)"""
+
+
+def f32_as_i64(x) -> int:
+    x = float(x)
+    if math.isnan(x):
+        return 0
+    if x >= 9223372036854775807.0:
+        return (1 << 63) - 1
+    if x <= -9223372036854775808.0:
+        return -(1 << 63)
+    return int(x)
+
+
+class PyTempo:                                   # blast_time.rs:58-145
+    def __init__(self, sample_rate):
+        self.sample_rate = sample_rate
+        self.mode, self.unit = TM_TBD, TU_SAMPLES        # TempoState::new(None)
+        self.interval = f32(sample_rate)
+        self.active = False
+        self.current = 0
+
+    def init(self, mode, unit, interval):        # blast_time.rs:99-104 + convert_interval :151-161
+        interval = f32(interval)
+        with np.errstate(all="ignore"):
+            if unit == TU_MILLIS:
+                interval = f32(f32(self.sample_rate) * f32(interval / f32(1000.0)))
+            elif unit == TU_BPM:
+                interval = f32(f32(self.sample_rate) * f32(f32(60.0) / interval))
+        self.mode, self.unit, self.interval = mode, unit, interval
+
+    def update(self):                            # update(1.0): current += 1.0 as u32, wrapping in release builds
+        self.current = (self.current + 1) & M32
+
+    def cur(self):                               # current(): current as f32 / interval
+        with np.errstate(all="ignore"):
+            return f32(f32(self.current) / self.interval)
+
+    def reset(self):
+        self.current = 0
+
+    def start(self):
+        self.reset()
+        self.active = True
+
+    def stop(self):
+        self.active = False
+        self.reset()
+
+
+class PySeq:                                     # processes.rs:52-99
+    def __init__(self, tempo, period, steps, chance, rng):
+        self.active, self.tempo, self.period = True, tempo, period
+        self.steps, self.chance, self.rng, self.idx = [f32(s) for s in steps], [f32(c) for c in chance], rng, 0
+
+    def process(self, voice):
+        if not self.active or not self.tempo.active:
+            return
+        with np.errstate(all="ignore"):
+            current = f32(np.fmod(self.tempo.cur(), f32(self.period)))     # Rust `%` on f32 = fmodf
+        if self.idx >= len(self.steps):
+            raise RefPanic("steps index out of bounds")
+        if current == self.steps[self.idx]:
+            rand = self.rng.next_i64_range(0, 100)
+            if rand < f32_as_i64(self.chance[self.idx]):
+                voice.position = f32(0.0) if voice.velocity >= f32(0.0) else f32(voice.end)
+            self.idx = (self.idx + 1) % len(self.steps)
+
+
+class PyCVoice:                                  # engine.rs:279-448
+    def __init__(self, samples, channels, tempo):
+        self.samples = [int(s) for s in samples]
+        self.channels = channels
+        self.end = len(self.samples) // channels - 1
+        self.active, self.position, self.velocity, self.gain = False, f32(0.0), f32(1.0), f32(1.0)
+        self.tempo, self.processes, self.proc_tempi = tempo, [], []
+
+    def home(self):
+        return f32(0.0) if self.velocity >= f32(0.0) else f32(self.end)
+
+    def start(self):
+        self.active = True
+        for p in self.processes:
+            p.idx = 0
+        if self.tempo.mode in (TM_VOICE, TM_TBD):
+            self.tempo.start()
+        for t in self.proc_tempi:
+            t.start()
+        self.position = self.home()
+
+    def stop(self):
+        self.active = False
+        for p in self.processes:
+            p.idx = 0
+        if self.tempo.mode == TM_VOICE:
+            self.tempo.stop()
+        for t in self.proc_tempi:
+            t.active = False
+            t.reset()
+        self.position = self.home()
+
+    def process(self, acc, ch):
+        if not self.active:
+            return acc
+        for p in self.processes:
+            p.process(self)
+        if self.tempo.mode in (TM_VOICE, TM_TBD):
+            self.tempo.update()
+        for t in self.proc_tempi:
+            t.update()
+        idx = f32_as_usize(self.position)
+        if idx >= self.end:
+            return acc
+        C = self.channels
+        if C == 1:
+            if ch < 2:
+                ch = 0
+            else:
+                return acc
+        elif ch >= C:
+            return acc
+        with np.errstate(all="ignore"):
+            s0 = f32(self.samples[idx * C + ch % C])
+            if self.velocity != f32(1.0):
+                frac = f32(self.position - np.trunc(self.position))
+                s1 = f32(self.samples[(idx + 1) * C + ch % C])
+                sample = f32(f32(s0 * f32(f32(1.0) - frac)) + f32(s1 * frac))
+            else:
+                sample = s0
+            acc = wrap_i16(acc + f32_as_i16(f32(sample * self.gain)))
+            if ch == C - 1:
+                self.position = f32(self.position + self.velocity)
+        return acc
+
+
+class PyGroup:                                   # engine.rs:451-542
+    def __init__(self, voices, tempo):
+        self.active, self.tempo, self.voices, self.processes = False, tempo, voices, []
+
+    def start(self):
+        self.active = True
+        if self.tempo.mode == TM_GROUP:
+            self.tempo.active = True
+            self.tempo.reset()
+        for v in self.voices:
+            v.start()
+
+    def stop(self):
+        self.active = False
+        for v in self.voices:
+            v.active = False
+        if self.tempo.mode == TM_GROUP:
+            self.tempo.active = False
+            self.tempo.reset()
+
+    def process(self, acc, ch):
+        if not self.active:
+            return acc
+        for v in self.voices:
+            acc = v.process(acc, ch)
+        if self.tempo.mode == TM_GROUP:
+            self.tempo.update()
+        return acc
+
+
+class PyConductor:                               # engine.rs:26-275
+    def __init__(self, out_channels, sample_rate, tracks):
+        self.out_channels, self.sample_rate = out_channels, sample_rate
+        self.tracks = tracks                     # [(samples, channels)]
+        self.voices, self.groups, self.tempo_cons = [], [], []
+
+    def tempo_from_repr(self, idx, owned, mode, unit, interval):
+        t = PyTempo(self.sample_rate)
+        try:
+            if owned:
+                t.init(mode, unit, interval)
+            elif mode == TM_VOICE:
+                t = self.voices[idx].tempo
+            elif mode == TM_GROUP:
+                t = self.groups[idx].tempo
+            elif mode == TM_CONTEXT:
+                t = self.tempo_cons[idx]
+        except IndexError:
+            raise RefPanic("tempo index")
+        return t
+
+    def load(self, track_idx, tempo):
+        if track_idx >= len(self.tracks):
+            raise RefPanic("track")
+        t = self.tempo_from_repr(*tempo)
+        s, ch = self.tracks[track_idx]
+        self.voices.append(PyCVoice(s, ch, t))
+
+    def _target(self, idx_kind, idx):
+        try:
+            return {"voice": self.voices, "group": self.groups, "tempo": self.tempo_cons}[idx_kind][idx]
+        except IndexError:
+            raise RefPanic(idx_kind)
+
+    def start(self, idx, idx_kind="voice"):
+        self._target(idx_kind, idx).start()
+
+    def stop(self, idx, idx_kind="voice"):
+        self._target(idx_kind, idx).stop()
+
+    def pause(self, idx, idx_kind="voice"):
+        self._target(idx_kind, idx).active = False
+
+    def resume(self, idx, idx_kind="voice"):
+        self._target(idx_kind, idx).active = True
+
+    def unload(self, idx):
+        if idx >= len(self.voices):
+            raise RefPanic("unload")
+        self.voices.pop(idx)
+
+    def velocity(self, idx, val):
+        if idx >= len(self.voices):
+            raise RefPanic("velocity")
+        self.voices[idx].velocity = f32(val)
+
+    def group(self, tempo, members):
+        t = self.tempo_from_repr(*tempo)
+        moved = []
+        for idx, update_tempo, p_ids in members:
+            if idx >= len(self.voices):
+                raise RefPanic("group member")
+            v = self.voices.pop(idx)
+            if update_tempo:
+                v.tempo = t
+                for p in p_ids:
+                    v.processes[p].tempo = t
+            moved.append(v)
+        self.groups.append(PyGroup(moved, t))
+
+    def tc(self, tempo):
+        self.tempo_cons.append(self.tempo_from_repr(*tempo))
+
+    def seq(self, idx, tempo, period, steps, chance, rng_state, idx_kind="voice"):
+        t = self.tempo_from_repr(*tempo)
+        s = PySeq(t, period, steps, chance, X128P(state=rng_state))
+        if idx_kind == "voice":
+            if idx >= len(self.voices):
+                raise RefPanic("seq voice")
+            self.voices[idx].processes.append(s)
+            if tempo[2] == TM_PROCESS:
+                self.voices[idx].proc_tempi.append(t)
+        elif idx_kind == "group":
+            if idx >= len(self.groups):
+                raise RefPanic("seq group")
+            self.groups[idx].processes.append(s)
+
+    def coordinate(self, frames):
+        out = []
+        for _f in range(frames):
+            for ch in range(self.out_channels):
+                acc = 0
+                for v in self.voices:
+                    if v.active:
+                        acc = v.process(acc, ch)
+                for g in self.groups:
+                    if g.active:
+                        acc = g.process(acc, ch)
+                out.append(acc)
+        return np.array(out, dtype=np.int16)
