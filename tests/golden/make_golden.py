@@ -113,7 +113,56 @@ def mpeg():
     np.savez_compressed(os.path.join(HERE, "mpeg.npz"), **out)
 
 
+CONDUCTOR_SCRIPT = [
+    # (op, args...) — tempo = (idx, owned, mode, unit, interval); modes / units as in blast_time.rs:67-82
+    ("tc", (0, True, 3, 0, 6.0)),
+    ("load", 0, (0, True, 1, 0, 16.0)),
+    ("load", 1, (0, False, 1, 0, 0.0)),                       # borrows voice 0's tempo: both tick it
+    ("load", 2, (0, True, 4, 2, 180000.0)),                   # TBD tempo, BPM -> 16 samples
+    ("load", 3, (0, True, 1, 1, 0.5)),                        # millis -> 24 samples
+    ("seq", 0, (0, False, 1, 0, 0.0), 4, [0.0, 2.0], [100.0, 50.0], 11),
+    ("seq", 1, (0, True, 0, 0, 9.0), 3, [1.0], [100.0], 12),  # own Process tempo
+    ("seq", 2, (0, False, 3, 0, 0.0), 2, [0.0], [100.0], 13), # context tempo (never ticked)
+    ("seq", 3, (3, False, 1, 0, 0.0), 5, [0.0, 1.0, 4.0], [100.0, 0.0, 75.0], 14),
+    ("velocity", 1, 0.75), ("velocity", 3, 1.5),
+    ("start", 0), ("start", 1), ("start", 2), ("start", 3),
+    ("render", 300),
+    ("tstart", 0), ("render", 40), ("tstop", 0),
+    ("group", (0, True, 2, 0, 10.0), [(2, True, [0]), (0, False, [])]),
+    ("gstart", 0), ("render", 200),
+    ("pause", 0), ("velocity", 1, -1.0), ("render", 1), ("resume", 0), ("render", 150),
+    ("gstop", 0), ("unload", 1), ("render", 64),
+]
+
+
+def conductor():
+    rng = np.random.default_rng(41)
+    tracks = [(rng.integers(-20000, 20000, size=n * ch).astype(np.int16), ch) for n, ch in ((500, 2), (400, 1), (300, 2), (350, 3))]
+    c = pyref.PyConductor(2, 48000, tracks)
+    out = []
+    for op in CONDUCTOR_SCRIPT:
+        k, a = op[0], op[1:]
+        if k == "render":
+            out.append(c.coordinate(a[0]))
+        elif k == "seq":
+            c.seq(a[0], a[1], a[2], a[3], a[4], (pyref.X128P(a[5]).s0, pyref.X128P(a[5]).s1))
+        elif k in ("tstart", "tstop"):
+            getattr(c, k[1:])(a[0], "tempo")
+        elif k in ("gstart", "gstop"):
+            getattr(c, k[1:])(a[0], "group")
+        elif k == "group":
+            c.group(a[0], a[1])
+        else:
+            getattr(c, k)(*a)
+    d = {"bus": np.concatenate(out)}
+    for i, (s, ch) in enumerate(tracks):
+        d[f"track{i}"] = s
+        d[f"track{i}_channels"] = np.array([ch])
+    np.savez_compressed(os.path.join(HERE, "conductor.npz"), **d)
+
+
 if __name__ == "__main__":
+    conductor()
     decode()
     render()
     rng()

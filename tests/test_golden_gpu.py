@@ -4,7 +4,7 @@ import pytest
 
 import audio_decoder_b200 as blast
 from audio_decoder_b200 import audio_processing as ap, blast_rand as br, file_parsing as fp
-from test_golden import DECODE_CASES, MPEG_CASES, RENDER_CASES, SEEDS, load, scene_of
+from test_golden import DECODE_CASES, MPEG_CASES, RENDER_CASES, SEEDS, conductor_tracks, load, replay_conductor, scene_of
 
 pytestmark = pytest.mark.gpu
 
@@ -72,3 +72,12 @@ def test_mpeg_golden_gpu(ctx):
         if ok:
             assert o.bitrate == bitrate and o.skip == skip
             assert (int(o.payload_len) if o.frame_len_ok else -1) == payload, hex(h)
+
+
+def test_conductor_golden_gpu(ctx):
+    z = load("conductor")
+    tracks = [ap.Track.from_host(ctx, s, ch, 48000) for s, ch in conductor_tracks(z)]
+    c = ap.Conductor(ctx, 2, 48000, tracks)
+    bus = replay_conductor(c, ap, br.seed_state)
+    assert np.array_equal(bus, z["bus"])
+    c.close()
