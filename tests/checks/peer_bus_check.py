@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import audio_decoder_b200 as blast  # noqa: E402
 from audio_decoder_b200 import audio_processing as ap, distributed as bd  # noqa: E402
 

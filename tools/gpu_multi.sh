@@ -5,8 +5,8 @@
 mkdir -p gpurun_out
 N=$(nvidia-smi -L | wc -l)
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 300 $RUN --master-port 29531 tools/peer_bus_check.py > gpurun_out/peer_n$N.json 2> gpurun_out/peer_n$N.err; echo "peer_rc=$?"; tail -1 gpurun_out/peer_n$N.json
-timeout 600 $RUN --master-port 29533 tools/mpeg_sharded_check.py --gib 8 > gpurun_out/mpeg_n$N.json 2> gpurun_out/mpeg_n$N.err; echo "mpeg_rc=$?"; tail -1 gpurun_out/mpeg_n$N.json
+timeout 300 $RUN --master-port 29531 tests/checks/peer_bus_check.py > gpurun_out/peer_n$N.json 2> gpurun_out/peer_n$N.err; echo "peer_rc=$?"; tail -1 gpurun_out/peer_n$N.json
+timeout 600 $RUN --master-port 29533 tests/checks/mpeg_sharded_check.py --gib 8 > gpurun_out/mpeg_n$N.json 2> gpurun_out/mpeg_n$N.err; echo "mpeg_rc=$?"; tail -1 gpurun_out/mpeg_n$N.json
 for mode in "p2p --peer-mode root" "p2p --peer-mode scatter" nccl; do
   tag=$(echo $mode | tr -d ' -')
   timeout 600 $RUN --master-port 29532 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu --reduce $mode > gpurun_out/bench_n${N}_$tag.json 2> gpurun_out/bench_n${N}_$tag.err; echo "bench_${tag}_rc=$?"
