@@ -610,8 +610,10 @@ constexpr int kStages = 4;
 constexpr int kStageBytes = 16 * 1024 + 256;
 constexpr int kConsumers = 256;
 constexpr int kTmaThreads = kConsumers + 32;
-enum : uint32_t { kModeStaged = 1, kModeDirect = 2, kModeEnd = 3 };
-enum : uint32_t { kPathGeneric = 0, kPathStereoUnit = 1, kPathStereoLerp = 2, kPathStereoMulti = 3 };
+enum : uint32_t { kModeStaged = 1, kModeDirect = 2, kModeEnd = 3, kModeFlush = 4 };
+enum : uint32_t { kPathGeneric = 0, kPathStereoUnit = 1, kPathStereoLerp = 2, kPathStereoMulti = 3, kPathStereoUnit2 = 4 };
+constexpr uint32_t kPairHalf = 8192 + 128;    // stage offset of the second voice of a kPathStereoUnit2 item (a full unit tile is <= 8,208 B)
+static_assert(2 * kPairHalf <= kStageBytes, "two unit tiles per stage");
 constexpr int kMaxPieces = 32;                // pieces of one voice in one tile handled by a single staged item
 
 struct StageMeta {            // written by the producer before it arrives on the stage's full barrier
@@ -636,9 +638,11 @@ struct StageMeta {            // written by the producer before it arrives on th
     uint32_t shape;           // C | S << 8 | nch << 16
     uint32_t nseg;
     uint32_t seg_hint;        // segment index at the piece start (slow pieces walk from here)
+    uint32_t f0;              // first frame of the work item's tile (generic path; kModeFlush items carry it in a0_off)
+    uint32_t pad_[3];
 };
-static_assert(sizeof(StageMeta) == 80, "StageMeta layout");
-constexpr size_t kMetaStride = 80;
+static_assert(sizeof(StageMeta) == 96, "StageMeta layout");
+constexpr size_t kMetaStride = 96;
 constexpr size_t kTmaSmem = (size_t)kStages * kStageBytes + kStages * kMetaStride + 2 * kStages * sizeof(uint64_t) +
                             (size_t)kStages * kMaxPieces * sizeof(uint4);
 
@@ -661,6 +665,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// the same on 32-bit shared addresses computed once (the consumer loop keeps them in registers)
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}"
+                 ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -676,11 +688,15 @@ __device__ __forceinline__ int32_t lds_s16(uint32_t addr) {
     return v;
 }
 
-// packed stereo frame (L | R << 16) -> two exact floats without the XU pipe
+// packed stereo frame (L | R << 16) -> two exact floats without the XU pipe: sign extension by PRMT (sign-replicate
+// selector) / SHF, then I2FP.F32.S32.  Written as PRMT so that ptxas cannot fold the extension into I2F.S16, which
+// runs on the 16-lane XU pipe; 4 instructions per frame against 5 for the 2^23 magic-number splice
+// (tools/micro/unit_loop.cu: 8.40 vs 8.04 TB/s for the bare unit loop, 4.52 with I2F.S16).
 __device__ __forceinline__ void unpack_pair(uint32_t w, float& l, float& r) {
-    const uint32_t x = w ^ 0x80008000u;                                   // bias both halves to unsigned
-    l = __fsub_rn(__uint_as_float(__byte_perm(x, 0x4B400000u, 0x7610)), 12615680.0f);   // 1.5*2^23 + 32768
-    r = __fsub_rn(__uint_as_float(__byte_perm(x, 0x4B400000u, 0x7632)), 12615680.0f);
+    uint32_t lo;
+    asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(lo) : "r"(w));
+    l = __int2float_rn((int32_t)lo);
+    r = __int2float_rn((int32_t)w >> 16);
 }
 
 // velocity == 1.0 inside a unit-step run: frame index advances by one per frame, no interpolation.
@@ -717,6 +733,33 @@ __device__ __forceinline__ void consume_stereo_unit(uint32_t stage_addr, uint32_
             if ((threadIdx.x + j * kConsumers - fa) < span) add(lds_u32(a0 + (uint32_t)j * kConsumers * 4u), acc[j][0], acc[j][1]);
         }
     }
+}
+
+// two full unit tiles (two voices) staged in one item: one barrier round trip and one meta read for 16 KB of samples
+template <bool kGainOne>
+__device__ __forceinline__ void consume_stereo_unit2(uint32_t stage_addr, uint32_t a0_off, float gain, uint32_t a1_off, float gain1,
+                                                     int32_t (&acc)[kFPT][2]) {
+    const uint32_t a0 = stage_addr + a0_off + threadIdx.x * 4u, a1 = stage_addr + a1_off + threadIdx.x * 4u;
+    auto add = [&](uint32_t w, float g, int32_t& al, int32_t& ar) {
+        if (kGainOne) {
+            al += (int32_t)(int16_t)(w & 0xFFFFu);
+            ar += (int32_t)w >> 16;
+        } else {
+            float l, r;
+            unpack_pair(w, l, r);
+            al += f2i16_sat(__fmul_rn(l, g));
+            ar += f2i16_sat(__fmul_rn(r, g));
+        }
+    };
+    uint32_t w[kFPT], x[kFPT];
+#pragma unroll
+    for (int j = 0; j < kFPT; ++j) w[j] = lds_u32(a0 + (uint32_t)j * kConsumers * 4u);
+#pragma unroll
+    for (int j = 0; j < kFPT; ++j) x[j] = lds_u32(a1 + (uint32_t)j * kConsumers * 4u);
+#pragma unroll
+    for (int j = 0; j < kFPT; ++j) add(w[j], gain, acc[j][0], acc[j][1]);
+#pragma unroll
+    for (int j = 0; j < kFPT; ++j) add(x[j], gain1, acc[j][0], acc[j][1]);
 }
 
 // any velocity inside one arithmetic segment with positions in [0, 2^24)
@@ -863,12 +906,16 @@ __device__ __forceinline__ void consume_generic(const StageMeta& m, uint32_t sta
     }
 }
 
+// Persistent: gridDim.x = min(work items, 3 per SM).  A work item is (tile, voice group); the producer warp takes the
+// next one from a global counter and keeps the stage ring full ACROSS items, so a CTA has no prologue / epilogue
+// bubble per item (as one CTA per item this cost ~11 us per CTA round: C2's mix ran at 5.3 TB/s, C3 at 6.7).  A
+// kModeFlush item at the end of each work item makes the consumers add their accumulators into the bus.
 template <int OC>
 __global__ void __launch_bounds__(kTmaThreads)
 voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t voices_per_group,
                      uint32_t n_groups, const Seg* __restrict__ segs, const uint32_t* __restrict__ nsegs,
                      const TileRec* __restrict__ recs, uint32_t frames, int32_t* __restrict__ bus, int use_atomic,
-                     const uint32_t* __restrict__ err, const uint32_t seg_cap) {
+                     const uint32_t* __restrict__ err, const uint32_t seg_cap, uint32_t* __restrict__ work) {
     extern __shared__ __align__(128) uint8_t smem[];
     if (*err) return;                                           // truncated trajectories must not be rendered (uniform exit)
     uint8_t* stages = smem;
@@ -876,16 +923,8 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
     uint64_t* full = reinterpret_cast<uint64_t*>(meta_base + kStages * kMetaStride);
     uint64_t* empty = full + kStages;
     uint4* ptabs = reinterpret_cast<uint4*>(empty + kStages);          // [kStages][kMaxPieces]
-
-    // tile-major block order: all voice groups of tile 0 first.  Early tiles are the expensive ones (a
-    // voice that starts at position 0 crosses ~20 binades inside its first tile), so they must not be
-    // the last CTAs to be scheduled.
-    const uint32_t tile = blockIdx.x / n_groups;
-    const uint32_t f0 = tile * (uint32_t)kFT;
-    const uint32_t nf = min((uint32_t)kFT, frames - f0);
-    const uint32_t vbeg = (blockIdx.x % n_groups) * voices_per_group;
-    const uint32_t vend = min(n_voices, vbeg + voices_per_group);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_items = ((frames + (uint32_t)kFT - 1u) / (uint32_t)kFT) * n_groups;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -898,7 +937,19 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
 
     if (warp == kConsumers / 32) {
         // ------------------------------------------------ producer warp
-        uint32_t o = 0;                                   // items enqueued so far (uniform across the warp)
+        uint32_t o = 0;                                   // stage items enqueued so far (uniform across the warp)
+        for (;;) {
+        // tile-major item order: all voice groups of tile 0 first.  Early tiles are the expensive ones (a voice that
+        // starts at position 0 crosses ~20 binades inside its first tile), so they must not be taken last.
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(work, 1u);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (item >= n_items) break;
+        const uint32_t tile = item / n_groups;
+        const uint32_t f0 = tile * (uint32_t)kFT;
+        const uint32_t nf = min((uint32_t)kFT, frames - f0);
+        const uint32_t vbeg = (item % n_groups) * voices_per_group;
+        const uint32_t vend = min(n_voices, vbeg + voices_per_group);
         for (uint32_t vb = vbeg; vb < vend; vb += 32) {
             const uint32_t vi = vb + lane;
             // per-lane voice state for the piece walk
@@ -1054,23 +1105,47 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                     m.shape = v.C | (v.S << 8) | (v.nch << 16);
                     m.nseg = nseg;
                     m.seg_hint = seg_j;
+                    m.f0 = f0;
                 }
-                // ---- issue the pieces of this round in lane order
+                // ---- issue the pieces of this round in lane order; two consecutive full unit tiles share one stage
                 const uint32_t have = __ballot_sync(0xFFFFFFFFu, (m.mode & 0xFF) != 0);
-                for (uint32_t rest = have; rest; rest &= rest - 1) {
+                constexpr uint32_t kUnitFull = kModeStaged | (kPathStereoUnit << 8) | (1u << 16);
+                const uint32_t pairable = OC == 2 ? __ballot_sync(0xFFFFFFFFu, m.mode == kUnitFull && bytes <= kPairHalf) : 0u;
+                for (uint32_t rest = have; rest;) {
                     const int i = __ffs(rest) - 1;
+                    rest &= rest - 1;
+                    int i2 = -1;
+                    if (((pairable >> i) & 1u) && rest) {
+                        const int n = __ffs(rest) - 1;
+                        if ((pairable >> n) & 1u) { i2 = n; rest &= rest - 1; }
+                    }
                     const uint32_t st = o % kStages, round = o / kStages;
+                    StageMeta* ms = reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride);
+                    const uint32_t bytes2 = i2 >= 0 ? __shfl_sync(0xFFFFFFFFu, bytes, i2) : 0u;
                     if (lane == i) {
                         if (round > 0) mbar_wait(empty + st, (round - 1) & 1);
-                        *reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride) = m;
+                        *ms = m;
+                        if (i2 >= 0) ms->mode = kModeStaged | (kPathStereoUnit2 << 8);
+                    }
+                    if (i2 >= 0) {
+                        __syncwarp();
+                        if (lane == i2) {                 // the second voice's stage offset and gain ride in the trajectory slots
+                            ms->q0 = (int32_t)(kPairHalf + m.a0_off);
+                            ms->scale = m.gain;
+                        }
+                        __syncwarp();
+                    }
+                    if (lane == i) {
                         if ((m.mode & 0xFF) == kModeStaged) {
-                            mbar_arrive_expect_tx(full + st, bytes);
+                            mbar_arrive_expect_tx(full + st, bytes + bytes2);
                             bulk_g2s(stages + (size_t)st * kStageBytes, reinterpret_cast<const void*>(src), bytes, full + st);
                         } else {
                             mbar_arrive(full + st);
                         }
                     }
                     __syncwarp();
+                    if (i2 >= 0 && lane == i2)
+                        bulk_g2s(stages + (size_t)st * kStageBytes + kPairHalf, reinterpret_cast<const void*>(src), bytes, full + st);
                     o += 1;
                 }
                 // ---- after the first round: voices held back for the multi-piece path, one at a time, with
@@ -1185,6 +1260,20 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                 first_round = false;
             }
         }
+        {   // end of the work item: the consumers add their accumulators into the bus
+            const uint32_t st = o % kStages, round = o / kStages;
+            if (lane == 0) {
+                if (round > 0) mbar_wait(empty + st, (round - 1) & 1);
+                StageMeta* ms = reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride);
+                ms->mode = kModeFlush;
+                ms->a0_off = f0;
+                ms->frange = nf;
+                mbar_arrive(full + st);
+            }
+            __syncwarp();
+            o += 1;
+        }
+        }   // next work item
         if (lane == 0) {
             const uint32_t st = o % kStages, round = o / kStages;
             if (round > 0) mbar_wait(empty + st, (round - 1) & 1);
@@ -1201,51 +1290,74 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
 #pragma unroll
         for (int c = 0; c < OC; ++c) acc[j][c] = 0;
 
-    const uint32_t stage0 = smem_u32(stages), meta0 = smem_u32(meta_base);
-    for (uint32_t o = 0;; ++o) {
-        const uint32_t st = o % kStages;
-        mbar_wait(full + st, (o / kStages) & 1);
-        const uint32_t stage_addr = stage0 + st * (uint32_t)kStageBytes;
+    // one opaque shared-window base (asm volatile: ptxas would otherwise rebuild it from SR_CgaCtaId every iteration)
+    uint32_t sm0;
+    asm volatile("mov.u32 %0, %1;" : "=r"(sm0) : "r"(smem_u32(smem)));
+    constexpr uint32_t kMetaOff = (uint32_t)kStages * kStageBytes, kFullOff = kMetaOff + (uint32_t)(kStages * kMetaStride),
+                       kEmptyOff = kFullOff + (uint32_t)kStages * 8u;
+    uint32_t st = 0, phase = 0;
+    for (;;) {
+        mbar_wait_a(sm0 + kFullOff + st * 8u, phase);
+        const uint32_t stage_addr = sm0 + st * (uint32_t)kStageBytes;
+        const uint32_t meta_addr = sm0 + kMetaOff + st * (uint32_t)kMetaStride;
         const StageMeta* mp = reinterpret_cast<const StageMeta*>(meta_base + st * kMetaStride);
         uint32_t mode; float gain; uint32_t a0_off, frange;
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(mode), "=f"(gain), "=r"(a0_off), "=r"(frange) : "r"(meta0 + st * (uint32_t)kMetaStride));
-        if ((mode & 0xFF) == kModeEnd) break;
-        const uint32_t path = (mode >> 8) & 0xFF;
-        const bool fullr = (mode >> 16) & 1;
-        if (OC == 2 && path == kPathStereoUnit) {
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(mode), "=f"(gain), "=r"(a0_off), "=r"(frange) : "r"(meta_addr));
+        if (OC == 2 && mode == (kModeStaged | (kPathStereoUnit2 << 8))) {            // the common item first: one compare
             auto& a2 = reinterpret_cast<int32_t (&)[kFPT][2]>(acc);
-            const bool g1 = gain == 1.0f;
-            if (fullr) { if (g1) consume_stereo_unit<true, true>(stage_addr, a0_off, gain, frange, a2); else consume_stereo_unit<true, false>(stage_addr, a0_off, gain, frange, a2); }
-            else { if (g1) consume_stereo_unit<false, true>(stage_addr, a0_off, gain, frange, a2); else consume_stereo_unit<false, false>(stage_addr, a0_off, gain, frange, a2); }
-        } else if (OC == 2 && path == kPathStereoLerp) {
-            auto& a2 = reinterpret_cast<int32_t (&)[kFPT][2]>(acc);
-            if (fullr) consume_stereo_lerp<true>(stage_addr, *mp, a2);
-            else consume_stereo_lerp<false>(stage_addr, *mp, a2);
-        } else if (OC == 2 && path == kPathStereoMulti) {
-            auto& a2 = reinterpret_cast<int32_t (&)[kFPT][2]>(acc);
-            const uint32_t ptab = smem_u32(ptabs + st * kMaxPieces);
-            if (frange & 1u) consume_stereo_multi<true>(stage_addr, *mp, ptab, a0_off, a2);
-            else consume_stereo_multi<false>(stage_addr, *mp, ptab, a0_off, a2);
-        } else if ((mode & 0xFF) == kModeStaged) {
-            consume_generic<OC, true>(*mp, stage_addr, f0, acc);
-        } else {
-            consume_generic<OC, false>(*mp, 0u, f0, acc);
+            uint32_t a1_off, d_, sh_; float gain1;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(a1_off), "=r"(d_), "=r"(sh_), "=f"(gain1) : "r"(meta_addr));
+            if (gain == 1.0f && gain1 == 1.0f) consume_stereo_unit2<true>(stage_addr, a0_off, gain, a1_off, gain1, a2);
+            else consume_stereo_unit2<false>(stage_addr, a0_off, gain, a1_off, gain1, a2);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(sm0 + kEmptyOff + st * 8u);
+            st = (st + 1) % kStages;
+            phase ^= (st == 0) ? 1u : 0u;
+            continue;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + st);
-    }
-
+        if ((mode & 0xFF) == kModeEnd) break;
+        if ((mode & 0xFF) == kModeFlush) {
+            // end of a work item: a0_off = first frame of its tile, frange = frames in it
 #pragma unroll
-    for (int j = 0; j < kFPT; ++j) {
-        const uint32_t fl = threadIdx.x + j * kConsumers;
-        if (fl < nf) {
-            int32_t* out = bus + (size_t)(f0 + fl) * OC;
+            for (int j = 0; j < kFPT; ++j) {
+                const uint32_t fl = threadIdx.x + j * kConsumers;
+                if (fl < frange) {
+                    int32_t* out = bus + (size_t)(a0_off + fl) * OC;
 #pragma unroll
-            for (int c = 0; c < OC; ++c) {
-                if (use_atomic) atomicAdd(out + c, acc[j][c]);
-                else out[c] = acc[j][c];
+                    for (int c = 0; c < OC; ++c) {
+                        if (use_atomic) atomicAdd(out + c, acc[j][c]);
+                        else out[c] = acc[j][c];
+                        acc[j][c] = 0;
+                    }
+                }
+            }
+        } else {
+            const uint32_t path = (mode >> 8) & 0xFF;
+            const bool fullr = (mode >> 16) & 1;
+            if (OC == 2 && path == kPathStereoUnit) {
+                auto& a2 = reinterpret_cast<int32_t (&)[kFPT][2]>(acc);
+                const bool g1 = gain == 1.0f;
+                if (fullr) { if (g1) consume_stereo_unit<true, true>(stage_addr, a0_off, gain, frange, a2); else consume_stereo_unit<true, false>(stage_addr, a0_off, gain, frange, a2); }
+                else { if (g1) consume_stereo_unit<false, true>(stage_addr, a0_off, gain, frange, a2); else consume_stereo_unit<false, false>(stage_addr, a0_off, gain, frange, a2); }
+            } else if (OC == 2 && path == kPathStereoLerp) {
+                auto& a2 = reinterpret_cast<int32_t (&)[kFPT][2]>(acc);
+                if (fullr) consume_stereo_lerp<true>(stage_addr, *mp, a2);
+                else consume_stereo_lerp<false>(stage_addr, *mp, a2);
+            } else if (OC == 2 && path == kPathStereoMulti) {
+                auto& a2 = reinterpret_cast<int32_t (&)[kFPT][2]>(acc);
+                const uint32_t ptab = smem_u32(ptabs + st * kMaxPieces);
+                if (frange & 1u) consume_stereo_multi<true>(stage_addr, *mp, ptab, a0_off, a2);
+                else consume_stereo_multi<false>(stage_addr, *mp, ptab, a0_off, a2);
+            } else if ((mode & 0xFF) == kModeStaged) {
+                consume_generic<OC, true>(*mp, stage_addr, mp->f0, acc);
+            } else {
+                consume_generic<OC, false>(*mp, 0u, mp->f0, acc);
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(sm0 + kEmptyOff + st * 8u);
+        st = (st + 1) % kStages;
+        phase ^= (st == 0) ? 1u : 0u;
     }
 }
 
@@ -1438,8 +1550,8 @@ int reserve_buffers(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32
         }
     }
     if (!rb.d_err) {
-        BLAST_CUDA_TRY(cudaMalloc(&rb.d_err, sizeof(uint32_t)));
-        BLAST_CUDA_TRY(cudaMemsetAsync(rb.d_err, 0, sizeof(uint32_t), ctx->stream));
+        BLAST_CUDA_TRY(cudaMalloc(&rb.d_err, 2 * sizeof(uint32_t)));                       // [0] error bits, [1] K4's work-item counter
+        BLAST_CUDA_TRY(cudaMemsetAsync(rb.d_err, 0, 2 * sizeof(uint32_t), ctx->stream));
     }
     if (n_seqs > 0) {
         if (n_seqs > rb.seqs_cap) {
@@ -1482,7 +1594,7 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         BLAST_CUDA_TRY(cudaMalloc(&rb.d_recs, need * sizeof(TileRec)));
         rb.recs_cap = need;
     }
-    BLAST_CUDA_TRY(cudaMemsetAsync(rb.d_err, 0, sizeof(uint32_t), ctx->stream));
+    BLAST_CUDA_TRY(cudaMemsetAsync(rb.d_err, 0, 2 * sizeof(uint32_t), ctx->stream));       // error bits + K4's work-item counter
     if (n_seqs > 0) {
         seq_event_scan<<<(n_voices + 31) / 32, 32, 0, ctx->stream>>>(rb.d_voices, n_voices, rb.d_seqs, (uint32_t)(frames * oc),
                                                                       rb.d_events, rb.d_nevents, rb.d_err);
@@ -1500,24 +1612,26 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
     uint32_t groups = 1;
     static const uint32_t ctas_per_sm = getenv("BLAST_RENDER_CTAS_PER_SM") ? (uint32_t)atoi(getenv("BLAST_RENDER_CTAS_PER_SM")) : 32u;
     const uint32_t want_ctas = (uint32_t)ctx->sm_count * ctas_per_sm;
-    while (n_tiles * groups < want_ctas && n_voices / (groups * 2) >= 64) groups *= 2;
+    static const uint32_t min_group = getenv("BLAST_RENDER_MIN_GROUP") ? (uint32_t)atoi(getenv("BLAST_RENDER_MIN_GROUP")) : 64u;
+    while (n_tiles * groups < want_ctas && n_voices / (groups * 2) >= min_group) groups *= 2;
     const uint32_t per_group = (n_voices + groups - 1) / groups;
     groups = (n_voices + per_group - 1) / per_group;
     const int use_atomic = groups > 1;
     if (use_atomic) BLAST_CUDA_TRY(cudaMemsetAsync(d_partial_bus, 0, slots * sizeof(int32_t), ctx->stream));
     dim3 grid(n_tiles, groups);
-    dim3 grid_tma(n_tiles * groups, 1);      // 1-D, decoded tile-major inside the kernel
+    // persistent: three CTAs per SM (shared memory bound) take (tile, group) items, tile-major, from a counter
+    dim3 grid_tma(std::min<uint32_t>(n_tiles * groups, (uint32_t)ctx->sm_count * 3u), 1);
     static const bool legacy = getenv("BLAST_RENDER_LEGACY") != nullptr;
     if (oc <= 2 && !legacy) {
         // TMA pipeline kernel (one producer warp + eight consumer warps)
         if (oc == 1) {
             BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
             voice_render_mix_tma<1><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(rb.d_voices, n_voices, per_group, groups, rb.d_segs,
-                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, rb.d_err, rb.seg_cap);
+                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, rb.d_err, rb.seg_cap, rb.d_err + 1);
         } else {
             BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
             voice_render_mix_tma<2><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(rb.d_voices, n_voices, per_group, groups, rb.d_segs,
-                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, rb.d_err, rb.seg_cap);
+                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, rb.d_err, rb.seg_cap, rb.d_err + 1);
         }
     } else {
 #define BLAST_LAUNCH_MIX(OCV)                                                                              \
