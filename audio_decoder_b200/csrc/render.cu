@@ -203,6 +203,24 @@ __device__ __forceinline__ float build_epoch(float p, const float vel, const uin
     if (total == 0) emit(0u, p, 0, 0.0f);
     while (s < total) {
         if (f2u_sat(p) >= end) { emit(s, p, 0, 0.0f); break; }                   // frozen (engine.rs:407-410)
+        if (vel >= 1.0f && vel < 16777216.0f && p >= 0.0f && p < 16777216.0f) {
+            // integer position, integer velocity (the default velocity 1.0 from position 0): every `position += velocity`
+            // below 2^24 is exact whatever binades it crosses, so the run up to the first frozen step (or 2^24, or the
+            // end of the epoch) is ONE segment in units of 1.0 instead of three or four pieces per binade
+            const uint32_t pi = (uint32_t)p, vv = (uint32_t)vel;
+            if ((float)pi == p && (float)vv == vel) {
+                uint32_t kmax = (16777215u - pi) / vv;
+                const uint64_t kf = ((uint64_t)(end - pi) + vv - 1u) / vv;         // first frozen step (end > pi here)
+                if (kf < (uint64_t)kmax) kmax = (uint32_t)kf;
+                if (kmax > total - s) kmax = total - s;
+                if (kmax >= 1) {
+                    emit(s, p, (int32_t)vv, 1.0f);
+                    p = (float)(pi + kmax * vv);
+                    s += kmax;
+                    continue;
+                }
+            }
+        }
         const float p1 = __fadd_rn(p, vel);
         if (__float_as_uint(p1) == __float_as_uint(p)) { emit(s, p, 0, 0.0f); break; }   // fixed point
         const float p2 = __fadd_rn(p1, vel);
@@ -258,16 +276,14 @@ __device__ __forceinline__ float build_epoch(float p, const float vel, const uin
     return p;
 }
 
-// One thread per voice.  Builds the segment list for `frames * S` steps (advance events, or calls for voices
-// with Seq processes, whose retrigger events start new epochs: processes.rs:82-85), the per-tile records, and
-// writes the position after the render back into the voice.
-__global__ void voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t frames,
-                                    Seg* __restrict__ segs, uint32_t* __restrict__ nsegs, uint32_t* __restrict__ err,
-                                    const uint32_t* __restrict__ events, const uint32_t* __restrict__ nevents,
-                                    const uint32_t seg_cap, const uint32_t oc, Split* __restrict__ splits,
-                                    uint32_t* __restrict__ nsplits) {
-    uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (vi >= n_voices) return;
+// The serial part of K3, run by lane 0 of the voice's warp.  Builds the segment list for `frames * S` steps (advance
+// events, or calls for voices with Seq processes, whose retrigger events start new epochs: processes.rs:82-85) and
+// writes the position after the render back into the voice.  Returns the number of segments.
+__device__ __noinline__ uint32_t scan_voice(VoiceDev* __restrict__ voices, const uint32_t vi, uint32_t frames,
+                                            Seg* __restrict__ segs, uint32_t* __restrict__ nsegs, uint32_t* __restrict__ err,
+                                            const uint32_t* __restrict__ events, const uint32_t* __restrict__ nevents,
+                                            const uint32_t seg_cap, const uint32_t oc, Split* __restrict__ splits,
+                                            uint32_t* __restrict__ nsplits) {
     VoiceDev v = voices[vi];
     Seg* sg = segs + (size_t)vi * seg_cap;
     uint32_t n = 0;
@@ -397,40 +413,50 @@ __global__ void voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_vo
     }
     nsegs[vi] = n;
     voices[vi].pos = p;
-
+    return n;
 }
 
-// K3b: one thread per (tile, voice): the state of the voice at the first step of the tile, found by bisection in the
-// voice's segment list.  Layout [tile][voice] so that K4's staging loads are coalesced.  (As a loop at the end of
-// K3 this was 131 us of serial work for C2's 1,024 voices x 352 tiles: 18 % of the whole mix.)
-__global__ void voice_tile_records(const VoiceDev* __restrict__ voices, uint32_t n_voices, const Seg* __restrict__ segs,
-                                   const uint32_t* __restrict__ nsegs, TileRec* __restrict__ recs, uint32_t n_tiles,
-                                   const uint32_t* __restrict__ err, const uint32_t seg_cap) {
-    if (*err) return;                                           // a segment / event list overflowed: this render is void
-    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (unsigned long long)n_tiles * n_voices) return;
-    const uint32_t t = (uint32_t)(idx / n_voices), vi = (uint32_t)(idx - (unsigned long long)t * n_voices);
-    const uint32_t active = voices[vi].active, S = voices[vi].S, adv = voices[vi].adv;
+// K3: one WARP per voice.  Lane 0 walks the trajectory (scan_voice); then the 32 lanes write the voice's per-tile
+// records — the state of the voice at the first step of every tile, found by bisection in the segment list the warp has
+// just written (still in L1).  Layout [tile][voice] so that K4's staging loads are coalesced.  (As a serial loop in the
+// walking thread the records were 131 us for C2's 1,024 voices x 352 tiles; as a kernel of their own, one thread per
+// (tile, voice), 24 us plus a launch boundary.)  A voice whose list overflowed leaves records K4 never reads: K4 exits
+// on *err.
+constexpr int kScanThreads = 128;
+__global__ void __launch_bounds__(kScanThreads)
+voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t frames,
+                    Seg* __restrict__ segs, uint32_t* __restrict__ nsegs, uint32_t* __restrict__ err,
+                    const uint32_t* __restrict__ events, const uint32_t* __restrict__ nevents,
+                    const uint32_t seg_cap, const uint32_t oc, Split* __restrict__ splits,
+                    uint32_t* __restrict__ nsplits, TileRec* __restrict__ recs, uint32_t n_tiles) {
+    const uint32_t vi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (vi >= n_voices) return;                                 // warp-uniform
+    const uint32_t active = voices[vi].active, S = voices[vi].S, adv = voices[vi].adv;      // scan_voice only writes .pos
+    uint32_t n = 0;
+    if (lane == 0) n = scan_voice(voices, vi, frames, segs, nsegs, err, events, nevents, seg_cap, oc, splits, nsplits);
+    n = __shfl_sync(0xFFFFFFFFu, n, 0);
+    __syncwarp();                                               // orders lane 0's segment stores before the reads below
     if (!active) return;                                        // K4 never reads the records of an inactive voice
-    const Seg* __restrict__ sg = segs + (size_t)vi * seg_cap;
-    const uint32_t n = nsegs[vi];
-    const uint32_t st = t * (uint32_t)kFT * S;
-    uint32_t lo = 0, hi = n;                                    // last j with sg[j].step0 <= st (sg[0].step0 == 0)
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (sg[mid].step0 <= st) lo = mid; else hi = mid;
+    const Seg* sg = segs + (size_t)vi * seg_cap;
+    for (uint32_t t = lane; t < n_tiles; t += 32) {
+        const uint32_t st = t * (uint32_t)kFT * S;
+        uint32_t lo = 0, hi = n;                                // last j with sg[j].step0 <= st (sg[0].step0 == 0)
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sg[mid].step0 <= st) lo = mid; else hi = mid;
+        }
+        const uint32_t j = lo;
+        const Seg g = sg[j];
+        const uint32_t next = (j + 1 < n) ? sg[j + 1].step0 : 0xFFFFFFFFu;
+        uint32_t left = next - st;
+        if (left > 0xFFFFu) left = 0xFFFFu;                  // only compared with kFT * S + 2 <= 16,386
+        TileRec r;
+        r.p0 = seg_pos(g, st, adv);
+        r.d = g.d;
+        r.scale = g.scale;
+        r.meta = left | (j << 16);
+        recs[(size_t)t * n_voices + vi] = r;
     }
-    const uint32_t j = lo;
-    const Seg g = sg[j];
-    const uint32_t next = (j + 1 < n) ? sg[j + 1].step0 : 0xFFFFFFFFu;
-    uint32_t left = next - st;
-    if (left > 0xFFFFu) left = 0xFFFFu;                      // only compared with kFT * S + 2 <= 16,386
-    TileRec r;
-    r.p0 = seg_pos(g, st, adv);
-    r.d = g.d;
-    r.scale = g.scale;
-    r.meta = left | (j << 16);
-    recs[idx] = r;
 }
 
 // ---------------------------------------------------------------- K4
@@ -938,13 +964,23 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
     if (warp == kConsumers / 32) {
         // ------------------------------------------------ producer warp
         uint32_t o = 0;                                   // stage items enqueued so far (uniform across the warp)
+        uint32_t grabbed = 0;                             // lane 0: the next work item, taken one item ahead
+        if (lane == 0) grabbed = atomicAdd(work, 1u);
+        auto prefetch_batch = [&](uint32_t t, uint32_t vi_, uint32_t vend_) {
+            // the voice row, its tile record and its segment count of a batch the producer will cut later: without this
+            // the two dependent misses (voice, then record: ~2 us under load) at every batch start outlast the ring's slack
+            if (vi_ < vend_) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(voices + vi_));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(recs + (size_t)t * n_voices + vi_));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(nsegs + vi_));
+            }
+        };
         for (;;) {
         // tile-major item order: all voice groups of tile 0 first.  Early tiles are the expensive ones (a voice that
         // starts at position 0 crosses ~20 binades inside its first tile), so they must not be taken last.
-        uint32_t item = 0;
-        if (lane == 0) item = atomicAdd(work, 1u);
-        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        const uint32_t item = __shfl_sync(0xFFFFFFFFu, grabbed, 0);
         if (item >= n_items) break;
+        if (lane == 0) grabbed = atomicAdd(work, 1u);     // the item after this one: in flight while this one is staged
         const uint32_t tile = item / n_groups;
         const uint32_t f0 = tile * (uint32_t)kFT;
         const uint32_t nf = min((uint32_t)kFT, frames - f0);
@@ -952,6 +988,15 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
         const uint32_t vend = min(n_voices, vbeg + voices_per_group);
         for (uint32_t vb = vbeg; vb < vend; vb += 32) {
             const uint32_t vi = vb + lane;
+            if (vb + 32 < vend) {
+                prefetch_batch(tile, vi + 32, vend);
+            } else {                                      // last batch of this item: the first batch of the next one
+                const uint32_t ni = __shfl_sync(0xFFFFFFFFu, grabbed, 0);
+                if (ni < n_items) {
+                    const uint32_t vb_n = (ni % n_groups) * voices_per_group;
+                    prefetch_batch(ni / n_groups, vb_n + lane, min(n_voices, vb_n + voices_per_group));
+                }
+            }
             // per-lane voice state for the piece walk
             VoiceDev v{};
             const Seg* sg = nullptr;
@@ -1601,12 +1646,11 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         BLAST_CUDA_TRY(cudaGetLastError());
         ctx->launches += 1;
     }
-    voice_position_scan<<<(n_voices + 31) / 32, 32, 0, ctx->stream>>>(rb.d_voices, n_voices, (uint32_t)frames, rb.d_segs, rb.d_nsegs,
-                                                                       rb.d_err, rb.d_events, rb.d_nevents, rb.seg_cap, oc, rb.d_splits, rb.d_nsplits);
-    voice_tile_records<<<(unsigned)((need + 255) / 256), 256, 0, ctx->stream>>>(rb.d_voices, n_voices, rb.d_segs, rb.d_nsegs,
-                                                                                rb.d_recs, n_tiles, rb.d_err, rb.seg_cap);
+    voice_position_scan<<<(n_voices + kScanThreads / 32 - 1) / (kScanThreads / 32), kScanThreads, 0, ctx->stream>>>(
+        rb.d_voices, n_voices, (uint32_t)frames, rb.d_segs, rb.d_nsegs, rb.d_err, rb.d_events, rb.d_nevents, rb.seg_cap, oc,
+        rb.d_splits, rb.d_nsplits, rb.d_recs, n_tiles);
     BLAST_CUDA_TRY(cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches += 1;
 
     // voice groups: enough CTAs to fill the GPU a few times over, groups of >= 64 voices
     uint32_t groups = 1;

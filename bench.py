@@ -280,7 +280,7 @@ def run_ours(args):
     roofline_mix = None
     if mix:
         ach = alg_bytes_mix / (ms_mix * 1e-3) / 1e9
-        roofline_mix = {"kernel": "voice_position_scan + voice_tile_records + voice_render_mix_tma + " +
+        roofline_mix = {"kernel": "voice_position_scan + voice_render_mix_tma + " +
                                   ("bus_finalize" if world == 1 else "bus_reduce_peers (peer memory)" if peer is not None
                                    else "NCCL all-reduce(int32) + bus_finalize"),
                         "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",

@@ -132,6 +132,28 @@ def test_binade_crossings_and_stall(ctx):
     assert all(same_pos(a, b) for a, b in zip(pos, epos))
 
 
+@pytest.mark.parametrize("out_channels", [1, 2])
+def test_integer_velocity_runs(ctx, out_channels):
+    """integer velocity from an integer position: K3 writes ONE segment in units of 1.0 up to the first frozen step
+    (or 2^24).  Clips that end inside the render, start positions next to the clip end, large integer velocities, mono
+    and stereo voices, several tiles."""
+    rng = np.random.default_rng(2024 + out_channels)
+    for trial in range(5):
+        voices = []
+        for _ in range(12):
+            ch = int(rng.choice([1, 2]))
+            nfr = int(rng.choice([3, 100, 5000, 20000, 70000]))
+            vel = float(rng.choice([1.0, 1.0, 2.0, 3.0, 5.0, 17.0, 1000.0, 65536.0]))
+            pos = float(rng.choice([0.0, 0.0, 1.0, 7.0, float(nfr - 1), float(nfr), float(max(0, nfr - 4097)), 4096.0]))
+            gain = float(np.float32(rng.choice([1.0, 0.5, 0.77])))
+            voices.append(V(rng.integers(-32768, 32768, size=nfr * ch).astype(np.int16), ch, vel, gain, pos))
+        frames = int(rng.integers(4097, 12000))
+        bus, pos = gpu_render(ctx, voices, out_channels, frames)
+        exp, epos = oracle_render(voices, out_channels, frames)
+        assert np.array_equal(bus, exp), (out_channels, trial, int(np.argmax(bus != exp)))
+        assert all(same_pos(a, b) for a, b in zip(pos, epos)), (pos, epos)
+
+
 def test_chained_renders_equal_one_long_render(ctx):
     rng = np.random.default_rng(5)
     voices = [_random_voice(rng, long_clip=True) for _ in range(12)]
