@@ -725,6 +725,21 @@ __device__ __forceinline__ void unpack_pair(uint32_t w, float& l, float& r) {
     r = __int2float_rn((int32_t)w >> 16);
 }
 
+// (a * s, b * s), each product rounded to nearest like the scalar FMUL: ONE issue slot (Blackwell FMUL2).  Never
+// followed by a packed add: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false, which
+// would change the rounding the reference's `s0 * (1 - frac) + s1 * frac` has (scalar adds are used there).
+__device__ __forceinline__ void mul2(float a, float b, float s, float& x, float& y) {
+    asm("{\n\t.reg .b64 t, u;\n\tmov.b64 t, {%2, %3};\n\tmov.b64 u, {%4, %4};\n\tmul.rn.f32x2 t, t, u;\n\tmov.b64 {%0, %1}, t;\n\t}"
+        : "=f"(x), "=f"(y) : "f"(a), "f"(b), "f"(s));
+}
+// (frame * gain) as i16 on both channels, added to the accumulators
+__device__ __forceinline__ void gain_cast_add(float l, float r, float gain, int32_t& al, int32_t& ar) {
+    float x, y;
+    mul2(l, r, gain, x, y);
+    al += f2i16_sat(x);
+    ar += f2i16_sat(y);
+}
+
 // velocity == 1.0 inside a unit-step run: frame index advances by one per frame, no interpolation.
 // kGainOne: gain == 1.0 — the reference's only value unless the host sets the field (no Command changes it,
 // engine.rs:304): (sample as f32 * 1.0) as i16 == sample, so the mix is two sign extensions and two integer adds.
@@ -739,8 +754,7 @@ __device__ __forceinline__ void consume_stereo_unit(uint32_t stage_addr, uint32_
         } else {
             float l, r;
             unpack_pair(w, l, r);
-            al += f2i16_sat(__fmul_rn(l, gain));
-            ar += f2i16_sat(__fmul_rn(r, gain));
+            gain_cast_add(l, r, gain, al, ar);
         }
     };
     if (kFull) {
@@ -773,8 +787,7 @@ __device__ __forceinline__ void consume_stereo_unit2(uint32_t stage_addr, uint32
         } else {
             float l, r;
             unpack_pair(w, l, r);
-            al += f2i16_sat(__fmul_rn(l, g));
-            ar += f2i16_sat(__fmul_rn(r, g));
+            gain_cast_add(l, r, g, al, ar);
         }
     };
     uint32_t w[kFPT], x[kFPT];
@@ -794,13 +807,12 @@ __device__ __forceinline__ void lerp_frame(uint32_t w0, uint32_t w1, uint32_t fb
     // fract = position - trunc(position), exactly (engine.rs:433); fbits < 2^24 so I2FP is exact
     const float frac = __fmul_rn(__int2float_rn((int)fbits), scale);
     const float om = __fsub_rn(1.0f, frac);
-    float l0, r0, l1, r1;
+    float l0, r0, l1, r1, a0, b0, a1, b1;
     unpack_pair(w0, l0, r0);
     unpack_pair(w1, l1, r1);
-    const float l = __fadd_rn(__fmul_rn(l0, om), __fmul_rn(l1, frac));
-    const float r = __fadd_rn(__fmul_rn(r0, om), __fmul_rn(r1, frac));
-    al += f2i16_sat(__fmul_rn(l, gain));
-    ar += f2i16_sat(__fmul_rn(r, gain));
+    mul2(l0, r0, om, a0, b0);
+    mul2(l1, r1, frac, a1, b1);
+    gain_cast_add(__fadd_rn(a0, a1), __fadd_rn(b0, b1), gain, al, ar);
 }
 
 template <bool kFull>
@@ -866,8 +878,7 @@ __device__ __forceinline__ void consume_stereo_multi(uint32_t stage_addr, const 
                 } else {
                     float l, r;
                     unpack_pair(lds_u32(a), l, r);
-                    acc[j][0] += f2i16_sat(__fmul_rn(l, gain));
-                    acc[j][1] += f2i16_sat(__fmul_rn(r, gain));
+                    gain_cast_add(l, r, gain, acc[j][0], acc[j][1]);
                 }
             }
         }
@@ -1160,9 +1171,9 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                     const int i = __ffs(rest) - 1;
                     rest &= rest - 1;
                     int i2 = -1;
-                    if (((pairable >> i) & 1u) && rest) {
-                        const int n = __ffs(rest) - 1;
-                        if ((pairable >> n) & 1u) { i2 = n; rest &= rest - 1; }
+                    if ((pairable >> i) & 1u) {           // the next full unit tile of this round, adjacent lane or not (adds commute)
+                        const uint32_t cand = rest & pairable;
+                        if (cand) { i2 = __ffs(cand) - 1; rest &= ~(1u << i2); }
                     }
                     const uint32_t st = o % kStages, round = o / kStages;
                     StageMeta* ms = reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride);
