@@ -420,7 +420,7 @@ int render_chunk(blast_ctx* ctx, blast_conductor* c, Flat& f, uint64_t frames, i
     uint8_t* back = h + up;
     BLAST_CUDA_TRY(cudaMemcpyAsync(back, c->rb.d_voices, vb, cudaMemcpyDeviceToHost, ctx->stream));
     if (sb) BLAST_CUDA_TRY(cudaMemcpyAsync(back + vb, c->rb.d_seqs, sb, cudaMemcpyDeviceToHost, ctx->stream));
-    BLAST_CUDA_TRY(cudaMemcpyAsync(back + vb + sb, c->rb.d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    BLAST_CUDA_TRY(cudaMemcpyAsync(back + vb + sb, c->rb.err_word(), sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     uint32_t err;
     memcpy(&err, back + vb + sb, sizeof(err));

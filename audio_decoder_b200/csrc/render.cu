@@ -423,12 +423,28 @@ __device__ __noinline__ uint32_t scan_voice(VoiceDev* __restrict__ voices, const
 // (tile, voice), 24 us plus a launch boundary.)  A voice whose list overflowed leaves records K4 never reads: K4 exits
 // on *err.
 constexpr int kScanThreads = 128;
+constexpr size_t kZeroPerBlock = 8192;           // int32 slots cleared per housekeeping block
 __global__ void __launch_bounds__(kScanThreads)
 voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t frames,
                     Seg* __restrict__ segs, uint32_t* __restrict__ nsegs, uint32_t* __restrict__ err,
                     const uint32_t* __restrict__ events, const uint32_t* __restrict__ nevents,
                     const uint32_t seg_cap, const uint32_t oc, Split* __restrict__ splits,
-                    uint32_t* __restrict__ nsplits, TileRec* __restrict__ recs, uint32_t n_tiles) {
+                    uint32_t* __restrict__ nsplits, TileRec* __restrict__ recs, uint32_t n_tiles,
+                    uint32_t n_voice_blocks, uint32_t* __restrict__ err_next, uint32_t* __restrict__ work,
+                    uint32_t* __restrict__ zero, size_t n_zero) {
+    if (blockIdx.x >= n_voice_blocks) {
+        // housekeeping blocks, concurrent with the walks: the next render's error word and K4's work counter, and the
+        // int32 partial bus when K4 will accumulate with atomics (as stream memsets these were two more operations —
+        // and engine switches — between the kernels of every render)
+        const uint32_t b = blockIdx.x - n_voice_blocks;
+        if (b == 0 && threadIdx.x == 0) {
+            *err_next = 0u;
+            *work = 0u;
+        }
+        const size_t lo = (size_t)b * kZeroPerBlock, hi = lo + kZeroPerBlock < n_zero ? lo + kZeroPerBlock : n_zero;
+        for (size_t i = lo + threadIdx.x; i < hi; i += kScanThreads) zero[i] = 0u;
+        return;
+    }
     const uint32_t vi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (vi >= n_voices) return;                                 // warp-uniform
     const uint32_t active = voices[vi].active, S = voices[vi].S, adv = voices[vi].adv;      // scan_voice only writes .pos
@@ -1437,6 +1453,11 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
     }
 }
 
+__global__ void copy_rows16(const uint4* __restrict__ src, uint4* __restrict__ dst, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
 // ---------------------------------------------------------------- K4b
 // Split frames of voices with Seq processes: a retrigger that landed between the channels of frame f.  K4 rendered
 // every channel of that frame from the NEW epoch (home position); the channels before the hit must carry the old
@@ -1626,8 +1647,8 @@ int reserve_buffers(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32
         }
     }
     if (!rb.d_err) {
-        BLAST_CUDA_TRY(cudaMalloc(&rb.d_err, 2 * sizeof(uint32_t)));                       // [0] error bits, [1] K4's work-item counter
-        BLAST_CUDA_TRY(cudaMemsetAsync(rb.d_err, 0, 2 * sizeof(uint32_t), ctx->stream));
+        BLAST_CUDA_TRY(cudaMalloc(&rb.d_err, 4 * sizeof(uint32_t)));                       // see RenderBuffers::d_err
+        BLAST_CUDA_TRY(cudaMemsetAsync(rb.d_err, 0, 4 * sizeof(uint32_t), ctx->stream));
     }
     if (n_seqs > 0) {
         if (n_seqs > rb.seqs_cap) {
@@ -1658,7 +1679,7 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
     const size_t slots = (size_t)frames * oc;
     if (n_voices == 0) {
         BLAST_CUDA_TRY(cudaMemsetAsync(d_partial_bus, 0, slots * sizeof(int32_t), ctx->stream));
-        BLAST_CUDA_TRY(cudaMemsetAsync(rb.d_err, 0, sizeof(uint32_t), ctx->stream));       // nothing can overflow
+        BLAST_CUDA_TRY(cudaMemsetAsync(rb.d_err, 0, 4 * sizeof(uint32_t), ctx->stream));   // nothing can overflow
         return BLAST_OK;
     }
     const size_t need = (size_t)n_tiles * n_voices;
@@ -1670,20 +1691,7 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         BLAST_CUDA_TRY(cudaMalloc(&rb.d_recs, need * sizeof(TileRec)));
         rb.recs_cap = need;
     }
-    BLAST_CUDA_TRY(cudaMemsetAsync(rb.d_err, 0, 2 * sizeof(uint32_t), ctx->stream));       // error bits + K4's work-item counter
-    if (n_seqs > 0) {
-        seq_event_scan<<<(n_voices + 31) / 32, 32, 0, ctx->stream>>>(rb.d_voices, n_voices, rb.d_seqs, (uint32_t)(frames * oc),
-                                                                      rb.d_events, rb.d_nevents, rb.d_err);
-        BLAST_CUDA_TRY(cudaGetLastError());
-        ctx->launches += 1;
-    }
-    voice_position_scan<<<(n_voices + kScanThreads / 32 - 1) / (kScanThreads / 32), kScanThreads, 0, ctx->stream>>>(
-        rb.d_voices, n_voices, (uint32_t)frames, rb.d_segs, rb.d_nsegs, rb.d_err, rb.d_events, rb.d_nevents, rb.seg_cap, oc,
-        rb.d_splits, rb.d_nsplits, rb.d_recs, n_tiles);
-    BLAST_CUDA_TRY(cudaGetLastError());
-    ctx->launches += 1;
-
-    // voice groups: enough CTAs to fill the GPU a few times over, groups of >= 64 voices
+    // voice groups: enough work items to fill the GPU a few times over, groups of >= 64 voices
     uint32_t groups = 1;
     static const uint32_t ctas_per_sm = getenv("BLAST_RENDER_CTAS_PER_SM") ? (uint32_t)atoi(getenv("BLAST_RENDER_CTAS_PER_SM")) : 32u;
     const uint32_t want_ctas = (uint32_t)ctx->sm_count * ctas_per_sm;
@@ -1692,7 +1700,28 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
     const uint32_t per_group = (n_voices + groups - 1) / groups;
     groups = (n_voices + per_group - 1) / per_group;
     const int use_atomic = groups > 1;
-    if (use_atomic) BLAST_CUDA_TRY(cudaMemsetAsync(d_partial_bus, 0, slots * sizeof(int32_t), ctx->stream));
+
+    rb.parity ^= 1u;                                         // this render's error word; cleared by the previous render's K3
+    uint32_t* d_err = rb.d_err + rb.parity;
+    uint32_t* d_work = rb.d_err + 2;
+    if (n_seqs > 0) {
+        seq_event_scan<<<(n_voices + 31) / 32, 32, 0, ctx->stream>>>(rb.d_voices, n_voices, rb.d_seqs, (uint32_t)(frames * oc),
+                                                                      rb.d_events, rb.d_nevents, d_err);
+        BLAST_CUDA_TRY(cudaGetLastError());
+        ctx->launches += 1;
+    }
+    {
+        // K3's extra blocks clear the NEXT render's error word, K4's work counter and (for atomics) the partial bus
+        const uint32_t n_voice_blocks = (n_voices + kScanThreads / 32 - 1) / (kScanThreads / 32);
+        const size_t n_zero = use_atomic ? slots : 0;
+        const uint32_t n_zero_blocks = (uint32_t)std::max<size_t>(1, (n_zero + kZeroPerBlock - 1) / kZeroPerBlock);
+        voice_position_scan<<<n_voice_blocks + n_zero_blocks, kScanThreads, 0, ctx->stream>>>(
+            rb.d_voices, n_voices, (uint32_t)frames, rb.d_segs, rb.d_nsegs, d_err, rb.d_events, rb.d_nevents, rb.seg_cap, oc,
+            rb.d_splits, rb.d_nsplits, rb.d_recs, n_tiles, n_voice_blocks, rb.d_err + (rb.parity ^ 1u), d_work,
+            reinterpret_cast<uint32_t*>(d_partial_bus), n_zero);
+        BLAST_CUDA_TRY(cudaGetLastError());
+        ctx->launches += 1;
+    }
     dim3 grid(n_tiles, groups);
     // persistent: three CTAs per SM (shared memory bound) take (tile, group) items, tile-major, from a counter
     dim3 grid_tma(std::min<uint32_t>(n_tiles * groups, (uint32_t)ctx->sm_count * 3u), 1);
@@ -1702,17 +1731,17 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         if (oc == 1) {
             BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
             voice_render_mix_tma<1><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(rb.d_voices, n_voices, per_group, groups, rb.d_segs,
-                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, rb.d_err, rb.seg_cap, rb.d_err + 1);
+                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, d_err, rb.seg_cap, d_work);
         } else {
             BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
             voice_render_mix_tma<2><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(rb.d_voices, n_voices, per_group, groups, rb.d_segs,
-                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, rb.d_err, rb.seg_cap, rb.d_err + 1);
+                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, d_err, rb.seg_cap, d_work);
         }
     } else {
 #define BLAST_LAUNCH_MIX(OCV)                                                                              \
     voice_render_mix<OCV><<<grid, kThreads, 0, ctx->stream>>>(rb.d_voices, n_voices, per_group, rb.d_segs,  \
                                                                rb.d_nsegs, rb.d_recs, (uint32_t)frames,      \
-                                                               d_partial_bus, use_atomic, rb.d_err, rb.seg_cap)
+                                                               d_partial_bus, use_atomic, d_err, rb.seg_cap)
         switch (oc) {
             case 1: BLAST_LAUNCH_MIX(1); break;
             case 2: BLAST_LAUNCH_MIX(2); break;
@@ -1729,7 +1758,7 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
     ctx->launches += 1;
     if (n_seqs > 0) {
         voice_split_fixup<<<(n_voices * (uint32_t)kMaxEvents + 255) / 256, 256, 0, ctx->stream>>>(rb.d_voices, n_voices, rb.d_splits,
-                                                                                              rb.d_nsplits, oc, d_partial_bus, rb.d_err);
+                                                                                              rb.d_nsplits, oc, d_partial_bus, d_err);
         BLAST_CUDA_TRY(cudaGetLastError());
         ctx->launches += 1;
     }
@@ -1834,9 +1863,13 @@ int blast_scene_set_voices(blast_ctx* ctx, blast_scene* sc, const blast_voice* v
 int blast_scene_restore_dev(blast_ctx* ctx, blast_scene* sc) {
     if (int rc = blast::bind(ctx)) return rc;
     BLAST_REQUIRE(sc != nullptr, BLAST_ERR_ARG, "blast_scene_restore_dev: null scene");
-    if (sc->n_voices)
-        BLAST_CUDA_TRY(cudaMemcpyAsync(sc->rb.d_voices, sc->d_voices0, (size_t)sc->n_voices * sizeof(VoiceDev),
-                                       cudaMemcpyDeviceToDevice, ctx->stream));
+    if (sc->n_voices) {                                      // a kernel, not a stream memcpy: no engine switch before the render
+        const uint32_t n16 = (uint32_t)((size_t)sc->n_voices * sizeof(VoiceDev) / 16);
+        copy_rows16<<<(n16 + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(sc->d_voices0),
+                                                                 reinterpret_cast<uint4*>(sc->rb.d_voices), n16);
+        BLAST_CUDA_TRY(cudaGetLastError());
+        ctx->launches += 1;
+    }
     return BLAST_OK;
 }
 
@@ -1866,7 +1899,7 @@ int blast_scene_check(blast_ctx* ctx, blast_scene* sc) {
     if (int rc = blast::bind(ctx)) return rc;
     BLAST_REQUIRE(sc != nullptr, BLAST_ERR_ARG, "blast_scene_check: null scene");
     uint32_t e = 0;
-    BLAST_CUDA_TRY(cudaMemcpyAsync(&e, sc->rb.d_err, sizeof(e), cudaMemcpyDeviceToHost, ctx->stream));
+    BLAST_CUDA_TRY(cudaMemcpyAsync(&e, sc->rb.err_word(), sizeof(e), cudaMemcpyDeviceToHost, ctx->stream));
     BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (e) return blast::set_error(BLAST_ERR_CAPACITY, "a voice trajectory needed more than %d position segments", kMaxSeg);
     return BLAST_OK;

@@ -66,7 +66,12 @@ struct RenderBuffers {     // device scratch of one render (owned by a scene or 
     VoiceDev* d_voices = nullptr;
     Seg* d_segs = nullptr;
     uint32_t* d_nsegs = nullptr;
-    uint32_t* d_err = nullptr;         // bit 0: a trajectory needed > kMaxSeg segments, bit 1: > kMaxEvents retriggers
+    uint32_t* d_err = nullptr;         // [0], [1]: error words of alternate renders (bit 0: a trajectory needed more segments
+                                       // than seg_cap, bit 1: > kMaxEvents retriggers); [2]: K4's work-item counter.  The
+                                       // render with parity p reports in d_err[p]; its K3 clears d_err[p ^ 1] and the counter,
+                                       // so no memset sits between the kernels of a render.
+    uint32_t parity = 0;               // of the last launch_render: its error word is d_err[parity]
+    uint32_t* err_word() const { return d_err + parity; }
     TileRec* d_recs = nullptr;
     size_t recs_cap = 0;               // in records
     size_t voices_cap = 0;
