@@ -1079,18 +1079,24 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                         const float u = ulp_of_binade((__float_as_uint(top) >> 23) & 0xFF);
                         const float qf = __fdiv_rn(r.p0, u);
                         const uint32_t idx_a = f2u_sat(r.p0);
-                        if (truncf(qf) == qf && idx_a + nf <= v.end) {
+                        // a plain voice that runs into its end inside the tile (a clip exactly as long as the render: the
+                        // LAST tile of every voice) plays unit steps up to the freeze and is silent after it: still one
+                        // piece.  (Left to the multi-piece path, whose table the producer builds one voice at a time, those
+                        // tiles — the last work items of the kernel — were a ~40 us tail on C2's mix.)
+                        uint32_t n_aud = nf;
+                        if (idx_a + nf > v.end) n_aud = ((v.first_seq >> 24) == 0 && idx_a < v.end) ? v.end - idx_a : 0u;
+                        if (truncf(qf) == qf && n_aud > 0) {
                             const unsigned long long base = (unsigned long long)v.smp;
                             const unsigned long long b0 = base + (unsigned long long)idx_a * 4ull;
-                            const unsigned long long b1 = base + ((unsigned long long)idx_a + nf) * 4ull;
+                            const unsigned long long b1 = base + ((unsigned long long)idx_a + n_aud) * 4ull;
                             const unsigned long long a0 = b0 & ~15ull, a1 = (b1 + 15ull) & ~15ull;
                             unit_tile = true;
                             src = a0;
                             bytes = (uint32_t)(a1 - a0);
                             m.a0_off = (uint32_t)(b0 - a0);
-                            m.mode = kModeStaged | (kPathStereoUnit << 8) | ((nf == (uint32_t)kFT ? 1u : 0u) << 16);
+                            m.mode = kModeStaged | (kPathStereoUnit << 8) | ((n_aud == (uint32_t)kFT ? 1u : 0u) << 16);
                             m.gain = v.gain;
-                            m.frange = 0u | (nf << 16);
+                            m.frange = 0u | (n_aud << 16);
                             cur = nf;
                         }
                     }
