@@ -12,8 +12,9 @@
 //    in-binade step (round-to-nearest-even settles the mantissa parity), so the whole trajectory
 //    is a short list of arithmetic segments  pos(step) = p0 + (step - step0) * d * 2^e  with an
 //    integer d — evaluated EXACTLY by one int multiply + one FFMA.  K3 builds that list per voice
-//    with ordinary f32 adds (one thread per voice, O(#binades) work) and also emits one 16-byte
-//    record per (tile, voice) so that K4 starts every tile with a single load.
+//    with ordinary f32 adds (one warp per voice: lane 0 walks, O(#binades) work — one segment for an
+//    integer velocity from an integer position) and the warp then emits one 16-byte record per
+//    (tile, voice) so that K4 starts every tile with a single load.
 //  * "steps" are advance events, not frames (engine.rs:419-427,445-447): a mono voice on >= 2
 //    outputs advances twice per frame (L reads step 2f, R reads step 2f+1); a C-channel voice on
 //    >= C outputs once per frame; on fewer outputs never.  A voice freezes at the first step whose
@@ -22,10 +23,12 @@
 //    into an i16 slot (engine.rs:441).  Wrapping i16 addition is addition mod 2^16, so K4 sums
 //    int32 partials (any order, any number of GPUs) and K5 keeps the low 16 bits.
 //
-// K4 layout: grid = (frame tiles of 2048) x (voice groups); 256 threads; lanes own consecutive
-// frames, so a warp reads 128 contiguous source bytes per stereo voice per load; every thread keeps
-// 8 frames x out_channels int32 accumulators in registers over all voices of its group and issues one
-// RED.ADD.S32 per bus slot at the end.  Roofline: HBM (2 B per voice-frame-channel of source, read once).
+// K4 layout: work items = (frame tiles of 2048) x (voice groups), taken from a counter by persistent
+// CTAs (3 per SM); 256 consumer threads + one producer warp; lanes own consecutive frames, so a warp reads
+// 128 contiguous staged bytes per stereo voice per load; every thread keeps 8 frames x out_channels int32
+// accumulators in registers over all voices of the item and issues one RED.ADD.S32 per bus slot at its
+// end.  Roofline: HBM (2 B per voice-frame-channel of source, read once).  (> 2 bus channels: the plain
+// one-CTA-per-item kernel `voice_render_mix`.)
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -646,8 +649,9 @@ voice_render_mix(const VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_
 //
 // Measured on B200 (tools/micro/pipe_rates.cu): F2I / I2F.S16 / FRND run on the XU pipe at 16
 // lanes/clk/SM, PRMT / LOP3 at 64, FADD / FMUL / FMNMX / IADD at 128.  The hot paths therefore keep
-// XU work to the two final saturating casts per frame: i16 -> f32 uses the 2^23 magic-number trick
-// (exact) and positions are carried as the integer significand of their segment.
+// XU work to the two final saturating casts per frame: i16 -> f32 is PRMT / SHF + I2FP.F32.S32 (32 lanes/clk/SM,
+// not XU; see unpack_pair), the per-channel products are FMUL2 pairs, and positions are carried as the integer
+// significand of their segment.
 constexpr int kStages = 4;
 constexpr int kStageBytes = 16 * 1024 + 256;
 constexpr int kConsumers = 256;
