@@ -118,16 +118,22 @@ __device__ __forceinline__ float seq_cur(uint32_t base, uint32_t rate, uint32_t 
     return fmodf(__fdiv_rn((float)cur, interval), period_f);                      // blast_time.rs:118-121, processes.rs:77
 }
 
-__global__ void seq_event_scan(const VoiceDev* __restrict__ voices, uint32_t n_voices, SeqDev* __restrict__ seqs,
-                               uint32_t n_calls, uint32_t* __restrict__ events, uint32_t* __restrict__ nevents,
-                               uint32_t* __restrict__ err) {
-    const uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (vi >= n_voices) return;
+// One WARP per voice: every lane carries the same Seq state (the walk over the hits is sequential: each hit draws from
+// the Seq's generator and moves its step index), and the search for a hit — the first call whose tick quotient reaches
+// the wanted value — is a 32-way search over the lanes instead of a bisection (5 dependent rounds of fdiv instead of 21
+// for 2^21 calls: the kernel is nothing but that latency chain).  Lane 0 writes.
+constexpr int kSeqScanThreads = 128;
+__global__ void __launch_bounds__(kSeqScanThreads)
+seq_event_scan(const VoiceDev* __restrict__ voices, uint32_t n_voices, SeqDev* __restrict__ seqs,
+               uint32_t n_calls, uint32_t* __restrict__ events, uint32_t* __restrict__ nevents,
+               uint32_t* __restrict__ err) {
+    const uint32_t vi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (vi >= n_voices) return;                                 // warp-uniform
     const VoiceDev v = voices[vi];
     const uint32_t n_seq = v.first_seq >> 24, s_first = v.first_seq & 0xFFFFFFu;
     uint32_t* ev = events + (size_t)vi * kMaxEvents;
     uint32_t n_ev = 0;
-    if (!v.active || n_seq == 0) { nevents[vi] = 0; return; }
+    if (!v.active || n_seq == 0) { if (lane == 0) nevents[vi] = 0; return; }
     for (uint32_t si = 0; si < n_seq && n_ev <= (uint32_t)kMaxEvents; ++si) {
         SeqDev q = seqs[s_first + si];
         // n_steps == 0: the host parks Seqs whose tempo is inactive this way (processes.rs:74-75).
@@ -155,10 +161,23 @@ __global__ void seq_event_scan(const VoiceDev* __restrict__ voices, uint32_t n_v
                     if (X > (double)x_last) break;
                     const float Xf = (float)X;
                     if ((double)Xf != X) continue;                              // not an f32: x(c) can never equal it
-                    uint32_t lo = c, hi = n_calls;                              // first call with x >= Xf
-                    while (lo < hi) {
-                        const uint32_t mid = lo + (hi - lo) / 2;
-                        if (__fdiv_rn((float)(q.base + q.rate * mid), q.interval) >= Xf) hi = mid; else lo = mid + 1;
+                    uint32_t lo = c, hi = n_calls;                              // first call with x >= Xf (x is monotone in the call)
+                    while (hi - lo > 32u) {
+                        const uint32_t step = (hi - lo) / 32u;                      // lane l probes lo + l * step  (< hi)
+                        const uint32_t probe = lo + lane * step;
+                        const uint32_t b = __ballot_sync(0xFFFFFFFFu, __fdiv_rn((float)(q.base + q.rate * probe), q.interval) >= Xf);
+                        if (b == 0u) { lo = lo + 31u * step + 1u; }
+                        else {
+                            const uint32_t f = (uint32_t)__ffs((int)b) - 1u;       // first lane whose probe is at or past the hit
+                            hi = lo + f * step;
+                            if (f == 0u) break;                                     // lo itself: hi == lo ends the search
+                            lo = lo + (f - 1u) * step + 1u;
+                        }
+                    }
+                    if (hi > lo) {
+                        const uint32_t probe = lo + lane;
+                        const uint32_t b = __ballot_sync(0xFFFFFFFFu, probe < hi && __fdiv_rn((float)(q.base + q.rate * probe), q.interval) >= Xf);
+                        lo = b ? lo + (uint32_t)__ffs((int)b) - 1u : hi;
                     }
                     if (lo < n_calls && seq_cur(q.base, q.rate, lo, q.interval, P) == t) { hit = lo; break; }
                 }
@@ -170,16 +189,19 @@ __global__ void seq_event_scan(const VoiceDev* __restrict__ voices, uint32_t n_v
             const uint64_t r = xo_next(q.s0, q.s1);                                // next_i64_range(0, 100): blast_rand.rs:50-59
             const long long draw = (long long)__umul64hi(r, 100ull);
             if (draw < f32_as_i64(q.chance[q.idx])) {
-                if (n_ev < (uint32_t)kMaxEvents) ev[n_ev] = hit;
+                if (n_ev < (uint32_t)kMaxEvents && lane == 0) ev[n_ev] = hit;
                 n_ev += 1;
             }
             q.idx = (q.idx + 1) % q.n_steps;
             c = hit + 1;
         }
-        seqs[s_first + si].idx = q.idx;
-        seqs[s_first + si].s0 = q.s0;
-        seqs[s_first + si].s1 = q.s1;
+        if (lane == 0) {
+            seqs[s_first + si].idx = q.idx;
+            seqs[s_first + si].s0 = q.s0;
+            seqs[s_first + si].s1 = q.s1;
+        }
     }
+    if (lane != 0) return;
     if (n_ev > (uint32_t)kMaxEvents) { atomicOr(err, 2u); n_ev = kMaxEvents; }
     // sort + de-duplicate (several Seqs of one voice may fire at the same call; the effect is the same reset)
     for (uint32_t i = 1; i < n_ev; ++i) {
@@ -1715,8 +1737,8 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
     uint32_t* d_err = rb.d_err + rb.parity;
     uint32_t* d_work = rb.d_err + 2;
     if (n_seqs > 0) {
-        seq_event_scan<<<(n_voices + 31) / 32, 32, 0, ctx->stream>>>(rb.d_voices, n_voices, rb.d_seqs, (uint32_t)(frames * oc),
-                                                                      rb.d_events, rb.d_nevents, d_err);
+        seq_event_scan<<<(n_voices + kSeqScanThreads / 32 - 1) / (kSeqScanThreads / 32), kSeqScanThreads, 0, ctx->stream>>>(
+            rb.d_voices, n_voices, rb.d_seqs, (uint32_t)(frames * oc), rb.d_events, rb.d_nevents, d_err);
         BLAST_CUDA_TRY(cudaGetLastError());
         ctx->launches += 1;
     }
