@@ -792,18 +792,35 @@ mpeg_classify(const unsigned long long* __restrict__ pos, const uint32_t* __rest
     const unsigned long long i0 = (unsigned long long)blockIdx.x * kClsBlock + (unsigned long long)threadIdx.x * kClsPerThread;
     uint32_t cnt[kClsPerThread];
     uint32_t mine = 0;
+    // the thread's eight candidates as four 128-bit loads up front (headers: 32 B, positions: 64 B, both aligned because
+    // i0 is a multiple of 8): as one dependent scalar load per candidate the two passes ran at half the HBM rate
+    uint32_t h8[kClsPerThread];
+    unsigned long long p8[kClsPerThread];
+    const bool aligned = (((unsigned long long)pos | (unsigned long long)hdr) & 15ull) == 0ull;      // caller-provided device pointers
+    if (aligned && i0 + kClsPerThread <= n) {
+        const uint4* hv = reinterpret_cast<const uint4*>(hdr + i0);
+        const uint4 ha = hv[0], hb = hv[1];
+        h8[0] = ha.x; h8[1] = ha.y; h8[2] = ha.z; h8[3] = ha.w; h8[4] = hb.x; h8[5] = hb.y; h8[6] = hb.z; h8[7] = hb.w;
+        const ulonglong2* pv = reinterpret_cast<const ulonglong2*>(pos + i0);
+#pragma unroll
+        for (int k = 0; k < kClsPerThread / 2; ++k) { const ulonglong2 t = pv[k]; p8[2 * k] = t.x; p8[2 * k + 1] = t.y; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kClsPerThread; ++k) {
+            const bool in = i0 + k < n;
+            h8[k] = in ? hdr[i0 + k] : 0u;                       // 0 has no sync bits: never valid
+            p8[k] = in ? pos[i0 + k] : 0ull;
+        }
+    }
 #pragma unroll
     for (int k = 0; k < kClsPerThread; ++k) {
-        const unsigned long long i = i0 + k;
         cnt[k] = 0;
-        if (i < n) {
-            const uint32_t h = hdr[i];
-            uint32_t pl, sk;
-            if (cand_valid_lut(h, ref_header, s_lut, pl, sk)) {
-                const unsigned long long p = pos[i];
-                cnt[k] = 1 + ((compat && first[h & (kHdrBins - 1)] == p) ? 1u : 0u);
-                if (p + sk + pl > file_len) atomicExch(err, 1u);            // mpeg.rs:95-97 indexes past EOF
-            }
+        const uint32_t h = h8[k];
+        uint32_t pl, sk;
+        if (i0 + k < n && cand_valid_lut(h, ref_header, s_lut, pl, sk)) {
+            const unsigned long long p = p8[k];
+            cnt[k] = 1 + ((compat && first[h & (kHdrBins - 1)] == p) ? 1u : 0u);
+            if (p + sk + pl > file_len) atomicExch(err, 1u);            // mpeg.rs:95-97 indexes past EOF
         }
         mine += cnt[k];
     }
@@ -831,7 +848,7 @@ mpeg_classify(const unsigned long long* __restrict__ pos, const uint32_t* __rest
 #pragma unroll
     for (int k = 0; k < kClsPerThread; ++k) {
         for (uint32_t r = 0; r < cnt[k]; ++r) {
-            if (o < cap) out[o] = pos[i0 + k];
+            if (o < cap) out[o] = p8[k];
             o += 1;
         }
     }
