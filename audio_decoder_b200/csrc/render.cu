@@ -308,7 +308,10 @@ __device__ __noinline__ uint32_t scan_voice(VoiceDev* __restrict__ voices, const
                                             Seg* __restrict__ segs, uint32_t* __restrict__ nsegs, uint32_t* __restrict__ err,
                                             const uint32_t* __restrict__ events, const uint32_t* __restrict__ nevents,
                                             const uint32_t seg_cap, const uint32_t oc, Split* __restrict__ splits,
-                                            uint32_t* __restrict__ nsplits) {
+                                            uint32_t* __restrict__ nsplits, uint3* cmds) {
+    // cmds (shared, one list per warp): cmds[0] = {number of commands, cap_eff, 0}; cmds[1 + i] = {first segment index,
+    // segment count, step offset} — epochs that are copies of the voice's template, left to the whole warp
+    cmds[0] = make_uint3(0u, 0u, 0u);
     VoiceDev v = voices[vi];
     Seg* sg = segs + (size_t)vi * seg_cap;
     uint32_t n = 0;
@@ -379,8 +382,21 @@ __device__ __noinline__ uint32_t scan_voice(VoiceDev* __restrict__ voices, const
             }
             const uint32_t base_step = cur, n_adv = a - cur;
             if (at_home && tpl_ok) {
-                uint32_t t = 0;
-                for (; t < n_tpl && (t == 0 || tpl[t].step0 < n_adv); ++t) put_capped(base_step + tpl[t].step0, tpl[t].p0, tpl[t].d, tpl[t].scale);
+                // the epoch uses template segments 0 .. t-1 (segment 0 always, then those that start before its last
+                // step; step0 ascends: bisection).  Equivalent to put_capped() on each of them, but only the bookkeeping
+                // is done here: the copy itself is the warp's (voice_position_scan), ~45 segments x ~87 epochs per voice
+                // on C3 + Seq were this thread's serial load-store chain.
+                uint32_t t = 1, t_hi = n_tpl;
+                while (t < t_hi) {
+                    const uint32_t mid = (t + t_hi) >> 1;
+                    if (tpl[mid].step0 < n_adv) t = mid + 1; else t_hi = mid;
+                }
+                const uint32_t start = (base_step == last0 && n > 0) ? n - 1 : n;   // an epoch of zero steps is replaced
+                const uint32_t n_cmd = cmds[0].x;
+                cmds[1 + n_cmd] = make_uint3(start, t, base_step);                   // at most n_ev + 1 <= kMaxEvents + 1 epochs
+                cmds[0] = make_uint3(n_cmd + 1, cap_eff, 0u);
+                n = start + t;
+                last0 = base_step + tpl[t - 1].step0;
                 // position after n_adv advances = position of step n_adv: in the last template segment that starts at or
                 // before it (a segment's closed form is only valid up to its own last step)
                 const Seg g = (t < n_tpl && tpl[t].step0 <= n_adv) ? tpl[t] : tpl[t - 1];
@@ -473,12 +489,34 @@ voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t f
     const uint32_t vi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (vi >= n_voices) return;                                 // warp-uniform
     const uint32_t active = voices[vi].active, S = voices[vi].S, adv = voices[vi].adv;      // scan_voice only writes .pos
+    __shared__ uint3 s_cmds[kScanThreads / 32][kMaxEvents + 2];
+    uint3* cmds = s_cmds[threadIdx.x >> 5];
     uint32_t n = 0;
-    if (lane == 0) n = scan_voice(voices, vi, frames, segs, nsegs, err, events, nevents, seg_cap, oc, splits, nsplits);
+    if (lane == 0) n = scan_voice(voices, vi, frames, segs, nsegs, err, events, nevents, seg_cap, oc, splits, nsplits, cmds);
     n = __shfl_sync(0xFFFFFFFFu, n, 0);
     __syncwarp();                                               // orders lane 0's segment stores before the reads below
+    Seg* sgw = segs + (size_t)vi * seg_cap;
+    {
+        // template epochs of a voice with Seq processes: copy segments 0 .. count-1 of the template (stored behind the
+        // voice's own cap_eff segments) to their place, step0 shifted; in order, a later epoch may replace the last
+        // segment of an earlier one
+        const uint32_t n_cmd = cmds[0].x, cap_eff = cmds[0].y;
+        const Seg* tpl = sgw + cap_eff;
+        for (uint32_t c = 0; c < n_cmd; ++c) {
+            const uint3 cm = cmds[1 + c];
+            for (uint32_t tt = lane; tt < cm.y; tt += 32) {
+                const uint32_t idx = cm.x + tt;
+                if (idx < cap_eff) {
+                    Seg g = tpl[tt];
+                    g.step0 += cm.z;
+                    sgw[idx] = g;
+                }
+            }
+            __syncwarp();
+        }
+    }
     if (!active) return;                                        // K4 never reads the records of an inactive voice
-    const Seg* sg = segs + (size_t)vi * seg_cap;
+    const Seg* sg = sgw;
     for (uint32_t t = lane; t < n_tiles; t += 32) {
         const uint32_t st = t * (uint32_t)kFT * S;
         uint32_t lo = 0, hi = n;                                // last j with sg[j].step0 <= st (sg[0].step0 == 0)
