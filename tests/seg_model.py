@@ -53,6 +53,19 @@ def build_segments(pos, vel, end, total):
             if f2u_sat(p) >= end:
                 segs.append((s, p, 0, f32(0)))
                 break
+            # integer position, integer velocity: every add below 2^24 is exact whatever binades it crosses, so the run up
+            # to the first frozen step (or 2^24, or the end of the epoch) is ONE segment in units of 1.0
+            if 1.0 <= float(vel) < 16777216.0 and 0.0 <= float(p) < 16777216.0:
+                pi, vv = int(float(p)), int(float(vel))
+                if float(pi) == float(p) and float(vv) == float(vel):
+                    kmax = (16777215 - pi) // vv
+                    kf = (end - pi + vv - 1) // vv                       # first frozen step (end > pi here)
+                    kmax = min(kmax, kf, total - s)
+                    if kmax >= 1:
+                        segs.append((s, p, vv, f32(1.0)))
+                        p = f32(pi + kmax * vv)
+                        s += kmax
+                        continue
             p1 = f32(p + vel)
             if bits(p1) == bits(p):
                 segs.append((s, p, 0, f32(0)))

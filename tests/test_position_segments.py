@@ -83,3 +83,25 @@ def test_random_velocities_with_ties():
 @pytest.mark.parametrize("v", [1.0, 0.5, 1.5, 0.3, 3.0, 0.1, 7.0 / 3.0])
 def test_long_runs(v):
     _check(0.0, v, (1 << 31) - 1, 1 << 21)
+
+
+def test_integer_velocity_runs_are_one_segment():
+    """integer velocity from an integer position: one segment in units of 1.0 up to the first frozen step, the 2^24
+    limit or the end of the walk — and still the reference's trajectory bit for bit"""
+    big = (1 << 31) - 1
+    segs, _ = sm.build_segments(0.0, 1.0, big, 1 << 20)
+    assert len(segs) == 1 and segs[0][2] == 1 and float(segs[0][3]) == 1.0
+    assert _check(0.0, 1.0, big, 1 << 20) == 1
+    assert _check(0.0, 1.0, 720_000 - 1, 720_000) <= 2            # C2: the clip ends with the render (frozen tail segment)
+    assert _check(7.0, 3.0, big, 1 << 18) == 1
+    assert _check(0.0, 2.0, 5000, 1 << 14) == 2                   # freezes at the clip end
+    _check(16777000.0, 1.0, big, 1000)                            # leaves the fast path at 2^24 (stall)
+    _check(16777210.0, 5.0, big, 100)
+    _check(0.0, 65536.0, big, 1000)
+    _check(3.0, 16777215.0, big, 10)
+    rng = np.random.default_rng(77)
+    for _ in range(200):
+        v = float(rng.choice([1.0, 2.0, 3.0, 5.0, 17.0, 1000.0, 65536.0, 8388608.0]))
+        p0 = float(rng.integers(0, 1 << 24))
+        end = int(rng.choice([big, 100_000, 5000, 3]))
+        _check(p0, v, end, int(rng.integers(1, 50_000)))
