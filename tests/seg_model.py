@@ -130,3 +130,27 @@ def expand(segs, total):
         else:
             out[step0:nxt] = (k * d * np.float64(scale) + np.float64(p0)).astype(np.float32)
     return out
+
+
+def warp_search(lo, hi, pred):
+    """Model of K3a's 32-way search (seq_event_scan): first c in [lo, hi) with pred(c), pred monotone (False..True);
+    hi if there is none.  Each round evaluates 32 probes (the lanes of the voice's warp) and keeps the sub-range
+    between the last False and the first True probe."""
+    rounds = 0
+    while hi - lo > 32:
+        step = (hi - lo) // 32
+        b = [pred(lo + lane * step) for lane in range(32)]
+        rounds += 1
+        if not any(b):
+            lo = lo + 31 * step + 1
+        else:
+            f = b.index(True)
+            hi = lo + f * step
+            if f == 0:
+                break
+            lo = lo + (f - 1) * step + 1
+    if hi > lo:
+        b = [(lo + lane < hi) and pred(lo + lane) for lane in range(32)]
+        rounds += 1
+        lo = lo + b.index(True) if any(b) else hi
+    return lo, rounds

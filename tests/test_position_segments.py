@@ -105,3 +105,15 @@ def test_integer_velocity_runs_are_one_segment():
         p0 = float(rng.integers(0, 1 << 24))
         end = int(rng.choice([big, 100_000, 5000, 3]))
         _check(p0, v, end, int(rng.integers(1, 50_000)))
+
+
+def test_warp_search_equals_bisection():
+    """K3a finds the first call whose tick quotient reaches a value by a 32-way search over the warp's lanes"""
+    rng = np.random.default_rng(5)
+    for _ in range(2000):
+        lo = int(rng.integers(0, 1000))
+        hi = lo + int(rng.choice([0, 1, 2, 31, 32, 33, 64, 1000, 1 << 21]))
+        first = int(rng.integers(lo - 5, hi + 5))                   # may lie outside the range (-> lo, or none -> hi)
+        got, rounds = sm.warp_search(lo, hi, lambda c: c >= first)
+        assert got == min(max(first, lo), hi), (lo, hi, first, got)
+        assert rounds <= 6
