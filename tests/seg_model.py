@@ -154,3 +154,43 @@ def warp_search(lo, hi, pred):
         rounds += 1
         lo = lo + b.index(True) if any(b) else hi
     return lo, rounds
+
+
+def epochs_put_capped(tpl_step0, epochs, n0=0, last0=None):
+    """K3's template epochs as the original per-segment put_capped() sequence: -> list of step0 per segment index"""
+    out = [None] * n0
+    n = n0
+    for base, n_adv in epochs:
+        t = 0
+        while t < len(tpl_step0) and (t == 0 or tpl_step0[t] < n_adv):
+            step0 = base + tpl_step0[t]
+            if step0 == last0 and n > 0:
+                out[n - 1] = (step0, t)
+            else:
+                last0 = step0
+                out.append((step0, t))
+                n += 1
+            t += 1
+    return out
+
+
+def epochs_booked(tpl_step0, epochs, n0=0, last0=None):
+    """the same as booked by K3's walking lane (first index, count, step offset) and copied by the warp afterwards"""
+    cmds, n = [], n0
+    for base, n_adv in epochs:
+        lo, hi = 1, len(tpl_step0)
+        while lo < hi:
+            mid = (lo + hi) >> 1
+            if tpl_step0[mid] < n_adv:
+                lo = mid + 1
+            else:
+                hi = mid
+        start = n - 1 if (base == last0 and n > 0) else n
+        cmds.append((start, lo, base))
+        n = start + lo
+        last0 = base + tpl_step0[lo - 1]
+    out = [None] * n
+    for start, count, base in cmds:
+        for t in range(count):
+            out[start + t] = (base + tpl_step0[t], t)
+    return out

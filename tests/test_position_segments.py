@@ -117,3 +117,23 @@ def test_warp_search_equals_bisection():
         got, rounds = sm.warp_search(lo, hi, lambda c: c >= first)
         assert got == min(max(first, lo), hi), (lo, hi, first, got)
         assert rounds <= 6
+
+
+def test_template_epoch_bookkeeping_equals_per_segment_puts():
+    """K3 with Seq processes: booking (first index, count, offset) per epoch + a parallel copy gives the segment list
+    of the per-segment put_capped() walk, zero-step epochs (replaced by their successor) included"""
+    rng = np.random.default_rng(11)
+    for _ in range(500):
+        n_tpl = int(rng.integers(1, 40))
+        tpl = [0] + sorted(set(int(x) for x in rng.integers(1, 5000, size=n_tpl - 1)))
+        epochs, base = [], int(rng.integers(0, 100))
+        for _e in range(int(rng.integers(1, 30))):
+            n_adv = int(rng.choice([0, 0, 1, 2, 7, 100, 3000, 6000]))
+            epochs.append((base, n_adv))
+            base += n_adv
+        n0 = int(rng.integers(0, 3))
+        last0 = epochs[0][0] if (n0 and rng.random() < 0.5) else None
+        a = sm.epochs_put_capped(tpl, epochs, n0, last0)
+        b = sm.epochs_booked(tpl, epochs, n0, last0)
+        assert a[n0 - 1 if (n0 and last0 is not None) else n0:] == b[n0 - 1 if (n0 and last0 is not None) else n0:], (tpl, epochs, n0, last0)
+        assert len(a) == len(b)
