@@ -623,10 +623,8 @@ __host__ __device__ inline bool parse_header_bits(uint32_t h, HdrInfo& o) {
     o.chmode = b3 >> 6;
     return true;
 }
-__host__ __device__ inline bool match_ref_bits(const HdrInfo& a, const HdrInfo& b) {   // mpeg.rs:194-204
-    // sr = base(version) * factor(ff): with equal versions, equal sr <=> equal ff
-    return a.version == b.version && a.layer == b.layer && a.ff == b.ff && a.chmode == b.chmode && a.not_prot == b.not_prot;
-}
+// match against the reference header (mpeg.rs:194-204): version, layer, sample rate, channel mode and protection must be
+// equal; sr = base(version) * factor(ff), so with equal versions equal sr <=> equal ff.  As header bits: kRefMask below.
 // compute_frame_len (mpeg.rs:207-234) in the same f64 arithmetic; false on "Frame length too small"
 __host__ __device__ inline bool frame_len_bits(const HdrInfo& o, uint32_t& payload, uint32_t& skip) {
     const uint32_t rates[14] = {8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160};   // BITRATES column 4
@@ -698,9 +696,9 @@ __global__ void mpeg_pick_ref(const uint32_t* __restrict__ hist, unsigned long l
     if ((threadIdx.x & 31) == 0 && key) atomicMax(best, key);
 }
 
-// per-candidate validity against the reference header = parse_header_bits && match_ref_bits && frame_len_bits, through a
-// table: a candidate that matches the reference header (match_ref_bits = equality of the version /
-// protection, layer, sample-rate and channel-mode bits: mask 0x00170CC0) can only differ from it in the bitrate index
+// per-candidate validity against the reference header = parse_header_bits && match (above) && frame_len_bits, through a
+// table: a candidate that matches the reference header (= equality of the version /
+// protection, layer, sample-rate and channel-mode bits: mask 0x00170CC0; tests/test_mpeg_lut_model.py) can only differ from it in the bitrate index
 // and the padding bit, so compute_frame_len's f64 divisions are done 28 times per block instead of once per candidate.
 // Entry: bit 31 valid, payload << 4, skip.
 constexpr uint32_t kRefMask = 0x00170CC0u;

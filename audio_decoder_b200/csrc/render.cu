@@ -334,15 +334,6 @@ __device__ __noinline__ uint32_t scan_voice(VoiceDev* __restrict__ voices, const
         const float home = v.vel >= 0.0f ? 0.0f : (float)v.end;
         Split* sp = splits + (size_t)vi * kMaxEvents;
         uint32_t n_sp = 0, cur = 0, last0 = 0xFFFFFFFFu;
-        auto put = [&](uint32_t step0, float p0, int32_t d, float scale) {
-            if (step0 == last0 && n > 0) {                                        // an epoch of zero steps: replaced by its successor
-                if (n <= seg_cap) sg[n - 1] = Seg{step0, p0, d, scale};
-                return;
-            }
-            last0 = step0;
-            if (n < seg_cap) sg[n] = Seg{step0, p0, d, scale};
-            n += 1;
-        };
         // Every epoch after a retrigger starts at `home` with the same velocity, so its segment sequence is the same
         // every time up to where it is cut off: it is built once, as a template at the tail of the voice's segment
         // area, and instantiated per epoch by shifting step0 (the closed form per segment is exact, so the position
@@ -362,7 +353,7 @@ __device__ __noinline__ uint32_t scan_voice(VoiceDev* __restrict__ voices, const
             tpl_ok = n_tpl <= kTpl;
         }
         auto put_capped = [&](uint32_t step0, float p0, int32_t d, float scale) {
-            if (step0 == last0 && n > 0) {
+            if (step0 == last0 && n > 0) {                                        // an epoch of zero steps: replaced by its successor
                 if (n <= cap_eff) sg[n - 1] = Seg{step0, p0, d, scale};
                 return;
             }
