@@ -14,7 +14,7 @@ SO_PATH = os.path.join(_HERE, "libblast_cuda.so")
 
 OK = 0
 ERR_IO, ERR_UNSUPPORTED_FORMAT, ERR_UNEXPECTED_EOF, ERR_INVALID_DATA, ERR_REF_PANIC = 1, 2, 3, 4, 5
-ERR_CUDA, ERR_ARG, ERR_NO_DEVICE, ERR_CAPACITY, ERR_UNSUPPORTED = 100, 101, 102, 103, 104
+ERR_CUDA, ERR_ARG, ERR_NO_DEVICE, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_TIMEOUT = 100, 101, 102, 103, 104, 105
 
 
 class PcmDesc(C.Structure):
@@ -162,12 +162,35 @@ SIGNATURES = {
     "blast_conductor_set_voice": (C.c_int, [_vp, C.c_int, _u32, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                             C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "blast_conductor_clock": (_u64, [_vp]),
-    "blast_ipc_export": (C.c_int, [_vp, _vp, _vp]),
-    "blast_ipc_open": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
-    "blast_ipc_close": (C.c_int, [_vp, _vp]),
-    "blast_peer_signal_dev": (C.c_int, [_vp, C.POINTER(_vp), _u32, _u32]),
-    "blast_peer_wait_dev": (C.c_int, [_vp, _vp, _u32, _u32]),
-    "blast_bus_reduce_peers_dev": (C.c_int, [_vp, C.POINTER(_vp), _u32, _vp, _u32, _u32, _vp, _u64, _u64, C.POINTER(_vp), _u32]),
+    "blast_peer_bus_create": (C.c_int, [_vp, _u64, _u32, _u32, _u32, C.POINTER(_vp)]),
+    "blast_peer_bus_destroy": (None, [_vp, _vp]),
+    "blast_peer_bus_export": (C.c_int, [_vp, _vp, _vp]),
+    "blast_peer_bus_connect_ipc": (C.c_int, [_vp, _vp, _vp]),
+    "blast_peer_bus_connect_local": (C.c_int, [C.POINTER(_vp), _u32]),
+    "blast_peer_bus_partial": (_vp, [_vp]),
+    "blast_peer_bus_bus": (_vp, [_vp]),
+    "blast_scene_render_reduce_dev": (C.c_int, [_vp, _vp, _u64, _vp]),
+    "blast_peer_bus_begin_dev": (C.c_int, [_vp, _vp]),
+    "blast_peer_bus_reduce_dev": (C.c_int, [_vp, _vp, _u64]),
+    "blast_peer_bus_wait_dev": (C.c_int, [_vp, _vp]),
+    "blast_peer_bus_check": (C.c_int, [_vp, _vp]),
+    "blast_conductor_set_shard_by_track": (C.c_int, [_vp, _u32, _u32]),
+    "blast_group_create": (C.c_int, [C.POINTER(_vp), C.POINTER(C.c_int), _u32]),
+    "blast_group_destroy": (None, [_vp]),
+    "blast_group_size": (_u32, [_vp]),
+    "blast_group_ctx": (_vp, [_vp, _u32]),
+    "blast_group_pcm_decode_batch": (C.c_int, [_vp, _u32, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(PcmDesc), C.POINTER(_vp),
+                                               C.POINTER(Track)]),
+    "blast_group_free_tracks": (C.c_int, [_vp]),
+    "blast_group_render": (C.c_int, [_vp, C.POINTER(Track), _u32, C.POINTER(Voice), _u32, _u32, _u64, _vp]),
+    "blast_group_conductor_create": (C.c_int, [_vp, _u32, _u32, C.POINTER(Track), _u32, C.POINTER(_vp)]),
+    "blast_group_conductor_destroy": (None, [_vp]),
+    "blast_group_conductor_apply": (C.c_int, [_vp, C.POINTER(Command)]),
+    "blast_group_conductor_coordinate": (C.c_int, [_vp, _u64, _vp]),
+    "blast_group_conductor_member": (_vp, [_vp, _u32]),
+    "blast_group_x128p_fill": (C.c_int, [_vp, _u64, _u64, _u64, _u64, C.c_int64, C.c_int64, _vp, _vp, _vp]),
+    "blast_group_mpeg_index": (C.c_int, [_vp, _vp, _u64, C.c_int, _vp, _u64, C.POINTER(_u64), C.POINTER(_u32),
+                                         C.POINTER(_u64)]),
     "blast_render": (C.c_int, [_vp, C.POINTER(Track), _u32, C.POINTER(Voice), _u32, _u32, _u64, _vp,
                                C.POINTER(Voice)]),
 }

@@ -60,6 +60,7 @@ struct SeqH {                  // processes.rs:56-65
 
 struct VoiceH {                // engine.rs:279-295
     uint64_t uid = 0;          // load order number (sharding key)
+    uint32_t track = 0;        // LoadArgs.track_idx (sharding key when the tracks themselves are sharded over GPUs)
     const int16_t* d_smp = nullptr;
     uint64_t end = 0;
     uint32_t C = 0;
@@ -130,6 +131,7 @@ struct blast_conductor {
     uint64_t clock = 0;
     uint64_t next_uid = 0;
     uint32_t rank = 0, world = 1;
+    bool shard_by_track = false;       // a voice is rendered where its track lives (track t on rank t mod world)
     RenderBuffers rb;
     float* d_fpool = nullptr;          // steps / chance of the live Seqs
     size_t fpool_cap = 0;
@@ -179,6 +181,7 @@ int apply_command(blast_conductor* c, const blast_command* cmd) {
             if (((uintptr_t)tr.d_samples & 3) != 0) return blast::set_error(BLAST_ERR_ARG, "load: track samples must be 4-byte aligned");
             VoiceH v;
             v.uid = c->next_uid++;
+            v.track = (uint32_t)cmd->idx;
             v.d_smp = tr.d_samples;
             v.end = frames - 1;
             v.C = tr.num_channels;
@@ -311,7 +314,7 @@ int flatten(blast_conductor* c, Flat& f) {
     std::vector<Pending> pending;
     auto visit = [&](VoiceH& v) -> int {
         f.called.push_back(&v);
-        const bool mine = (v.uid % c->world) == c->rank;
+        const bool mine = ((c->shard_by_track ? (uint64_t)v.track : v.uid) % c->world) == c->rank;
         // processes run first and see the ticks of the voices before this one in the same call (engine.rs:392-394)
         uint32_t n_live = 0;
         const size_t first = f.seqs.size();
@@ -524,6 +527,16 @@ int blast_conductor_set_shard(blast_conductor* c, uint32_t rank, uint32_t world)
     BLAST_REQUIRE(world >= 1 && rank < world, BLAST_ERR_ARG, "blast_conductor_set_shard: need rank < world");
     c->rank = rank;
     c->world = world;
+    c->shard_by_track = false;
+    return BLAST_OK;
+}
+
+int blast_conductor_set_shard_by_track(blast_conductor* c, uint32_t rank, uint32_t world) {
+    BLAST_REQUIRE(c != nullptr, BLAST_ERR_ARG, "blast_conductor_set_shard_by_track: null conductor");
+    BLAST_REQUIRE(world >= 1 && rank < world, BLAST_ERR_ARG, "blast_conductor_set_shard_by_track: need rank < world");
+    c->rank = rank;
+    c->world = world;
+    c->shard_by_track = true;
     return BLAST_OK;
 }
 

@@ -1,4 +1,6 @@
 // ctx.cu — context lifecycle, memory helpers, event timing for libblast_cuda.so
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "blast_internal.h"
@@ -65,6 +67,9 @@ void* scratch(blast_ctx* ctx, int slot, size_t bytes) {
         cudaFree(ctx->scratch[slot]);
         ctx->scratch[slot] = nullptr;
         ctx->scratch_cap[slot] = 0;
+        // slot 5 caches the RNG's sub-stream jump matrices: a new allocation may come back at the same address with
+        // undefined contents, so the cache key (which includes the pointer) is dropped with the memory
+        if (slot == 5) ctx->x128p_split_ptr = nullptr;
     }
     size_t want = (bytes + (bytes >> 2) + 255) & ~(size_t)255;      // 25 % head-room
     if (cudaMalloc(&ctx->scratch[slot], want) != cudaSuccess) {
@@ -119,6 +124,7 @@ int blast_ctx_create(blast_ctx** out, int device) {
         return set_error(BLAST_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(se));
     }
     ctx->owns_stream = true;
+    if (const char* e = getenv("BLAST_RENDER_MAX_CTAS_PER_SM")) ctx->render_ctas_per_sm = std::min(3, std::max(1, atoi(e)));
     *out = ctx;
     return BLAST_OK;
 }
@@ -214,32 +220,6 @@ int blast_memcpy_d2h(blast_ctx* ctx, void* dst, const void* d_src, size_t bytes)
 int blast_memset_dev(blast_ctx* ctx, void* d_dst, int value, size_t bytes) {
     if (int rc = blast::bind(ctx)) return rc;
     if (bytes) BLAST_CUDA_TRY(cudaMemsetAsync(d_dst, value, bytes, ctx->stream));
-    return BLAST_OK;
-}
-
-// ---- peer memory between the one-process-per-GPU ranks of a box (CUDA IPC over NVLink / NVSwitch)
-int blast_ipc_export(blast_ctx* ctx, void* d_ptr, uint8_t handle_out[64]) {
-    if (int rc = blast::bind(ctx)) return rc;
-    BLAST_REQUIRE(d_ptr && handle_out, BLAST_ERR_ARG, "blast_ipc_export: null argument");
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-    cudaIpcMemHandle_t h;
-    BLAST_CUDA_TRY(cudaIpcGetMemHandle(&h, d_ptr));
-    std::memcpy(handle_out, &h, 64);
-    return BLAST_OK;
-}
-
-int blast_ipc_open(blast_ctx* ctx, const uint8_t handle[64], void** d_ptr_out) {
-    if (int rc = blast::bind(ctx)) return rc;
-    BLAST_REQUIRE(handle && d_ptr_out, BLAST_ERR_ARG, "blast_ipc_open: null argument");
-    cudaIpcMemHandle_t h;
-    std::memcpy(&h, handle, 64);
-    BLAST_CUDA_TRY(cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
-    return BLAST_OK;
-}
-
-int blast_ipc_close(blast_ctx* ctx, void* d_ptr) {
-    if (int rc = blast::bind(ctx)) return rc;
-    if (d_ptr) BLAST_CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
     return BLAST_OK;
 }
 

@@ -91,6 +91,107 @@ __device__ __forceinline__ float seg_pos(const Seg& g, uint32_t abs_step, uint32
     return seg_eval(g.p0, g.d, g.scale, adv_count(abs_step, adv) - adv_count(g.step0, adv));
 }
 
+
+// ---------------------------------------------------------------- bus sink: tile hand-off between ranks (peer memory)
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Step counters compared with wrap-around.  The spin is bounded: a rank that never publishes (it failed, or its process
+// died) costs its peers timeout_ms, then bit 2 of *err is set and the caller carries on — blast_peer_bus_check reports it.
+__device__ __noinline__ void wait_flag(const uint32_t* flag, uint32_t value, uint32_t timeout_ms, uint32_t* err) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if ((int32_t)(v - value) >= 0) return;
+    const uint64_t t0 = global_ns(), budget = (uint64_t)timeout_ms * 1000000ull;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - value) >= 0) return;
+        if (timeout_ms && global_ns() - t0 > budget) {
+            if (err) atomicOr(err, 4u);
+            return;
+        }
+        __nanosleep(64);
+    }
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// One thread, after a CTA-level barrier that follows the CTA's bus writes of one (tile, voice group) work item:
+// the CTA that flushes the last group of a tile publishes the tile to the rank that will reduce it.
+__device__ __forceinline__ void sink_tile_flushed(const BusSink& s, uint32_t tile, uint32_t n_groups) {
+    __threadfence();
+    const uint32_t prev = atomicAdd(s.tile_count + tile, 1u);
+    if (prev + 1u == n_groups) {
+        __threadfence_system();
+        st_release_sys(s.ready_at[tile % s.world] + tile, s.step);
+    }
+}
+// The reduction of one tile by `nthreads` threads of one CTA (sync = their barrier): wait until every rank has published
+// it, sum the int32 partial tiles of all ranks (peer memory: system-scope loads, never the non-coherent path), keep the
+// low 16 bits (== i16 wrapping accumulate, engine.rs:441) and store them into the root's S16 bus.  The rank's last tile
+// raises the done / ack flags.
+template <typename Sync>
+__device__ __forceinline__ void sink_reduce_tile(const BusSink& s, uint32_t tile, uint32_t tid, uint32_t nthreads, Sync sync) {
+    if (tid < s.world) wait_flag(s.ready_mine + (size_t)tid * s.max_tiles + tile, s.step, s.timeout_ms, s.err);
+    sync();
+    const uint64_t base = (uint64_t)tile * s.tile_slots;
+    const uint64_t left = s.n_slots - base;
+    const uint32_t n = left < (uint64_t)s.tile_slots ? (uint32_t)left : s.tile_slots;
+    const uint32_t n4 = n / 4;                                   // base is a multiple of 4 (tile_slots is)
+    for (uint32_t k = tid; k < n4; k += nthreads) {
+        int4 acc = make_int4(0, 0, 0, 0);
+        for (uint32_t r0 = 0; r0 < s.world; r0 += 4) {           // four NVLink round trips in flight per thread
+            uint4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[j] = make_uint4(0, 0, 0, 0);
+                if (r0 + j < s.world)
+                    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w)
+                                 : "l"(reinterpret_cast<const uint4*>(s.part[r0 + j] + base) + k));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc.x += (int32_t)v[j].x; acc.y += (int32_t)v[j].y; acc.z += (int32_t)v[j].z; acc.w += (int32_t)v[j].w;
+            }
+        }
+        uint2 o;
+        o.x = ((uint32_t)acc.x & 0xFFFF) | ((uint32_t)acc.y << 16);
+        o.y = ((uint32_t)acc.z & 0xFFFF) | ((uint32_t)acc.w << 16);
+        reinterpret_cast<uint2*>(s.out + base)[k] = o;           // local on the root, an NVLink store elsewhere
+    }
+    for (uint32_t k = n4 * 4 + tid; k < n; k += nthreads) {
+        int32_t acc = 0;
+        for (uint32_t r = 0; r < s.world; ++r) {
+            uint32_t x;
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(x) : "l"(s.part[r] + base + k));
+            acc += (int32_t)x;
+        }
+        s.out[base + k] = (int16_t)acc;
+    }
+    sync();
+    if (tid == 0) {
+        __threadfence_system();
+        const uint32_t prev = atomicAdd(s.red_count, 1u);
+        if (prev + 1u == s.n_my_tiles) {
+            *s.red_count = 0u;                                   // every other reduction of this step has finished
+            __threadfence_system();
+            for (uint32_t i = 0; i < s.n_done; ++i) st_release_sys(s.done[i], s.step);
+        }
+    }
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// out of line: the rare tile hand-off must not take registers from K4's consumer loop (72 at 3 CTAs per SM)
+__device__ __noinline__ void k4_reduce_tile(const BusSink& s, uint32_t tile) {
+    sink_reduce_tile(s, tile, threadIdx.x, 256u, [] { consumer_bar(); });
+}
+__device__ __noinline__ void k4_tile_flushed(const BusSink& s, uint32_t tile, uint32_t n_groups) {
+    consumer_bar();
+    if (threadIdx.x == 0) sink_tile_flushed(s, tile, n_groups);
+}
+
 // ---------------------------------------------------------------- K3a: Seq event scan (processes.rs:69-90)
 // One thread per voice that carries Seq processes.  A Seq fires at call c when
 //   fmodf((tempo.current as f32) / interval, period as f32) == steps[idx]        (exact f32 equality)
@@ -463,15 +564,25 @@ voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t f
                     const uint32_t seg_cap, const uint32_t oc, Split* __restrict__ splits,
                     uint32_t* __restrict__ nsplits, TileRec* __restrict__ recs, uint32_t n_tiles,
                     uint32_t n_voice_blocks, uint32_t* __restrict__ err_next, uint32_t* __restrict__ work,
-                    uint32_t* __restrict__ zero, size_t n_zero) {
+                    uint32_t* __restrict__ zero, size_t n_zero, const BusSink sink) {
     if (blockIdx.x >= n_voice_blocks) {
         // housekeeping blocks, concurrent with the walks: the next render's error word and K4's work counter, and the
         // int32 partial bus when K4 will accumulate with atomics (as stream memsets these were two more operations —
         // and engine switches — between the kernels of every render)
         const uint32_t b = blockIdx.x - n_voice_blocks;
-        if (b == 0 && threadIdx.x == 0) {
-            *err_next = 0u;
-            *work = 0u;
+        if (sink.world > 1) {
+            // the partial bus is read by the peers that reduce its tiles: nobody clears it (and K4, which follows this
+            // kernel, does not write it) before every rank has finished with the previous step
+            if (threadIdx.x < sink.world) wait_flag(sink.ack_mine + threadIdx.x, sink.step - 1u, sink.timeout_ms, sink.err);
+            __syncthreads();
+        }
+        if (b == 0) {
+            if (threadIdx.x == 0) {
+                *err_next = 0u;
+                *work = 0u;
+            }
+            if (sink.world)
+                for (uint32_t i = threadIdx.x; i < sink.n_tiles; i += kScanThreads) sink.tile_count[i] = 0u;
         }
         const size_t lo = (size_t)b * kZeroPerBlock, hi = lo + kZeroPerBlock < n_zero ? lo + kZeroPerBlock : n_zero;
         for (size_t i = lo + threadIdx.x; i < hi; i += kScanThreads) zero[i] = 0u;
@@ -707,7 +818,7 @@ constexpr int kStages = 4;
 constexpr int kStageBytes = 16 * 1024 + 256;
 constexpr int kConsumers = 256;
 constexpr int kTmaThreads = kConsumers + 32;
-enum : uint32_t { kModeStaged = 1, kModeDirect = 2, kModeEnd = 3, kModeFlush = 4 };
+enum : uint32_t { kModeStaged = 1, kModeDirect = 2, kModeEnd = 3, kModeFlush = 4, kModeReduce = 5 };
 enum : uint32_t { kPathGeneric = 0, kPathStereoUnit = 1, kPathStereoLerp = 2, kPathStereoMulti = 3, kPathStereoUnit2 = 4 };
 constexpr uint32_t kPairHalf = 8192 + 128;    // stage offset of the second voice of a kPathStereoUnit2 item (a full unit tile is <= 8,208 B)
 static_assert(2 * kPairHalf <= kStageBytes, "two unit tiles per stage");
@@ -1039,11 +1150,12 @@ __device__ __forceinline__ void consume_generic(const StageMeta& m, uint32_t sta
 // bubble per item (as one CTA per item this cost ~11 us per CTA round: C2's mix ran at 5.3 TB/s, C3 at 6.7).  A
 // kModeFlush item at the end of each work item makes the consumers add their accumulators into the bus.
 template <int OC>
-__global__ void __launch_bounds__(kTmaThreads)
+__global__ void __launch_bounds__(kTmaThreads, 3)
 voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t voices_per_group,
                      uint32_t n_groups, const Seg* __restrict__ segs, const uint32_t* __restrict__ nsegs,
                      const TileRec* __restrict__ recs, uint32_t frames, int32_t* __restrict__ bus, int use_atomic,
-                     const uint32_t* __restrict__ err, const uint32_t seg_cap, uint32_t* __restrict__ work) {
+                     const uint32_t* __restrict__ err, const uint32_t seg_cap, uint32_t* __restrict__ work,
+                     const __grid_constant__ BusSink sink) {
     extern __shared__ __align__(128) uint8_t smem[];
     if (*err) return;                                           // truncated trajectories must not be rendered (uniform exit)
     uint8_t* stages = smem;
@@ -1052,7 +1164,12 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
     uint64_t* empty = full + kStages;
     uint4* ptabs = reinterpret_cast<uint4*>(empty + kStages);          // [kStages][kMaxPieces]
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t n_items = ((frames + (uint32_t)kFT - 1u) / (uint32_t)kFT) * n_groups;
+    // With a sink the queue runs `lag` virtual tiles past the last one: the item that renders group 0 of tile T also
+    // reduces tile T - lag when this rank owns it.  Every work item a reduction waits for (here or on a peer) has a smaller
+    // index than its own, i.e. is already held by a running CTA: no CTA ever waits for work nobody has taken.
+    const uint32_t n_tiles = (frames + (uint32_t)kFT - 1u) / (uint32_t)kFT;
+    const uint32_t n_render_items = n_tiles * n_groups;
+    const uint32_t n_items = sink.world ? (n_tiles + sink.lag) * n_groups : n_render_items;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -1084,17 +1201,18 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
         if (item >= n_items) break;
         if (lane == 0) grabbed = atomicAdd(work, 1u);     // the item after this one: in flight while this one is staged
         const uint32_t tile = item / n_groups;
+        const bool render_item = tile < n_tiles;
         const uint32_t f0 = tile * (uint32_t)kFT;
-        const uint32_t nf = min((uint32_t)kFT, frames - f0);
+        const uint32_t nf = render_item ? min((uint32_t)kFT, frames - f0) : 0u;
         const uint32_t vbeg = (item % n_groups) * voices_per_group;
-        const uint32_t vend = min(n_voices, vbeg + voices_per_group);
+        const uint32_t vend = render_item ? min(n_voices, vbeg + voices_per_group) : vbeg;
         for (uint32_t vb = vbeg; vb < vend; vb += 32) {
             const uint32_t vi = vb + lane;
             if (vb + 32 < vend) {
                 prefetch_batch(tile, vi + 32, vend);
             } else {                                      // last batch of this item: the first batch of the next one
                 const uint32_t ni = __shfl_sync(0xFFFFFFFFu, grabbed, 0);
-                if (ni < n_items) {
+                if (ni < n_render_items) {
                     const uint32_t vb_n = (ni % n_groups) * voices_per_group;
                     prefetch_batch(ni / n_groups, vb_n + lane, min(n_voices, vb_n + voices_per_group));
                 }
@@ -1413,7 +1531,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                 first_round = false;
             }
         }
-        {   // end of the work item: the consumers add their accumulators into the bus
+        if (render_item) {   // end of the work item: the consumers add their accumulators into the bus
             const uint32_t st = o % kStages, round = o / kStages;
             if (lane == 0) {
                 if (round > 0) mbar_wait(empty + st, (round - 1) & 1);
@@ -1421,6 +1539,19 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                 ms->mode = kModeFlush;
                 ms->a0_off = f0;
                 ms->frange = nf;
+                ms->q0 = (int32_t)tile;
+                mbar_arrive(full + st);
+            }
+            __syncwarp();
+            o += 1;
+        }
+        if (sink.world && item % n_groups == 0 && tile >= sink.lag && (tile - sink.lag) % sink.world == sink.rank) {
+            const uint32_t st = o % kStages, round = o / kStages;
+            if (lane == 0) {
+                if (round > 0) mbar_wait(empty + st, (round - 1) & 1);
+                StageMeta* ms = reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride);
+                ms->mode = kModeReduce;
+                ms->a0_off = tile - sink.lag;
                 mbar_arrive(full + st);
             }
             __syncwarp();
@@ -1484,6 +1615,9 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                     }
                 }
             }
+            if (sink.world) k4_tile_flushed(sink, a0_off / (uint32_t)kFT, n_groups);   // the tile's last voice group publishes it
+        } else if ((mode & 0xFF) == kModeReduce) {
+            k4_reduce_tile(sink, a0_off);
         } else {
             const uint32_t path = (mode >> 8) & 0xFF;
             const bool fullr = (mode >> 16) & 1;
@@ -1563,88 +1697,34 @@ __global__ void bus_finalize(const int32_t* __restrict__ partial, int16_t* __res
     }
 }
 
-// ---------------------------------------------------------------- K5p: the mix reduction over peer memory
-// One process per GPU; every rank's int32 partial bus (and a small block of step-counter flags) is mapped into its
-// peers' address spaces (CUDA IPC over NVLink / NVSwitch).  Per step every rank (1) publishes "my partial bus of step
-// s is complete" with one system-scope store per peer, (2) runs ONE kernel that waits for all ready flags, pulls ITS
-// slice of every peer's bus with 128-bit loads, adds its own, wraps to S16 (K5) and stores the slice straight into
-// the root's bus, then (3) tells every peer "I am done with your bus" and the root "slice s is in place".
-// Reduce-scatter, finalize and gather-to-root in one kernel, no collective library, no intermediate int32 bus, and
-// 1/N of the bus crosses each GPU's links.  Exact for the same reason as the all-reduce: i16 wrapping addition is
-// addition mod 2^16.
-constexpr int kMaxPeers = 16;
-struct FlagList {
-    uint32_t* p[2 * kMaxPeers];
-};
-struct PartList {
-    const int32_t* part[kMaxPeers];                 // part[0] = own partial bus, the rest = peers' (IPC-mapped)
-};
-
-__global__ void peer_signal(FlagList fl, uint32_t n, uint32_t value) {
+// ---------------------------------------------------------------- K5p: the bus reduction on its own
+// The same tile protocol as inside K4 (sink_tile_flushed / sink_reduce_tile) for partial buses that were filled by
+// earlier stream work — the Conductor's spans, buses with more than two channels, a rank without voices:
+// `peer_publish_tiles` raises this rank's ready flag of every tile at the tile's owner, `bus_reduce_tiles` reduces the
+// tiles this rank owns, one CTA each.
+__global__ void peer_publish_tiles(const BusSink sink) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= sink.n_tiles) return;
     __threadfence_system();                         // everything this stream wrote before is visible before the flags
-    if (threadIdx.x < n) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(fl.p[threadIdx.x]), "r"(value) : "memory");
-}
-
-__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t value) {
-    uint32_t v;
-    for (;;) {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if ((int32_t)(v - value) >= 0) break;       // step counters, compared with wrap-around
-        __nanosleep(100);
-    }
-}
-
-__global__ void peer_wait(const uint32_t* flags, uint32_t n, uint32_t value) {
-    if (threadIdx.x < n) wait_flag(flags + threadIdx.x, value);
+    st_release_sys(sink.ready_at[t % sink.world] + t, sink.step);
 }
 
 __global__ void __launch_bounds__(256)
-bus_reduce_peers(PartList pp, uint32_t n_parts, const uint32_t* __restrict__ ready, uint32_t n_ready, uint32_t step,
-                 int16_t* __restrict__ bus, uint64_t slot0, uint64_t n, FlagList after, uint32_t n_after,
-                 uint32_t* __restrict__ done_count) {
-    // every thread block waits for every ready flag (they all become visible within a microsecond of each other)
-    if (threadIdx.x < n_ready) wait_flag(ready + threadIdx.x, step);
-    __syncthreads();
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t n4 = n / 4;
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += stride) {
-        // all remote loads of this vector are issued before the first add: an NVLink round trip is microseconds
-        uint4 v[kMaxPeers - 1];
-#pragma unroll
-        for (int r = 1; r < kMaxPeers; ++r) {
-            v[r - 1] = make_uint4(0, 0, 0, 0);
-            if ((uint32_t)r < n_parts)                                   // system-coherent loads (never the .nc path)
-                asm("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-                    : "=r"(v[r - 1].x), "=r"(v[r - 1].y), "=r"(v[r - 1].z), "=r"(v[r - 1].w)
-                    : "l"(reinterpret_cast<const uint4*>(pp.part[r] + slot0) + k));
-        }
-        int4 acc = reinterpret_cast<const int4*>(pp.part[0] + slot0)[k];
-#pragma unroll
-        for (int r = 1; r < kMaxPeers; ++r) {
-            acc.x += (int32_t)v[r - 1].x; acc.y += (int32_t)v[r - 1].y; acc.z += (int32_t)v[r - 1].z; acc.w += (int32_t)v[r - 1].w;
-        }
-        uint2 o;
-        o.x = ((uint32_t)acc.x & 0xFFFF) | ((uint32_t)acc.y << 16);
-        o.y = ((uint32_t)acc.z & 0xFFFF) | ((uint32_t)acc.w << 16);
-        reinterpret_cast<uint2*>(bus + slot0)[k] = o;                    // local on the root, an NVLink store elsewhere
-    }
-    for (uint64_t k = n4 * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
-        int32_t acc = pp.part[0][slot0 + k];
-        for (uint32_t r = 1; r < n_parts; ++r) acc += *reinterpret_cast<const volatile int32_t*>(pp.part[r] + slot0 + k);
-        bus[slot0 + k] = (int16_t)acc;
-    }
-    // the last block to finish publishes: peers may overwrite their partial buses, the root's slice is in place
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        const uint32_t prev = atomicAdd(done_count, 1u);
-        if (prev + 1 == gridDim.x) {
-            *done_count = 0;
-            __threadfence_system();
-            for (uint32_t i = 0; i < n_after; ++i)
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(after.p[i]), "r"(step) : "memory");
-        }
-    }
+bus_reduce_tiles(const BusSink sink) {
+    const uint32_t tile = sink.rank + blockIdx.x * sink.world;
+    if (tile >= sink.n_tiles) return;
+    sink_reduce_tile(sink, tile, threadIdx.x, 256u, [] { __syncthreads(); });
+}
+
+// a rank that owns no tile of this step (fewer tiles than ranks) still tells the root "my part is in place" and every
+// rank "I am not reading your partial bus"
+__global__ void peer_raise(const BusSink sink) {
+    __threadfence_system();
+    if (threadIdx.x < sink.n_done) st_release_sys(sink.done[threadIdx.x], sink.step);
+}
+
+__global__ void flag_wait(const uint32_t* flags, uint32_t n, uint32_t value, uint32_t timeout_ms, uint32_t* err) {
+    if (threadIdx.x < n) wait_flag(flags + threadIdx.x, value, timeout_ms, err);
 }
 
 }  // namespace
@@ -1730,17 +1810,52 @@ int reserve_buffers(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32
     return BLAST_OK;
 }
 
+int launch_flag_wait(blast_ctx* ctx, const uint32_t* d_flags, uint32_t n, uint32_t value, uint32_t timeout_ms, uint32_t* d_err) {
+    if (n == 0) return BLAST_OK;
+    if (n > 32) return blast::set_error(BLAST_ERR_CAPACITY, "at most 32 flags per wait");
+    flag_wait<<<1, 32, 0, ctx->stream>>>(d_flags, n, value, timeout_ms, d_err);
+    BLAST_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    return BLAST_OK;
+}
+
+static int launch_peer_raise(blast_ctx* ctx, const BusSink& sink) {
+    peer_raise<<<1, 2 * kMaxPeers, 0, ctx->stream>>>(sink);
+    BLAST_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    return BLAST_OK;
+}
+
+int launch_bus_reduce(blast_ctx* ctx, const BusSink& sink) {
+    if (sink.n_tiles) {
+        peer_publish_tiles<<<(sink.n_tiles + 255) / 256, 256, 0, ctx->stream>>>(sink);
+        BLAST_CUDA_TRY(cudaGetLastError());
+        ctx->launches += 1;
+    }
+    if (sink.n_my_tiles == 0) return launch_peer_raise(ctx, sink);
+    bus_reduce_tiles<<<sink.n_my_tiles, 256, 0, ctx->stream>>>(sink);
+    BLAST_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    return BLAST_OK;
+}
+
 int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t n_seqs, uint32_t oc, uint64_t frames,
-                  int32_t* d_partial_bus) {
-    if (frames == 0) return BLAST_OK;
+                  int32_t* d_partial_bus, const BusSink* sink_in) {
+    if (frames == 0) return (sink_in && sink_in->world) ? launch_bus_reduce(ctx, *sink_in) : BLAST_OK;
     if (frames > 0x7FFFFFFFull) return blast::set_error(BLAST_ERR_CAPACITY, "at most 2^31-1 frames per render call");
     if (n_seqs > 0 && frames * oc > 0x7FFFFFFFull)
         return blast::set_error(BLAST_ERR_CAPACITY, "at most 2^31-1 calls (frames x channels) per render call with Seq processes");
     const uint32_t n_tiles = (uint32_t)((frames + kFT - 1) / kFT);
     const size_t slots = (size_t)frames * oc;
+    static const bool legacy = getenv("BLAST_RENDER_LEGACY") != nullptr;
+    const bool fused = sink_in && sink_in->world && oc <= 2 && !legacy && n_voices > 0 && n_seqs == 0;   // the reduction rides in K4's work queue
+    // (K4b patches the partial bus after K4, so voices with Seq processes take the two-kernel reduction)
+    if (sink_in && sink_in->world && !fused && sink_in->world > 1)                         // nobody reads the previous partial bus any more
+        if (int rc = launch_flag_wait(ctx, sink_in->ack_mine, sink_in->world, sink_in->step - 1u, sink_in->timeout_ms, sink_in->err)) return rc;
     if (n_voices == 0) {
         BLAST_CUDA_TRY(cudaMemsetAsync(d_partial_bus, 0, slots * sizeof(int32_t), ctx->stream));
         BLAST_CUDA_TRY(cudaMemsetAsync(rb.d_err, 0, 4 * sizeof(uint32_t), ctx->stream));   // nothing can overflow
+        if (sink_in && sink_in->world) return launch_bus_reduce(ctx, *sink_in);
         return BLAST_OK;
     }
     const size_t need = (size_t)n_tiles * n_voices;
@@ -1758,9 +1873,35 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
     const uint32_t want_ctas = (uint32_t)ctx->sm_count * ctas_per_sm;
     static const uint32_t min_group = getenv("BLAST_RENDER_MIN_GROUP") ? (uint32_t)atoi(getenv("BLAST_RENDER_MIN_GROUP")) : 64u;
     while (n_tiles * groups < want_ctas && n_voices / (groups * 2) >= min_group) groups *= 2;
+    // persistent: CTAs per SM (three fit: shared-memory bound) take (tile, group) items, tile-major, from a counter
+    const uint32_t resident = (uint32_t)ctx->sm_count * (uint32_t)ctx->render_ctas_per_sm;
+    if (oc <= 2 && !legacy && n_tiles * groups < 8 * resident) {
+        // few equal items per CTA: a kernel as long as ceil(items / CTAs) items.  Among the group counts allowed (groups of
+        // >= 16 voices) take the one that wastes the least of the last round (1,024 files over 8 GPUs: 128 voices per rank,
+        // 352 tiles -> 704 items on 444 CTAs would leave 44 % of the second round idle).
+        uint32_t best = groups;
+        double best_cost = 1e30;
+        for (uint32_t g = 1; g <= 64 && n_voices / g >= 16; ++g) {
+            const uint32_t per = (n_voices + g - 1) / g, gg = (n_voices + per - 1) / per;
+            const uint64_t items = (uint64_t)n_tiles * gg;
+            const uint64_t rounds = (items + resident - 1) / resident;
+            // per item: `per` voice tiles of work + ~3 voice tiles' worth of fixed cost (flush, barriers, queue)
+            const double cost = (double)rounds * ((double)per + 3.0);
+            if (cost < best_cost) { best_cost = cost; best = gg; }
+        }
+        groups = best;
+    }
     const uint32_t per_group = (n_voices + groups - 1) / groups;
     groups = (n_voices + per_group - 1) / per_group;
     const int use_atomic = groups > 1;
+    BusSink sink{};
+    if (fused) {
+        sink = *sink_in;
+        // tile t is reduced once the queue is `lag` tiles further: by then its last voice group has normally been flushed
+        // on every rank (1.5 x the CTAs in flight, plus slack for the skew between ranks), so the reduction seldom waits
+        sink.lag = std::min<uint32_t>(n_tiles, (3 * resident / 2 + groups - 1) / groups + 2);
+        if (sink.lag < 1) sink.lag = 1;
+    }
 
     rb.parity ^= 1u;                                         // this render's error word; cleared by the previous render's K3
     uint32_t* d_err = rb.d_err + rb.parity;
@@ -1779,24 +1920,22 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         voice_position_scan<<<n_voice_blocks + n_zero_blocks, kScanThreads, 0, ctx->stream>>>(
             rb.d_voices, n_voices, (uint32_t)frames, rb.d_segs, rb.d_nsegs, d_err, rb.d_events, rb.d_nevents, rb.seg_cap, oc,
             rb.d_splits, rb.d_nsplits, rb.d_recs, n_tiles, n_voice_blocks, rb.d_err + (rb.parity ^ 1u), d_work,
-            reinterpret_cast<uint32_t*>(d_partial_bus), n_zero);
+            reinterpret_cast<uint32_t*>(d_partial_bus), n_zero, sink);
         BLAST_CUDA_TRY(cudaGetLastError());
         ctx->launches += 1;
     }
     dim3 grid(n_tiles, groups);
-    // persistent: three CTAs per SM (shared memory bound) take (tile, group) items, tile-major, from a counter
-    dim3 grid_tma(std::min<uint32_t>(n_tiles * groups, (uint32_t)ctx->sm_count * 3u), 1);
-    static const bool legacy = getenv("BLAST_RENDER_LEGACY") != nullptr;
+    dim3 grid_tma(std::min<uint32_t>(n_tiles * groups, resident), 1);
     if (oc <= 2 && !legacy) {
         // TMA pipeline kernel (one producer warp + eight consumer warps)
         if (oc == 1) {
             BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
             voice_render_mix_tma<1><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(rb.d_voices, n_voices, per_group, groups, rb.d_segs,
-                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, d_err, rb.seg_cap, d_work);
+                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, d_err, rb.seg_cap, d_work, sink);
         } else {
             BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
             voice_render_mix_tma<2><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(rb.d_voices, n_voices, per_group, groups, rb.d_segs,
-                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, d_err, rb.seg_cap, d_work);
+                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, d_err, rb.seg_cap, d_work, sink);
         }
     } else {
 #define BLAST_LAUNCH_MIX(OCV)                                                                              \
@@ -1823,6 +1962,8 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         BLAST_CUDA_TRY(cudaGetLastError());
         ctx->launches += 1;
     }
+    if (sink_in && sink_in->world && !fused) return launch_bus_reduce(ctx, *sink_in);
+    if (fused && sink.n_my_tiles == 0) return launch_peer_raise(ctx, sink);
     return BLAST_OK;
 }
 
@@ -1978,59 +2119,12 @@ int blast_bus_finalize_dev(blast_ctx* ctx, const int32_t* d_partial, int16_t* d_
     return BLAST_OK;
 }
 
-int blast_peer_signal_dev(blast_ctx* ctx, uint32_t* const* d_flags, uint32_t n_flags, uint32_t value) {
+int blast_scene_render_reduce_dev(blast_ctx* ctx, blast_scene* sc, uint64_t frames, blast_peer_bus* pb) {
     if (int rc = blast::bind(ctx)) return rc;
-    BLAST_REQUIRE(d_flags != nullptr || n_flags == 0, BLAST_ERR_ARG, "blast_peer_signal_dev: null flags");
-    if (n_flags > 2u * kMaxPeers) return blast::set_error(BLAST_ERR_CAPACITY, "at most %d flags per signal", 2 * kMaxPeers);
-    if (n_flags == 0) return BLAST_OK;
-    FlagList fl{};
-    for (uint32_t i = 0; i < n_flags; ++i) fl.p[i] = d_flags[i];
-    peer_signal<<<1, 32, 0, ctx->stream>>>(fl, n_flags, value);
-    BLAST_CUDA_TRY(cudaGetLastError());
-    ctx->launches += 1;
-    return BLAST_OK;
-}
-
-int blast_peer_wait_dev(blast_ctx* ctx, const uint32_t* d_flags, uint32_t n_flags, uint32_t value) {
-    if (int rc = blast::bind(ctx)) return rc;
-    BLAST_REQUIRE(d_flags != nullptr || n_flags == 0, BLAST_ERR_ARG, "blast_peer_wait_dev: null flags");
-    if (n_flags > 32) return blast::set_error(BLAST_ERR_CAPACITY, "at most 32 flags per wait");
-    if (n_flags == 0) return BLAST_OK;
-    peer_wait<<<1, 32, 0, ctx->stream>>>(d_flags, n_flags, value);
-    BLAST_CUDA_TRY(cudaGetLastError());
-    ctx->launches += 1;
-    return BLAST_OK;
-}
-
-int blast_bus_reduce_peers_dev(blast_ctx* ctx, const int32_t* const* d_parts, uint32_t n_parts, const uint32_t* d_ready,
-                               uint32_t n_ready, uint32_t step, int16_t* d_bus, uint64_t slot0, uint64_t n_slots,
-                               uint32_t* const* d_signal, uint32_t n_signal) {
-    if (int rc = blast::bind(ctx)) return rc;
-    BLAST_REQUIRE(d_parts && d_bus && n_parts >= 1 && (d_ready || n_ready == 0) && (d_signal || n_signal == 0), BLAST_ERR_ARG,
-                  "blast_bus_reduce_peers_dev: null argument");
-    if (n_parts > (uint32_t)kMaxPeers || n_ready > 32 || n_signal > 2u * kMaxPeers)
-        return blast::set_error(BLAST_ERR_CAPACITY, "at most %d partial buses / 32 ready flags / %d signals", kMaxPeers, 2 * kMaxPeers);
-    BLAST_REQUIRE((slot0 & 3) == 0, BLAST_ERR_ARG, "slot0 must be a multiple of 4");
-    PartList pp{};
-    for (uint32_t r = 0; r < n_parts; ++r) {
-        BLAST_REQUIRE(d_parts[r] != nullptr && ((uintptr_t)d_parts[r] & 15) == 0, BLAST_ERR_ARG, "partial buses must be 16-byte aligned");
-        pp.part[r] = d_parts[r];
-    }
-    BLAST_REQUIRE(((uintptr_t)d_bus & 7) == 0, BLAST_ERR_ARG, "the bus must be 8-byte aligned");
-    FlagList after{};
-    for (uint32_t i = 0; i < n_signal; ++i) after.p[i] = d_signal[i];
-    uint32_t* d_count = static_cast<uint32_t*>(blast::scratch(ctx, 8, 256));
-    if (!d_count) return BLAST_ERR_CUDA;
-    if (!ctx->peer_count_zeroed) {
-        BLAST_CUDA_TRY(cudaMemsetAsync(d_count, 0, 256, ctx->stream));
-        ctx->peer_count_zeroed = true;
-    }
-    const uint64_t blocks = (n_slots / 4 + 255) / 256;
-    const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(blocks, 1), (uint64_t)ctx->sm_count * 4);   // all resident: they spin
-    bus_reduce_peers<<<grid, 256, 0, ctx->stream>>>(pp, n_parts, d_ready, n_ready, step, d_bus, slot0, n_slots, after, n_signal, d_count);
-    BLAST_CUDA_TRY(cudaGetLastError());
-    ctx->launches += 1;
-    return BLAST_OK;
+    BLAST_REQUIRE(sc && pb, BLAST_ERR_ARG, "blast_scene_render_reduce_dev: null argument");
+    BusSink sink;
+    if (int rc = peer_bus_next_step(ctx, pb, frames, sc->out_channels, true, &sink)) return rc;
+    return launch_render(ctx, sc->rb, sc->n_voices, 0, sc->out_channels, frames, peer_bus_partial(pb), &sink);
 }
 
 int blast_render(blast_ctx* ctx, const blast_track* tracks, uint32_t n_tracks, const blast_voice* voices,

@@ -84,12 +84,51 @@ struct RenderBuffers {     // device scratch of one render (owned by a scene or 
     uint32_t* d_nsplits = nullptr;     // [voices_cap]
 };
 
+// Where finished bus tiles go when the render feeds a peer bus (blast_peer_bus, peer_bus.cu): the render kernel itself
+// publishes every completed tile to the rank that owns it (tile t -> rank t mod world), and takes "reduce items" from
+// the same work queue: wait for the tile's ready flags of all ranks, sum the int32 partial tiles over peer memory
+// (NVLink / NVSwitch loads), wrap to S16 and store into the root's bus.  world == 1 is the single-GPU finalize.
+constexpr int kMaxPeers = 16;
+struct BusSink {
+    uint32_t world = 0;                    // 0: no sink, the render leaves int32 partial sums only
+    uint32_t rank = 0;
+    uint32_t step = 0;                     // value the flags of this render carry (counters compared with wrap-around)
+    uint32_t lag = 1;                      // tile t is reduced by the work item that renders tile t + lag (>= 1)
+    uint32_t max_tiles = 0;                // row length of the ready tables
+    uint32_t n_tiles = 0;                  // tiles of this render
+    uint32_t n_my_tiles = 0;               // ... of which this rank reduces
+    uint32_t tile_slots = 0;               // bus slots per tile (kFT * out_channels inside the render kernel)
+    uint64_t n_slots = 0;                  // bus slots of this render
+    uint32_t n_done = 0;
+    uint32_t timeout_ms = 0;
+    const int32_t* part[kMaxPeers] = {};   // slot 0 of every rank's partial bus (part[rank] is local), mapped here
+    uint32_t* ready_at[kMaxPeers] = {};    // ready_at[o] = this rank's row of owner o's ready table
+    const uint32_t* ready_mine = nullptr;  // this rank's table [world][max_tiles], written by the peers
+    int16_t* out = nullptr;                // slot 0 of the ROOT's S16 bus, mapped here
+    uint32_t* tile_count = nullptr;        // local [max_tiles]: flushed voice groups per tile
+    uint32_t* red_count = nullptr;         // local: tiles reduced so far in this step
+    uint32_t* done[2 * kMaxPeers] = {};    // flags that receive `step` when this rank has reduced all its tiles
+    const uint32_t* ack_mine = nullptr;    // this rank's ack flags [world]: rank p is done reading my partial bus
+    uint32_t* err = nullptr;               // local: bit 2 = a flag wait timed out
+};
+
 int  reserve_buffers(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t n_seqs);
 void free_buffers(RenderBuffers& rb);
 // Seq event scan (when n_seqs > 0) + position scan + render/mix of the first n_voices records of rb.d_voices into
 // the int32 partial bus (overwritten); async on ctx->stream.  Device-side capacity errors land in rb.d_err.
+// sink != nullptr: the partial bus is sink->part[sink->rank] and finished tiles are reduced into sink->out (fused into the
+// render kernel for out_channels <= 2, as two small kernels after it otherwise).
 int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t n_seqs, uint32_t out_channels,
-                  uint64_t frames, int32_t* d_partial_bus);
+                  uint64_t frames, int32_t* d_partial_bus, const BusSink* sink = nullptr);
+// the reduction on its own: publish every tile of this rank's partial bus (filled by earlier stream work), reduce the
+// tiles this rank owns.  Async on ctx->stream.
+int launch_bus_reduce(blast_ctx* ctx, const BusSink& sink);
+// async: the stream waits (on the device, bounded) until the n flags have reached `value`
+int launch_flag_wait(blast_ctx* ctx, const uint32_t* d_flags, uint32_t n, uint32_t value, uint32_t timeout_ms, uint32_t* d_err);
+// peer_bus.cu: starts the next step of a peer bus for a render of `frames` frames on an out_channels bus and fills the
+// sink the kernels take.  in_render: tiles are the render kernel's (kFT frames); else 4,096-slot tiles.
+int peer_bus_next_step(blast_ctx* ctx, blast_peer_bus* pb, uint64_t frames, uint32_t out_channels, bool in_render, BusSink* out);
+int32_t* peer_bus_partial(blast_peer_bus* pb);
 // VoiceDev routing fields (S, nch, adv) for a voice with C channels on an out_channels bus
 void route_voice(VoiceDev& v, uint32_t out_channels, bool has_seq);
 

@@ -168,130 +168,107 @@ class ShardedMpegIndex:
 
 # ---------------------------------------------------------------------------------- the mix reduction over peer memory
 class PeerBus:
-    """The render's one exchange step without a collective library: every rank's int32 partial bus and flag block are
-    mapped into every peer's address space (CUDA IPC over NVLink / NVSwitch); each rank reduces ITS 1/N slice of all
-    buses, wraps it to S16 and stores it straight into the root's bus — one kernel per rank
-    (blast_bus_reduce_peers_dev).  torch.distributed only carries the 64-byte IPC handles at set-up time.
+    """The render's one exchange step without a collective library (include/blast_cuda.h, blast_peer_bus_*): every
+    rank's window — int32 partial bus, S16 bus, flag tables — is mapped into every peer's address space (CUDA IPC over
+    NVLink / NVSwitch); the bus is cut into tiles, tile t is reduced by rank t mod world INSIDE the render kernel as the
+    tiles complete.  This class only creates the window and carries the 64-byte handles (torch.distributed, set-up
+    time); the protocol itself lives in the library.
 
-    Per step, on every rank:      pb.wait_ack(); <render into pb.part.ptr>; pb.reduce()      (the bus: pb.bus on the root)
-    Flag block of a rank (uint32 step counters): ready[w] at byte 0, ack[w] at byte 256, done[w] at byte 512.
+    Per step, on every rank:      pb.render_reduce(scene, frames)     then, on the root:   pb.wait();  bus = pb.bus_ptr
+    or (Conductor spans):         pb.begin(); <render into pb.part_ptr>; pb.reduce(n_slots)
     """
-    READY, ACK, DONE = 0, 256, 512
 
-    def __init__(self, ctx, n_slots: int, rank: int, world: int, group=None, root: int = 0, mode: str = "root"):
-        """mode "root":    the root pulls and reduces the whole of every peer's bus (the other ranks only signal and
-                           never wait for each other: no lock step; the root's NVLink ingress carries N-1 buses);
-           mode "scatter": every rank reduces its 1/N slice and stores it into the root's bus (1/N of the traffic per
-                           GPU, but every rank waits for every other one each step)."""
+    def __init__(self, ctx, n_slots: int, rank: int, world: int, group=None, root: int = 0):
         import ctypes as C
-        import torch.distributed as dist
         from .errors import check
-        assert world <= 16 and mode in ("root", "scatter")
-        self.mode = mode
         self.ctx, self.rank, self.world, self.root, self.n_slots = ctx, rank, world, root, n_slots
-        self.part = ctx.alloc(max(256, 4 * n_slots))
-        self.bus = ctx.alloc(max(256, 2 * n_slots))          # the S16 bus (complete on the root only)
-        self.flags = ctx.alloc(1024)
-        self.flags.zero()
-        self.part.zero()
-        ctx.sync()
-        self.step = 0
-        self._opened = []
-        # my slice of the bus: multiples of 8 slots so that int32 / int16 vector accesses stay aligned
-        per = ((n_slots + world - 1) // world + 7) // 8 * 8
-        self.slot0 = min(n_slots, rank * per)
-        self.slice_len = min(n_slots, (rank + 1) * per) - self.slot0
-        if world == 1:
-            self.peer_parts, self.peer_flags, self.root_bus = [], [], self.bus.ptr
-            return
-
-        def export(ptr):
-            h = (C.c_uint8 * 64)()
-            check(ctx.lib.blast_ipc_export(ctx.h, ptr, h))
-            return bytes(h)
-
-        def open_(handle):
-            p = C.c_void_p()
-            check(ctx.lib.blast_ipc_open(ctx.h, (C.c_uint8 * 64).from_buffer_copy(handle), C.byref(p)))
-            self._opened.append(p.value)
-            return p.value
-
-        # every rank reaches every collective below even if its own IPC calls fail, and all ranks then agree on the
-        # outcome: either everybody has the mapping or everybody raises (the caller may then choose the NCCL variant)
+        self.h = None
+        p = C.c_void_p()
         err = None
         try:
-            mine = (export(self.part.ptr), export(self.flags.ptr), export(self.bus.ptr))
+            check(ctx.lib.blast_peer_bus_create(ctx.h, n_slots, rank, world, root, C.byref(p)))
+            self.h = p.value
         except Exception as e:                                         # noqa: BLE001
-            mine, err = None, f"rank {rank}: {e}"
-        everyone = [None] * world
-        dist.all_gather_object(everyone, mine, group=group)
-        self.peers = [r for r in range(world) if r != rank]
-        if err is None and all(x is not None for x in everyone):
-            try:
-                self.peer_parts = [open_(everyone[r][0]) for r in self.peers]
-                self.peer_flags = [open_(everyone[r][1]) for r in self.peers]
-                self.root_bus = self.bus.ptr if rank == root else open_(everyone[root][2])
-                self.root_flags = self.flags.ptr if rank == root else self.peer_flags[self.peers.index(root)]
-            except Exception as e:                                     # noqa: BLE001
-                err = f"rank {rank}: {e}"
-        elif err is None:
-            err = "a peer could not export its buffers"
-        errs = [None] * world
-        dist.all_gather_object(errs, err, group=group)
-        bad = [e for e in errs if e]
-        if bad:
-            for p in self._opened:
-                ctx.lib.blast_ipc_close(ctx.h, p)
-            self._opened = []
-            raise RuntimeError("peer memory (CUDA IPC) is not available on this box: " + "; ".join(bad))
+            err = f"rank {rank}: {e}"
+        if world > 1:
+            import torch.distributed as dist
+            # every rank reaches every collective below even if its own calls fail, and all ranks agree on the
+            # outcome: either everybody has the mapping or everybody raises (the caller may then choose NCCL)
+            mine = None
+            if err is None:
+                try:
+                    hb = (C.c_uint8 * 64)()
+                    check(ctx.lib.blast_peer_bus_export(ctx.h, self.h, hb))
+                    mine = bytes(hb)
+                except Exception as e:                                 # noqa: BLE001
+                    err = f"rank {rank}: {e}"
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine, group=group)
+            if err is None and all(x is not None for x in everyone):
+                try:
+                    blob = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(everyone))
+                    check(ctx.lib.blast_peer_bus_connect_ipc(ctx.h, self.h, blob))
+                except Exception as e:                                 # noqa: BLE001
+                    err = f"rank {rank}: {e}"
+            elif err is None:
+                err = f"rank {rank}: a peer could not export its window"
+            errs = [None] * world
+            dist.all_gather_object(errs, err, group=group)
+            bad = [e for e in errs if e]
+            if bad:
+                self.close()
+                raise RuntimeError("peer memory (CUDA IPC) is not available on this box: " + "; ".join(bad))
+        elif err:
+            raise RuntimeError(err)
+        self.part_ptr = ctx.lib.blast_peer_bus_partial(self.h)
+        self.bus_ptr = ctx.lib.blast_peer_bus_bus(self.h)
 
-    def _ptrs(self, values):
+    def render_reduce(self, scene, frames: int):
+        """async: render the scene's voices of this rank and reduce the bus tile by tile inside the render kernel"""
+        from .errors import check
+        check(self.ctx.lib.blast_scene_render_reduce_dev(self.ctx.h, scene.h, frames, self.h))
+
+    def begin(self):
+        """async: before this rank overwrites its partial bus outside render_reduce (every rank is done reading it)"""
+        from .errors import check
+        check(self.ctx.lib.blast_peer_bus_begin_dev(self.ctx.h, self.h))
+
+    def reduce(self, n_slots: int | None = None):
+        """async: publish + reduce the partial bus filled by earlier stream work (the first n_slots slots)"""
+        from .errors import check
+        check(self.ctx.lib.blast_peer_bus_reduce_dev(self.ctx.h, self.h, self.n_slots if n_slots is None else n_slots))
+
+    def wait(self):
+        """async, root: the stream waits until every rank's tiles of the current step are in the bus"""
+        from .errors import check
+        check(self.ctx.lib.blast_peer_bus_wait_dev(self.ctx.h, self.h))
+
+    def check(self):
+        """synchronises; raises BlastError(ERR_TIMEOUT) if a device-side wait for a peer gave up"""
+        from .errors import check
+        check(self.ctx.lib.blast_peer_bus_check(self.ctx.h, self.h))
+
+    def download_bus(self, n_slots: int | None = None):
+        """root: wait + copy the S16 bus to the host"""
         import ctypes as C
-        return (C.c_void_p * max(1, len(values)))(*values), len(values)
-
-    def wait_ack(self):
-        """before overwriting the partial bus again: the stream waits until every rank is done reading the previous one"""
         from .errors import check
-        if self.world > 1 and self.step > 0:
-            if self.mode == "scatter":
-                check(self.ctx.lib.blast_peer_wait_dev(self.ctx.h, self.flags.ptr + self.ACK, self.world, self.step))
-            elif self.rank != self.root:
-                check(self.ctx.lib.blast_peer_wait_dev(self.ctx.h, self.flags.ptr + self.ACK + 4 * self.root, 1, self.step))
-
-    def reduce(self):
-        """after the render: publish the partial bus, reduce + wrap this rank's slice into the root's bus; on the root the
-        stream then waits until every slice is in place (the bus is complete for whatever is enqueued next)"""
-        from .errors import check
-        self.step += 1
-        L, ctx, w = self.ctx.lib, self.ctx, self.world
-        if w == 1:
-            check(L.blast_bus_finalize_dev(ctx.h, self.part.ptr, self.bus.ptr, self.n_slots))
-            return
-        me = 4 * self.rank
-        if self.mode == "root":
-            mine, n = self._ptrs([self.root_flags + self.READY + me])
-            check(L.blast_peer_signal_dev(ctx.h, mine, n, self.step))
-            if self.rank == self.root:
-                parts, n_parts = self._ptrs([self.part.ptr] + self.peer_parts)
-                after, n_after = self._ptrs([f + self.ACK + me for f in self.peer_flags])
-                check(L.blast_bus_reduce_peers_dev(ctx.h, parts, n_parts, self.flags.ptr + self.READY, w, self.step,
-                                                   self.bus.ptr, 0, self.n_slots, after, n_after))
-            return
-        ready, n = self._ptrs([f + self.READY + me for f in self.peer_flags] + [self.flags.ptr + self.READY + me])
-        check(L.blast_peer_signal_dev(ctx.h, ready, n, self.step))
-        parts, n_parts = self._ptrs([self.part.ptr] + self.peer_parts)
-        after, n_after = self._ptrs([f + self.ACK + me for f in self.peer_flags] + [self.flags.ptr + self.ACK + me,
-                                                                                  self.root_flags + self.DONE + me])
-        check(L.blast_bus_reduce_peers_dev(ctx.h, parts, n_parts, self.flags.ptr + self.READY, w, self.step, self.root_bus,
-                                           self.slot0, self.slice_len, after, n_after))
-        if self.rank == self.root:
-            check(L.blast_peer_wait_dev(ctx.h, self.flags.ptr + self.DONE, w, self.step))
+        n = self.n_slots if n_slots is None else n_slots
+        self.wait()
+        out = np.empty(n, dtype=np.int16)
+        check(self.ctx.lib.blast_memcpy_d2h(self.ctx.h, out.ctypes.data, self.bus_ptr, out.nbytes))
+        self.check()
+        return out
 
     def close(self):
-        self.ctx.sync()
-        for p in self._opened:
-            self.ctx.lib.blast_ipc_close(self.ctx.h, p)
-        self._opened = []
+        if self.h and self.ctx.h:
+            self.ctx.lib.blast_peer_bus_destroy(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class ShardedConductor:
@@ -301,13 +278,13 @@ class ShardedConductor:
     (None elsewhere).  max_frames = the longest coordinate() span that will be asked for."""
 
     def __init__(self, ctx, out_channels: int, sample_rate: int, tracks, max_frames: int, rank: int, world: int,
-                 group=None, root: int = 0, mode: str = "root"):
+                 group=None, root: int = 0):
         from . import audio_processing as ap
         self.ctx, self.rank, self.world, self.root = ctx, rank, world, root
         self.out_channels, self.max_frames = out_channels, max_frames
         self.conductor = ap.Conductor(ctx, out_channels, sample_rate, tracks)
         self.conductor.set_shard(rank, world)
-        self.peer = PeerBus(ctx, max_frames * out_channels, rank, world, group=group, root=root, mode=mode)
+        self.peer = PeerBus(ctx, max_frames * out_channels, rank, world, group=group, root=root)
 
     def __getattr__(self, name):                      # load / start / stop / velocity / seq / group / tc / apply / set_voice ...
         return getattr(self.conductor, name)
@@ -315,17 +292,23 @@ class ShardedConductor:
     def coordinate(self, frames: int):
         assert frames <= self.max_frames
         n = frames * self.out_channels
-        self.peer.wait_ack()
-        # the reduction always covers the whole mapped bus: clear the tail this span does not write
-        if n < self.peer.n_slots:
-            from .errors import check
-            check(self.ctx.lib.blast_memset_dev(self.ctx.h, self.peer.part.ptr + 4 * n, 0, 4 * (self.peer.n_slots - n)))
-        self.conductor.render_partial_dev(frames, self.peer.part.ptr)
-        self.peer.reduce()
+        self.peer.begin()
+        failure = None
+        try:
+            self.conductor.render_partial_dev(frames, self.peer.part_ptr)
+        except Exception as e:                        # noqa: BLE001
+            # a rank-local failure (capacity overflow, allocation) must not leave the peers waiting for this rank's
+            # tiles: the step is published all the same (its bus is void), then the error is raised here
+            failure = e
+        self.peer.reduce(n)
         if self.rank == self.root:
-            return self.peer.bus.download(np.int16, n)
-        self.ctx.sync()
-        return None
+            bus = self.peer.download_bus(n)
+        else:
+            self.peer.check()
+            bus = None
+        if failure is not None:
+            raise failure
+        return bus
 
     def close(self):
         self.peer.close()

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BLAST_ABI_VERSION 2
+#define BLAST_ABI_VERSION 3
 
 enum {
     BLAST_OK = 0,
@@ -48,7 +48,8 @@ enum {
     BLAST_ERR_ARG = 101,
     BLAST_ERR_NO_DEVICE = 102,
     BLAST_ERR_CAPACITY = 103,
-    BLAST_ERR_UNSUPPORTED = 104
+    BLAST_ERR_UNSUPPORTED = 104,
+    BLAST_ERR_TIMEOUT = 105           /* a bounded device-side wait for a peer GPU gave up */
 };
 
 typedef struct blast_ctx blast_ctx;
@@ -195,26 +196,40 @@ int  blast_scene_render_dev(blast_ctx* ctx, blast_scene* scene, uint64_t frames,
 int  blast_scene_check(blast_ctx* ctx, blast_scene* scene);
 /* S16 bus = low 16 bits of the int32 partial sums (== i16 wrapping accumulate, engine.rs:441) */
 int  blast_bus_finalize_dev(blast_ctx* ctx, const int32_t* d_partial, int16_t* d_bus, uint64_t n_slots);
-/* The same reduction + finalize across the GPUs of one box WITHOUT a collective library.  Every rank renders its
- * voices into its own int32 partial bus; buses and a block of uint32 step-counter flags per rank are mapped into the
- * peers' address spaces (blast_ipc_*: CUDA IPC over NVLink / NVSwitch).  Per step s every rank
- *   1. blast_peer_signal_dev: stores s into its entry of every rank's "ready" flags (after its render, stream-ordered);
- *   2. blast_bus_reduce_peers_dev: ONE kernel waits until all n_ready flags at d_ready have reached s, sums slots
- *      [slot0, slot0 + n_slots) of all n_parts buses (d_parts[0] = its own), wraps to S16 and stores them into d_bus —
- *      the ROOT's bus, local or IPC-mapped — and then stores s into the n_signal flags of d_signal (every peer's "ack"
- *      entry for this rank: "I am done with your bus", and the root's "done" entry: "my slice is in place");
- *   3. blast_peer_wait_dev on its own ack flags before it overwrites its partial bus again; the root also on its
- *      done flags before it uses the bus.
- * Reduce-scatter + finalize + gather-to-root in one kernel; 1/N of the bus crosses each GPU's links.
- * audio_decoder_b200/distributed.py: PeerBus is the host-side choreography. Flags compare with wrap-around. */
-int  blast_ipc_export(blast_ctx* ctx, void* d_ptr, uint8_t handle_out[64]);
-int  blast_ipc_open(blast_ctx* ctx, const uint8_t handle[64], void** d_ptr_out);
-int  blast_ipc_close(blast_ctx* ctx, void* d_ptr);
-int  blast_peer_signal_dev(blast_ctx* ctx, uint32_t* const* d_flags, uint32_t n_flags, uint32_t value);   /* async, after all prior stream work */
-int  blast_peer_wait_dev(blast_ctx* ctx, const uint32_t* d_flags, uint32_t n_flags, uint32_t value);      /* async: the stream waits on device */
-int  blast_bus_reduce_peers_dev(blast_ctx* ctx, const int32_t* const* d_parts, uint32_t n_parts, const uint32_t* d_ready,
-                                uint32_t n_ready, uint32_t step, int16_t* d_bus, uint64_t slot0, uint64_t n_slots,
-                                uint32_t* const* d_signal, uint32_t n_signal);
+/* ---- The mix reduction across the GPUs of one box WITHOUT a collective library (SURVEY.md §8 e: the render's one
+ * exchange step).  Every rank (one per GPU; ranks may be processes — CUDA IPC — or contexts of one process — peer
+ * access) owns a WINDOW: its int32 partial bus, an S16 bus (the result, complete on the root) and flag tables, mapped
+ * into every peer's address space.  The bus is cut into tiles; tile t is reduced by rank t mod world.  Per step, on
+ * every rank, in the same order on every rank:
+ *     blast_scene_render_reduce_dev    the render kernel publishes each tile as its last voice group lands (a
+ *                                      system-scope flag store to the tile's owner) and reduces the tiles it owns from
+ *                                      the same work queue: wait for the tile's flags, sum the peers' int32 tiles with
+ *                                      NVLink loads, wrap to S16 (engine.rs:441), store into the ROOT's bus.  The
+ *                                      exchange overlaps the render tile by tile; no kernel sits between them.
+ *  or blast_peer_bus_begin_dev, <stream work that fills blast_peer_bus_partial>, blast_peer_bus_reduce_dev
+ *                                      the same protocol as two small kernels (Conductor spans, > 2 bus channels).
+ *     blast_peer_bus_wait_dev          root only: the stream waits until every rank's tiles are in place.
+ * A rank may overwrite its partial bus again only after every rank has finished reading it: the next step's first
+ * kernel waits for those acknowledgements on the device.  All waits are bounded (BLAST_PEER_TIMEOUT_MS, default
+ * 20,000): a rank that never publishes costs its peers the timeout and BLAST_ERR_TIMEOUT from blast_peer_bus_check,
+ * not a hung GPU.  world == 1 is the single-GPU case: the render finalizes its own tiles (no bus_finalize launch). */
+typedef struct blast_peer_bus blast_peer_bus;
+#define BLAST_PEER_HANDLE_BYTES 64
+int  blast_peer_bus_create(blast_ctx* ctx, uint64_t n_slots, uint32_t rank, uint32_t world, uint32_t root, blast_peer_bus** out);
+void blast_peer_bus_destroy(blast_ctx* ctx, blast_peer_bus* pb);
+/* multi-process: export this rank's window, exchange the handles (any transport), connect with all of them in rank order */
+int  blast_peer_bus_export(blast_ctx* ctx, blast_peer_bus* pb, uint8_t handle_out[BLAST_PEER_HANDLE_BYTES]);
+int  blast_peer_bus_connect_ipc(blast_ctx* ctx, blast_peer_bus* pb, const uint8_t* handles /* world x 64 bytes */);
+/* one process: all[r] = rank r's peer bus (peer access between the GPUs is enabled here); call once, for all ranks */
+int  blast_peer_bus_connect_local(blast_peer_bus* const* all, uint32_t world);
+int32_t* blast_peer_bus_partial(blast_peer_bus* pb);     /* this rank's int32 partial bus [n_slots] */
+int16_t* blast_peer_bus_bus(blast_peer_bus* pb);         /* this rank's S16 bus [n_slots]: the result on the root */
+int  blast_scene_render_reduce_dev(blast_ctx* ctx, blast_scene* scene, uint64_t frames, blast_peer_bus* pb);
+int  blast_peer_bus_begin_dev(blast_ctx* ctx, blast_peer_bus* pb);
+int  blast_peer_bus_reduce_dev(blast_ctx* ctx, blast_peer_bus* pb, uint64_t n_slots_used);
+int  blast_peer_bus_wait_dev(blast_ctx* ctx, blast_peer_bus* pb);
+/* synchronises; BLAST_ERR_TIMEOUT if a device-side wait of this rank gave up since the last check */
+int  blast_peer_bus_check(blast_ctx* ctx, blast_peer_bus* pb);
 /* one-shot with a host bus (interleaved S16_LE like the ALSA area, runtime.rs:272-276) */
 int  blast_render(blast_ctx* ctx, const blast_track* tracks, uint32_t n_tracks, const blast_voice* voices,
                   uint32_t n_voices, uint32_t out_channels, uint64_t frames, int16_t* host_bus_out,
@@ -295,6 +310,9 @@ int  blast_conductor_apply(blast_ctx* ctx, blast_conductor* c, const blast_comma
 /* Multi-GPU: this rank renders the voices whose load order number is congruent to rank mod world; every rank
  * applies every command and tracks every tempo.  Partial buses are summed (int32) before finalising. */
 int  blast_conductor_set_shard(blast_conductor* c, uint32_t rank, uint32_t world);
+/* The same when the TRACKS are sharded (file i decoded on GPU i mod world, blast_group): a voice is rendered on the
+ * rank that holds its track, track t on rank t mod world; tracks of other ranks are never dereferenced here. */
+int  blast_conductor_set_shard_by_track(blast_conductor* c, uint32_t rank, uint32_t world);
 /* `frames` iterations of coordinate()'s frame loop (engine.rs:46-81) into the int32 partial bus
  * d_partial_bus[frames * out_channels] (overwritten); voices, Seqs, tempi and the clock advance.  Returns after
  * the device work has finished (the Seq / position state is read back). BLAST_ERR_REF_PANIC where a Seq would index
@@ -409,6 +427,43 @@ int  blast_mpeg_gather_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len,
 int  blast_mpeg_parse(blast_ctx* ctx, const uint8_t* bytes, uint64_t len, int reference_compat, uint64_t* offsets_out,
                       uint64_t offsets_cap, uint64_t* n_offsets_out, uint32_t* ref_header_out, uint64_t* n_candidates_out,
                       uint8_t* payload_out, uint64_t payload_cap, uint64_t* payload_len_out);
+
+/* ------------------------------------------------------------------ several GPUs, one host process
+ * The reference is ONE process (blast/src/main.rs:13-128: decode every asset, then run the Conductor); a host like that
+ * drives all GPUs of a box through a blast_group — no launcher, no collective library.  The path shards as
+ * SURVEY.md §8(e) lays out:  file i is decoded on member i mod n and its track stays there;  a voice is rendered on the
+ * member that holds its track, and the partial buses are reduced tile by tile inside the render kernel over peer
+ * memory (blast_peer_bus);  RNG stream s is generated on member s mod n;  one MPEG stream is cut into byte ranges whose
+ * 48-byte aggregates are folded on the host, with the header histogram and the first-position table reduced through
+ * peer memory.  Results are identical to the single-GPU entry points.  A device id may repeat (at most 3 members per
+ * GPU): the multi-member protocol can then be exercised on a single-GPU box. */
+typedef struct blast_group blast_group;
+int  blast_group_create(blast_group** out, const int* device_ids, uint32_t n_devices);
+void blast_group_destroy(blast_group* g);
+uint32_t   blast_group_size(const blast_group* g);
+blast_ctx* blast_group_ctx(blast_group* g, uint32_t member);
+/* main.rs:18-89 over the group: like blast_pcm_decode_batch; tracks_out[i] (nullable array) is file i's AudioFile.samples
+ * in the HBM of member i mod n, owned by the group until blast_group_free_tracks / blast_group_destroy. */
+int  blast_group_pcm_decode_batch(blast_group* g, uint32_t n, const uint8_t* const* files, const size_t* lens,
+                                  const blast_pcm_desc* descs, int16_t* const* host_out, blast_track* tracks_out);
+int  blast_group_free_tracks(blast_group* g);
+/* blast_render over the group: tracks[t] must live on member t mod n (as blast_group_pcm_decode_batch leaves them) */
+int  blast_group_render(blast_group* g, const blast_track* tracks, uint32_t n_tracks, const blast_voice* voices,
+                        uint32_t n_voices, uint32_t out_channels, uint64_t frames, int16_t* host_bus_out);
+/* Conductor::{prepare, apply, coordinate} over the group (every member applies every command and tracks every tempo) */
+typedef struct blast_group_conductor blast_group_conductor;
+int  blast_group_conductor_create(blast_group* g, uint32_t out_channels, uint32_t sample_rate, const blast_track* tracks,
+                                  uint32_t n_tracks, blast_group_conductor** out);
+void blast_group_conductor_destroy(blast_group_conductor* gc);
+int  blast_group_conductor_apply(blast_group_conductor* gc, const blast_command* cmd);
+int  blast_group_conductor_coordinate(blast_group_conductor* gc, uint64_t frames, int16_t* host_bus_out);
+blast_conductor* blast_group_conductor_member(blast_group_conductor* gc, uint32_t member);   /* state access (get / set_voice) */
+/* blast_x128p_fill over the group: same outputs, stream s generated on member s mod n */
+int  blast_group_x128p_fill(blast_group* g, uint64_t seed, uint64_t stride, uint64_t n_streams, uint64_t draws_per_stream,
+                            int64_t lower, int64_t upper, uint64_t* raw_out, int64_t* ranged_out, uint64_t* checks_out);
+/* the frame-offset index of mpeg::parse (mpeg.rs:7-116) for one host buffer cut into byte ranges over the members */
+int  blast_group_mpeg_index(blast_group* g, const uint8_t* bytes, uint64_t len, int reference_compat, uint64_t* offsets_out,
+                            uint64_t cap, uint64_t* n_offsets_out, uint32_t* ref_header_out, uint64_t* n_candidates_out);
 
 #ifdef __cplusplus
 }

@@ -9,11 +9,15 @@ pub const BLAST_ERR_UNSUPPORTED_FORMAT: c_int = 2;
 pub const BLAST_ERR_UNEXPECTED_EOF: c_int = 3;
 pub const BLAST_ERR_INVALID_DATA: c_int = 4;
 pub const BLAST_ERR_REF_PANIC: c_int = 5;
+pub const BLAST_ERR_TIMEOUT: c_int = 105;
 
 #[repr(C)] pub struct blast_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct blast_scene { _p: [u8; 0] }
 #[repr(C)] pub struct blast_pcm_plan { _p: [u8; 0] }
 #[repr(C)] pub struct blast_conductor { _p: [u8; 0] }
+#[repr(C)] pub struct blast_peer_bus { _p: [u8; 0] }
+#[repr(C)] pub struct blast_group { _p: [u8; 0] }
+#[repr(C)] pub struct blast_group_conductor { _p: [u8; 0] }
 
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct blast_pcm_desc {
@@ -88,6 +92,8 @@ extern "C" {
     pub fn blast_dev_free(ctx: *mut blast_ctx, p: *mut c_void) -> c_int;
     pub fn blast_host_alloc(ctx: *mut blast_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
     pub fn blast_host_free(ctx: *mut blast_ctx, p: *mut c_void) -> c_int;
+    pub fn blast_memcpy_h2d(ctx: *mut blast_ctx, d_dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
+    pub fn blast_memcpy_d2h(ctx: *mut blast_ctx, dst: *mut c_void, d_src: *const c_void, bytes: usize) -> c_int;
 
     pub fn blast_wav_probe(file: *const u8, len: usize, out: *mut blast_pcm_desc) -> c_int;
     pub fn blast_aiff_probe(file: *const u8, len: usize, out: *mut blast_pcm_desc) -> c_int;
@@ -136,15 +142,41 @@ extern "C" {
     pub fn blast_mpeg_shard_emit_dev(ctx: *mut blast_ctx, d_bytes: *const u8, own_len: u64, halo_len: u64, entry_state: u32,
                                      pos_offset: u64, d_pos_out: *mut u64, d_hdr_out: *mut u32, cap: u64, n_out: *mut u64) -> c_int;
 
-    // the mix reduction over peer memory (one process per GPU)
-    pub fn blast_ipc_export(ctx: *mut blast_ctx, d_ptr: *mut c_void, handle_out: *mut u8) -> c_int;
-    pub fn blast_ipc_open(ctx: *mut blast_ctx, handle: *const u8, d_ptr_out: *mut *mut c_void) -> c_int;
-    pub fn blast_ipc_close(ctx: *mut blast_ctx, d_ptr: *mut c_void) -> c_int;
-    pub fn blast_peer_signal_dev(ctx: *mut blast_ctx, d_flags: *const *mut u32, n_flags: u32, value: u32) -> c_int;
-    pub fn blast_peer_wait_dev(ctx: *mut blast_ctx, d_flags: *const u32, n_flags: u32, value: u32) -> c_int;
-    pub fn blast_bus_reduce_peers_dev(ctx: *mut blast_ctx, d_parts: *const *const i32, n_parts: u32, d_ready: *const u32,
-                                      n_ready: u32, step: u32, d_bus: *mut i16, slot0: u64, n_slots: u64,
-                                      d_signal: *const *mut u32, n_signal: u32) -> c_int;
+    // the mix reduction over peer memory: tile protocol inside the render kernel (ranks = processes or group members)
+    pub fn blast_peer_bus_create(ctx: *mut blast_ctx, n_slots: u64, rank: u32, world: u32, root: u32, out: *mut *mut blast_peer_bus) -> c_int;
+    pub fn blast_peer_bus_destroy(ctx: *mut blast_ctx, pb: *mut blast_peer_bus);
+    pub fn blast_peer_bus_export(ctx: *mut blast_ctx, pb: *mut blast_peer_bus, handle_out: *mut u8) -> c_int;
+    pub fn blast_peer_bus_connect_ipc(ctx: *mut blast_ctx, pb: *mut blast_peer_bus, handles: *const u8) -> c_int;
+    pub fn blast_peer_bus_connect_local(all: *const *mut blast_peer_bus, world: u32) -> c_int;
+    pub fn blast_peer_bus_partial(pb: *mut blast_peer_bus) -> *mut i32;
+    pub fn blast_peer_bus_bus(pb: *mut blast_peer_bus) -> *mut i16;
+    pub fn blast_scene_render_reduce_dev(ctx: *mut blast_ctx, scene: *mut blast_scene, frames: u64, pb: *mut blast_peer_bus) -> c_int;
+    pub fn blast_peer_bus_begin_dev(ctx: *mut blast_ctx, pb: *mut blast_peer_bus) -> c_int;
+    pub fn blast_peer_bus_reduce_dev(ctx: *mut blast_ctx, pb: *mut blast_peer_bus, n_slots_used: u64) -> c_int;
+    pub fn blast_peer_bus_wait_dev(ctx: *mut blast_ctx, pb: *mut blast_peer_bus) -> c_int;
+    pub fn blast_peer_bus_check(ctx: *mut blast_ctx, pb: *mut blast_peer_bus) -> c_int;
+    pub fn blast_conductor_set_shard_by_track(c: *mut blast_conductor, rank: u32, world: u32) -> c_int;
+
+    // several GPUs driven by this one process (main.rs is one process): decode by file, render by track, RNG by stream
+    pub fn blast_group_create(out: *mut *mut blast_group, device_ids: *const c_int, n_devices: u32) -> c_int;
+    pub fn blast_group_destroy(g: *mut blast_group);
+    pub fn blast_group_size(g: *const blast_group) -> u32;
+    pub fn blast_group_ctx(g: *mut blast_group, member: u32) -> *mut blast_ctx;
+    pub fn blast_group_pcm_decode_batch(g: *mut blast_group, n: u32, files: *const *const u8, lens: *const usize,
+                                        descs: *const blast_pcm_desc, host_out: *const *mut i16, tracks_out: *mut blast_track) -> c_int;
+    pub fn blast_group_free_tracks(g: *mut blast_group) -> c_int;
+    pub fn blast_group_render(g: *mut blast_group, tracks: *const blast_track, n_tracks: u32, voices: *const blast_voice,
+                              n_voices: u32, out_channels: u32, frames: u64, host_bus_out: *mut i16) -> c_int;
+    pub fn blast_group_conductor_create(g: *mut blast_group, out_channels: u32, sample_rate: u32, tracks: *const blast_track,
+                                        n_tracks: u32, out: *mut *mut blast_group_conductor) -> c_int;
+    pub fn blast_group_conductor_destroy(gc: *mut blast_group_conductor);
+    pub fn blast_group_conductor_apply(gc: *mut blast_group_conductor, cmd: *const blast_command) -> c_int;
+    pub fn blast_group_conductor_coordinate(gc: *mut blast_group_conductor, frames: u64, host_bus_out: *mut i16) -> c_int;
+    pub fn blast_group_conductor_member(gc: *mut blast_group_conductor, member: u32) -> *mut blast_conductor;
+    pub fn blast_group_x128p_fill(g: *mut blast_group, seed: u64, stride: u64, n_streams: u64, draws_per_stream: u64,
+                                  lower: i64, upper: i64, raw_out: *mut u64, ranged_out: *mut i64, checks_out: *mut u64) -> c_int;
+    pub fn blast_group_mpeg_index(g: *mut blast_group, bytes: *const u8, len: u64, reference_compat: c_int, offsets_out: *mut u64,
+                                  cap: u64, n_offsets_out: *mut u64, ref_header_out: *mut u32, n_candidates_out: *mut u64) -> c_int;
 
     pub fn blast_mpeg_parse(ctx: *mut blast_ctx, bytes: *const u8, len: u64, reference_compat: c_int,
                             offsets_out: *mut u64, offsets_cap: u64, n_offsets_out: *mut u64, ref_header_out: *mut u32,

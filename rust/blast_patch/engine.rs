@@ -10,6 +10,7 @@ use blast_cuda_sys as sys;
 use crate::audio_processing::commands::*;
 use crate::audio_processing::blast_time::{sample_rate, blast_time::{TempoMode, TempoUnit}};
 use crate::file_parsing::decode_helpers::AudioFile;
+use crate::file_parsing::DeviceTrack;       // defined in the file_parsing patch (file_parsing.rs in this directory)
 
 pub struct Conductor {
     ctx: *mut sys::blast_ctx,
@@ -76,7 +77,8 @@ impl Conductor {
                 c.period = a.period as u64; c.n_steps = a.steps.len() as u32;
                 steps = a.steps; chance = a.chance;
                 c.steps = steps.as_ptr(); c.chance = chance.as_ptr();
-                (c.rng_s0, c.rng_s1) = a.rng.state();           // X128P { s0, s1 } (blast_rand.rs:4-8)
+                // X128P's fields are private (blast_rand.rs:4-8): the patch adds the accessor in blast_rand.rs (this directory)
+                (c.rng_s0, c.rng_s1) = a.rng.state();
             }
             Command::Quit(_) => { unsafe { libc::raise(libc::SIGTERM); } return; }
         }

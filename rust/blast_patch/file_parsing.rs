@@ -12,6 +12,10 @@ unsafe impl Send for Gpu {}
 unsafe impl Sync for Gpu {}
 static GPU: OnceLock<Gpu> = OnceLock::new();
 
+/// The process-wide GPU context (the reference is single-threaded on both decode, main.rs:18-89, and render,
+/// runtime.rs:320-380: one blast_ctx serves both).  Used by engine.rs's Conductor::prepare.
+pub fn gpu_ctx() -> *mut sys::blast_ctx { ctx() }
+
 fn ctx() -> *mut sys::blast_ctx {
     GPU.get_or_init(|| {
         let mut c = std::ptr::null_mut();
@@ -21,7 +25,7 @@ fn ctx() -> *mut sys::blast_ctx {
     }).0
 }
 
-fn last_error() -> String {
+pub fn last_error() -> String {
     unsafe { CStr::from_ptr(sys::blast_last_error()) }.to_string_lossy().into_owned()
 }
 
@@ -54,6 +58,30 @@ fn parse_pcm(path: &str, format: &str,
     if rc != sys::BLAST_OK { return Err(to_err(rc)); }
     let name = CStr::from_bytes_until_nul(&name).unwrap().to_string_lossy();
     Ok(AudioFile::new(&name, format, desc.sample_rate, desc.num_channels, desc.bits_per_sample, samples))
+}
+
+/// AudioFile.samples resident in HBM: what Conductor::prepare hands to blast_conductor_create instead of the per-voice
+/// clone of the sample Vec (engine.rs:309).  Owns its device allocation.
+pub struct DeviceTrack { d_samples: *mut i16, n_samples: u64, num_channels: u32, sample_rate: u32 }
+
+impl DeviceTrack {
+    pub fn upload(ctx: *mut sys::blast_ctx, t: &AudioFile) -> Self {
+        let bytes = t.samples.len() * std::mem::size_of::<i16>();
+        let mut p: *mut std::ffi::c_void = std::ptr::null_mut();
+        let rc = unsafe { sys::blast_dev_alloc(ctx, bytes.max(4), &mut p) };
+        assert_eq!(rc, sys::BLAST_OK, "{}", last_error());
+        let rc = unsafe { sys::blast_memcpy_h2d(ctx, p, t.samples.as_ptr() as *const _, bytes) };
+        assert_eq!(rc, sys::BLAST_OK, "{}", last_error());
+        assert_eq!(unsafe { sys::blast_ctx_sync(ctx) }, sys::BLAST_OK, "{}", last_error());
+        Self { d_samples: p as *mut i16, n_samples: t.samples.len() as u64, num_channels: t.num_channels, sample_rate: t.sample_rate }
+    }
+    pub fn as_c(&self) -> sys::blast_track {
+        sys::blast_track { d_samples: self.d_samples, n_samples: self.n_samples, num_channels: self.num_channels, sample_rate: self.sample_rate }
+    }
+}
+
+impl Drop for DeviceTrack {
+    fn drop(&mut self) { unsafe { sys::blast_dev_free(ctx(), self.d_samples as *mut _); } }
 }
 
 pub mod wav  { pub fn parse(path: &str) -> super::DecodeResult<super::AudioFile> { super::parse_pcm(path, "wav",  super::sys::blast_wav_probe) } }

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
     # and the ctypes table covers the whole header (no unbound entry points)
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert L.blast_abi_version() == 2
+    assert L.blast_abi_version() == 3
 
 
 def test_no_cpu_fallback():
@@ -235,3 +235,24 @@ def test_rust_sys_crate_names_exist_in_the_header():
     for need in ("blast_wav_probe", "blast_aiff_probe", "blast_pcm_decode_batch", "blast_file_name", "blast_conductor_apply",
                  "blast_conductor_coordinate", "blast_render", "blast_x128p_seed", "blast_mpeg_parse", "blast_asset_consensus"):
         assert need in bound, need
+
+
+def test_rust_patch_is_self_consistent():
+    """rust/blast_patch cannot be compiled here: every `sys::` item it uses must be bound (or defined) by the sys crate,
+    every `crate::file_parsing::` item must be a `pub` item of the file_parsing patch, and what engine.rs needs of X128P
+    must be added by the blast_rand patch."""
+    d = os.path.join(ROOT, "rust", "blast_patch")
+    sys_rs = open(os.path.join(ROOT, "rust", "blast-cuda-sys", "src", "lib.rs")).read()
+    sys_items = set(re.findall(r"pub (?:fn|const|struct) ([A-Za-z0-9_]+)", sys_rs))
+    fp_rs = open(os.path.join(d, "file_parsing.rs")).read()
+    fp_pub = set(re.findall(r"pub (?:fn|struct|mod) ([A-Za-z0-9_]+)", fp_rs))
+    for fn in ("engine.rs", "file_parsing.rs"):
+        text = re.sub(r"//.*", "", open(os.path.join(d, fn)).read())
+        used = set(re.findall(r"\bsys::([A-Za-z0-9_]+)", text))
+        assert used and used <= sys_items, (fn, sorted(used - sys_items))
+        for item in re.findall(r"crate::file_parsing::([A-Za-z0-9_]+)", text):
+            assert item in fp_pub | {"decode_helpers"}, (fn, item)
+    eng = re.sub(r"//.*", "", open(os.path.join(d, "engine.rs")).read())
+    assert "DeviceTrack" in fp_pub and "use crate::file_parsing::DeviceTrack" in eng
+    if ".state()" in eng:
+        assert re.search(r"pub fn state\(&self\)", open(os.path.join(d, "blast_rand.rs")).read())
