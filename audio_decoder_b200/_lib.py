@@ -103,6 +103,7 @@ SIGNATURES = {
     "blast_host_free": (C.c_int, [_vp, _vp]),
     "blast_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, _sz]),
     "blast_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, _sz]),
+    "blast_memcpy_d2d": (C.c_int, [_vp, _vp, _vp, _sz]),
     "blast_memset_dev": (C.c_int, [_vp, _vp, C.c_int, _sz]),
     "blast_event_create": (C.c_int, [_vp, C.POINTER(_vp)]),
     "blast_event_destroy": (None, [_vp]),

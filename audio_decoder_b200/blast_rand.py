@@ -33,6 +33,17 @@ class Streams:
         self.states = ctx.alloc(max(16, 16 * n_streams))
         check(ctx.lib.blast_x128p_jump_dev(ctx.h, C.byref(base), stride, n_streams, self.states.ptr))
 
+    @classmethod
+    def from_seeds(cls, ctx: Context, seeds) -> "Streams":
+        """one independent generator per seed: stream i = X128P::new(seeds[i]) (blast_rand.rs:10-24)"""
+        self = cls.__new__(cls)
+        self.ctx, self.n = ctx, len(seeds)
+        st = np.empty((max(1, self.n), 2), dtype=np.uint64)
+        for i, s in enumerate(seeds):
+            st[i] = seed_state(int(s))
+        self.states = ctx.alloc(max(16, 16 * self.n)).upload(st)
+        return self
+
     def get_states(self) -> np.ndarray:
         return self.states.download(np.uint64, 2 * self.n).reshape(self.n, 2)
 

@@ -217,6 +217,12 @@ int blast_memcpy_d2h(blast_ctx* ctx, void* dst, const void* d_src, size_t bytes)
     return BLAST_OK;
 }
 
+int blast_memcpy_d2d(blast_ctx* ctx, void* d_dst, const void* d_src, size_t bytes) {
+    if (int rc = blast::bind(ctx)) return rc;
+    if (bytes) BLAST_CUDA_TRY(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return BLAST_OK;
+}
+
 int blast_memset_dev(blast_ctx* ctx, void* d_dst, int value, size_t bytes) {
     if (int rc = blast::bind(ctx)) return rc;
     if (bytes) BLAST_CUDA_TRY(cudaMemsetAsync(d_dst, value, bytes, ctx->stream));

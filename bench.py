@@ -4,16 +4,24 @@
   python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, libblast_cuda.so)
   python bench.py --impl reference --gpus N ...            # CPU restatement of the reference, all host threads
 
-Workload (config.workload): BASELINE config[1] — batch decode of 1,024 synthetic 24-bit big-endian
-48 kHz stereo AIFF files (2,880,000 payload bytes each, reference-exact byte-pair decode into i16
-words), followed by the mix of the decoded tracks where the render path is built.  One "step" = one
-pass over the whole batch.  At N > 1 every rank owns its own 1,024-file shard (weak scaling,
-no data-path collective for decode).
+Workload (config.workload): BASELINE config[1] — batch decode of 1,024 synthetic 24-bit big-endian 48 kHz stereo AIFF
+files (2,880,000 payload bytes each = successive next_u64 bytes of X128P::new(0xC2_0000 + file_index), SURVEY §8 d;
+reference-exact byte-pair decode into i16 words), followed by the mix of the decoded tracks (stereo voices, velocity 1,
+per-voice gain) into one stereo S16 bus.  One "step" = one pass over the whole batch.
 
-The JSON line follows the driver contract; `value` is device-resident throughput (CUDA events on the
-launching stream), `e2e` the same metric through the host-buffer C-ABI call (pinned host file images in, S16
-bus out, copies inside the timed region; decoded tracks stay in HBM), `e2e_parse_dropin` the variant that also
-returns every AudioFile.samples Vec to the host like a literal aiff::parse() drop-in.
+Scaling is STRONG: at N > 1 the same 1,024 files are sharded, file i -> rank i mod N (north_star: "1,024 ... files
+sharded across GPUs"); the decoded tracks are mixed where they were decoded and the int32 partial buses are reduced
+tile by tile inside the render kernel over peer memory (blast_peer_bus).  `weak` is the extra key: every rank decodes
+and mixes its own 1,024 files.  Before anything is timed the bus of one step is checked (`bus_check`): the fused
+peer-memory path against the unfused render + NCCL all-reduce + finalize, byte for byte, and a 4,096-frame window
+against the CPU oracle's Conductor::coordinate over the voices of all ranks.
+
+The JSON line follows the driver contract; `value` is device-resident throughput (CUDA events on the launching
+stream), `e2e` the same metric through the host-buffer C-ABI call (pinned host file images in, S16 bus out, copies
+inside the timed region; decoded tracks stay in HBM), `e2e_parse_dropin` the variant that also returns every
+AudioFile.samples Vec to the host like a literal aiff::parse() drop-in.  `configs` carries the other BASELINE configs
+(C1, C3 unit / mixed / +Seq, C4, C5, true 24-bit unpack), each device-timed with its algorithmic bytes and roofline
+fraction.
 """
 from __future__ import annotations
 
@@ -35,6 +43,7 @@ import synth  # noqa: E402
 
 METRIC = "pcm_decode_mix_gsamples_per_s"
 UNIT = "Gsamples/s"
+CHECK_FRAMES = 4096
 
 
 def measured_peaks():
@@ -96,7 +105,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def dist_setup(n_gpus: int):
+def dist_setup():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -125,12 +134,88 @@ def barrier(dist, local):
         torch.cuda.synchronize(local)
 
 
-# ------------------------------------------------------------------ our arm
+def c2_gains(n_files: int):
+    """per-voice gain of the mix half: f32(next_f32() * 2^-5) from X128P::new(0xC2), in file order (both arms)"""
+    g = synth.X128P(0xC2)
+    return [float(np.float32(g.next_f32() * np.float32(2.0 ** -5))) for _ in range(n_files)]
+
+
+def sub_track(blast, ap, ctx, ptr, n_samples, channels, rate=48000):
+    buf = blast.DevBuf.__new__(blast.DevBuf)
+    buf.ctx, buf.ptr, buf.nbytes = ctx, ptr, n_samples * 2
+    buf.free = lambda: None
+    return ap.Track(buf, n_samples, channels, rate)
+
+
+# ------------------------------------------------------------------ our arm: the C2 decode + mix workload
+class C2Shard:
+    """the files `ids` of the C2 batch on this rank: file images in HBM (256-byte aligned slots, payload at +54) and in
+    pinned host memory (same layout), the decode plan, the scene of the decoded tracks"""
+
+    def __init__(self, ctx, ids, data_len, layout, gains, host_images=True):
+        import audio_decoder_b200 as blast
+        from audio_decoder_b200 import audio_processing as ap, blast_rand as br, file_parsing as fp
+        L = ctx.lib
+        self.ctx, self.ids, self.data_len = ctx, list(ids), data_len
+        n = self.n = len(self.ids)
+        hdr = np.frombuffer(synth.aiff_header(data_len), dtype=np.uint8)
+        self.image_len = len(hdr) + data_len
+        self.slot = slot = (self.image_len + 255) // 256 * 256
+        self.words = (data_len + 1) // 2
+        self.frames = self.words // 2                                  # stereo
+        draws = (data_len + 7) // 8
+        # payload bytes = successive next_u64 bytes of X128P::new(0xC2_0000 + file_index), generated by the library's
+        # own stream kernel (K6) straight into HBM: [file][draws] rows of u64
+        d_pay = ctx.alloc(max(1, n) * draws * 8)
+        if n:
+            br.Streams.from_seeds(ctx, [0xC20000 + i for i in self.ids]).fill_dev(draws, 0, 100, d_pay.ptr, None, None)
+        self.d_in = ctx.alloc(max(1, n) * slot)
+        self.h_in = ctx.pinned(max(1, n) * slot) if host_images else None
+        h_hdr = ctx.pinned(256)
+        h_hdr.u8[:len(hdr)] = hdr
+        for k in range(n):
+            L.blast_memcpy_h2d(ctx.h, self.d_in.ptr + k * slot, h_hdr.ptr, len(hdr))
+            L.blast_memcpy_d2d(ctx.h, self.d_in.ptr + k * slot + len(hdr), d_pay.ptr + k * draws * 8, data_len)
+        if host_images and n:
+            L.blast_memcpy_d2h(ctx.h, self.h_in.ptr, self.d_in.ptr, n * slot)
+        ctx.sync()
+        h_hdr.free()
+        self.view = self.h_in.u8.reshape(max(1, n), slot)[:n, :self.image_len] if host_images else None
+        self.desc = fp.probe("aiff", self.view[0] if host_images and n else np.concatenate([hdr, np.zeros(data_len, np.uint8)]))
+        off = self.off = self.desc.data_off
+        self.d_out = ctx.alloc(max(1, n) * self.words * 2)
+        if layout == "payload":
+            self.d_pay = d_pay
+            src = [d_pay.ptr + k * draws * 8 for k in range(n)]
+        else:
+            d_pay.free()
+            src = [self.d_in.ptr + k * slot + off for k in range(n)]
+        self.plan = fp.PcmPlan(ctx, [(src[k], self.d_out.ptr + k * self.words * 2, self.words, True) for k in range(n)]) if n else None
+        self.samples = n * self.words
+        self.tracks = [sub_track(blast, ap, ctx, self.d_out.ptr + k * self.words * 2, self.words, 2) for k in range(n)]
+        self.voices = [ap.VoiceParams(k, True, 0.0, 1.0, gains[i]) for k, i in enumerate(self.ids)]
+        self.scene = ap.Scene(ctx, self.tracks, self.voices, 2)
+        self.alg_decode = 4 * self.samples                               # 2 B read + 2 B written per i16 word
+        self.alg_mix = 4 * (self.frames - 1) * n                         # source frames touched (+ the S16 bus, once)
+
+    def decode(self):
+        if self.plan:
+            self.plan.run()
+
+    def close(self):
+        if self.plan:
+            self.plan.close()
+        self.scene.close()
+        for b in (self.d_in, self.d_out, self.h_in):
+            if b is not None:
+                b.free()
+
+
 def run_ours(args):
     import audio_decoder_b200 as blast
-    from audio_decoder_b200 import _lib, audio_processing as ap, blast_rand as br, file_parsing as fp
+    from audio_decoder_b200 import _lib, audio_processing as ap, distributed as bd
 
-    rank, world, local, dist = dist_setup(args.gpus)
+    rank, world, local, dist = dist_setup()
     torch = None
     if world > 1:
         import torch
@@ -139,136 +224,142 @@ def run_ours(args):
         ctx = blast.Context(local)
     L = ctx.lib
     n_files, data_len = args.files, args.data_len
-    hdr = np.frombuffer(synth.aiff_header(data_len), dtype=np.uint8)
-    image_len = len(hdr) + data_len
-    slot = (image_len + 255) // 256 * 256                      # file images at 256-byte aligned slots in HBM
-    words_per_file = (data_len + 1) // 2
-    frames_per_file = words_per_file // 2                      # stereo
-
-    # ---- synthetic file images: pinned host slab (e2e input; the images lie back to back like an asset directory
-    #      read into one buffer) + HBM slab (device-resident input, one 256-byte aligned slot per file)
-    h_in = ctx.pinned(n_files * image_len)
-    rng = np.random.default_rng(0xC20000 + rank)
-    view = h_in.u8.reshape(n_files, image_len)
-    view[:, :len(hdr)] = hdr
-    chunk = 64
-    for i in range(0, n_files, chunk):
-        view[i:i + chunk, len(hdr):image_len] = rng.integers(0, 256, size=(min(chunk, n_files - i), data_len), dtype=np.uint8)
-    d_in = ctx.alloc(n_files * slot)
-    d_out = ctx.alloc(n_files * words_per_file * 2)
-    for i in range(n_files):
-        L.blast_memcpy_h2d(ctx.h, d_in.ptr + i * slot, h_in.ptr + i * image_len, image_len)
-    ctx.sync()
-    descs = [fp.probe("aiff", view[0, :image_len])] * n_files
-    off = descs[0].data_off
-    if args.layout == "payload":
-        # payload-only layout: what blast_pcm_decode_batch stages (16-byte aligned payloads)
-        d_pay = ctx.alloc(n_files * slot)
-        for i in range(n_files):
-            L.blast_memcpy_h2d(ctx.h, d_pay.ptr + i * slot, h_in.ptr + i * image_len + off, data_len)
-        ctx.sync()
-        d_src_base, src_extra = d_pay.ptr, 0
-    else:
-        d_src_base, src_extra = d_in.ptr, off
-    jobs = [(d_src_base + i * slot + src_extra, d_out.ptr + i * words_per_file * 2, words_per_file, True)
-            for i in range(n_files)]
-    plan = fp.PcmPlan(ctx, jobs)
-    samples_per_step = n_files * words_per_file
-    alg_bytes_decode = 4 * samples_per_step                      # 2 B read + 2 B written per i16 word
-
-    # ---- mix: every decoded file is one stereo voice (velocity 1, per-voice gain) on one stereo bus
+    gains = c2_gains(n_files)
     mix = not args.no_mix
+    shard = C2Shard(ctx, range(rank, n_files, world), data_len, args.layout, gains)
+    frames = shard.frames
+    n_slots = frames * 2
+    peak, peak_src = measured_peaks()
+
+    # ---- the mix's exchange step: partial buses reduced tile by tile inside the render kernel over peer memory
+    peer = t_part = d_bus2 = None
     if mix:
-        tracks, voices = [], []
-        g = br.fill(ctx, 0xC2, 0, 1, n_files, 0, 100, ranged=False, checks=False)[0][0]
-        for i in range(n_files):
-            buf = blast.DevBuf.__new__(blast.DevBuf)
-            buf.ctx, buf.ptr, buf.nbytes = ctx, d_out.ptr + i * words_per_file * 2, words_per_file * 2
-            buf.free = lambda: None
-            tracks.append(ap.Track(buf, words_per_file, 2, 48000))
-            gain = float(np.float32((int(g[i]) >> 11) * 2.0 ** -53) * np.float32(2.0 ** -5))
-            voices.append(ap.VoiceParams(i, True, 0.0, 1.0, gain))
-        scene = ap.Scene(ctx, tracks, voices, 2)
-        n_slots = frames_per_file * 2
-        peer = None
-        if world > 1 and args.reduce == "p2p":
-            # the one exchange step over peer memory: partial buses mapped into rank 0, ONE reduce + finalize kernel
-            from audio_decoder_b200 import distributed as bd
+        if args.reduce == "p2p":
             try:
-                peer = bd.PeerBus(ctx, n_slots, rank, world, mode=args.peer_mode)
-                part_ptr = peer.part.ptr
-            except RuntimeError as e:                              # raised on EVERY rank or on none
+                peer = bd.PeerBus(ctx, n_slots, rank, world)
+            except RuntimeError as e:                                  # raised on EVERY rank or on none
                 if rank == 0:
                     print(f"bench.py: {e}; using the NCCL all-reduce instead", file=sys.stderr)
-                peer = None
                 args.reduce = "nccl"
-        if world > 1 and peer is None:
-            t_part = torch.empty(n_slots, dtype=torch.int32, device=f"cuda:{local}")
-            part_ptr = t_part.data_ptr()
-        elif peer is None:
-            d_part = ctx.alloc(4 * n_slots)
-            part_ptr = d_part.ptr
-        d_bus = peer.bus if peer is not None else ctx.alloc(2 * n_slots)
-        alg_bytes_mix = 4 * (frames_per_file - 1) * n_files + 2 * n_slots   # source frames touched + S16 bus
-    n_ev = 3 if mix else 2
-
-    def mix_step():
-        if peer is not None:
-            peer.wait_ack()                                        # rank 0 has consumed the previous partial bus
-            scene.restore_dev()
-            scene.render_partial_dev(frames_per_file, part_ptr)
-            peer.reduce()                                          # signal, then ONE kernel: wait + reduce my slice + wrap + store to rank 0
-            return
-        scene.restore_dev()
-        scene.render_partial_dev(frames_per_file, part_ptr)
         if world > 1:
-            dist.all_reduce(t_part, op=dist.ReduceOp.SUM)          # NCCL variant: int32 partial buses
-        ap.finalize_bus(ctx, part_ptr, d_bus.ptr, n_slots)
+            t_part = torch.empty(n_slots, dtype=torch.int32, device=f"cuda:{local}")
+            part2 = t_part.data_ptr()
+        else:
+            d_part2 = ctx.alloc(4 * n_slots)
+            part2 = d_part2.ptr
+        d_bus2 = ctx.alloc(2 * n_slots)
 
-    def step(evs=None):
-        if evs:
-            evs[0].record()
-        plan.run()
-        if evs:
-            evs[1].record()
-        if mix:
-            mix_step()
-            if evs:
-                evs[2].record()
+    def mix_unfused(sh):
+        """the baseline the fused path is measured against: render, NCCL all-reduce of the int32 bus, finalize"""
+        sh.scene.restore_dev()
+        sh.scene.render_partial_dev(frames, part2)
+        if world > 1:
+            dist.all_reduce(t_part, op=dist.ReduceOp.SUM)
+        ap.finalize_bus(ctx, part2, d_bus2.ptr, n_slots)
 
-    for _ in range(args.warmup):
-        step()
-    ctx.sync()
+    def mix_step(sh):
+        if peer is None:
+            return mix_unfused(sh)
+        sh.scene.restore_dev()
+        peer.render_reduce(sh.scene, frames)                            # K3 + K4 (render, publish, reduce, finalize)
+        peer.wait()                                                     # root: every rank's tiles are in the bus
+
+    bus_ptr = (peer.bus_ptr if peer is not None else d_bus2.ptr) if mix else None
+
+    # ---- bus_check (not timed): fused peer-memory bus == NCCL bus, and a window of it == the CPU oracle
+    bus_check = None
     if mix:
-        scene.check()
-    barrier(dist, local)
+        shard.decode()
+        mix_step(shard)
+        a = np.empty(n_slots, dtype=np.int16)
+        if rank == 0:
+            L.blast_memcpy_d2h(ctx.h, a.ctypes.data, bus_ptr, a.nbytes)
+        ctx.sync()
+        if peer is not None:
+            peer.check()
+            mix_unfused(shard)
+            b = d_bus2.download(np.int16, n_slots)
+            same = bool(np.array_equal(a, b)) if rank == 0 else True
+        else:
+            same = True
+        w = min(CHECK_FRAMES, frames - 2)
+        heads = (np.stack([ctx_download(ctx, t.buf.ptr, (w + 2) * 2) for t in shard.tracks]) if shard.n
+                 else np.zeros((0, (w + 2) * 2), np.int16))                 # the first w + 2 decoded frames of every track
+        if dist is not None:
+            box = [None] * world if rank == 0 else None
+            dist.gather_object((shard.ids, heads), box, dst=0)
+        else:
+            box = [(shard.ids, heads)]
+        if rank == 0:
+            import oracle                                               # the checker, outside every timed region
+            order = {}
+            for ids, hh in box:
+                for i, h in zip(ids, hh):
+                    order[i] = h
+            oc = oracle.Conductor(2, 48000, [(order[i], 2, 48000) for i in range(n_files)])
+            for i in range(n_files):
+                oc.load(i)
+                oc.set_voice(i, gain=gains[i], active=True)
+            exp = oc.coordinate(w)
+            window_ok = bool(np.array_equal(a[:2 * w], exp))
+            nonzero = int(np.count_nonzero(a))
+            bus_check = "ok" if (same and window_ok and nonzero > n_slots // 2) else \
+                f"FAILED (fused == nccl: {same}, {w}-frame window == oracle: {window_ok}, nonzero slots {nonzero})"
+        if dist is not None:
+            box = [bus_check]
+            dist.broadcast_object_list(box, src=0)
+            bus_check = box[0]
+        if bus_check != "ok":
+            raise SystemExit(f"bench.py: bus_check {bus_check}")
+
+    def timed(sh, steps, warmup):
+        """W warm-up + K timed steps of decode + mix on shard `sh`; CUDA events on the launching stream"""
+        n_ev = 3 if mix else 2
+
+        def step(evs=None):
+            if evs:
+                evs[0].record()
+            sh.decode()
+            if evs:
+                evs[1].record()
+            if mix:
+                mix_step(sh)
+                if evs:
+                    evs[2].record()
+
+        for _ in range(warmup):
+            step()
+        ctx.sync()
+        if mix:
+            sh.scene.check()
+            if peer is not None:
+                peer.check()
+        barrier(dist, local)
+        launches0 = ctx.launch_count
+        evs = [[ctx.event() for _ in range(n_ev)] for _ in range(steps)]
+        e_end = ctx.event()
+        for k in range(steps):
+            step(evs[k])
+        e_end.record()
+        ms_total = evs[0][0].elapsed_ms(e_end)
+        ctx.sync()
+        barrier(dist, local)
+        launches = ctx.launch_count - launches0
+        ms_decode = sum(e[0].elapsed_ms(e[1]) for e in evs) / steps
+        ms_mix = sum(e[1].elapsed_ms(e[2]) for e in evs) / steps if mix else 0.0
+        ms_step = max_over_ranks(dist, local, ms_total) / steps
+        return dict(ms_step=ms_step, ms_decode=ms_decode, ms_mix=ms_mix, launches=launches,
+                    ms_decode_max=max_over_ranks(dist, local, ms_decode), ms_mix_max=max_over_ranks(dist, local, ms_mix))
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = ctx.launch_count
-    evs = [[ctx.event() for _ in range(n_ev)] for _ in range(args.steps)]
-    e_end = ctx.event()
-    for k in range(args.steps):
-        step(evs[k])
-    e_end.record()
-    ms_total = evs[0][0].elapsed_ms(e_end)
-    ctx.sync()
-    barrier(dist, local)
-    launches = ctx.launch_count - launches0
-    clocks = None
-    ms_decode = sum(e[0].elapsed_ms(e[1]) for e in evs) / args.steps
-    ms_mix = sum(e[1].elapsed_ms(e[2]) for e in evs) / args.steps if mix else 0.0
-    ms_total = max_over_ranks(dist, local, ms_total)
-    ms_step = ms_total / args.steps
-    value = world * samples_per_step / (ms_step * 1e-3) / 1e9
+    t = timed(shard, args.steps, args.warmup)
+    ms_step = t["ms_step"]
+    total_samples = n_files * shard.words
+    value = total_samples / (ms_step * 1e-3) / 1e9
 
-    # ---- roofline of the dominant kernel (decode moves 2x the bytes of the mix), per-launch average
-    peak, peak_src = measured_peaks()
-    achieved = alg_bytes_decode / (ms_decode * 1e-3) / 1e9
-    roofline = {"kernel": "pcm16_decode_batch", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 4), "frac_of_nominal_8000": round(achieved / 8000.0, 4),
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_decode,
-                "ms_per_launch": round(ms_decode, 4)}
+    # ---- roofline of the dominant kernel (decode moves 2x the bytes of the mix), per-launch average on this rank
     traffic = {}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
@@ -276,22 +367,35 @@ def run_ours(args):
             traffic = json.load(open(tr))
         except Exception:
             traffic = {}
-    roofline["traffic"] = traffic.get("pcm16_decode_batch")
+    achieved = shard.alg_decode / (t["ms_decode"] * 1e-3) / 1e9
+    roofline = {"kernel": "pcm16_decode_batch", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "frac_of_nominal_8000": round(achieved / 8000.0, 4),
+                "traffic": traffic.get("pcm16_decode_batch") if world == 1 else None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": shard.alg_decode, "ms_per_launch": round(t["ms_decode"], 4),
+                "note": "rank 0's shard" if world > 1 else None}
     roofline_mix = None
+    alg_mix = shard.alg_mix + 2 * n_slots // world
     if mix:
-        ach = alg_bytes_mix / (ms_mix * 1e-3) / 1e9
-        roofline_mix = {"kernel": "voice_position_scan + voice_render_mix_tma + " +
-                                  ("bus_finalize" if world == 1 else "bus_reduce_peers (peer memory)" if peer is not None
-                                   else "NCCL all-reduce(int32) + bus_finalize"),
-                        "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                        "frac": round(ach / peak, 4), "algorithmic_bytes_per_step": alg_bytes_mix,
-                        "ms_per_step": round(ms_mix, 4), "traffic": traffic.get("voice_render_mix_tma_c2")}
-
-    # the whole step against the same roofline (north star: decode + mix at >= 70 % of the HBM roofline per GPU)
-    alg_step = alg_bytes_decode + (alg_bytes_mix if mix else 0)
+        ach = alg_mix / (t["ms_mix"] * 1e-3) / 1e9
+        roofline_mix = {"kernel": "voice_position_scan + voice_render_mix_tma (render, tile publish, peer reduce, S16 wrap in one kernel)"
+                        if peer is not None else "voice_position_scan + voice_render_mix_tma + NCCL all-reduce(int32) + bus_finalize",
+                        "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                        "algorithmic_bytes_per_step": alg_mix, "ms_per_step": round(t["ms_mix"], 4),
+                        "traffic": traffic.get("voice_render_mix_tma_c2") if world == 1 else None}
+    alg_step = shard.alg_decode + (alg_mix if mix else 0)
     roofline_step = {"bound": "hbm", "achieved": round(alg_step / (ms_step * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(alg_step / (ms_step * 1e-3) / 1e9 / peak, 4), "algorithmic_bytes_per_step": alg_step,
                      "note": "decode + mix of one rank, max-over-ranks step time"}
+
+    # ---- weak scaling as the extra key (N > 1): every rank decodes and mixes its own 1,024 files
+    weak = None
+    if world > 1 and not args.no_weak:
+        full = C2Shard(ctx, range(n_files), data_len, args.layout, gains, host_images=False)
+        tw = timed(full, max(3, args.steps // 2), 3)
+        weak = {"value": round(world * full.samples / (tw["ms_step"] * 1e-3) / 1e9, 3), "unit": UNIT,
+                "ms_per_step": round(tw["ms_step"], 4), "files_per_gpu": n_files,
+                "kernel_ms": {"decode": round(tw["ms_decode_max"], 4), "mix": round(tw["ms_mix_max"], 4)}}
+        full.close()
 
     # ---- e2e: the same step through the host-buffer C ABI.  Pinned host file images -> blast_pcm_decode_batch
     #      (H2D inside) -> render of the decoded tracks -> S16 bus copied back to the host.
@@ -300,26 +404,28 @@ def run_ours(args):
     #                    aiff::parse() drop-in must (doubles the PCIe traffic)
     e2e = e2e_dropin = None
     if not args.no_e2e:
-        h_out = ctx.pinned(n_files * words_per_file * 2)
-        h_bus = ctx.pinned(2 * frames_per_file * 2) if mix else None
-        files = (C.c_void_p * n_files)(*[h_in.ptr + i * image_len for i in range(n_files)])
-        lens = (C.c_size_t * n_files)(*([image_len] * n_files))
-        dd = (_lib.PcmDesc * n_files)(*descs)
-        host_out = (C.c_void_p * n_files)(*[h_out.ptr + i * words_per_file * 2 for i in range(n_files)])
-        dev_out = (C.c_void_p * n_files)(*[d_out.ptr + i * words_per_file * 2 for i in range(n_files)])
+        n = shard.n
+        wpf = shard.words
+        h_out = ctx.pinned(max(1, n) * wpf * 2)
+        h_bus = ctx.pinned(2 * n_slots) if mix else None
+        files = (C.c_void_p * max(1, n))(*[shard.h_in.ptr + k * shard.slot for k in range(n)])
+        lens = (C.c_size_t * max(1, n))(*([shard.image_len] * n))
+        dd = (_lib.PcmDesc * max(1, n))(*([shard.desc] * n))
+        host_out = (C.c_void_p * max(1, n))(*[h_out.ptr + k * wpf * 2 for k in range(n)])
+        dev_out = (C.c_void_p * max(1, n))(*[shard.d_out.ptr + k * wpf * 2 for k in range(n)])
         pcie = {}
         pp = os.path.join(ROOT, "profiles", "r01_pcie_probe.json")
         if os.path.exists(pp):
             pcie = json.load(open(pp))
 
         def e2e_step(to_host):
-            rc = L.blast_pcm_decode_batch(ctx.h, n_files, files, lens, dd, host_out if to_host else None, dev_out)
+            rc = L.blast_pcm_decode_batch(ctx.h, n, files, lens, dd, host_out if to_host else None, dev_out)
             if rc != 0:
                 raise RuntimeError(L.blast_last_error().decode())
             if mix:
-                mix_step()
-                if peer is None or rank == 0:                      # over peer memory the bus exists on rank 0 only
-                    L.blast_memcpy_d2h(ctx.h, h_bus.ptr, d_bus.ptr, 2 * n_slots)
+                mix_step(shard)
+                if rank == 0:                                          # the bus exists on the root
+                    L.blast_memcpy_d2h(ctx.h, h_bus.ptr, bus_ptr, 2 * n_slots)
                 ctx.sync()
 
         def e2e_run(to_host):
@@ -332,64 +438,78 @@ def run_ours(args):
             ctx.sync()
             dt = (time.perf_counter() - t0) / args.e2e_steps
             dt = max_over_ranks(dist, local, dt)
-            h2d = n_files * data_len
-            d2h = (n_files * words_per_file * 2 if to_host else 0) + (2 * n_slots if mix else 0)
-            r = {"value": round(world * samples_per_step / dt / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            h2d = n * data_len
+            d2h = (n * wpf * 2 if to_host else 0) + (2 * n_slots if mix and rank == 0 else 0)
+            r = {"value": round(total_samples / dt / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                  "d2h_bytes_per_step": d2h, "ms_per_step": round(dt * 1e3, 3),
-                 "pcie_GBps": round(max(h2d, d2h) / dt / 1e9, 2)}
+                 "pcie_GBps_per_gpu": round(max(h2d, d2h) / dt / 1e9, 2),
+                 "bytes_note": "per rank (rank 0)" if world > 1 else None}
             if pcie:
                 r["pcie_peak_GBps"] = pcie.get("bidir_each_GBps" if to_host else "h2d_GBps")
-                r["pcie_frac"] = round(r["pcie_GBps"] / r["pcie_peak_GBps"], 3)
+                r["pcie_frac"] = round(r["pcie_GBps_per_gpu"] / r["pcie_peak_GBps"], 3)
                 r["pcie_peak_source"] = "tools/pcie_probe.py on this pool's B200 box (profiles/r01_pcie_probe.json)"
             return r
 
         e2e = e2e_run(False)
         e2e["api"] = ("blast_pcm_decode_batch (pinned host file images in, decoded tracks kept in HBM)" +
-                      (" + blast_scene_render_dev + blast_bus_finalize_dev + S16 bus D2H" if mix else ""))
+                      (" + blast_scene_render_reduce_dev + S16 bus D2H" if mix else ""))
         e2e_dropin = e2e_run(True)
         e2e_dropin["api"] = e2e["api"].replace("decoded tracks kept in HBM", "host AudioFile.samples out AND tracks kept in HBM")
-        # spot-check the e2e result against numpy (not timed)
-        got = h_out.view(np.int16, words_per_file, 0)
-        assert np.array_equal(got, view[0, off:off + data_len].view(">i2").astype(np.int16)), "e2e output mismatch"
-    if rank == 0:
-        clocks = sampler.stop()
+        if n:   # spot-check the e2e result against numpy (not timed)
+            got = h_out.view(np.int16, wpf, 0)
+            assert np.array_equal(got, shard.view[0, shard.off:shard.off + data_len].view(">i2").astype(np.int16)), "e2e output mismatch"
+        h_out.free()
+    clocks = sampler.stop() if rank == 0 else None
 
-    workload = (f"C2: batch decode {n_files} x 24-bit BE 48 kHz stereo AIFF ({data_len} payload B each), reference-exact "
-                "byte-pair decode to i16" + (f", then mix of the {n_files} decoded tracks (stereo voices, velocity 1, "
-                                             "per-voice gain) into one stereo S16 bus" if mix else ""))
+    workload = (f"C2: batch decode {n_files} x 24-bit BE 48 kHz stereo AIFF ({data_len} payload B each, X128P::new(0xC2_0000 + i) bytes), "
+                "reference-exact byte-pair decode to i16" + (f", then mix of the {n_files} decoded tracks (stereo voices, velocity 1, "
+                                                             "per-voice gain) into one stereo S16 bus" if mix else ""))
     out = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "i16", "data": "synthetic",
-        "config": {"workload": workload, "files_per_gpu": n_files, "samples_per_step_per_gpu": samples_per_step,
+        "config": {"workload": workload, "files_total": n_files, "files_per_gpu": shard.n,
+                   "samples_per_step": total_samples,
                    "sample_definition": "one i16 PCM word that is decoded" + (" and then mixed" if mix else ""),
                    "layout": args.layout,
-                   "l2": f"per step {n_files * data_len / 1e6:.0f} MB of file images are read and {samples_per_step * 2 / 1e6:.0f} MB of "
-                         "samples written then re-read: far larger than the 126 MB L2 (no flush needed)",
-                   "parallelism": f"files / voices sharded over {world} rank(s)" +
-                                  ((f"; partial buses reduced + finalized over peer memory (CUDA IPC / NVLink, mode {args.peer_mode}: one fused kernel), no collective library"
+                   "l2": f"per step and GPU {shard.n * data_len / 1e6:.0f} MB of file images are read and {shard.samples * 2 / 1e6:.0f} MB of "
+                         "samples written then re-read" + (": far larger than the 126 MB L2 (no flush needed)" if shard.n * data_len > 4e8 else
+                                                           ": larger than the 126 MB L2 only in sum; no flush between steps — see the weak key for the > L2 per-GPU shard"),
+                   "parallelism": f"strong scaling: the {n_files} files / voices sharded over {world} rank(s), file i -> rank i mod N" +
+                                  (("; partial buses reduced tile by tile inside the render kernel over peer memory (CUDA IPC / NVLink), no collective library"
                                     if peer is not None else "; one int32 all-reduce of the partial bus per step (NCCL)") if world > 1 and mix else "; no collective")},
         "roofline": roofline, "roofline_mix": roofline_mix, "roofline_step": roofline_step,
-        "kernel_ms": {"decode": round(ms_decode, 4), "mix": round(ms_mix, 4)},
-        "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "e2e_parse_dropin": e2e_dropin,
+        "kernel_ms": {"decode": round(t["ms_decode_max"], 4), "mix": round(t["ms_mix_max"], 4),
+                      "note": "max over ranks of each rank's per-step average"},
+        "bus_check": bus_check, "weak": weak,
+        "gpu_launches": int(t["launches"]), "clocks": clocks, "e2e": e2e, "e2e_parse_dropin": e2e_dropin,
     }
-    if rank == 0 and not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(view, image_len, n_files, threads=1, budget_s=args.cpu_seconds, mix=mix)
-        out["cpu_fast_decode"] = cpu_fast_decode(view, image_len, n_files)
+    if rank == 0 and not args.no_cpu and shard.n:
+        out["cpu_baseline"] = cpu_baseline(shard.view, shard.image_len, shard.n, [gains[i] for i in shard.ids], threads=1,
+                                           budget_s=args.cpu_seconds, mix=mix)
+        out["cpu_fast_decode"] = cpu_fast_decode(shard.view, shard.image_len, shard.n)
+    shard.close()
+    if not args.no_configs:
+        import bench_configs
+        out["configs"] = bench_configs.run(ctx, rank, world, local, dist, peak, quick=args.quick_configs)
     if rank == 0:
         print(json.dumps(out))
-    plan.close()
-    if mix:
-        if peer is not None:
-            barrier(dist, local)
-            peer.close()
-        scene.close()
+    if peer is not None:
+        barrier(dist, local)
+        peer.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
+def ctx_download(ctx, ptr, count, dtype=np.int16):
+    out = np.empty(count, dtype=dtype)
+    ctx.lib.blast_memcpy_d2h(ctx.h, out.ctypes.data, ptr, out.nbytes)
+    ctx.sync()
+    return out
+
+
 # ------------------------------------------------------------------ CPU arms (oracle = checker, timed as the baseline)
-def _cpu_decode_mix(view, image_len, idx, mix):
+def _cpu_decode_mix(view, image_len, idx, gains, mix):
     """faithful aiff::parse of files idx, then (mix) Conductor::coordinate over them as voices -> words"""
     import oracle
     L = oracle.lib()
@@ -406,10 +526,10 @@ def _cpu_decode_mix(view, image_len, idx, mix):
     if mix and bufs:
         arr = (oracle.Track * len(bufs))(*[oracle.Track(b.value, n, 2, 48000) for b, n in bufs])
         h = L.orc_conductor_new(2, 48000, arr, len(bufs))
-        for k in range(len(bufs)):
+        for k, i in enumerate(idx):
             L.orc_conductor_apply(h, C.byref(oracle.Command(kind=oracle.CMD_LOAD, idx=k, tempo=oracle.tempo_repr())))
             L.orc_conductor_apply(h, C.byref(oracle.Command(kind=oracle.CMD_START, idx_kind=oracle.IDX_VOICE, idx=k)))
-            L.orc_conductor_set_voice(h, -1, k, None, None, C.byref(C.c_float(0.01)), None)
+            L.orc_conductor_set_voice(h, -1, k, None, None, C.byref(C.c_float(gains[i])), None)
         frames = bufs[0][1] // 2
         bus = np.empty(frames * 2, dtype=np.int16)
         L.orc_conductor_coordinate(h, frames, bus.ctypes.data)
@@ -419,29 +539,30 @@ def _cpu_decode_mix(view, image_len, idx, mix):
     return words
 
 
-def cpu_baseline(view, image_len, n_files, threads: int, budget_s: float, mix: bool = True):
+def cpu_baseline(view, image_len, n_files, gains, threads: int, budget_s: float, mix: bool = True):
     """faithful CPU restatement (per-pair bounds-checked reads, Vec growth; frame->channel->voice scalar
     render loop) on a bounded sample; threads > 1 shard the files / voices (generous comparison)"""
     import oracle
     oracle.lib()
     t0 = time.perf_counter()
-    _cpu_decode_mix(view, image_len, [0], mix)
+    _cpu_decode_mix(view, image_len, [0], gains, mix)
     per_file = max(1e-4, time.perf_counter() - t0)
     n = int(max(threads, min(n_files, budget_s / per_file * threads)))
     n = max(threads, n // threads * threads)
+    n = min(n, n_files)
     idx = list(range(n))
     t0 = time.perf_counter()
     if threads == 1:
-        words = _cpu_decode_mix(view, image_len, idx, mix)
+        words = _cpu_decode_mix(view, image_len, idx, gains, mix)
     else:
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(threads) as ex:
-            words = sum(ex.map(lambda k: _cpu_decode_mix(view, image_len, idx[k::threads], mix), range(threads)))
+            words = sum(ex.map(lambda k: _cpu_decode_mix(view, image_len, idx[k::threads], gains, mix), range(threads)))
     dt = time.perf_counter() - t0
     what = "aiff::parse" + (" + Conductor::coordinate (each thread mixes its own voice shard)" if mix else "")
     return {"value": round(words / dt / 1e9, 4), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{n} of {n_files} files ({words} i16 words) through the faithful C++ restatement of {what} "
-                      f"(oracle/blast_oracle.cpp, g++ -O2 -ffp-contract=off), {dt:.1f} s",
+            "sample": f"{n} of the C2 files ({words} i16 words, the same X128P bytes and gains as the GPU arm) through the faithful C++ "
+                      f"restatement of {what} (oracle/blast_oracle.cpp, g++ -O2 -ffp-contract=off), {dt:.1f} s",
             "note": "CPU restatement of the reference, not the Rust binary (no rustc in the image)"}
 
 
@@ -477,6 +598,7 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    import oracle
     n_files, data_len = args.files, args.data_len
     mix = not args.no_mix
     threads = os.cpu_count() or 1
@@ -484,25 +606,28 @@ def run_reference(args):
     image_len = len(hdr) + data_len
     sample_files = min(n_files, args.ref_files_per_thread * threads)
     view = np.empty((sample_files, image_len), dtype=np.uint8)
-    rng = np.random.default_rng(0xC20000)
     view[:, :len(hdr)] = hdr
-    view[:, len(hdr):] = rng.integers(0, 256, size=(sample_files, data_len), dtype=np.uint8)
+    for i in range(sample_files):                                       # the GPU arm's inputs: X128P::new(0xC2_0000 + i) bytes
+        view[i, len(hdr):] = oracle.Rng(0xC20000 + i).fill_u64((data_len + 7) // 8).view(np.uint8)[:data_len]
+    gains = c2_gains(n_files)
     res, times = None, []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        res = cpu_baseline(view, image_len, sample_files, threads=threads, budget_s=1e9, mix=mix)
+        res = cpu_baseline(view, image_len, sample_files, gains, threads=threads, budget_s=1e9, mix=mix)
         if it >= args.warmup:
             times.append(time.perf_counter() - t0)
     words = sample_files * ((data_len + 1) // 2)
     value = words / (sum(times) / len(times)) / 1e9
     res["value"] = round(value, 4)
-    workload = (f"C2: batch decode {n_files} x 24-bit BE 48 kHz stereo AIFF ({data_len} payload B each), reference-exact "
-                "byte-pair decode to i16" + (", then mix of the decoded tracks into one stereo S16 bus" if mix else ""))
+    workload = (f"C2: batch decode {n_files} x 24-bit BE 48 kHz stereo AIFF ({data_len} payload B each, X128P::new(0xC2_0000 + i) bytes), "
+                "reference-exact byte-pair decode to i16" + (", then mix of the decoded tracks into one stereo S16 bus" if mix else ""))
     out = {
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * sum(times) / len(times), 3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16", "data": "synthetic",
-        "config": {"workload": workload, "sample_files_per_step": sample_files, "threads": threads},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "i16", "data": "synthetic",
+        "config": {"workload": workload, "sample_files_per_step": sample_files, "threads": threads,
+                   "sample": f"each step decodes + mixes the first {sample_files} of the {n_files} files (same per-file work, "
+                             "throughput-normalised subset of the GPU arm's batch) on all host threads"},
         "cpu_baseline": res,
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -523,12 +648,13 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-mix", action="store_true", help="decode only (no render/mix of the decoded tracks)")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling extra key")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (C1, C3, C4, C5, true 24-bit)")
+    ap.add_argument("--quick-configs", action="store_true", help="other configs at reduced sizes (development)")
     ap.add_argument("--ref-files-per-thread", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--peer-mode", default="root", choices=["root", "scatter"],
-                    help="p2p reduction: the root pulls every bus (no lock step) / every rank reduces its 1/N slice")
     ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"],
-                    help="N > 1: the mix reduction over peer memory (one fused kernel on rank 0) or as an NCCL all-reduce")
+                    help="the mix reduction: inside the render kernel over peer memory, or as an NCCL all-reduce + finalize")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -80,6 +80,7 @@ int blast_host_alloc(blast_ctx* ctx, size_t bytes, void** out);   /* pinned */
 int blast_host_free(blast_ctx* ctx, void* ptr);
 int blast_memcpy_h2d(blast_ctx* ctx, void* d_dst, const void* src, size_t bytes);   /* async */
 int blast_memcpy_d2h(blast_ctx* ctx, void* dst, const void* d_src, size_t bytes);   /* async */
+int blast_memcpy_d2d(blast_ctx* ctx, void* d_dst, const void* d_src, size_t bytes); /* async */
 int blast_memset_dev(blast_ctx* ctx, void* d_dst, int value, size_t bytes);         /* async */
 
 /* CUDA-event timing on the context's stream (the stream the kernels are launched on) */
@@ -160,6 +161,9 @@ int  blast_pcm24_unpack_dev(blast_ctx* ctx, const blast_pcm24_job* jobs, uint32_
  * replaces Conductor::coordinate (blast/src/audio_processing/engine.rs:46-81) and Voice::process
  * (engine.rs:386-448) for a set of voices over `frames` output frames.  Output is bit-exact with
  * the reference's release-build semantics (saturating `as i16`, wrapping i16 accumulate). */
+/* d_samples must be readable from the 16-byte boundary at or below it up to the 16-byte boundary at or above its last
+ * sample (the render stages source spans with 16-byte aligned bulk copies): true for blast_dev_alloc / cudaMalloc
+ * buffers and for tracks sub-allocated from them. */
 typedef struct {
     const int16_t* d_samples;  /* device, interleaved, 4-byte aligned (AudioFile.samples) */
     uint64_t n_samples;        /* samples.len() */

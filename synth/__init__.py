@@ -70,3 +70,53 @@ def mp3_like(seed: int, n_frames: int, tail: int = 1100, frame_payload: int = 41
     out[starts + 3] = 0x64
     out[total:] = 0
     return out
+
+
+# ---------------------------------------------------------------- SURVEY §8(d) generators (exact, pure Python ints)
+_M64 = (1 << 64) - 1
+
+
+class X128P:
+    """blast_rand.rs:4-48 on Python ints: SplitMix64 seeding, xoroshiro128+ (55, 14, 36), next_f64 / next_f32.
+    For the handful of per-voice parameters the configs derive from a generator; bulk sample bytes come from the CUDA
+    generator (bench) or the C oracle (tests)."""
+
+    def __init__(self, seed: int):
+        def splitmix64(x):
+            x = (x + 0x9E3779B97F4A7C15) & _M64
+            z = x
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+            return z ^ (z >> 31)
+        self.s0 = splitmix64(seed & _M64)
+        self.s1 = splitmix64((seed + 0x9E3779B97F4A7C15) & _M64)
+
+    def next_u64(self) -> int:
+        r = (self.s0 + self.s1) & _M64
+        t = self.s1 ^ self.s0
+        self.s0 = (((self.s0 << 55) | (self.s0 >> 9)) & _M64) ^ t ^ ((t << 14) & _M64)
+        self.s1 = ((t << 36) | (t >> 28)) & _M64
+        return r
+
+    def next_f64(self) -> float:
+        return (self.next_u64() >> 11) * (1.0 / (1 << 53))
+
+    def next_f32(self) -> np.float32:
+        return np.float32(self.next_f64())
+
+
+def c3_voice_params(n_voices: int = C3_VOICES):
+    """SURVEY §8(d) C3: per-voice (velocity, gain) from X128P::new(0xC3) in voice order: gain = next_f32() * 2^-7;
+    velocity = 1.0 for even v, 0.5 + next_f32() for odd v (f32 arithmetic)"""
+    g = X128P(0xC3)
+    out = []
+    for v in range(n_voices):
+        gain = np.float32(g.next_f32() * np.float32(2.0 ** -7))
+        vel = np.float32(1.0) if v % 2 == 0 else np.float32(np.float32(0.5) + g.next_f32())
+        out.append((float(vel), float(gain)))
+    return out
+
+
+def c3_clip_frames(v: int, frames: int) -> int:
+    """clip length of voice v for an N-frame render: N + 2 frames (even v), ceil(1.5 N) + 2 (odd v)"""
+    return frames + 2 if v % 2 == 0 else (3 * frames + 1) // 2 + 2

@@ -19,6 +19,7 @@ import synth  # noqa: E402
 if __name__ == "__main__":
     a = argparse.ArgumentParser()
     a.add_argument("--gib", type=int, default=4)
+    a.add_argument("--quick", action="store_true", help="parity only (the pytest -m gpu entry)")
     args = a.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -48,6 +49,13 @@ if __name__ == "__main__":
                   and np.array_equal(cat, exp["offsets"]))
             res[f"parity_compat{int(compat)}"] = bool(ok)
             assert ok, "sharded index differs from the oracle"
+    res["parity"] = bool(res.get("parity_compat1") and res.get("parity_compat0")) if rank == 0 else None
+    if args.quick:
+        if rank == 0:
+            print(json.dumps(res))
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(0)
     # ---- timing: --gib per rank of ONE logical stream of world * gib GiB
     per = args.gib << 30
     block = synth.mp3_like(0xC5, (1 << 28) // 418 - 4)

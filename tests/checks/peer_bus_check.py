@@ -1,7 +1,9 @@
 #!/usr/bin/env python
-"""Run under torchrun: the mix reduction over peer memory (distributed.PeerBus, both modes) against (a) the NCCL
-all-reduce + finalize path and (b) a single-GPU render of the whole scene on rank 0, over several steps with changing
-gains (exercises the ready / ack / done flag protocol); then timings of the exchange alone."""
+"""Run under torchrun (one rank per GPU, windows mapped by CUDA IPC): the render's exchange step over peer memory
+(distributed.PeerBus -> blast_peer_bus) — fused into the render kernel, and as the two-kernel reduction — against (a) the
+NCCL all-reduce + finalize path and (b) a single-GPU render of the whole scene on rank 0, over several steps with changing
+gains (exercises the ready / done / ack step counters); the sharded Conductor against the CPU oracle; then timings of the
+exchange alone (skipped with --quick, the pytest -m gpu entry)."""
 import json
 import os
 import sys
@@ -15,6 +17,7 @@ import audio_decoder_b200 as blast  # noqa: E402
 from audio_decoder_b200 import audio_processing as ap, distributed as bd  # noqa: E402
 
 if __name__ == "__main__":
+    quick = "--quick" in sys.argv
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -27,17 +30,22 @@ if __name__ == "__main__":
     t_part = torch.empty(n, dtype=torch.int32, device=f"cuda:{local}")
     d_bus2 = ctx.alloc(2 * n)
     res = {"world": world}
-    for mode in ("root", "scatter"):
-        peer = bd.PeerBus(ctx, n, rank, world, mode=mode)
+    for mode in ("fused", "two_kernel"):
+        peer = bd.PeerBus(ctx, n, rank, world)
         ok = True
         for step in range(5):
             vps = [ap.VoiceParams(v, True, 0.0, 1.0 if v % 3 else 0.77, float(np.float32(0.3 + 0.1 * step + 0.01 * v)))
                    for v in range(n_voices)]
             mine = [p if v % world == rank else ap.VoiceParams(v, False) for v, p in enumerate(vps)]
             sc = ap.Scene(ctx, tracks, mine, 2)
-            peer.wait_ack()
-            sc.render_partial_dev(frames, peer.part.ptr)
-            peer.reduce()
+            if mode == "fused":
+                peer.render_reduce(sc, frames)
+            else:
+                peer.begin()
+                sc.render_partial_dev(frames, peer.part_ptr)
+                peer.reduce(n)
+            a = peer.download_bus(n) if rank == 0 else None
+            peer.check()
             sc.set_voices(mine)
             sc.render_partial_dev(frames, t_part.data_ptr())
             dist.all_reduce(t_part, op=dist.ReduceOp.SUM)
@@ -45,7 +53,7 @@ if __name__ == "__main__":
             ctx.sync()
             sc.close()
             if rank == 0:
-                a, b = peer.bus.download(np.int16, n), d_bus2.download(np.int16, n)
+                b = d_bus2.download(np.int16, n)
                 whole, _ = ap.render(ctx, tracks, vps, 2, frames)
                 ok = ok and np.array_equal(a, b) and np.array_equal(a, whole)
                 assert ok, f"mode {mode} step {step}: peer-memory bus differs"
@@ -73,10 +81,10 @@ if __name__ == "__main__":
             c.seq(t, m.tempo_repr(owned=False, mode=m.TM_VOICE, idx=t), 4, [0.0, 2.0], [100.0, 60.0], seed_state)
             c.velocity(t, [1.0, 0.8, 1.3, 1.0, 0.5, 1.0][t])
             c.start(t)
-    for frames, cmd in ((20_000, None), (1, ("velocity", 2, 0.9)), (33_333, ("stop", 4)), (60_000, None)):
-        got = sc.coordinate(frames)
+    for nfr, cmd in ((20_000, None), (1, ("velocity", 2, 0.9)), (33_333, ("stop", 4)), (60_000, None)):
+        got = sc.coordinate(nfr)
         if rank == 0:
-            ok = ok and np.array_equal(got, oc.coordinate(frames))
+            ok = ok and np.array_equal(got, oc.coordinate(nfr))
             assert ok, "sharded conductor differs from the oracle"
         if cmd:
             getattr(sc, cmd[0])(*cmd[1:])
@@ -85,34 +93,36 @@ if __name__ == "__main__":
     res["parity_sharded_conductor"] = bool(ok)
     dist.barrier()
     sc.close()
-    # ---- timing of the exchange alone (partial buses already rendered): C3-sized bus (2^20 frames x 2)
-    n = 1 << 21
-    d_b = ctx.alloc(2 * n)
-    t_p = torch.zeros(n, dtype=torch.int32, device=f"cuda:{local}")
-    for name in ("root", "scatter", "nccl"):
-        peer2 = bd.PeerBus(ctx, n, rank, world, mode=name) if name != "nccl" else None
-        times = []
-        for it in range(12):
+    if not quick:
+        # ---- timing of the exchange alone (partial buses already rendered): C3-sized bus (2^20 frames x 2)
+        n = 1 << 21
+        d_b = ctx.alloc(2 * n)
+        t_p = torch.zeros(n, dtype=torch.int32, device=f"cuda:{local}")
+        for name in ("two_kernel", "nccl"):
+            peer2 = bd.PeerBus(ctx, n, rank, world) if name != "nccl" else None
+            times = []
+            for it in range(12):
+                dist.barrier()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                if peer2 is not None:
+                    peer2.begin()
+                    peer2.reduce(n)
+                    peer2.wait()
+                else:
+                    dist.all_reduce(t_p, op=dist.ReduceOp.SUM)
+                    ap.finalize_bus(ctx, t_p.data_ptr(), d_b.ptr, n)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                if it >= 2:
+                    times.append(float(ms))
+            res[name + "_us"] = round(1e3 * float(np.median(times)), 1)
             dist.barrier()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
             if peer2 is not None:
-                peer2.wait_ack()
-                peer2.reduce()
-            else:
-                dist.all_reduce(t_p, op=dist.ReduceOp.SUM)
-                ap.finalize_bus(ctx, t_p.data_ptr(), d_b.ptr, n)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            if it >= 2:
-                times.append(float(ms))
-        res[name + "_us"] = round(1e3 * float(np.median(times)), 1)
-        dist.barrier()
-        if peer2 is not None:
-            peer2.close()
+                peer2.close()
     if rank == 0:
         print(json.dumps(res))
     dist.destroy_process_group()

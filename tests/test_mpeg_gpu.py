@@ -186,3 +186,52 @@ def test_sharded_index_world1_equals_index(ctx):
         got = bd.ShardedMpegIndex(ctx, 0, 1).run(d.ptr, buf.size, reference_compat=compat)
         assert got["ref_header"] == exp["ref_header"] and got["n_candidates"] == exp["n_candidates"]
         assert np.array_equal(got["d_offsets"].download(np.uint64, got["n_offsets"]), exp["offsets"])
+
+
+def test_offsets_beyond_4GiB(ctx):
+    """C5's point is 64-bit positions (mpeg.rs:17-50 indexes with usize): a 5 GiB + stream of zeros with frame clusters
+    at the start, straddling 2^32 and at the very end.  Zeros hold no sync byte and leave the scan in its idle state, so
+    the candidates / frame offsets are those of the three clusters laid end to end (each followed by zeros) — which the
+    oracle parses — translated to where the clusters lie in the large stream."""
+    total = (5 << 30) + 123_457
+    rng = np.random.default_rng(0x5C5)
+    wins = []                                   # (start in the large stream, bytes)
+    for k, start in enumerate([0, (1 << 32) - (1 << 20) - 77, total - 1100 - (2 << 20) - 33]):
+        w = synth.mp3_like(0xC50 + k, (2 << 20) // 418, tail=0)
+        w[int(rng.integers(1000, 5000))] = 0xFF            # some stray sync bytes
+        if k == 1:
+            w[100_000:100_300] = 0xFF                      # a 0xFF run in the cluster that straddles 2^32
+            w[100_300] = 0
+        wins.append((start, w))
+    assert wins[1][0] < (1 << 32) < wins[1][0] + wins[1][1].size and wins[2][0] + wins[2][1].size + 1100 == total
+    gap = 4096                                             # zeros between the clusters of the small stream (> any payload)
+    small, base = [], []
+    at = 0
+    for start, w in wins:
+        base.append((at, start, w.size))
+        small += [w, np.zeros(gap if start != wins[-1][0] else 1100, np.uint8)]
+        at += w.size + gap
+    small = np.concatenate(small)
+
+    def translate(pos):
+        out = np.empty_like(pos)
+        for s_at, b_at, n in base:
+            m = (pos >= s_at) & (pos < s_at + n + gap)
+            out[m] = pos[m] - s_at + b_at
+        return out
+
+    d = ctx.alloc(total + 256)
+    d.zero()
+    for start, w in wins:
+        d.upload(w, offset=start)
+    epos, ehdr = oracle.mpeg_sync_scan(small)
+    pos, hdr = fp.mpeg.scan_dev(ctx, d.ptr, total, cap=len(epos) + 1024)
+    assert np.array_equal(pos, translate(epos)) and np.array_equal(hdr, ehdr)
+    assert int(np.count_nonzero(pos >= (1 << 32))) > 5000 and pos.max() > (5 << 30)
+    for compat in (True, False):
+        exp = oracle.mpeg_parse(small, reference_compat=compat, want_payload=False)
+        got = fp.mpeg.index_dev(ctx, d.ptr, total, reference_compat=compat)
+        assert got["ref_header"] == exp["ref_header"] and got["n_candidates"] == exp["n_candidates"]
+        assert np.array_equal(got["offsets"], translate(exp["offsets"])), compat
+    d.free()
+    ctx.trim()

@@ -294,3 +294,24 @@ def test_mono_unit_velocity_on_stereo_bus(ctx):
         got, gpos = gpu_render(ctx, voices, 2, frames)
         assert np.array_equal(got, exp), frames
         assert all(same_pos(a, b) for a, b in zip(gpos, epos))
+
+
+def test_c3_all_4096_voices_16k_frames_vs_oracle(ctx):
+    """SURVEY §8(d) C3 at the full voice count, generated as specified (clips from X128P::new(0xC3_0000 + v), gains and
+    velocities from X128P::new(0xC3): odd voices interpolate at 0.5..1.5), over the frames the oracle finishes in
+    seconds: 4,096 voices x 16,384 frames against Conductor::coordinate (engine.rs:46-81, 386-448)"""
+    import synth
+    nv, frames = synth.C3_VOICES, 1 << 14
+    params = synth.c3_voice_params(nv)
+    clips = []
+    for v in range(nv):
+        n = synth.c3_clip_frames(v, frames) * 2                       # stereo samples
+        raw = oracle.Rng(0xC30000 + v).fill_u64((n + 3) // 4)         # successive next_u64 bytes, little-endian
+        clips.append(raw.view(np.int16)[:n].copy())
+    tracks = [ap.Track.from_host(ctx, c, 2) for c in clips]
+    vp = [ap.VoiceParams(v, True, 0.0, params[v][0], params[v][1]) for v in range(nv)]
+    bus, after = ap.render(ctx, tracks, vp, 2, frames)
+    exp, epos = oracle_render([V(clips[v], 2, params[v][0], params[v][1]) for v in range(nv)], 2, frames)
+    assert np.array_equal(bus, exp), int(np.argmax(bus != exp))
+    assert all(same_pos(a.position, b) for a, b in zip(after, epos))
+    assert int(np.count_nonzero(bus)) > frames                         # not a silent bus
