@@ -140,9 +140,15 @@ pcm16_decode_batch(const JobDev* __restrict__ jobs, const TileRef* __restrict__ 
     }
 }
 
-// ---- K2: packed 24-bit -> i32 (sign-extended) or i16 (top 16 bits); extension, not in the reference.
-// One thread turns 12 source bytes (4 samples) into one 16-byte (i32) or 8-byte (i16) store; the
-// 12-byte stride is staged through shared memory so that global loads stay 128-bit and coalesced.
+// ---- K2: packed 24-bit -> i32 (sign-extended) or i16 (top 16 bits); extension, not in the reference (SURVEY §8 a4,
+// north_star: "24-bit packed samples byte-swapped and unpacked in registers or shared-memory-staged tiles").
+// A tile is 4,096 samples = 12,288 source bytes.  Global -> shared by 16-byte cp.async (LDGSTS, L1 bypassed) from the
+// 16-byte boundary below the tile, two tiles deep, so the loads of tile i+1 are in flight while tile i is unpacked.  A
+// thread unpacks 4 consecutive samples (12 bytes) per 1,024-sample slab: four conflict-free LDS.32 (the 12-byte thread
+// stride is 3 banks), three funnel shifts that remove the tile's byte misalignment (0..3, the rest is whole words), and
+// ONE PRMT per sample: the selector picks the three bytes in endian order and replicates the sign of the top byte
+// (selector nibble | 8), i.e. byte swap and sign extension are the same instruction.  Stores are 16 bytes (i32) or
+// 8 bytes (i16) per thread, coalesced.  Roofline: HBM, 3 B read + 4 B (or 2 B) written per sample.
 struct Job24Dev {
     const uint8_t* src;
     void* dst;
@@ -152,12 +158,21 @@ struct Job24Dev {
 };
 
 constexpr int k24Threads = 256;
-constexpr int k24SamplesPerTile = k24Threads * 4;       // 1024 samples = 3072 source bytes
+constexpr int k24Slabs = 4;                                          // 1,024-sample slabs per tile
+constexpr int k24SamplesPerTile = k24Threads * 4 * k24Slabs;         // 4,096 samples = 12,288 source bytes
+constexpr int k24StageBytes = k24SamplesPerTile * 3 + 32;            // + the misalignment in front, + the last vector's slack
+constexpr int k24CtasPerSm = 6;
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
 
 __global__ void __launch_bounds__(k24Threads)
 pcm24_unpack_batch(const Job24Dev* __restrict__ jobs, const TileRef* __restrict__ tiles, uint32_t n_tiles) {
-    __shared__ __align__(16) uint32_t stage[k24SamplesPerTile * 3 / 4 + 8];          // 3072 B + slack for misalignment
-    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    __shared__ __align__(16) uint8_t stage[2][k24StageBytes];
+    auto issue = [&](uint32_t t, int buf) {
         const TileRef ref = tiles[t];
         const Job24Dev job = jobs[ref.job];
         const uint64_t s0 = (uint64_t)ref.tile * k24SamplesPerTile;
@@ -165,49 +180,65 @@ pcm24_unpack_batch(const Job24Dev* __restrict__ jobs, const TileRef* __restrict_
         const uint32_t ns = left < (uint64_t)k24SamplesPerTile ? (uint32_t)left : (uint32_t)k24SamplesPerTile;
         const uint8_t* base = job.src + s0 * 3;
         const uint32_t mis = (uint32_t)((uintptr_t)base & 15);
-        const uint4* vsrc = reinterpret_cast<const uint4*>(base - mis);
-        const uint32_t nbytes = ns * 3 + mis;
-        const uint32_t nvec = (nbytes + 15) / 16;
-        __syncthreads();                                               // previous tile fully consumed
-        for (uint32_t i = threadIdx.x; i < nvec; i += k24Threads) {
-            uint4 v = blast::ld_stream(vsrc + i);
-            reinterpret_cast<uint4*>(stage)[i] = v;
-        }
-        __syncthreads();
-        const uint8_t* sb = reinterpret_cast<const uint8_t*>(stage) + mis;
+        const uint8_t* vsrc = base - mis;
+        const uint32_t nvec = (ns * 3 + mis + 15) / 16;
+        const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(stage[buf]);
+        for (uint32_t i = threadIdx.x; i < nvec; i += k24Threads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + i * 16u), "l"(vsrc + (size_t)i * 16) : "memory");
+    };
+    uint32_t t = blockIdx.x;
+    int buf = 0;
+    if (t < n_tiles) issue(t, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (; t < n_tiles; t += gridDim.x, buf ^= 1) {
+        if (t + gridDim.x < n_tiles) issue(t + gridDim.x, buf ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();                                               // tile t is staged
+        const TileRef ref = tiles[t];
+        const Job24Dev job = jobs[ref.job];
+        const uint64_t s0 = (uint64_t)ref.tile * k24SamplesPerTile;
+        const uint64_t left = job.n_samples - s0;
+        const uint32_t ns = left < (uint64_t)k24SamplesPerTile ? (uint32_t)left : (uint32_t)k24SamplesPerTile;
+        const uint32_t mis = (uint32_t)((uintptr_t)(job.src + s0 * 3) & 15);
+        const uint32_t sh = (mis & 3u) * 8u;                           // byte misalignment inside a word: uniform over the tile
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage[buf]) + (mis & ~3u);
         const bool be = job.big_endian != 0;
-        const uint32_t q = threadIdx.x * 4;
-        if (q < ns) {
-            int32_t out[4];
+        // selectors over the funnel-shifted words (y0, y1, y2) = the thread's 12 bytes b0..b11; nibble | 8 = sign of that byte
+        const uint32_t w0 = be ? 0x8012u : 0xA210u, w1 = be ? 0xB345u : 0xD543u, w2 = be ? 0xA234u : 0xC432u, w3 = be ? 0x9123u : 0xB321u;
+        const uint32_t h01 = be ? 0x3401u : 0x5421u, h23 = be ? 0x5623u : 0x7643u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (q + k < ns) {
-                    uint32_t b0 = sb[(q + k) * 3], b1 = sb[(q + k) * 3 + 1], b2 = sb[(q + k) * 3 + 2];
-                    uint32_t u = be ? (b0 << 24) | (b1 << 16) | (b2 << 8) : (b2 << 24) | (b1 << 16) | (b0 << 8);
-                    out[k] = (int32_t)u >> 8;
-                } else {
-                    out[k] = 0;
-                }
-            }
+        for (int g = 0; g < k24Slabs; ++g) {
+            const uint32_t q = (uint32_t)g * (k24Threads * 4) + threadIdx.x * 4;       // first sample of this thread in the slab
+            if (q >= ns) break;
+            const uint32_t a = sbase + q * 3u;                         // word aligned: q * 3 is a multiple of 4
+            uint32_t x0, x1, x2, x3;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x0) : "r"(a));
+            asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(x1) : "r"(a));
+            asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(x2) : "r"(a));
+            asm volatile("ld.shared.u32 %0, [%1+12];" : "=r"(x3) : "r"(a));
+            const uint32_t y0 = __funnelshift_r(x0, x1, sh), y1 = __funnelshift_r(x1, x2, sh), y2 = __funnelshift_r(x2, x3, sh);
             if (job.out_kind == 0) {
+                const int4 o = make_int4((int32_t)prmt(y0, 0u, w0), (int32_t)prmt(y0, y1, w1), (int32_t)prmt(y1, y2, w2), (int32_t)prmt(y2, 0u, w3));
                 int32_t* d = reinterpret_cast<int32_t*>(job.dst) + s0 + q;
                 if (q + 4 <= ns && ((uintptr_t)d & 15) == 0) {
-                    *reinterpret_cast<int4*>(d) = make_int4(out[0], out[1], out[2], out[3]);
+                    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(d), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
                 } else {
-                    for (int k = 0; k < 4 && q + k < ns; ++k) d[k] = out[k];
+                    const int32_t v[4] = {o.x, o.y, o.z, o.w};
+                    for (int k = 0; k < 4 && q + k < ns; ++k) d[k] = v[k];
                 }
             } else {
+                const uint32_t p0 = prmt(y0, y1, h01), p1 = prmt(y1, y2, h23);   // two top-16 samples per word
                 int16_t* d = reinterpret_cast<int16_t*>(job.dst) + s0 + q;
                 if (q + 4 <= ns && ((uintptr_t)d & 7) == 0) {
-                    uint2 pk;
-                    pk.x = ((uint32_t)(out[0] >> 8) & 0xFFFF) | ((uint32_t)(out[1] >> 8) << 16);
-                    pk.y = ((uint32_t)(out[2] >> 8) & 0xFFFF) | ((uint32_t)(out[3] >> 8) << 16);
-                    *reinterpret_cast<uint2*>(d) = pk;
+                    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(d), "r"(p0), "r"(p1) : "memory");
                 } else {
-                    for (int k = 0; k < 4 && q + k < ns; ++k) d[k] = (int16_t)(out[k] >> 8);
+                    const uint32_t v[2] = {p0, p1};
+                    for (int k = 0; k < 4 && q + k < ns; ++k) d[k] = (int16_t)(v[k >> 1] >> ((k & 1) * 16));
                 }
             }
         }
+        __syncthreads();                                               // tile t consumed: its stage may be refilled
     }
 }
 
@@ -332,12 +363,25 @@ void blast_pcm_plan_destroy(blast_ctx* ctx, blast_pcm_plan* plan) {
 uint64_t blast_pcm_plan_words(const blast_pcm_plan* plan) { return plan ? plan->words : 0; }
 
 int blast_pcm_decode_dev(blast_ctx* ctx, const blast_pcm_job* jobs, uint32_t n_jobs) {
-    blast_pcm_plan* plan = nullptr;
-    int rc = blast_pcm_plan_create(ctx, jobs, n_jobs, &plan);
-    if (rc != BLAST_OK) return rc;
-    rc = run_plan(ctx, plan, ctx->stream);
-    blast_pcm_plan_destroy(ctx, plan);   // synchronises the stream first
-    return rc;
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_REQUIRE(jobs != nullptr || n_jobs == 0, BLAST_ERR_ARG, "blast_pcm_decode_dev: null jobs");
+    std::vector<JobDev> hj(n_jobs);
+    std::vector<TileRef> ht;
+    uint64_t words = 0;
+    if (int rc = fill_tables(jobs, n_jobs, hj.data(), ht, &words)) return rc;
+    if (ht.empty()) return BLAST_OK;
+    // the tables go into the context's grow-only scratch (shared with the 24-bit unpack): no cudaMalloc / cudaFree and no
+    // stream synchronisation once warm; the uploads come from pageable vectors, staged before cudaMemcpyAsync returns
+    JobDev* d_jobs = static_cast<JobDev*>(blast::scratch(ctx, 8, hj.size() * sizeof(JobDev)));
+    TileRef* d_tiles = static_cast<TileRef*>(blast::scratch(ctx, 9, ht.size() * sizeof(TileRef)));
+    if (!d_jobs || !d_tiles) return BLAST_ERR_CUDA;
+    BLAST_CUDA_TRY(cudaMemcpyAsync(d_jobs, hj.data(), hj.size() * sizeof(JobDev), cudaMemcpyHostToDevice, ctx->stream));
+    BLAST_CUDA_TRY(cudaMemcpyAsync(d_tiles, ht.data(), ht.size() * sizeof(TileRef), cudaMemcpyHostToDevice, ctx->stream));
+    const int grid = (int)std::min<uint64_t>(ht.size(), (uint64_t)ctx->sm_count * kCtasPerSm);
+    pcm16_decode_batch<<<grid, kThreads, 0, ctx->stream>>>(d_jobs, d_tiles, (uint32_t)ht.size());
+    BLAST_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    return BLAST_OK;
 }
 
 // Host-buffer batch decode.  Every file's payload is cut into pieces of <= 8 MiB; pieces are
@@ -492,21 +536,17 @@ int blast_pcm24_unpack_dev(blast_ctx* ctx, const blast_pcm24_job* jobs, uint32_t
         for (uint64_t t = 0; t < nt; ++t) ht.push_back(TileRef{j, (uint32_t)t});
     }
     if (ht.empty()) return BLAST_OK;
-    Job24Dev* d_jobs = nullptr;
-    TileRef* d_tiles = nullptr;
-    BLAST_CUDA_TRY(cudaMalloc(&d_jobs, hj.size() * sizeof(Job24Dev)));
-    BLAST_CUDA_TRY(cudaMalloc(&d_tiles, ht.size() * sizeof(TileRef)));
+    // tables live in the context's grow-only scratch (never cudaMalloc once warm); the uploads come from pageable
+    // vectors, which the runtime stages before cudaMemcpyAsync returns
+    Job24Dev* d_jobs = static_cast<Job24Dev*>(blast::scratch(ctx, 8, hj.size() * sizeof(Job24Dev)));
+    TileRef* d_tiles = static_cast<TileRef*>(blast::scratch(ctx, 9, ht.size() * sizeof(TileRef)));
+    if (!d_jobs || !d_tiles) return BLAST_ERR_CUDA;
     BLAST_CUDA_TRY(cudaMemcpyAsync(d_jobs, hj.data(), hj.size() * sizeof(Job24Dev), cudaMemcpyHostToDevice, ctx->stream));
     BLAST_CUDA_TRY(cudaMemcpyAsync(d_tiles, ht.data(), ht.size() * sizeof(TileRef), cudaMemcpyHostToDevice, ctx->stream));
-    int grid = (int)std::min<uint64_t>(ht.size(), (uint64_t)ctx->sm_count * 8);
+    int grid = (int)std::min<uint64_t>(ht.size(), (uint64_t)ctx->sm_count * k24CtasPerSm);
     pcm24_unpack_batch<<<grid, k24Threads, 0, ctx->stream>>>(d_jobs, d_tiles, (uint32_t)ht.size());
-    cudaError_t le = cudaGetLastError();
+    BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
-    cudaError_t se = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_jobs);
-    cudaFree(d_tiles);
-    if (le != cudaSuccess) return blast::set_error(BLAST_ERR_CUDA, "pcm24 launch failed: %s", cudaGetErrorString(le));
-    if (se != cudaSuccess) return blast::set_error(BLAST_ERR_CUDA, "pcm24 kernel failed: %s", cudaGetErrorString(se));
     return BLAST_OK;
 }
 

@@ -120,9 +120,13 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
 }
 // One thread, after a CTA-level barrier that follows the CTA's bus writes of one (tile, voice group) work item:
 // the CTA that flushes the last group of a tile publishes the tile to the rank that will reduce it.
+// The count is a RELEASE atomic (MEMBAR.ALL.GPU + ATOMG): unlike __threadfence() it does not invalidate the SM's L1
+// (CCTL.IVALL), which the render's producer warps keep warm with voice rows and tile records.  Only the CTA that
+// completes a tile pays the acquire side (the fence after the atomic makes the other CTAs' bus writes part of what its
+// system-scope flag store releases).
 __device__ __forceinline__ void sink_tile_flushed(const BusSink& s, uint32_t tile, uint32_t n_groups) {
-    __threadfence();
-    const uint32_t prev = atomicAdd(s.tile_count + tile, 1u);
+    uint32_t prev;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(s.tile_count + tile) : "memory");
     if (prev + 1u == n_groups) {
         __threadfence_system();
         st_release_sys(s.ready_at[tile % s.world] + tile, s.step);
@@ -188,8 +192,7 @@ __device__ __noinline__ void k4_reduce_tile(const BusSink& s, uint32_t tile) {
     sink_reduce_tile(s, tile, threadIdx.x, 256u, [] { consumer_bar(); });
 }
 __device__ __noinline__ void k4_tile_flushed(const BusSink& s, uint32_t tile, uint32_t n_groups) {
-    consumer_bar();
-    if (threadIdx.x == 0) sink_tile_flushed(s, tile, n_groups);
+    sink_tile_flushed(s, tile, n_groups);
 }
 
 // ---------------------------------------------------------------- K3a: Seq event scan (processes.rs:69-90)
@@ -852,7 +855,7 @@ struct StageMeta {            // written by the producer before it arrives on th
 static_assert(sizeof(StageMeta) == 96, "StageMeta layout");
 constexpr size_t kMetaStride = 96;
 constexpr size_t kTmaSmem = (size_t)kStages * kStageBytes + kStages * kMetaStride + 2 * kStages * sizeof(uint64_t) +
-                            (size_t)kStages * kMaxPieces * sizeof(uint4);
+                            (size_t)kStages * kMaxPieces * sizeof(uint4) + 16;     // + the consumers' pending-tile word
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -985,39 +988,68 @@ __device__ __forceinline__ void consume_stereo_unit2(uint32_t stage_addr, uint32
     for (int j = 0; j < kFPT; ++j) add(x[j], gain1, acc[j][0], acc[j][1]);
 }
 
+// (a * s, b * s), each rounded once, issued as an FMA with a -0.0 addend that only exists at run time (a kernel
+// parameter): x * s + (-0.0) == rn(x * s) for every x and s (signed zeros, infinities, NaNs and denormals included).
+// As FMAs the products cannot be contracted with the packed add that follows them — ptxas turns mul.rn.f32x2 +
+// add.rn.f32x2 into FFMA2 even under -fmad=false, which would round `s0 * (1 - frac) + s1 * frac` once instead of three
+// times (engine.rs:430-438) — so the interpolation of a stereo frame is FFMA2, FFMA2, FADD2 and the gain a fourth FFMA2.
+__device__ __forceinline__ void mulz2(float a, float b, float s, float nz, float& x, float& y) {
+    asm("{\n\t.reg .b64 t, u, v;\n\tmov.b64 t, {%2, %3};\n\tmov.b64 u, {%4, %4};\n\tmov.b64 v, {%5, %5};\n\tfma.rn.f32x2 t, t, u, v;\n\tmov.b64 {%0, %1}, t;\n\t}"
+        : "=f"(x), "=f"(y) : "f"(a), "f"(b), "f"(s), "f"(nz));
+}
+__device__ __forceinline__ void add2(float a, float b, float c, float d, float& x, float& y) {
+    asm("{\n\t.reg .b64 t, u;\n\tmov.b64 t, {%2, %3};\n\tmov.b64 u, {%4, %5};\n\tadd.rn.f32x2 t, t, u;\n\tmov.b64 {%0, %1}, t;\n\t}"
+        : "=f"(x), "=f"(y) : "f"(a), "f"(b), "f"(c), "f"(d));
+}
+// one interpolated stereo frame: s0 * (1 - frac) + s1 * frac per channel, four separately rounded operations, then
+// (x * gain) as i16 (engine.rs:430-442)
+__device__ __forceinline__ void lerp_math(uint32_t w0, uint32_t w1, float frac, float om, float gain, float nz,
+                                          int32_t& al, int32_t& ar) {
+    float l0, r0, l1, r1, a0, b0, a1, b1, x, y;
+    unpack_pair(w0, l0, r0);
+    unpack_pair(w1, l1, r1);
+    mulz2(l0, r0, om, nz, a0, b0);
+    mulz2(l1, r1, frac, nz, a1, b1);
+    add2(a0, b0, a1, b1, x, y);
+    mulz2(x, y, gain, nz, a0, b0);
+    al += f2i16_sat(a0);
+    ar += f2i16_sat(b0);
+}
 // any velocity inside one arithmetic segment with positions in [0, 2^24)
-__device__ __forceinline__ void lerp_frame(uint32_t w0, uint32_t w1, uint32_t fbits, float scale, float gain,
+__device__ __forceinline__ void lerp_frame(uint32_t w0, uint32_t w1, uint32_t fbits, float scale, float gain, float nz,
                                            int32_t& al, int32_t& ar) {
     // fract = position - trunc(position), exactly (engine.rs:433); fbits < 2^24 so I2FP is exact
     const float frac = __fmul_rn(__int2float_rn((int)fbits), scale);
-    const float om = __fsub_rn(1.0f, frac);
-    float l0, r0, l1, r1, a0, b0, a1, b1;
-    unpack_pair(w0, l0, r0);
-    unpack_pair(w1, l1, r1);
-    mul2(l0, r0, om, a0, b0);
-    mul2(l1, r1, frac, a1, b1);
-    gain_cast_add(__fadd_rn(a0, a1), __fadd_rn(b0, b1), gain, al, ar);
+    lerp_math(w0, w1, frac, __fsub_rn(1.0f, frac), gain, nz, al, ar);
 }
 
+// The fraction without a conversion: with sh <= 23 fraction bits, (q & mask) | (150 - sh) << 23 is the float
+// 2^(23-sh) + fract, so fract = that - 2^(23-sh) and 1 - fract = (2^(23-sh) + 1) - that, both exact: one LOP3 and two
+// FADDs instead of LOP + I2FP (quarter rate) + FMUL + FSUB.
 template <bool kFull>
-__device__ __forceinline__ void consume_stereo_lerp(uint32_t stage_addr, const StageMeta& m, int32_t (&acc)[kFPT][2]) {
+__device__ __forceinline__ void consume_stereo_lerp(uint32_t stage_addr, const StageMeta& m, float nz, int32_t (&acc)[kFPT][2]) {
     const uint32_t mask = (1u << m.sh) - 1u;
     const uint32_t sbase = stage_addr + m.byte_off - m.base_idx * 4u;
     const int32_t q0 = m.q0, d = m.d;
     const uint32_t sh = m.sh;
-    const float scale = m.scale, gain = m.gain;
+    const float gain = m.gain;
+    const uint32_t magic = (150u - sh) << 23;
+    const float neg_c = -__uint_as_float(magic), one_c = __fadd_rn(__uint_as_float(magic), 1.0f);
     if (kFull) {
         uint32_t w0[kFPT], w1[kFPT], fb[kFPT];
 #pragma unroll
         for (int j = 0; j < kFPT; ++j) {
             const uint32_t q = (uint32_t)(q0 + (int32_t)(threadIdx.x + j * kConsumers) * d);
             const uint32_t a = sbase + (q >> sh) * 4u;
-            fb[j] = q & mask;
+            fb[j] = (q & mask) | magic;
             w0[j] = lds_u32(a);
             w1[j] = lds_u32(a + 4u);
         }
 #pragma unroll
-        for (int j = 0; j < kFPT; ++j) lerp_frame(w0[j], w1[j], fb[j], scale, gain, acc[j][0], acc[j][1]);
+        for (int j = 0; j < kFPT; ++j) {
+            const float v = __uint_as_float(fb[j]);
+            lerp_math(w0[j], w1[j], __fadd_rn(v, neg_c), __fsub_rn(one_c, v), gain, nz, acc[j][0], acc[j][1]);
+        }
     } else {
         const uint32_t fa = m.frange & 0xFFFF, fe = m.frange >> 16, span = fe - fa;
         const uint32_t j_lo = fa / kConsumers, j_hi = (fe - 1) / kConsumers;
@@ -1028,7 +1060,8 @@ __device__ __forceinline__ void consume_stereo_lerp(uint32_t stage_addr, const S
             if ((fl - fa) < span) {
                 const uint32_t q = (uint32_t)(q0 + (int32_t)fl * d);
                 const uint32_t a = sbase + (q >> sh) * 4u;
-                lerp_frame(lds_u32(a), lds_u32(a + 4u), q & mask, scale, gain, acc[j][0], acc[j][1]);
+                const float v = __uint_as_float((q & mask) | magic);
+                lerp_math(lds_u32(a), lds_u32(a + 4u), __fadd_rn(v, neg_c), __fsub_rn(one_c, v), gain, nz, acc[j][0], acc[j][1]);
             }
         }
     }
@@ -1041,7 +1074,7 @@ __device__ __forceinline__ void consume_stereo_lerp(uint32_t stage_addr, const S
 // C3 + Seq, where the tile after a retrigger crosses ~20 binades), the loads of four frames are issued back to back,
 // and a frame outside every audible piece reads as the zero frame ((0 * gain) as i16 == 0, NaN / inf gains included).
 template <bool kLerp>
-__device__ __forceinline__ void consume_stereo_multi(uint32_t stage_addr, const StageMeta& m, uint32_t ptab, uint32_t n_p,
+__device__ __forceinline__ void consume_stereo_multi(uint32_t stage_addr, const StageMeta& m, uint32_t ptab, uint32_t n_p, float nz,
                                                      int32_t (&acc)[kFPT][2]) {
     const uint32_t sbase = stage_addr + m.byte_off - m.base_idx * 4u;
     const float gain = m.gain;
@@ -1077,7 +1110,7 @@ __device__ __forceinline__ void consume_stereo_multi(uint32_t stage_addr, const 
 #pragma unroll
         for (int jj = 0; jj < kHalf; ++jj) {
             if (kLerp) {
-                lerp_frame(w0[jj], w1[jj], fb[jj], sc[jj], gain, acc[h + jj][0], acc[h + jj][1]);
+                lerp_frame(w0[jj], w1[jj], fb[jj], sc[jj], gain, nz, acc[h + jj][0], acc[h + jj][1]);
             } else {
                 float l, r;
                 unpack_pair(w0[jj], l, r);
@@ -1150,12 +1183,12 @@ __device__ __forceinline__ void consume_generic(const StageMeta& m, uint32_t sta
 // bubble per item (as one CTA per item this cost ~11 us per CTA round: C2's mix ran at 5.3 TB/s, C3 at 6.7).  A
 // kModeFlush item at the end of each work item makes the consumers add their accumulators into the bus.
 template <int OC>
-__global__ void __launch_bounds__(kTmaThreads, 3)
+__global__ void __launch_bounds__(kTmaThreads)
 voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t voices_per_group,
                      uint32_t n_groups, const Seg* __restrict__ segs, const uint32_t* __restrict__ nsegs,
                      const TileRec* __restrict__ recs, uint32_t frames, int32_t* __restrict__ bus, int use_atomic,
                      const uint32_t* __restrict__ err, const uint32_t seg_cap, uint32_t* __restrict__ work,
-                     const __grid_constant__ BusSink sink) {
+                     const __grid_constant__ BusSink sink, const float nz) {
     extern __shared__ __align__(128) uint8_t smem[];
     if (*err) return;                                           // truncated trajectories must not be rendered (uniform exit)
     uint8_t* stages = smem;
@@ -1342,7 +1375,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                                     m.a0_off = m.byte_off + (f2u_sat(p_a) - idx_lo - fa) * 4u;
                                 } else if (v.vel != 1.0f && d != 0) {
                                     const uint32_t eb = (__float_as_uint(scale) >> 23) & 0xFF;     // scale = 2^(eb-127)
-                                    if (eb >= 96 && eb <= 127) {
+                                    if (eb >= 104 && eb <= 127) {             // <= 23 fraction bits: consume_stereo_lerp's fraction trick
                                         path = kPathStereoLerp;
                                         m.sh = 127 - eb;
                                         const int32_t qa = __float2int_rz(__fmul_rn(p_a, __uint_as_float((127u + m.sh) << 23)));
@@ -1580,6 +1613,18 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
     constexpr uint32_t kMetaOff = (uint32_t)kStages * kStageBytes, kFullOff = kMetaOff + (uint32_t)(kStages * kMetaStride),
                        kEmptyOff = kFullOff + (uint32_t)kStages * 8u;
     uint32_t st = 0, phase = 0;
+    // thread 0: the tile of this CTA's last flush, not yet counted.  The count is a release (it waits for the bus writes
+    // before it), so it is made one work item later — at the next flush, before a reduction, at the end — when those
+    // writes have long landed and the wait costs nothing.  A CTA never waits for a peer while it holds one back.
+    // (kept in shared memory: the consumer loop has no register to spare at 72)
+    volatile uint32_t* pending = reinterpret_cast<volatile uint32_t*>(ptabs + kStages * kMaxPieces);
+    if (threadIdx.x == 0) *pending = 0xFFFFFFFFu;
+    auto publish_pending = [&]() {
+        if (threadIdx.x == 0) {
+            const uint32_t t = *pending;
+            if (t != 0xFFFFFFFFu) { k4_tile_flushed(sink, t, n_groups); *pending = 0xFFFFFFFFu; }
+        }
+    };
     for (;;) {
         mbar_wait_a(sm0 + kFullOff + st * 8u, phase);
         const uint32_t stage_addr = sm0 + st * (uint32_t)kStageBytes;
@@ -1599,9 +1644,13 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
             phase ^= (st == 0) ? 1u : 0u;
             continue;
         }
-        if ((mode & 0xFF) == kModeEnd) break;
+        if ((mode & 0xFF) == kModeEnd) {
+            if (sink.world) publish_pending();
+            break;
+        }
         if ((mode & 0xFF) == kModeFlush) {
             // end of a work item: a0_off = first frame of its tile, frange = frames in it
+            if (sink.world) publish_pending();
 #pragma unroll
             for (int j = 0; j < kFPT; ++j) {
                 const uint32_t fl = threadIdx.x + j * kConsumers;
@@ -1615,8 +1664,12 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                     }
                 }
             }
-            if (sink.world) k4_tile_flushed(sink, a0_off / (uint32_t)kFT, n_groups);   // the tile's last voice group publishes it
+            if (sink.world) {                                    // every consumer's bus writes are issued: thread 0 may count the item
+                consumer_bar();
+                if (threadIdx.x == 0) *pending = a0_off / (uint32_t)kFT;
+            }
         } else if ((mode & 0xFF) == kModeReduce) {
+            publish_pending();
             k4_reduce_tile(sink, a0_off);
         } else {
             const uint32_t path = (mode >> 8) & 0xFF;
@@ -1628,13 +1681,13 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                 else { if (g1) consume_stereo_unit<false, true>(stage_addr, a0_off, gain, frange, a2); else consume_stereo_unit<false, false>(stage_addr, a0_off, gain, frange, a2); }
             } else if (OC == 2 && path == kPathStereoLerp) {
                 auto& a2 = reinterpret_cast<int32_t (&)[kFPT][2]>(acc);
-                if (fullr) consume_stereo_lerp<true>(stage_addr, *mp, a2);
-                else consume_stereo_lerp<false>(stage_addr, *mp, a2);
+                if (fullr) consume_stereo_lerp<true>(stage_addr, *mp, nz, a2);
+                else consume_stereo_lerp<false>(stage_addr, *mp, nz, a2);
             } else if (OC == 2 && path == kPathStereoMulti) {
                 auto& a2 = reinterpret_cast<int32_t (&)[kFPT][2]>(acc);
                 const uint32_t ptab = smem_u32(ptabs + st * kMaxPieces);
-                if (frange & 1u) consume_stereo_multi<true>(stage_addr, *mp, ptab, a0_off, a2);
-                else consume_stereo_multi<false>(stage_addr, *mp, ptab, a0_off, a2);
+                if (frange & 1u) consume_stereo_multi<true>(stage_addr, *mp, ptab, a0_off, nz, a2);
+                else consume_stereo_multi<false>(stage_addr, *mp, ptab, a0_off, nz, a2);
             } else if ((mode & 0xFF) == kModeStaged) {
                 consume_generic<OC, true>(*mp, stage_addr, mp->f0, acc);
             } else {
@@ -1931,11 +1984,11 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         if (oc == 1) {
             BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
             voice_render_mix_tma<1><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(rb.d_voices, n_voices, per_group, groups, rb.d_segs,
-                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, d_err, rb.seg_cap, d_work, sink);
+                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, d_err, rb.seg_cap, d_work, sink, -0.0f);
         } else {
             BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
             voice_render_mix_tma<2><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(rb.d_voices, n_voices, per_group, groups, rb.d_segs,
-                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, d_err, rb.seg_cap, d_work, sink);
+                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, d_err, rb.seg_cap, d_work, sink, -0.0f);
         }
     } else {
 #define BLAST_LAUNCH_MIX(OCV)                                                                              \

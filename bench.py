@@ -544,10 +544,13 @@ def cpu_baseline(view, image_len, n_files, gains, threads: int, budget_s: float,
     render loop) on a bounded sample; threads > 1 shard the files / voices (generous comparison)"""
     import oracle
     oracle.lib()
+    # the cost per file grows with the batch (the frame -> channel -> voice loop strides over every track), so the sample
+    # is sized from a probe batch and capped: the run must fit the budget
+    probe = min(n_files, 8)
     t0 = time.perf_counter()
-    _cpu_decode_mix(view, image_len, [0], gains, mix)
-    per_file = max(1e-4, time.perf_counter() - t0)
-    n = int(max(threads, min(n_files, budget_s / per_file * threads)))
+    _cpu_decode_mix(view, image_len, list(range(probe)), gains, mix)
+    per_file = max(1e-4, (time.perf_counter() - t0) / probe)
+    n = int(max(threads, min(n_files, 256 * threads, budget_s / (2.0 * per_file) * threads)))
     n = max(threads, n // threads * threads)
     n = min(n, n_files)
     idx = list(range(n))

@@ -196,8 +196,9 @@ def test_offsets_beyond_4GiB(ctx):
     total = (5 << 30) + 123_457
     rng = np.random.default_rng(0x5C5)
     wins = []                                   # (start in the large stream, bytes)
-    for k, start in enumerate([0, (1 << 32) - (1 << 20) - 77, total - 1100 - (2 << 20) - 33]):
+    for k in range(3):
         w = synth.mp3_like(0xC50 + k, (2 << 20) // 418, tail=0)
+        start = [0, (1 << 32) - (1 << 20) - 77, total - 1100 - w.size][k]
         w[int(rng.integers(1000, 5000))] = 0xFF            # some stray sync bytes
         if k == 1:
             w[100_000:100_300] = 0xFF                      # a 0xFF run in the cluster that straddles 2^32
