@@ -13,6 +13,7 @@
 // (~25 32-bit ops per draw) against 8 or 16 bytes written per draw: HBM-write-bound when the
 // streams are materialised, ALU-bound when only checksums are kept.  Draws are staged through a
 // padded shared-memory tile and written out as 128-byte contiguous rows per stream.
+#include <algorithm>
 #include <vector>
 
 #include "blast_internal.h"
@@ -316,6 +317,32 @@ int launch_fill(blast_ctx* ctx, U128* st, uint64_t n_streams, uint64_t draws, in
     return BLAST_OK;
 }
 
+// resident warps per SM of the fill kernel for these outputs (shared memory bound when something is materialised)
+int fill_warps_per_sm(bool raw, bool ranged, bool checks) {
+    const int sel = (raw ? 1 : 0) | (ranged ? 2 : 0) | (checks ? 4 : 0);
+    const size_t smem = (size_t)kWarps * 32 * kPitch * sizeof(uint64_t) * ((raw ? 1 : 0) + (ranged ? 1 : 0));
+    int blocks = 0;
+#define BLAST_OCC(R, G, K)                                                                                   \
+    do {                                                                                                     \
+        auto kern = x128p_streams<R, G, K>;                                                                  \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, kWarps * 32, smem) != cudaSuccess) blocks = 0; \
+    } while (0)
+    switch (sel) {
+        case 0: BLAST_OCC(false, false, false); break;
+        case 1: BLAST_OCC(true, false, false); break;
+        case 2: BLAST_OCC(false, true, false); break;
+        case 3: BLAST_OCC(true, true, false); break;
+        case 4: BLAST_OCC(false, false, true); break;
+        case 5: BLAST_OCC(true, false, true); break;
+        case 6: BLAST_OCC(false, true, true); break;
+        default: BLAST_OCC(true, true, true); break;
+    }
+#undef BLAST_OCC
+    cudaGetLastError();
+    return std::max(1, blocks) * kWarps;
+}
+
 }  // namespace
 
 int blast_x128p_fill_dev(blast_ctx* ctx, blast_x128p* d_states, uint64_t n_streams, uint64_t draws_per_stream,
@@ -331,11 +358,21 @@ int blast_x128p_fill_dev(blast_ctx* ctx, blast_x128p* d_states, uint64_t n_strea
     // 22 % of the resident threads, each a serial chain of 65,536 draws).  The generator is GF(2)-linear, so a stream
     // can be cut into `split` sub-streams that start at J^k * state (J = T^(draws/split)); draw j of sub-stream k is
     // draw k*draws/split + j of the stream and lands at the same address.
+    // The split also sets how the warps fall into waves: all warps do the same work, so the kernel takes
+    // ceil(warps / resident warps) rounds of draws / split draws each.  With 67 KB of staging per block only 24 warps
+    // are resident per SM: C4's raw fill at split 4 was 8,192 warps in 2.3 -> 3 rounds (8.0 ms); at split 64 it is
+    // 36.9 -> 37 rounds of a sixteenth the length.  Take the split with the least total, the smaller one when within 2 %.
     uint32_t split = 1;
-    const uint64_t want_threads = (uint64_t)ctx->sm_count * 1536;
-    while (split < 64 && n_streams * split < want_threads && draws_per_stream % (2ull * split) == 0 &&
-           draws_per_stream / (2ull * split) >= 1024)
-        split *= 2;
+    {
+        const uint64_t resident = (uint64_t)fill_warps_per_sm(d_raw != nullptr, d_ranged != nullptr, d_checks != nullptr) * ctx->sm_count;
+        double best = 0.0;
+        for (uint32_t sp = 1; sp <= 64; sp *= 2) {
+            if (sp > 1 && (draws_per_stream % sp != 0 || draws_per_stream / sp < 1024)) break;
+            const uint64_t warps = (n_streams * sp + 31) / 32;
+            const double cost = (double)((warps + resident - 1) / resident) * (double)(draws_per_stream / sp);
+            if (sp == 1 || cost < best * 0.98) { best = cost; split = sp; }
+        }
+    }
     if (split == 1) return launch_fill(ctx, st, n_streams, draws_per_stream, lower, range, d_raw, d_ranged, d_checks);
 
     const uint64_t sub = draws_per_stream / split, n_sub = n_streams * split;
