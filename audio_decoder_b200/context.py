@@ -166,3 +166,14 @@ class Context:
     def to_device(self, arr: np.ndarray) -> DevBuf:
         a = np.ascontiguousarray(arr)
         return self.alloc(max(a.nbytes, 1)).upload(a)
+
+
+class BorrowedContext(Context):
+    """A blast_ctx owned by somebody else (a blast_group member): same methods, never destroyed from here."""
+
+    def __init__(self, lib, handle: int):
+        self.lib = lib
+        self.h = handle
+
+    def close(self):
+        self.h = None

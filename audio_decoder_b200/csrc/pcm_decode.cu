@@ -155,6 +155,8 @@ struct Job24Dev {
     uint64_t n_samples;
     uint32_t big_endian;
     uint32_t out_kind;
+    uint32_t tile0;            // index of the job's first tile in the batch (ascending: tiles find their job by bisection)
+    uint32_t pad;
 };
 
 constexpr int k24Threads = 256;
@@ -169,13 +171,26 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     return r;
 }
 
+// the job of tile t: the last one whose first tile is <= t (the job table is a few KB and stays in L1 / L2; a tile table
+// of the whole batch — a quarter of a million entries for C2 — would have to be built and uploaded by the host per call)
+__device__ __forceinline__ uint32_t job_of_tile(const Job24Dev* __restrict__ jobs, uint32_t n_jobs, uint32_t t) {
+    uint32_t lo = 0, hi = n_jobs;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (jobs[mid].tile0 <= t) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(k24Threads)
-pcm24_unpack_batch(const Job24Dev* __restrict__ jobs, const TileRef* __restrict__ tiles, uint32_t n_tiles) {
+pcm24_unpack_batch(const Job24Dev* __restrict__ jobs, uint32_t n_jobs, uint32_t n_tiles) {
     __shared__ __align__(16) uint8_t stage[2][k24StageBytes];
+    __shared__ uint32_t s_job[2];
     auto issue = [&](uint32_t t, int buf) {
-        const TileRef ref = tiles[t];
-        const Job24Dev job = jobs[ref.job];
-        const uint64_t s0 = (uint64_t)ref.tile * k24SamplesPerTile;
+        const uint32_t j = job_of_tile(jobs, n_jobs, t);
+        if (threadIdx.x == 0) s_job[buf] = j;                          // read after the barrier that follows the copies
+        const Job24Dev job = jobs[j];
+        const uint64_t s0 = (uint64_t)(t - job.tile0) * k24SamplesPerTile;
         const uint64_t left = job.n_samples - s0;
         const uint32_t ns = left < (uint64_t)k24SamplesPerTile ? (uint32_t)left : (uint32_t)k24SamplesPerTile;
         const uint8_t* base = job.src + s0 * 3;
@@ -195,9 +210,8 @@ pcm24_unpack_batch(const Job24Dev* __restrict__ jobs, const TileRef* __restrict_
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();                                               // tile t is staged
-        const TileRef ref = tiles[t];
-        const Job24Dev job = jobs[ref.job];
-        const uint64_t s0 = (uint64_t)ref.tile * k24SamplesPerTile;
+        const Job24Dev job = jobs[s_job[buf]];
+        const uint64_t s0 = (uint64_t)(t - job.tile0) * k24SamplesPerTile;
         const uint64_t left = job.n_samples - s0;
         const uint32_t ns = left < (uint64_t)k24SamplesPerTile ? (uint32_t)left : (uint32_t)k24SamplesPerTile;
         const uint32_t mis = (uint32_t)((uintptr_t)(job.src + s0 * 3) & 15);
@@ -523,28 +537,28 @@ int blast_pcm_decode_batch(blast_ctx* ctx, uint32_t n, const uint8_t* const* fil
 int blast_pcm24_unpack_dev(blast_ctx* ctx, const blast_pcm24_job* jobs, uint32_t n_jobs) {
     if (int rc = blast::bind(ctx)) return rc;
     BLAST_REQUIRE(jobs != nullptr || n_jobs == 0, BLAST_ERR_ARG, "blast_pcm24_unpack_dev: null jobs");
-    std::vector<Job24Dev> hj(n_jobs);
-    std::vector<TileRef> ht;
+    std::vector<Job24Dev> hj;
+    hj.reserve(n_jobs);
+    uint64_t n_tiles = 0;
     for (uint32_t j = 0; j < n_jobs; ++j) {
         const blast_pcm24_job& in = jobs[j];
         if (in.n_samples && (!in.d_src || !in.d_dst)) return blast::set_error(BLAST_ERR_ARG, "pcm24 job %u: null pointer", j);
         if (in.out_kind > 1) return blast::set_error(BLAST_ERR_ARG, "pcm24 job %u: out_kind must be 0 or 1", j);
         if ((uintptr_t)in.d_dst & (in.out_kind == 0 ? 3 : 1)) return blast::set_error(BLAST_ERR_ARG, "pcm24 job %u: misaligned d_dst", j);
-        hj[j] = Job24Dev{in.d_src, in.d_dst, in.n_samples, in.big_endian, in.out_kind};
-        uint64_t nt = (in.n_samples + k24SamplesPerTile - 1) / k24SamplesPerTile;
-        if (nt > 0xFFFFFFFFull) return blast::set_error(BLAST_ERR_CAPACITY, "pcm24 job %u too large", j);
-        for (uint64_t t = 0; t < nt; ++t) ht.push_back(TileRef{j, (uint32_t)t});
+        const uint64_t nt = (in.n_samples + k24SamplesPerTile - 1) / k24SamplesPerTile;
+        if (nt == 0) continue;                                         // empty jobs own no tile
+        if (n_tiles + nt > 0xFFFFFFFFull) return blast::set_error(BLAST_ERR_CAPACITY, "pcm24 batch too large");
+        hj.push_back(Job24Dev{in.d_src, in.d_dst, in.n_samples, in.big_endian, in.out_kind, (uint32_t)n_tiles, 0u});
+        n_tiles += nt;
     }
-    if (ht.empty()) return BLAST_OK;
-    // tables live in the context's grow-only scratch (never cudaMalloc once warm); the uploads come from pageable
-    // vectors, which the runtime stages before cudaMemcpyAsync returns
+    if (hj.empty()) return BLAST_OK;
+    // the job table lives in the context's grow-only scratch (never cudaMalloc once warm); the upload comes from a
+    // pageable vector, which the runtime stages before cudaMemcpyAsync returns
     Job24Dev* d_jobs = static_cast<Job24Dev*>(blast::scratch(ctx, 8, hj.size() * sizeof(Job24Dev)));
-    TileRef* d_tiles = static_cast<TileRef*>(blast::scratch(ctx, 9, ht.size() * sizeof(TileRef)));
-    if (!d_jobs || !d_tiles) return BLAST_ERR_CUDA;
+    if (!d_jobs) return BLAST_ERR_CUDA;
     BLAST_CUDA_TRY(cudaMemcpyAsync(d_jobs, hj.data(), hj.size() * sizeof(Job24Dev), cudaMemcpyHostToDevice, ctx->stream));
-    BLAST_CUDA_TRY(cudaMemcpyAsync(d_tiles, ht.data(), ht.size() * sizeof(TileRef), cudaMemcpyHostToDevice, ctx->stream));
-    int grid = (int)std::min<uint64_t>(ht.size(), (uint64_t)ctx->sm_count * k24CtasPerSm);
-    pcm24_unpack_batch<<<grid, k24Threads, 0, ctx->stream>>>(d_jobs, d_tiles, (uint32_t)ht.size());
+    const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * k24CtasPerSm);
+    pcm24_unpack_batch<<<grid, k24Threads, 0, ctx->stream>>>(d_jobs, (uint32_t)hj.size(), (uint32_t)n_tiles);
     BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
     return BLAST_OK;

@@ -552,6 +552,82 @@ __device__ __noinline__ uint32_t scan_voice(VoiceDev* __restrict__ voices, const
     return n;
 }
 
+// The piece table of one tile of a stereo voice on a stereo bus whose trajectory has several segments inside the tile
+// (binade crossings after a retrigger, a freeze, ...): every segment's part of the tile is a PIECE — frame range, integer
+// significand at tile frame 0, increment, fraction bits — and consecutive pieces whose source spans fit one stage together
+// form an ITEM that K4 stages with one bulk copy.  Layout in the voice's pool: per item one header row
+// {first source frame, last source frame, piece count, 0} followed by its piece rows {fa | fe << 16, q0, d, sh | silent << 8}
+// (what consume_stereo_multi reads).  Returns the rows used, 0 when the tile cannot be tabulated (a piece with a NaN or
+// negative position, more than kMaxPieces segments, a piece that does not fit a stage): K4 then cuts it itself.
+// rows == nullptr: count only.  *n_items_out = items written.
+constexpr int kMaxPieces = 32;                // pieces of one voice in one tile handled by a single staged item
+__device__ __forceinline__ bool tab_span_fits(const int16_t* smp, uint32_t lo, uint32_t hi, uint32_t stage_bytes) {
+    const unsigned long long b0 = (unsigned long long)smp + (unsigned long long)lo * 4ull;
+    const unsigned long long b1 = (unsigned long long)smp + ((unsigned long long)hi + 2ull) * 4ull;
+    return ((b1 + 15ull) & ~15ull) - (b0 & ~15ull) <= (unsigned long long)stage_bytes;
+}
+__device__ __noinline__ uint32_t build_tile_table(const Seg* __restrict__ sg, uint32_t nseg, uint32_t j0, uint32_t f0, uint32_t nf,
+                                                  uint32_t end, const int16_t* smp, uint32_t stage_bytes, uint4* rows,
+                                                  uint32_t* n_items_out) {
+    const uint32_t last_abs = f0 + nf - 1;
+    uint32_t used = 0, n_items = 0, n_in_item = 0, hdr_at = 0;
+    uint32_t lo_run = 0xFFFFFFFFu, hi_run = 0u;
+    auto close_item = [&]() {
+        if (n_in_item == 0) return;
+        if (lo_run != 0xFFFFFFFFu) {                               // something audible: keep the item
+            if (rows) rows[hdr_at] = make_uint4(lo_run, hi_run, n_in_item, 0u);
+            n_items += 1;
+        } else {
+            used = hdr_at;                                         // a run of silent pieces: dropped (frames outside every piece read as zero)
+        }
+        n_in_item = 0;
+        lo_run = 0xFFFFFFFFu;
+        hi_run = 0u;
+    };
+    uint32_t n_pieces = 0;
+    for (uint32_t j = j0; j < nseg; ++j) {
+        const Seg g = sg[j];
+        if (j > j0 && g.step0 > last_abs) break;
+        if (++n_pieces > (uint32_t)kMaxPieces) return 0u;
+        const uint32_t nxt = (j + 1 < nseg) ? sg[j + 1].step0 : 0xFFFFFFFFu;
+        const uint32_t ls = max(g.step0, f0), le = min(nxt, f0 + nf);
+        const uint32_t fa = ls - f0, fe = le - f0;
+        const float p_a = seg_eval(g.p0, g.d, g.scale, ls - g.step0);
+        const float p_l = seg_eval(g.p0, g.d, g.scale, le - 1 - g.step0);
+        const bool weird = (p_a != p_a) || (p_l != p_l);
+        const uint32_t lo = f2u_sat(fminf(p_a, p_l)), hi = f2u_sat(fmaxf(p_a, p_l));
+        const bool silent = !weird && lo >= end;
+        uint32_t shv = 0;
+        int32_t q0v = 0;
+        if (!silent) {
+            if (weird || !(p_a >= 0.0f) || !(p_l >= 0.0f) || hi >= end) return 0u;
+            if (g.d != 0) {
+                const uint32_t eb = (__float_as_uint(g.scale) >> 23) & 0xFF;
+                if (eb < 96 || eb > 127) return 0u;
+                shv = 127 - eb;
+            } else {
+                const int E = (int)((__float_as_uint(p_a) >> 23) & 0xFF);
+                const int s_ = p_a == 0.0f ? 0 : max(0, 150 - E);
+                if (s_ > 31) return 0u;
+                shv = (uint32_t)s_;
+            }
+            q0v = __float2int_rz(__fmul_rn(p_a, __uint_as_float((127u + shv) << 23))) - (int32_t)fa * g.d;
+            if (!tab_span_fits(smp, lo, hi, stage_bytes)) return 0u;
+            // does the piece still fit the stage of the current item?
+            const uint32_t nlo = min(lo_run, lo), nhi = max(hi_run, hi);
+            if (n_in_item > 0 && lo_run != 0xFFFFFFFFu && !tab_span_fits(smp, nlo, nhi, stage_bytes)) close_item();
+        }
+        if (n_in_item == 0) { hdr_at = used; used += 1; }
+        if (!silent) { lo_run = min(lo_run, lo); hi_run = max(hi_run, hi); }
+        if (rows) rows[used] = make_uint4(fa | (fe << 16), (uint32_t)q0v, (uint32_t)g.d, shv | (silent ? 0x100u : 0u));
+        used += 1;
+        n_in_item += 1;
+    }
+    close_item();
+    *n_items_out = n_items;
+    return n_items ? used : 0u;
+}
+
 // K3: one WARP per voice.  Lane 0 walks the trajectory (scan_voice); then the 32 lanes write the voice's per-tile
 // records — the state of the voice at the first step of every tile, found by bisection in the segment list the warp has
 // just written (still in L1).  Layout [tile][voice] so that K4's staging loads are coalesced.  (As a serial loop in the
@@ -567,7 +643,8 @@ voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t f
                     const uint32_t seg_cap, const uint32_t oc, Split* __restrict__ splits,
                     uint32_t* __restrict__ nsplits, TileRec* __restrict__ recs, uint32_t n_tiles,
                     uint32_t n_voice_blocks, uint32_t* __restrict__ err_next, uint32_t* __restrict__ work,
-                    uint32_t* __restrict__ zero, size_t n_zero, const BusSink sink) {
+                    uint32_t* __restrict__ zero, size_t n_zero, const BusSink sink, uint4* __restrict__ pool,
+                    const uint32_t pool_rows, const uint32_t stage_bytes) {
     if (blockIdx.x >= n_voice_blocks) {
         // housekeeping blocks, concurrent with the walks: the next render's error word and K4's work counter, and the
         // int32 partial bus when K4 will accumulate with atomics (as stream memsets these were two more operations —
@@ -622,24 +699,53 @@ voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t f
     }
     if (!active) return;                                        // K4 never reads the records of an inactive voice
     const Seg* sg = sgw;
-    for (uint32_t t = lane; t < n_tiles; t += 32) {
-        const uint32_t st = t * (uint32_t)kFT * S;
-        uint32_t lo = 0, hi = n;                                // last j with sg[j].step0 <= st (sg[0].step0 == 0)
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (sg[mid].step0 <= st) lo = mid; else hi = mid;
+    // piece tables (stereo voice on a stereo bus, steps = frames): built here, where a warp per voice has the segments
+    // at hand, so that K4's single producer warp only bulk-copies them
+    const VoiceDev vd = voices[vi];
+    const bool tabulate = pool != nullptr && oc == 2 && vd.C == 2 && vd.nch == 2 && adv == 0 && S == 1;
+    uint4* vpool = pool ? pool + (size_t)vi * pool_rows : nullptr;
+    uint32_t pool_used = 0;                                     // warp-uniform
+    for (uint32_t t0 = 0; t0 < n_tiles; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        const bool in = t < n_tiles;
+        TileRec r{};
+        uint32_t j = 0, need = 0, n_it = 0, f0 = 0, nf = 0;
+        if (in) {
+            const uint32_t st = t * (uint32_t)kFT * S;
+            uint32_t lo = 0, hi = n;                            // last j with sg[j].step0 <= st (sg[0].step0 == 0)
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (sg[mid].step0 <= st) lo = mid; else hi = mid;
+            }
+            j = lo;
+            const Seg g = sg[j];
+            const uint32_t next = (j + 1 < n) ? sg[j + 1].step0 : 0xFFFFFFFFu;
+            uint32_t left = next - st;
+            if (left > 0xFFFFu) left = 0xFFFFu;              // only compared with kFT * S + 2 <= 16,386
+            r.p0 = seg_pos(g, st, adv);
+            r.d = g.d;
+            r.scale = g.scale;
+            r.meta = left | (j << 16);
+            f0 = t * (uint32_t)kFT;
+            nf = min((uint32_t)kFT, frames - f0);
+            if (tabulate && left < nf) need = build_tile_table(sg, n, j, f0, nf, vd.end, vd.smp, stage_bytes, nullptr, &n_it);
         }
-        const uint32_t j = lo;
-        const Seg g = sg[j];
-        const uint32_t next = (j + 1 < n) ? sg[j + 1].step0 : 0xFFFFFFFFu;
-        uint32_t left = next - st;
-        if (left > 0xFFFFu) left = 0xFFFFu;                  // only compared with kFT * S + 2 <= 16,386
-        TileRec r;
-        r.p0 = seg_pos(g, st, adv);
-        r.d = g.d;
-        r.scale = g.scale;
-        r.meta = left | (j << 16);
-        recs[(size_t)t * n_voices + vi] = r;
+        if (tabulate && __any_sync(0xFFFFFFFFu, need != 0u)) {
+            uint32_t inc = need;                                // exclusive scan over the lanes: where each tile's rows go
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, inc, dlt);
+                if ((int)lane >= dlt) inc += a;
+            }
+            const uint32_t at = pool_used + inc - need;
+            if (need != 0u && at + need <= pool_rows) {
+                build_tile_table(sg, n, j, f0, nf, vd.end, vd.smp, stage_bytes, vpool + at, &n_it);
+                r.d = (int32_t)at;                              // (neither field is read for a tile with several segments)
+                r.scale = __uint_as_float(kTabTag | n_it);
+            }
+            pool_used += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
+        if (in) recs[(size_t)t * n_voices + vi] = r;
     }
 }
 
@@ -825,7 +931,6 @@ enum : uint32_t { kModeStaged = 1, kModeDirect = 2, kModeEnd = 3, kModeFlush = 4
 enum : uint32_t { kPathGeneric = 0, kPathStereoUnit = 1, kPathStereoLerp = 2, kPathStereoMulti = 3, kPathStereoUnit2 = 4 };
 constexpr uint32_t kPairHalf = 8192 + 128;    // stage offset of the second voice of a kPathStereoUnit2 item (a full unit tile is <= 8,208 B)
 static_assert(2 * kPairHalf <= kStageBytes, "two unit tiles per stage");
-constexpr int kMaxPieces = 32;                // pieces of one voice in one tile handled by a single staged item
 
 struct StageMeta {            // written by the producer before it arrives on the stage's full barrier
     // hot header (one LDS.128)
@@ -1183,12 +1288,13 @@ __device__ __forceinline__ void consume_generic(const StageMeta& m, uint32_t sta
 // bubble per item (as one CTA per item this cost ~11 us per CTA round: C2's mix ran at 5.3 TB/s, C3 at 6.7).  A
 // kModeFlush item at the end of each work item makes the consumers add their accumulators into the bus.
 template <int OC>
-__global__ void __launch_bounds__(kTmaThreads)
+__global__ void __launch_bounds__(kTmaThreads, 3)
 voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t voices_per_group,
                      uint32_t n_groups, const Seg* __restrict__ segs, const uint32_t* __restrict__ nsegs,
                      const TileRec* __restrict__ recs, uint32_t frames, int32_t* __restrict__ bus, int use_atomic,
                      const uint32_t* __restrict__ err, const uint32_t seg_cap, uint32_t* __restrict__ work,
-                     const __grid_constant__ BusSink sink, const float nz) {
+                     const __grid_constant__ BusSink sink, const float nz, const uint4* __restrict__ pool,
+                     const uint32_t pool_rows) {
     extern __shared__ __align__(128) uint8_t smem[];
     if (*err) return;                                           // truncated trajectories must not be rendered (uniform exit)
     uint8_t* stages = smem;
@@ -1455,6 +1561,50 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                 // ---- after the first round: voices held back for the multi-piece path, one at a time, with
                 // the whole warp cooperating (lane l looks at segment j0 + l of that voice)
                 if (first_round) {
+                    // tiles whose piece table K3 has already built (TileRec.scale carries the tag): the lane reads its
+                    // item headers and issues two bulk copies per item — the source span and the piece rows — nothing
+                    // is computed here.  (Cutting these tiles in this warp, one voice at a time, was what K4 waited for on
+                    // scenes with retriggers: a quarter of all voice-tiles, ~6 segments each.)
+                    {
+                        const bool has_tab = hold_multi && pool != nullptr && (__float_as_uint(r.scale) & 0xFFC00000u) == kTabTag;
+                        const uint4* vrows = has_tab ? pool + (size_t)vi * pool_rows + (uint32_t)r.d : nullptr;
+                        uint4 hdr = make_uint4(0, 0, 0, 0);
+                        if (has_tab) hdr = __ldg(vrows);                            // all lanes' first headers in one round trip
+                        for (uint32_t rest = __ballot_sync(0xFFFFFFFFu, has_tab); rest; rest &= rest - 1) {
+                            const int i = __ffs(rest) - 1;
+                            uint32_t o_mine = o;
+                            if ((int)lane == i) {
+                                const uint32_t n_it = __float_as_uint(r.scale) & 0x003FFFFFu;
+                                const uint4* row = vrows;
+                                for (uint32_t it = 0; it < n_it; ++it) {
+                                    if (it) hdr = __ldg(row);
+                                    const uint32_t lo_g = hdr.x, hi_g = hdr.y, cnt = hdr.z;
+                                    const unsigned long long base = (unsigned long long)v.smp;
+                                    const unsigned long long b0 = base + (unsigned long long)lo_g * 4ull;
+                                    const unsigned long long b1 = base + ((unsigned long long)hi_g + 2ull) * 4ull;
+                                    const unsigned long long a0 = b0 & ~15ull, a1 = (b1 + 15ull) & ~15ull;
+                                    const uint32_t st = o_mine % kStages, round = o_mine / kStages;
+                                    if (round > 0) mbar_wait(empty + st, (round - 1) & 1);
+                                    StageMeta mm{};
+                                    mm.mode = kModeStaged | (kPathStereoMulti << 8);
+                                    mm.gain = v.gain;
+                                    mm.a0_off = cnt;
+                                    mm.frange = (v.vel != 1.0f) ? 1u : 0u;
+                                    mm.base_idx = lo_g;
+                                    mm.byte_off = (uint32_t)(b0 - a0);
+                                    *reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride) = mm;
+                                    mbar_arrive_expect_tx(full + st, (uint32_t)(a1 - a0) + cnt * 16u);
+                                    bulk_g2s(stages + (size_t)st * kStageBytes, reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0), full + st);
+                                    bulk_g2s(ptabs + st * kMaxPieces, row + 1, cnt * 16u, full + st);
+                                    row += 1u + cnt;
+                                    o_mine += 1;
+                                }
+                                cur = nf;
+                                hold_multi = false;
+                            }
+                            o = __shfl_sync(0xFFFFFFFFu, o_mine, i);
+                        }
+                    }
                     for (uint32_t rest = __ballot_sync(0xFFFFFFFFu, hold_multi); rest; rest &= rest - 1) {
                         const int i = __ffs(rest) - 1;
                         const Seg* sgi = reinterpret_cast<const Seg*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)sg, i));
@@ -1614,8 +1764,9 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                        kEmptyOff = kFullOff + (uint32_t)kStages * 8u;
     uint32_t st = 0, phase = 0;
     // thread 0: the tile of this CTA's last flush, not yet counted.  The count is a release (it waits for the bus writes
-    // before it), so it is made one work item later — at the next flush, before a reduction, at the end — when those
-    // writes have long landed and the wait costs nothing.  A CTA never waits for a peer while it holds one back.
+    // before it), so it is made one STAGE later, when those writes have landed and the wait costs next to nothing — not
+    // later than that: the tile's reduction is queued `lag` tiles behind and must not find the count missing.  A CTA
+    // never waits for a peer while it holds a count back.
     // (kept in shared memory: the consumer loop has no register to spare at 72)
     volatile uint32_t* pending = reinterpret_cast<volatile uint32_t*>(ptabs + kStages * kMaxPieces);
     if (threadIdx.x == 0) *pending = 0xFFFFFFFFu;
@@ -1625,8 +1776,10 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
             if (t != 0xFFFFFFFFu) { k4_tile_flushed(sink, t, n_groups); *pending = 0xFFFFFFFFu; }
         }
     };
+    bool just_flushed = false;
     for (;;) {
         mbar_wait_a(sm0 + kFullOff + st * 8u, phase);
+        if (just_flushed) { publish_pending(); just_flushed = false; }
         const uint32_t stage_addr = sm0 + st * (uint32_t)kStageBytes;
         const uint32_t meta_addr = sm0 + kMetaOff + st * (uint32_t)kMetaStride;
         const StageMeta* mp = reinterpret_cast<const StageMeta*>(meta_base + st * kMetaStride);
@@ -1644,13 +1797,9 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
             phase ^= (st == 0) ? 1u : 0u;
             continue;
         }
-        if ((mode & 0xFF) == kModeEnd) {
-            if (sink.world) publish_pending();
-            break;
-        }
+        if ((mode & 0xFF) == kModeEnd) break;
         if ((mode & 0xFF) == kModeFlush) {
             // end of a work item: a0_off = first frame of its tile, frange = frames in it
-            if (sink.world) publish_pending();
 #pragma unroll
             for (int j = 0; j < kFPT; ++j) {
                 const uint32_t fl = threadIdx.x + j * kConsumers;
@@ -1667,9 +1816,9 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
             if (sink.world) {                                    // every consumer's bus writes are issued: thread 0 may count the item
                 consumer_bar();
                 if (threadIdx.x == 0) *pending = a0_off / (uint32_t)kFT;
+                just_flushed = true;
             }
         } else if ((mode & 0xFF) == kModeReduce) {
-            publish_pending();
             k4_reduce_tile(sink, a0_off);
         } else {
             const uint32_t path = (mode >> 8) & 0xFF;
@@ -1811,6 +1960,7 @@ void free_buffers(RenderBuffers& rb) {
     if (rb.d_nsegs) cudaFree(rb.d_nsegs);
     if (rb.d_err) cudaFree(rb.d_err);
     if (rb.d_recs) cudaFree(rb.d_recs);
+    if (rb.d_pool) cudaFree(rb.d_pool);
     if (rb.d_seqs) cudaFree(rb.d_seqs);
     if (rb.d_events) cudaFree(rb.d_events);
     if (rb.d_nevents) cudaFree(rb.d_nevents);
@@ -1956,6 +2106,22 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         if (sink.lag < 1) sink.lag = 1;
     }
 
+    // piece-table pool of the tiles with several segments (stereo bus, TMA kernel): grow-only, sized by voices x segments
+    uint4* tab_pool = nullptr;
+    static const bool no_tables = getenv("BLAST_RENDER_NO_TABLES") != nullptr;
+    if (oc == 2 && !legacy && !no_tables) {
+        const uint32_t rows = pool_rows_for(rb.seg_cap);
+        if (rb.pool_voices < rb.voices_cap || rb.pool_rows != rows) {
+            BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (rb.d_pool) cudaFree(rb.d_pool);
+            rb.d_pool = nullptr;
+            rb.pool_voices = 0;
+            BLAST_CUDA_TRY(cudaMalloc(&rb.d_pool, rb.voices_cap * (size_t)rows * sizeof(uint4)));
+            rb.pool_voices = rb.voices_cap;
+            rb.pool_rows = rows;
+        }
+        tab_pool = rb.d_pool;
+    }
     rb.parity ^= 1u;                                         // this render's error word; cleared by the previous render's K3
     uint32_t* d_err = rb.d_err + rb.parity;
     uint32_t* d_work = rb.d_err + 2;
@@ -1973,7 +2139,7 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         voice_position_scan<<<n_voice_blocks + n_zero_blocks, kScanThreads, 0, ctx->stream>>>(
             rb.d_voices, n_voices, (uint32_t)frames, rb.d_segs, rb.d_nsegs, d_err, rb.d_events, rb.d_nevents, rb.seg_cap, oc,
             rb.d_splits, rb.d_nsplits, rb.d_recs, n_tiles, n_voice_blocks, rb.d_err + (rb.parity ^ 1u), d_work,
-            reinterpret_cast<uint32_t*>(d_partial_bus), n_zero, sink);
+            reinterpret_cast<uint32_t*>(d_partial_bus), n_zero, sink, tab_pool, rb.pool_rows, (uint32_t)kStageBytes);
         BLAST_CUDA_TRY(cudaGetLastError());
         ctx->launches += 1;
     }
@@ -1984,11 +2150,11 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         if (oc == 1) {
             BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
             voice_render_mix_tma<1><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(rb.d_voices, n_voices, per_group, groups, rb.d_segs,
-                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, d_err, rb.seg_cap, d_work, sink, -0.0f);
+                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, d_err, rb.seg_cap, d_work, sink, -0.0f, tab_pool, rb.pool_rows);
         } else {
             BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
             voice_render_mix_tma<2><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(rb.d_voices, n_voices, per_group, groups, rb.d_segs,
-                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, d_err, rb.seg_cap, d_work, sink, -0.0f);
+                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, d_err, rb.seg_cap, d_work, sink, -0.0f, tab_pool, rb.pool_rows);
         }
     } else {
 #define BLAST_LAUNCH_MIX(OCV)                                                                              \

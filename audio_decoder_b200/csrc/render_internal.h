@@ -42,6 +42,10 @@ struct TileRec {           // state of one voice at the first step of one tile
 
 
 constexpr int kMaxEvents = 256;        // retrigger events per voice per render call
+// rows of a voice's piece-table pool: one header row per staged item + one row per piece; a tile that does not fit is
+// left to K4's own (slower) cutting
+constexpr uint32_t pool_rows_for(uint32_t seg_cap) { return 3u * seg_cap; }
+constexpr uint32_t kTabTag = 0x7FC00000u;      // TileRec.scale of a tile with a table: this quiet-NaN pattern | item count
 
 struct Split {             // a retrigger between the channels of one frame (C >= 2 voices): channels < k keep the old sample
     uint32_t frame;
@@ -74,6 +78,9 @@ struct RenderBuffers {     // device scratch of one render (owned by a scene or 
     uint32_t* err_word() const { return d_err + parity; }
     TileRec* d_recs = nullptr;
     size_t recs_cap = 0;               // in records
+    uint4* d_pool = nullptr;           // piece tables of the tiles whose trajectory has several segments: kPoolRows(seg_cap)
+    size_t pool_voices = 0;            // rows per voice, written by K3, bulk-copied into K4's shared memory
+    uint32_t pool_rows = 0;
     size_t voices_cap = 0;
     uint32_t seg_cap = 0;              // segments per voice in d_segs
     SeqDev* d_seqs = nullptr;          // only with Seq processes

@@ -14,6 +14,7 @@
 // streams are materialised, ALU-bound when only checksums are kept.  Draws are staged through a
 // padded shared-memory tile and written out as 128-byte contiguous rows per stream.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "blast_internal.h"
@@ -172,13 +173,24 @@ x128p_streams(U128* __restrict__ states, uint64_t n_streams, uint64_t draws, int
     const uint32_t rows = (uint32_t)min((uint64_t)32, n_streams - stream0);
     // 16-byte stores need 16-byte aligned rows in memory: row start = (stream * draws + j0) * 8
     const bool vec_ok = (draws % 2 == 0) && (((uintptr_t)raw | (uintptr_t)ranged) & 15) == 0;
+    const bool range32 = (range >> 32) == 0;
+    const uint32_t rg = (uint32_t)range;
 
     for (uint64_t j0 = 0; j0 < draws; j0 += kRound) {
         const int nj = (int)min((uint64_t)kRound, draws - j0);
 #pragma unroll 4
         for (int j = 0; j < nj; ++j) {
             const uint64_t r = next_u64(s0, s1);
-            const uint64_t v = (uint64_t)lo + __umul64hi(r, range);           // blast_rand.rs:57-58
+            // blast_rand.rs:57-58: lower + ((r as u128 * range as u128) >> 64).  A range below 2^32 (every range the
+            // reference draws from) needs two 32 x 32 -> 64 multiplies instead of the four of a full 64 x 64 high product.
+            uint64_t m;
+            if (range32) {
+                const uint64_t t = (uint64_t)(uint32_t)r * rg;
+                m = ((uint64_t)(uint32_t)(r >> 32) * rg + (t >> 32)) >> 32;
+            } else {
+                m = __umul64hi(r, range);
+            }
+            const uint64_t v = (uint64_t)lo + m;
             if (kChecks) { xr ^= r; sr += r; xg ^= v; sg += v; }
             if (kRaw) tile_raw[lane * kPitch + j] = r;
             if (kRanged) tile_rng[lane * kPitch + j] = v;
@@ -317,32 +329,6 @@ int launch_fill(blast_ctx* ctx, U128* st, uint64_t n_streams, uint64_t draws, in
     return BLAST_OK;
 }
 
-// resident warps per SM of the fill kernel for these outputs (shared memory bound when something is materialised)
-int fill_warps_per_sm(bool raw, bool ranged, bool checks) {
-    const int sel = (raw ? 1 : 0) | (ranged ? 2 : 0) | (checks ? 4 : 0);
-    const size_t smem = (size_t)kWarps * 32 * kPitch * sizeof(uint64_t) * ((raw ? 1 : 0) + (ranged ? 1 : 0));
-    int blocks = 0;
-#define BLAST_OCC(R, G, K)                                                                                   \
-    do {                                                                                                     \
-        auto kern = x128p_streams<R, G, K>;                                                                  \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, kWarps * 32, smem) != cudaSuccess) blocks = 0; \
-    } while (0)
-    switch (sel) {
-        case 0: BLAST_OCC(false, false, false); break;
-        case 1: BLAST_OCC(true, false, false); break;
-        case 2: BLAST_OCC(false, true, false); break;
-        case 3: BLAST_OCC(true, true, false); break;
-        case 4: BLAST_OCC(false, false, true); break;
-        case 5: BLAST_OCC(true, false, true); break;
-        case 6: BLAST_OCC(false, true, true); break;
-        default: BLAST_OCC(true, true, true); break;
-    }
-#undef BLAST_OCC
-    cudaGetLastError();
-    return std::max(1, blocks) * kWarps;
-}
-
 }  // namespace
 
 int blast_x128p_fill_dev(blast_ctx* ctx, blast_x128p* d_states, uint64_t n_streams, uint64_t draws_per_stream,
@@ -358,20 +344,15 @@ int blast_x128p_fill_dev(blast_ctx* ctx, blast_x128p* d_states, uint64_t n_strea
     // 22 % of the resident threads, each a serial chain of 65,536 draws).  The generator is GF(2)-linear, so a stream
     // can be cut into `split` sub-streams that start at J^k * state (J = T^(draws/split)); draw j of sub-stream k is
     // draw k*draws/split + j of the stream and lands at the same address.
-    // The split also sets how the warps fall into waves: all warps do the same work, so the kernel takes
-    // ceil(warps / resident warps) rounds of draws / split draws each.  With 67 KB of staging per block only 24 warps
-    // are resident per SM: C4's raw fill at split 4 was 8,192 warps in 2.3 -> 3 rounds (8.0 ms); at split 64 it is
-    // 36.9 -> 37 rounds of a sixteenth the length.  Take the split with the least total, the smaller one when within 2 %.
     uint32_t split = 1;
-    {
-        const uint64_t resident = (uint64_t)fill_warps_per_sm(d_raw != nullptr, d_ranged != nullptr, d_checks != nullptr) * ctx->sm_count;
-        double best = 0.0;
-        for (uint32_t sp = 1; sp <= 64; sp *= 2) {
-            if (sp > 1 && (draws_per_stream % sp != 0 || draws_per_stream / sp < 1024)) break;
-            const uint64_t warps = (n_streams * sp + 31) / 32;
-            const double cost = (double)((warps + resident - 1) / resident) * (double)(draws_per_stream / sp);
-            if (sp == 1 || cost < best * 0.98) { best = cost; split = sp; }
-        }
+    const uint64_t want_threads = (uint64_t)ctx->sm_count * 1536;
+    while (split < 64 && n_streams * split < want_threads && draws_per_stream % (2ull * split) == 0 &&
+           draws_per_stream / (2ull * split) >= 1024)
+        split *= 2;
+    static const uint32_t forced = getenv("BLAST_X128P_SPLIT") ? (uint32_t)atoi(getenv("BLAST_X128P_SPLIT")) : 0u;   // development
+    if (forced) {
+        split = 1;
+        while (split < forced && split < 64 && draws_per_stream % (2ull * split) == 0 && draws_per_stream / (2ull * split) >= 1024) split *= 2;
     }
     if (split == 1) return launch_fill(ctx, st, n_streams, draws_per_stream, lower, range, d_raw, d_ranged, d_checks);
 

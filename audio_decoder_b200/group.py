@@ -38,6 +38,11 @@ class Group:
         except Exception:
             pass
 
+    def member_context(self, member: int):
+        """member's blast_ctx as a (non-owning) Context: uploads / downloads on that member's GPU"""
+        from .context import BorrowedContext
+        return BorrowedContext(self.lib, self.lib.blast_group_ctx(self.h, member))
+
     # ---- main.rs:18-89: decode every asset; file i lands on member i mod n
     def decode_batch(self, images, descs, to_host: bool = True):
         """-> (host sample arrays or None, ctypes array of blast_track living on the members)"""

@@ -124,11 +124,7 @@ def test_group_conductor_with_seq_against_the_oracle(devices):
         # tracks must live where the sharding rule says: upload clip t on member t mod n
         bufs, tracks = [], (_lib.Track * len(clips))()
         for t, s in enumerate(clips):
-            m = t % g.n
-            cm = blast.Context.__new__(blast.Context)            # borrow the member's context (owned by the group)
-            cm.lib, cm.h = g.lib, g.lib.blast_group_ctx(g.h, m)
-            b = cm.to_device(s)
-            b.free = lambda: None
+            b = g.member_context(t % g.n).to_device(s)
             bufs.append(b)
             tracks[t] = _lib.Track(b.ptr, s.size, 2, 48000)
         gc = GroupConductor(g, 2, 48000, tracks, len(clips))
@@ -145,6 +141,8 @@ def test_group_conductor_with_seq_against_the_oracle(devices):
                 getattr(gc, cmd[0])(*cmd[1:])
                 getattr(oc, cmd[0])(*cmd[1:])
         gc.close()
+        for b in bufs:
+            b.free()
 
 
 @pytest.mark.parametrize("devices", member_sets()[1:], ids=lambda d: "gpus_" + "_".join(map(str, d)))
