@@ -124,11 +124,16 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
 // (CCTL.IVALL), which the render's producer warps keep warm with voice rows and tile records.  Only the CTA that
 // completes a tile pays the acquire side (the fence after the atomic makes the other CTAs' bus writes part of what its
 // system-scope flag store releases).
-__device__ __forceinline__ void sink_tile_flushed(const BusSink& s, uint32_t tile, uint32_t n_groups) {
+// `n_parts` = counts a tile needs: K4 counts per consumer WARP (voice groups x 8), so no barrier joins the warps of a CTA
+// after a flush.  A single rank (world == 1) never leaves gpu scope.
+__device__ __forceinline__ void sink_fence(const BusSink& s) {
+    if (s.world > 1) __threadfence_system(); else __threadfence();
+}
+__device__ __forceinline__ void sink_tile_flushed(const BusSink& s, uint32_t tile, uint32_t n_parts) {
     uint32_t prev;
     asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(s.tile_count + tile) : "memory");
-    if (prev + 1u == n_groups) {
-        __threadfence_system();
+    if (prev + 1u == n_parts) {
+        sink_fence(s);
         st_release_sys(s.ready_at[tile % s.world] + tile, s.step);
     }
 }
@@ -177,11 +182,11 @@ __device__ __forceinline__ void sink_reduce_tile(const BusSink& s, uint32_t tile
     }
     sync();
     if (tid == 0) {
-        __threadfence_system();
+        sink_fence(s);
         const uint32_t prev = atomicAdd(s.red_count, 1u);
         if (prev + 1u == s.n_my_tiles) {
             *s.red_count = 0u;                                   // every other reduction of this step has finished
-            __threadfence_system();
+            sink_fence(s);
             for (uint32_t i = 0; i < s.n_done; ++i) st_release_sys(s.done[i], s.step);
         }
     }
@@ -191,8 +196,8 @@ __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;"
 __device__ __noinline__ void k4_reduce_tile(const BusSink& s, uint32_t tile) {
     sink_reduce_tile(s, tile, threadIdx.x, 256u, [] { consumer_bar(); });
 }
-__device__ __noinline__ void k4_tile_flushed(const BusSink& s, uint32_t tile, uint32_t n_groups) {
-    sink_tile_flushed(s, tile, n_groups);
+__device__ __noinline__ void k4_tile_flushed(const BusSink& s, uint32_t tile, uint32_t n_parts) {
+    sink_tile_flushed(s, tile, n_parts);
 }
 
 // ---------------------------------------------------------------- K3a: Seq event scan (processes.rs:69-90)
@@ -960,7 +965,7 @@ struct StageMeta {            // written by the producer before it arrives on th
 static_assert(sizeof(StageMeta) == 96, "StageMeta layout");
 constexpr size_t kMetaStride = 96;
 constexpr size_t kTmaSmem = (size_t)kStages * kStageBytes + kStages * kMetaStride + 2 * kStages * sizeof(uint64_t) +
-                            (size_t)kStages * kMaxPieces * sizeof(uint4) + 16;     // + the consumers' pending-tile word
+                            (size_t)kStages * kMaxPieces * sizeof(uint4) + 32;     // + the consumer warps' pending-tile words
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -1763,17 +1768,18 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
     constexpr uint32_t kMetaOff = (uint32_t)kStages * kStageBytes, kFullOff = kMetaOff + (uint32_t)(kStages * kMetaStride),
                        kEmptyOff = kFullOff + (uint32_t)kStages * 8u;
     uint32_t st = 0, phase = 0;
-    // thread 0: the tile of this CTA's last flush, not yet counted.  The count is a release (it waits for the bus writes
-    // before it), so it is made one STAGE later, when those writes have landed and the wait costs next to nothing — not
-    // later than that: the tile's reduction is queued `lag` tiles behind and must not find the count missing.  A CTA
-    // never waits for a peer while it holds a count back.
-    // (kept in shared memory: the consumer loop has no register to spare at 72)
-    volatile uint32_t* pending = reinterpret_cast<volatile uint32_t*>(ptabs + kStages * kMaxPieces);
-    if (threadIdx.x == 0) *pending = 0xFFFFFFFFu;
+    // lane 0 of every consumer warp: the tile of the warp's last flush, not yet counted.  The count is a release (it waits
+    // for the warp's bus writes), so it is made one STAGE later, when those writes have landed and the wait costs next to
+    // nothing — not later than that: the tile's reduction is queued `lag` tiles behind and must not find a count missing.
+    // Counting per warp (a tile needs voice groups x 8 counts) means no barrier joins the consumer warps after a flush.
+    // A warp never waits for a peer while it holds a count back.  (Kept in shared memory: the consumer loop has no
+    // register to spare at 72.)
+    volatile uint32_t* pending = reinterpret_cast<volatile uint32_t*>(ptabs + kStages * kMaxPieces) + warp;
+    if (lane == 0) *pending = 0xFFFFFFFFu;
     auto publish_pending = [&]() {
-        if (threadIdx.x == 0) {
+        if (lane == 0) {
             const uint32_t t = *pending;
-            if (t != 0xFFFFFFFFu) { k4_tile_flushed(sink, t, n_groups); *pending = 0xFFFFFFFFu; }
+            if (t != 0xFFFFFFFFu) { k4_tile_flushed(sink, t, n_groups * (uint32_t)(kConsumers / 32)); *pending = 0xFFFFFFFFu; }
         }
     };
     bool just_flushed = false;
@@ -1813,9 +1819,9 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                     }
                 }
             }
-            if (sink.world) {                                    // every consumer's bus writes are issued: thread 0 may count the item
-                consumer_bar();
-                if (threadIdx.x == 0) *pending = a0_off / (uint32_t)kFT;
+            if (sink.world) {                                    // the warp's bus writes are issued: its lane 0 may count them
+                __syncwarp();
+                if (lane == 0) *pending = a0_off / (uint32_t)kFT;
                 just_flushed = true;
             }
         } else if ((mode & 0xFF) == kModeReduce) {
@@ -2108,8 +2114,8 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
 
     // piece-table pool of the tiles with several segments (stereo bus, TMA kernel): grow-only, sized by voices x segments
     uint4* tab_pool = nullptr;
-    static const bool no_tables = getenv("BLAST_RENDER_NO_TABLES") != nullptr;
-    if (oc == 2 && !legacy && !no_tables) {
+    static const bool tables = getenv("BLAST_RENDER_TABLES") != nullptr;
+    if (oc == 2 && !legacy && tables) {
         const uint32_t rows = pool_rows_for(rb.seg_cap);
         if (rb.pool_voices < rb.voices_cap || rb.pool_rows != rows) {
             BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));

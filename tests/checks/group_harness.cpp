@@ -47,7 +47,9 @@ int main(int argc, char** argv) {
     std::vector<const uint8_t*> files;
     std::vector<size_t> lens;
     std::vector<blast_pcm_desc> descs(n_files);
-    for (uint32_t i = 0; i < n_files; ++i) images.push_back(wav_image(1000 + i, (frames + 7 * i) * 4));
+    // clips longer than the render: a voice is silent from the step whose trunc(position) reaches end = frames - 1
+    // (engine.rs:407-410), so the last frame of a clip exactly as long as the render would not play
+    for (uint32_t i = 0; i < n_files; ++i) images.push_back(wav_image(1000 + i, (frames + 7 * (i + 1)) * 4));
     for (uint32_t i = 0; i < n_files; ++i) {
         files.push_back(images[i].data());
         lens.push_back(images[i].size());
