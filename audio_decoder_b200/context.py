@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -18,6 +19,7 @@ class DevBuf:
         p = C.c_void_p()
         check(ctx.lib.blast_dev_alloc(ctx.h, self.nbytes, C.byref(p)))
         self.ptr = p.value
+        ctx._bufs.add(self)               # weakly: a context that is closed first frees what is still allocated
 
     def free(self):
         if self.ptr is not None and self.ctx.h:
@@ -108,6 +110,7 @@ class Context:
 
     def __init__(self, device: int = 0, stream: int | None = None):
         self.lib = _lib.load()
+        self._bufs = weakref.WeakSet()
         p = C.c_void_p()
         check(self.lib.blast_ctx_create(C.byref(p), device))
         self.h = p.value
@@ -116,6 +119,11 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for b in list(getattr(self, "_bufs", ())):      # device buffers that outlive the context would never be freed
+                try:
+                    b.free()
+                except Exception:
+                    pass
             self.lib.blast_ctx_destroy(self.h)
             self.h = None
 
@@ -174,6 +182,7 @@ class BorrowedContext(Context):
     def __init__(self, lib, handle: int):
         self.lib = lib
         self.h = handle
+        self._bufs = weakref.WeakSet()
 
     def close(self):
         self.h = None

@@ -163,7 +163,7 @@ constexpr int k24Threads = 256;
 constexpr int k24Slabs = 4;                                          // 1,024-sample slabs per tile
 constexpr int k24SamplesPerTile = k24Threads * 4 * k24Slabs;         // 4,096 samples = 12,288 source bytes
 constexpr int k24StageBytes = k24SamplesPerTile * 3 + 32;            // + the misalignment in front, + the last vector's slack
-constexpr int k24CtasPerSm = 6;
+constexpr int k24CtasPerSm = 8;                                     // 8 x 24.6 KB of staging fit an SM; 256-thread blocks: 64 warps
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t r;

@@ -1011,14 +1011,15 @@ __device__ __forceinline__ int32_t lds_s16(uint32_t addr) {
     return v;
 }
 
-// packed stereo frame (L | R << 16) -> two exact floats without the XU pipe: sign extension by PRMT (sign-replicate
-// selector) / SHF, then I2FP.F32.S32.  Written as PRMT so that ptxas cannot fold the extension into I2F.S16, which
-// runs on the 16-lane XU pipe; 4 instructions per frame against 5 for the 2^23 magic-number splice
-// (tools/micro/unit_loop.cu: 8.40 vs 8.04 TB/s for the bare unit loop, 4.52 with I2F.S16).
+// packed stereo frame (L | R << 16) -> two exact floats without the XU pipe, and with as little of the half-rate ALU pipe
+// as possible (on the interpolated scene ALU is the busiest pipe, 66 %, the FMA pipe idles at 21 %:
+// profiles/r02_render_c3mixed_full.txt).  L: ((w & 0xFFFF) ^ 0x4B008000) is the float 2^23 + (L + 32768), so one LOP3 and
+// one FADD (FMA pipe) give L exactly.  R: arithmetic shift + I2FP.F32.S32 (written so that ptxas cannot pick I2F.S16, which
+// runs on the 16-lane XU pipe).  3 ALU + 1 FMA instructions per frame instead of 4 ALU (PRMT, SHF, 2 x I2FP).
 __device__ __forceinline__ void unpack_pair(uint32_t w, float& l, float& r) {
     uint32_t lo;
-    asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(lo) : "r"(w));
-    l = __int2float_rn((int32_t)lo);
+    asm("lop3.b32 %0, %1, 0x0000FFFF, 0x4B008000, 0x6A;" : "=r"(lo) : "r"(w));      // (a & b) ^ c
+    l = __fadd_rn(__uint_as_float(lo), -8421376.0f);                                  // -(2^23 + 32768): exact
     r = __int2float_rn((int32_t)w >> 16);
 }
 

@@ -93,21 +93,28 @@ def decode_batch(ctx: Context, images, descs, *, to_host=True, keep_on_device=Fa
     return outs, dev
 
 
+_default_ctx: Context | None = None
+
+
+def default_context() -> Context:
+    """The process-wide context of the parse() drop-ins (the reference calls them in a loop over an asset directory,
+    main.rs:18-89): created on first use and kept, so that loop pays for streams and staging slabs once, not per file."""
+    global _default_ctx
+    if _default_ctx is None or not _default_ctx.h:
+        _default_ctx = Context()
+    return _default_ctx
+
+
 class _Format:
     def __init__(self, kind: str, fmt: str):
         self.kind, self.fmt = kind, fmt
 
     def parse_bytes(self, image, path: str = "assets/memory." + "bin", ctx: Context | None = None) -> AudioFile:
-        own = ctx is None
-        ctx = ctx or Context()
-        try:
-            d = probe(self.kind, image)
-            outs, _ = decode_batch(ctx, [image], [d])
-            name = file_name(path)                      # checked after decoding, like the reference
-            return AudioFile(name, self.fmt, d.sample_rate, d.num_channels, d.bits_per_sample, outs[0])
-        finally:
-            if own:
-                ctx.close()
+        ctx = ctx or default_context()
+        d = probe(self.kind, image)
+        outs, _ = decode_batch(ctx, [image], [d])
+        name = file_name(path)                      # checked after decoding, like the reference
+        return AudioFile(name, self.fmt, d.sample_rate, d.num_channels, d.bits_per_sample, outs[0])
 
     def parse(self, path: str, ctx: Context | None = None) -> AudioFile:
         """`pub fn parse(path: &str) -> DecodeResult<AudioFile>` (wav.rs:69 / aiff.rs:99)."""
@@ -233,24 +240,19 @@ class _Mpeg:
     @staticmethod
     def parse_bytes(image, ctx: Context | None = None, reference_compat: bool = True, want_payload: bool = True):
         """blast_mpeg_parse on a host buffer -> dict(offsets, ref_header, n_candidates, payload)"""
-        own = ctx is None
-        ctx = ctx or Context()
-        try:
-            a = _as_u8(image)
-            n, ncand, ref, plen = C.c_uint64(), C.c_uint64(), C.c_uint32(), C.c_uint64()
-            ptr = a.ctypes.data if a.size else None
-            check(ctx.lib.blast_mpeg_parse(ctx.h, ptr, a.size, int(reference_compat), None, 0, C.byref(n), C.byref(ref),
-                                           C.byref(ncand), None, 0, C.byref(plen) if want_payload else None))
-            offs = np.empty(n.value, dtype=np.uint64)
-            pay = np.empty(plen.value if want_payload else 0, dtype=np.uint8)
-            check(ctx.lib.blast_mpeg_parse(ctx.h, ptr, a.size, int(reference_compat), offs.ctypes.data, offs.size,
-                                           C.byref(n), C.byref(ref), C.byref(ncand),
-                                           pay.ctypes.data if want_payload and pay.size else None, pay.size,
-                                           C.byref(plen) if want_payload else None))
-            return dict(offsets=offs, ref_header=ref.value, n_candidates=ncand.value, payload=pay)
-        finally:
-            if own:
-                ctx.close()
+        ctx = ctx or default_context()
+        a = _as_u8(image)
+        n, ncand, ref, plen = C.c_uint64(), C.c_uint64(), C.c_uint32(), C.c_uint64()
+        ptr = a.ctypes.data if a.size else None
+        check(ctx.lib.blast_mpeg_parse(ctx.h, ptr, a.size, int(reference_compat), None, 0, C.byref(n), C.byref(ref),
+                                       C.byref(ncand), None, 0, C.byref(plen) if want_payload else None))
+        offs = np.empty(n.value, dtype=np.uint64)
+        pay = np.empty(plen.value if want_payload else 0, dtype=np.uint8)
+        check(ctx.lib.blast_mpeg_parse(ctx.h, ptr, a.size, int(reference_compat), offs.ctypes.data, offs.size,
+                                       C.byref(n), C.byref(ref), C.byref(ncand),
+                                       pay.ctypes.data if want_payload and pay.size else None, pay.size,
+                                       C.byref(plen) if want_payload else None))
+        return dict(offsets=offs, ref_header=ref.value, n_candidates=ncand.value, payload=pay)
 
     def parse(self, path: str, ctx: Context | None = None) -> np.ndarray:
         """`pub fn parse(path: &str) -> DecodeResult<Vec<u8>>` (mpeg.rs:7): the concatenated frame payloads"""

@@ -99,8 +99,12 @@ def c2_true24(ctx, peak, quick):
     out = {}
     for name, kind, width in (("i32", 0, 4), ("i16_top", 1, 2)):
         d_out = ctx.alloc(n_files * n_s * width)
-        jobs = [(d_pay.ptr + i * data_len, d_out.ptr + i * n_s * width, n_s, True, kind) for i in range(n_files)]
-        ms = _median_ms(ctx, lambda: fp.pcm24_unpack_dev(ctx, jobs), 5, warm=2)
+        from audio_decoder_b200 import _lib
+        from audio_decoder_b200.errors import check
+        # the job array is marshalled once: the timed region is the C call (job table upload + one launch)
+        arr = (_lib.Pcm24Job * n_files)(*[_lib.Pcm24Job(d_pay.ptr + i * data_len, d_out.ptr + i * n_s * width, n_s, 1, kind)
+                                          for i in range(n_files)])
+        ms = _median_ms(ctx, lambda: check(ctx.lib.blast_pcm24_unpack_dev(ctx.h, arr, n_files)), 5, warm=2)
         # property: the top 16 bits of the sign-extended i32 are the big-endian i16 made of the sample's first two bytes
         raw = d_pay.download(np.uint8, 3 * 4096)
         got = d_out.download(np.int32 if kind == 0 else np.int16, 4096)

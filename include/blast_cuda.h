@@ -440,7 +440,9 @@ int  blast_mpeg_parse(blast_ctx* ctx, const uint8_t* bytes, uint64_t len, int re
  * memory (blast_peer_bus);  RNG stream s is generated on member s mod n;  one MPEG stream is cut into byte ranges whose
  * 48-byte aggregates are folded on the host, with the header histogram and the first-position table reduced through
  * peer memory.  Results are identical to the single-GPU entry points.  A device id may repeat (at most 3 members per
- * GPU): the multi-member protocol can then be exercised on a single-GPU box. */
+ * GPU): the multi-member protocol can then be exercised on a single-GPU box — members that share a GPU wait for each
+ * other on the device, so their streams need separate hardware work queues (CUDA_DEVICE_MAX_CONNECTIONS=32 in the
+ * environment before the first CUDA call). */
 typedef struct blast_group blast_group;
 int  blast_group_create(blast_group** out, const int* device_ids, uint32_t n_devices);
 void blast_group_destroy(blast_group* g);

@@ -1,6 +1,11 @@
 import os
 import sys
 
+# Group members that share one GPU (blast_group over a repeated device id) wait for each other on the device; their
+# streams must not share a hardware work queue (a waiting kernel at the head of a queue would hold back the kernel it
+# waits for).  The driver reads this when the CUDA context is created.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

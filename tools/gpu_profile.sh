@@ -1,16 +1,10 @@
 #!/bin/bash
 # ncu evidence for profiles/: launch list of the bench command, full captures of the dominant kernels (each only after
-# the same command has exited 0 without ncu), the other configs' device-resident timings.
+# the same command has exited 0 without ncu).
 #   gpurun --timeout 2400 -- 'bash tools/gpu_profile.sh'      then: python tools/ncu_summary.py gpurun_out/<x>.ncu-rep profiles/<y>.txt <traffic key>
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"
+CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-configs"
 timeout 300 $CMD > gpurun_out/plain.log 2>&1 || exit 1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/bench_launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:pcm16_decode_batch -s 3 -c 1 -f -o gpurun_out/prof_decode $CMD > gpurun_out/ncu_decode.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:voice_render_mix_tma -s 3 -c 1 -f -o gpurun_out/prof_render_c2 $CMD > gpurun_out/ncu_render.log 2>&1
-MP="python tools/bench_mpeg.py --gib 4 --iters 1"
-timeout 300 $MP > gpurun_out/plain_mpeg.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:mpeg_walk -s 1 -c 1 -f -o gpurun_out/prof_mpeg_walk $MP > gpurun_out/ncu_mpeg.log 2>&1
-timeout 300 python tools/bench_render.py > gpurun_out/bench_render.json 2> gpurun_out/bench_render.err      # C3, C3 + Seq, C4
-timeout 300 python tools/bench_mpeg.py > gpurun_out/bench_mpeg.json 2> gpurun_out/bench_mpeg.err            # C5
-timeout 300 python tools/bench_c1.py > gpurun_out/bench_c1.json 2> gpurun_out/bench_c1.err                  # C1
-timeout 300 python tools/pcie_probe.py > gpurun_out/pcie.json 2> gpurun_out/pcie.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_bench_launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:pcm16_decode_batch -s 3 -c 1 -f -o gpurun_out/r02_prof_decode $CMD > gpurun_out/ncu_decode.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:voice_render_mix_tma -s 3 -c 1 -f -o gpurun_out/r02_prof_render_c2 $CMD > gpurun_out/ncu_render.log 2>&1
