@@ -276,22 +276,34 @@ int blast_group_conductor_coordinate(blast_group_conductor* gc, uint64_t frames,
     const uint64_t slots = frames * gc->out_channels;
     if (slots == 0) return BLAST_OK;
     if (int rc = ensure_peer_buses(g, slots)) return rc;
-    return for_members(g, [&](uint32_t m) -> int {
-        blast_ctx* ctx = g->ctx[m];
-        blast_peer_bus* pb = g->pb[m];
-        int rc = blast_peer_bus_begin_dev(ctx, pb);
-        if (rc == BLAST_OK) rc = blast_conductor_render_dev(ctx, gc->c[m], frames, blast_peer_bus_partial(pb));
-        const std::string keep = rc != BLAST_OK ? blast_last_error() : "";
-        // a member that failed (capacity, allocation) still publishes its step: the others must not wait for it
-        int r = blast_peer_bus_reduce_dev(ctx, pb, slots);
-        if (r == BLAST_OK && m == 0) {
-            r = blast_peer_bus_wait_dev(ctx, pb);
-            if (r == BLAST_OK) r = blast_memcpy_d2h(ctx, host_bus_out, blast_peer_bus_bus(pb), slots * sizeof(int16_t));
-        }
-        if (r == BLAST_OK) r = blast_peer_bus_check(ctx, pb);
-        if (rc != BLAST_OK) return blast::set_error(rc, "%s", keep.c_str());
-        return r;
+    // Phase 1, one host thread per member: the span is rendered into the member's partial bus.  Everything that may
+    // allocate or synchronise (the Conductor reads its state back) happens here, while no kernel of the group waits for a
+    // peer — members may share a GPU, and a device-wide synchronisation behind a waiting kernel would never return.
+    std::vector<int> rcs(g->n, BLAST_OK);
+    std::vector<std::string> msgs(g->n);
+    for_members(g, [&](uint32_t m) -> int {
+        int rc = blast_peer_bus_begin_dev(g->ctx[m], g->pb[m]);
+        if (rc == BLAST_OK) rc = blast_conductor_render_dev(g->ctx[m], gc->c[m], frames, blast_peer_bus_partial(g->pb[m]));
+        rcs[m] = rc;
+        if (rc != BLAST_OK) msgs[m] = blast_last_error();
+        return BLAST_OK;
     });
+    // Phase 2: every member takes its step of the exchange, also one that failed (capacity, allocation): the others must
+    // not wait for it.  Asynchronous launches from this thread; nothing blocks between them.
+    int rc = BLAST_OK;
+    for (uint32_t m = 0; m < g->n; ++m) {
+        const int r = blast_peer_bus_reduce_dev(g->ctx[m], g->pb[m], slots);
+        if (r != BLAST_OK && rc == BLAST_OK) rc = r;
+    }
+    if (rc == BLAST_OK) rc = blast_peer_bus_wait_dev(g->ctx[0], g->pb[0]);
+    if (rc == BLAST_OK) rc = blast_memcpy_d2h(g->ctx[0], host_bus_out, blast_peer_bus_bus(g->pb[0]), slots * sizeof(int16_t));
+    for (uint32_t m = 0; m < g->n; ++m) {
+        const int r = blast_peer_bus_check(g->ctx[m], g->pb[m]);
+        if (r != BLAST_OK && rc == BLAST_OK) rc = r;
+    }
+    for (uint32_t m = 0; m < g->n; ++m)
+        if (rcs[m] != BLAST_OK) return blast::set_error(rcs[m], "member %u (GPU %d): %s", m, g->device[m], msgs[m].c_str());
+    return rc;
 }
 
 int blast_group_x128p_fill(blast_group* g, uint64_t seed, uint64_t stride, uint64_t n_streams, uint64_t draws_per_stream,

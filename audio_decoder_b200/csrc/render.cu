@@ -649,7 +649,7 @@ voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t f
                     uint32_t* __restrict__ nsplits, TileRec* __restrict__ recs, uint32_t n_tiles,
                     uint32_t n_voice_blocks, uint32_t* __restrict__ err_next, uint32_t* __restrict__ work,
                     uint32_t* __restrict__ zero, size_t n_zero, const BusSink sink, uint4* __restrict__ pool,
-                    const uint32_t pool_rows, const uint32_t stage_bytes) {
+                    const uint32_t pool_rows, const uint32_t stage_bytes, const VoiceDev* __restrict__ rewind) {
     if (blockIdx.x >= n_voice_blocks) {
         // housekeeping blocks, concurrent with the walks: the next render's error word and K4's work counter, and the
         // int32 partial bus when K4 will accumulate with atomics (as stream memsets these were two more operations —
@@ -675,6 +675,10 @@ voice_position_scan(VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t f
     }
     const uint32_t vi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (vi >= n_voices) return;                                 // warp-uniform
+    if (rewind) {                                               // blast_scene_restore_dev: start from the uploaded voice, no copy kernel
+        if (lane == 0) voices[vi] = rewind[vi];
+        __syncwarp();
+    }
     const uint32_t active = voices[vi].active, S = voices[vi].S, adv = voices[vi].adv;      // scan_voice only writes .pos
     __shared__ uint3 s_cmds[kScanThreads / 32][kMaxEvents + 2];
     uint3* cmds = s_cmds[threadIdx.x >> 5];
@@ -1857,11 +1861,6 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
     }
 }
 
-__global__ void copy_rows16(const uint4* __restrict__ src, uint4* __restrict__ dst, uint32_t n) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[i];
-}
-
 // ---------------------------------------------------------------- K4b
 // Split frames of voices with Seq processes: a retrigger that landed between the channels of frame f.  K4 rendered
 // every channel of that frame from the NEW epoch (home position); the channels before the hit must carry the old
@@ -2050,7 +2049,7 @@ int launch_bus_reduce(blast_ctx* ctx, const BusSink& sink) {
 }
 
 int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t n_seqs, uint32_t oc, uint64_t frames,
-                  int32_t* d_partial_bus, const BusSink* sink_in) {
+                  int32_t* d_partial_bus, const BusSink* sink_in, const VoiceDev* rewind) {
     if (frames == 0) return (sink_in && sink_in->world) ? launch_bus_reduce(ctx, *sink_in) : BLAST_OK;
     if (frames > 0x7FFFFFFFull) return blast::set_error(BLAST_ERR_CAPACITY, "at most 2^31-1 frames per render call");
     if (n_seqs > 0 && frames * oc > 0x7FFFFFFFull)
@@ -2110,6 +2109,8 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         // tile t is reduced once the queue is `lag` tiles further: by then its last voice group has normally been flushed
         // on every rank (1.5 x the CTAs in flight, plus slack for the skew between ranks), so the reduction seldom waits
         sink.lag = std::min<uint32_t>(n_tiles, (3 * resident / 2 + groups - 1) / groups + 2);
+        static const int forced_lag = getenv("BLAST_SINK_LAG") ? atoi(getenv("BLAST_SINK_LAG")) : 0;      // development
+        if (forced_lag > 0) sink.lag = std::min<uint32_t>(n_tiles, (uint32_t)forced_lag);
         if (sink.lag < 1) sink.lag = 1;
     }
 
@@ -2146,7 +2147,7 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         voice_position_scan<<<n_voice_blocks + n_zero_blocks, kScanThreads, 0, ctx->stream>>>(
             rb.d_voices, n_voices, (uint32_t)frames, rb.d_segs, rb.d_nsegs, d_err, rb.d_events, rb.d_nevents, rb.seg_cap, oc,
             rb.d_splits, rb.d_nsplits, rb.d_recs, n_tiles, n_voice_blocks, rb.d_err + (rb.parity ^ 1u), d_work,
-            reinterpret_cast<uint32_t*>(d_partial_bus), n_zero, sink, tab_pool, rb.pool_rows, (uint32_t)kStageBytes);
+            reinterpret_cast<uint32_t*>(d_partial_bus), n_zero, sink, tab_pool, rb.pool_rows, (uint32_t)kStageBytes, rewind);
         BLAST_CUDA_TRY(cudaGetLastError());
         ctx->launches += 1;
     }
@@ -2202,6 +2203,7 @@ struct blast_scene {
     std::vector<blast_voice> voices;     // host mirror of the ABI voices (positions refreshed on get)
     RenderBuffers rb;
     VoiceDev* d_voices0 = nullptr;       // the table as last uploaded (blast_scene_restore_dev)
+    bool rewind = false;                 // the next render starts from d_voices0 (its position scan copies the voice rows)
 };
 
 namespace {
@@ -2236,6 +2238,7 @@ int upload_voices(blast_ctx* ctx, blast_scene* sc) {
         BLAST_CUDA_TRY(cudaMemcpyAsync(sc->d_voices0, sc->rb.d_voices, hv.size() * sizeof(VoiceDev), cudaMemcpyDeviceToDevice, ctx->stream));
         BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
+    sc->rewind = false;
     return BLAST_OK;
 }
 
@@ -2291,13 +2294,7 @@ int blast_scene_set_voices(blast_ctx* ctx, blast_scene* sc, const blast_voice* v
 int blast_scene_restore_dev(blast_ctx* ctx, blast_scene* sc) {
     if (int rc = blast::bind(ctx)) return rc;
     BLAST_REQUIRE(sc != nullptr, BLAST_ERR_ARG, "blast_scene_restore_dev: null scene");
-    if (sc->n_voices) {                                      // a kernel, not a stream memcpy: no engine switch before the render
-        const uint32_t n16 = (uint32_t)((size_t)sc->n_voices * sizeof(VoiceDev) / 16);
-        copy_rows16<<<(n16 + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(sc->d_voices0),
-                                                                 reinterpret_cast<uint4*>(sc->rb.d_voices), n16);
-        BLAST_CUDA_TRY(cudaGetLastError());
-        ctx->launches += 1;
-    }
+    sc->rewind = true;                   // no launch: the next render's position scan reads the uploaded rows
     return BLAST_OK;
 }
 
@@ -2307,7 +2304,7 @@ int blast_scene_get_voices(blast_ctx* ctx, blast_scene* sc, blast_voice* out, ui
     BLAST_REQUIRE(n_voices == sc->n_voices, BLAST_ERR_ARG, "blast_scene_get_voices: voice count differs from the scene's");
     std::vector<VoiceDev> hv(sc->n_voices);
     if (sc->n_voices) {
-        BLAST_CUDA_TRY(cudaMemcpyAsync(hv.data(), sc->rb.d_voices, hv.size() * sizeof(VoiceDev), cudaMemcpyDeviceToHost, ctx->stream));
+        BLAST_CUDA_TRY(cudaMemcpyAsync(hv.data(), sc->rewind ? sc->d_voices0 : sc->rb.d_voices, hv.size() * sizeof(VoiceDev), cudaMemcpyDeviceToHost, ctx->stream));
         BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
     for (uint32_t i = 0; i < sc->n_voices; ++i) {
@@ -2320,7 +2317,9 @@ int blast_scene_get_voices(blast_ctx* ctx, blast_scene* sc, blast_voice* out, ui
 int blast_scene_render_dev(blast_ctx* ctx, blast_scene* sc, uint64_t frames, int32_t* d_partial_bus) {
     if (int rc = blast::bind(ctx)) return rc;
     BLAST_REQUIRE(sc && (d_partial_bus || frames == 0), BLAST_ERR_ARG, "blast_scene_render_dev: null argument");
-    return launch_render(ctx, sc->rb, sc->n_voices, 0, sc->out_channels, frames, d_partial_bus);
+    const VoiceDev* rewind = (sc->rewind && frames) ? sc->d_voices0 : nullptr;
+    if (frames) sc->rewind = false;
+    return launch_render(ctx, sc->rb, sc->n_voices, 0, sc->out_channels, frames, d_partial_bus, nullptr, rewind);
 }
 
 int blast_scene_check(blast_ctx* ctx, blast_scene* sc) {
@@ -2350,7 +2349,9 @@ int blast_scene_render_reduce_dev(blast_ctx* ctx, blast_scene* sc, uint64_t fram
     BLAST_REQUIRE(sc && pb, BLAST_ERR_ARG, "blast_scene_render_reduce_dev: null argument");
     BusSink sink;
     if (int rc = peer_bus_next_step(ctx, pb, frames, sc->out_channels, true, &sink)) return rc;
-    return launch_render(ctx, sc->rb, sc->n_voices, 0, sc->out_channels, frames, peer_bus_partial(pb), &sink);
+    const VoiceDev* rewind = (sc->rewind && frames) ? sc->d_voices0 : nullptr;
+    if (frames) sc->rewind = false;
+    return launch_render(ctx, sc->rb, sc->n_voices, 0, sc->out_channels, frames, peer_bus_partial(pb), &sink, rewind);
 }
 
 int blast_render(blast_ctx* ctx, const blast_track* tracks, uint32_t n_tracks, const blast_voice* voices,

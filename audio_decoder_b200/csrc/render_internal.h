@@ -125,8 +125,9 @@ void free_buffers(RenderBuffers& rb);
 // the int32 partial bus (overwritten); async on ctx->stream.  Device-side capacity errors land in rb.d_err.
 // sink != nullptr: the partial bus is sink->part[sink->rank] and finished tiles are reduced into sink->out (fused into the
 // render kernel for out_channels <= 2, as two small kernels after it otherwise).
+// rewind != nullptr: the voice rows are first copied from there (by the position scan itself).
 int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t n_seqs, uint32_t out_channels,
-                  uint64_t frames, int32_t* d_partial_bus, const BusSink* sink = nullptr);
+                  uint64_t frames, int32_t* d_partial_bus, const BusSink* sink = nullptr, const VoiceDev* rewind = nullptr);
 // the reduction on its own: publish every tile of this rank's partial bus (filled by earlier stream work), reduce the
 // tiles this rank owns.  Async on ctx->stream.
 int launch_bus_reduce(blast_ctx* ctx, const BusSink& sink);
