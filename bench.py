@@ -234,7 +234,7 @@ def run_ours(args):
     # ---- the mix's exchange step: partial buses reduced tile by tile inside the render kernel over peer memory
     peer = t_part = d_bus2 = None
     if mix:
-        if args.reduce == "p2p":
+        if args.reduce in ("p2p", "p2p2"):
             try:
                 peer = bd.PeerBus(ctx, n_slots, rank, world)
             except RuntimeError as e:                                  # raised on EVERY rank or on none
@@ -261,7 +261,12 @@ def run_ours(args):
         if peer is None:
             return mix_unfused(sh)
         sh.scene.restore_dev()
-        peer.render_reduce(sh.scene, frames)                            # K3 + K4 (render, publish, reduce, finalize)
+        if args.reduce == "p2p2":                                       # the same exchange as two small kernels after the render
+            peer.begin()
+            sh.scene.render_partial_dev(frames, peer.part_ptr)
+            peer.reduce(n_slots)
+        else:
+            peer.render_reduce(sh.scene, frames)                        # K3 + K4 (render, publish, reduce, finalize)
         peer.wait()                                                     # root: every rank's tiles are in the bus
 
     bus_ptr = (peer.bus_ptr if peer is not None else d_bus2.ptr) if mix else None
@@ -377,7 +382,9 @@ def run_ours(args):
     alg_mix = shard.alg_mix + 2 * n_slots // world
     if mix:
         ach = alg_mix / (t["ms_mix"] * 1e-3) / 1e9
-        roofline_mix = {"kernel": "voice_position_scan + voice_render_mix_tma (render, tile publish, peer reduce, S16 wrap in one kernel)"
+        roofline_mix = {"kernel": ("voice_position_scan + voice_render_mix_tma + bus_finalize" if world == 1 else
+                                   "voice_position_scan + voice_render_mix_tma (render, tile publish, peer reduce, S16 wrap in one kernel)"
+                                   if args.reduce == "p2p" else "voice_position_scan + voice_render_mix_tma + peer_publish_tiles + bus_reduce_tiles")
                         if peer is not None else "voice_position_scan + voice_render_mix_tma + NCCL all-reduce(int32) + bus_finalize",
                         "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                         "algorithmic_bytes_per_step": alg_mix, "ms_per_step": round(t["ms_mix"], 4),
@@ -656,8 +663,9 @@ def main():
     ap.add_argument("--quick-configs", action="store_true", help="other configs at reduced sizes (development)")
     ap.add_argument("--ref-files-per-thread", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"],
-                    help="the mix reduction: inside the render kernel over peer memory, or as an NCCL all-reduce + finalize")
+    ap.add_argument("--reduce", default="p2p", choices=["p2p", "p2p2", "nccl"],
+                    help="the mix reduction: inside the render kernel over peer memory (p2p), the same tile exchange as two "
+                         "kernels after the render (p2p2), or an NCCL all-reduce + finalize")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
