@@ -124,8 +124,7 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
 // (CCTL.IVALL), which the render's producer warps keep warm with voice rows and tile records.  Only the CTA that
 // completes a tile pays the acquire side (the fence after the atomic makes the other CTAs' bus writes part of what its
 // system-scope flag store releases).
-// `n_parts` = counts a tile needs: K4 counts per consumer WARP (voice groups x 8), so no barrier joins the warps of a CTA
-// after a flush.  A single rank (world == 1) never leaves gpu scope.
+// `n_parts` = counts a tile needs (its voice groups).  A single rank (world == 1) never leaves gpu scope.
 __device__ __forceinline__ void sink_fence(const BusSink& s) {
     if (s.world > 1) __threadfence_system(); else __threadfence();
 }
@@ -969,7 +968,7 @@ struct StageMeta {            // written by the producer before it arrives on th
 static_assert(sizeof(StageMeta) == 96, "StageMeta layout");
 constexpr size_t kMetaStride = 96;
 constexpr size_t kTmaSmem = (size_t)kStages * kStageBytes + kStages * kMetaStride + 2 * kStages * sizeof(uint64_t) +
-                            (size_t)kStages * kMaxPieces * sizeof(uint4) + 32;     // + the consumer warps' pending-tile words
+                            (size_t)kStages * kMaxPieces * sizeof(uint4) + 32;     // + the producer's uncounted-flush words
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -1334,6 +1333,37 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
         uint32_t o = 0;                                   // stage items enqueued so far (uniform across the warp)
         uint32_t grabbed = 0;                             // lane 0: the next work item, taken one item ahead
         if (lane == 0) grabbed = atomicAdd(work, 1u);
+        // Tile hand-off (bus sink).  A flush stage makes the consumers write the work item into the bus; once they have
+        // released that stage (its empty barrier) all of their bus writes are issued, and THIS warp — which mostly waits —
+        // counts the item with a release atomic and publishes the tile when it was the last one.  The consumers pay
+        // nothing.  s_ft[stage] = tile of a flush stage that has not been counted yet.
+        volatile uint32_t* s_ft = reinterpret_cast<volatile uint32_t*>(ptabs + kStages * kMaxPieces);
+        if (lane == 0)
+            for (int k = 0; k < kStages; ++k) s_ft[k] = 0xFFFFFFFFu;
+        __syncwarp();
+        // one lane: wait until fill number o_idx may overwrite its stage; count the flush it replaces
+        auto acquire = [&](uint32_t o_idx) {
+            const uint32_t st = o_idx % kStages, round = o_idx / kStages;
+            if (round > 0) mbar_wait(empty + st, (round - 1) & 1);
+            if (sink.world) {
+                const uint32_t t = s_ft[st];
+                if (t != 0xFFFFFFFFu) { k4_tile_flushed(sink, t, n_groups); s_ft[st] = 0xFFFFFFFFu; }
+            }
+        };
+        // one lane: every flush stage enqueued so far is consumed and counted (before this CTA's consumers are sent to
+        // wait for a peer, and at the end): a CTA never waits for a tile while it holds a count back
+        auto drain = [&](uint32_t o_now) {
+            if (!sink.world) return;
+            for (uint32_t k = 1; k <= (uint32_t)kStages && k <= o_now; ++k) {
+                const uint32_t oi = o_now - k, st = oi % kStages;
+                const uint32_t t = s_ft[st];
+                if (t != 0xFFFFFFFFu) {
+                    mbar_wait(empty + st, (oi / kStages) & 1);
+                    k4_tile_flushed(sink, t, n_groups);
+                    s_ft[st] = 0xFFFFFFFFu;
+                }
+            }
+        };
         auto prefetch_batch = [&](uint32_t t, uint32_t vi_, uint32_t vend_) {
             // the voice row, its tile record and its segment count of a batch the producer will cut later: without this
             // the two dependent misses (voice, then record: ~2 us under load) at every batch start outlast the ring's slack
@@ -1543,7 +1573,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                     StageMeta* ms = reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride);
                     const uint32_t bytes2 = i2 >= 0 ? __shfl_sync(0xFFFFFFFFu, bytes, i2) : 0u;
                     if (lane == i) {
-                        if (round > 0) mbar_wait(empty + st, (round - 1) & 1);
+                        acquire(o);
                         *ms = m;
                         if (i2 >= 0) ms->mode = kModeStaged | (kPathStereoUnit2 << 8);
                     }
@@ -1593,8 +1623,8 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                                     const unsigned long long b0 = base + (unsigned long long)lo_g * 4ull;
                                     const unsigned long long b1 = base + ((unsigned long long)hi_g + 2ull) * 4ull;
                                     const unsigned long long a0 = b0 & ~15ull, a1 = (b1 + 15ull) & ~15ull;
-                                    const uint32_t st = o_mine % kStages, round = o_mine / kStages;
-                                    if (round > 0) mbar_wait(empty + st, (round - 1) & 1);
+                                    const uint32_t st = o_mine % kStages;
+                                    acquire(o_mine);
                                     StageMeta mm{};
                                     mm.mode = kModeStaged | (kPathStereoMulti << 8);
                                     mm.gain = v.gain;
@@ -1692,8 +1722,8 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                                     const unsigned long long b0 = smp_i + (unsigned long long)lo_g * 4ull;
                                     const unsigned long long b1 = smp_i + ((unsigned long long)hi_g + 2ull) * 4ull;
                                     const unsigned long long a0 = b0 & ~15ull, a1 = (b1 + 15ull) & ~15ull;
-                                    const uint32_t st = o % kStages, round = o / kStages;
-                                    if (lane == 0 && round > 0) mbar_wait(empty + st, (round - 1) & 1);
+                                    const uint32_t st = o % kStages;
+                                    if (lane == 0) acquire(o);
                                     __syncwarp();
                                     if (ex && lane >= g0 && lane <= L)
                                         ptabs[st * kMaxPieces + lane - g0] = make_uint4(fa | (fe << 16), (uint32_t)q0v, (uint32_t)g.d, shv | (silent ? 0x100u : 0u));
@@ -1725,23 +1755,24 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
             }
         }
         if (render_item) {   // end of the work item: the consumers add their accumulators into the bus
-            const uint32_t st = o % kStages, round = o / kStages;
+            const uint32_t st = o % kStages;
             if (lane == 0) {
-                if (round > 0) mbar_wait(empty + st, (round - 1) & 1);
+                acquire(o);
                 StageMeta* ms = reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride);
                 ms->mode = kModeFlush;
                 ms->a0_off = f0;
                 ms->frange = nf;
-                ms->q0 = (int32_t)tile;
+                if (sink.world) s_ft[st] = tile;
                 mbar_arrive(full + st);
             }
             __syncwarp();
             o += 1;
         }
         if (sink.world && item % n_groups == 0 && tile >= sink.lag && (tile - sink.lag) % sink.world == sink.rank) {
-            const uint32_t st = o % kStages, round = o / kStages;
+            const uint32_t st = o % kStages;
             if (lane == 0) {
-                if (round > 0) mbar_wait(empty + st, (round - 1) & 1);
+                drain(o);
+                acquire(o);
                 StageMeta* ms = reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride);
                 ms->mode = kModeReduce;
                 ms->a0_off = tile - sink.lag;
@@ -1752,8 +1783,9 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
         }
         }   // next work item
         if (lane == 0) {
-            const uint32_t st = o % kStages, round = o / kStages;
-            if (round > 0) mbar_wait(empty + st, (round - 1) & 1);
+            const uint32_t st = o % kStages;
+            drain(o);
+            acquire(o);
             reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride)->mode = kModeEnd;
             mbar_arrive(full + st);
         }
@@ -1773,24 +1805,8 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
     constexpr uint32_t kMetaOff = (uint32_t)kStages * kStageBytes, kFullOff = kMetaOff + (uint32_t)(kStages * kMetaStride),
                        kEmptyOff = kFullOff + (uint32_t)kStages * 8u;
     uint32_t st = 0, phase = 0;
-    // lane 0 of every consumer warp: the tile of the warp's last flush, not yet counted.  The count is a release (it waits
-    // for the warp's bus writes), so it is made one STAGE later, when those writes have landed and the wait costs next to
-    // nothing — not later than that: the tile's reduction is queued `lag` tiles behind and must not find a count missing.
-    // Counting per warp (a tile needs voice groups x 8 counts) means no barrier joins the consumer warps after a flush.
-    // A warp never waits for a peer while it holds a count back.  (Kept in shared memory: the consumer loop has no
-    // register to spare at 72.)
-    volatile uint32_t* pending = reinterpret_cast<volatile uint32_t*>(ptabs + kStages * kMaxPieces) + warp;
-    if (lane == 0) *pending = 0xFFFFFFFFu;
-    auto publish_pending = [&]() {
-        if (lane == 0) {
-            const uint32_t t = *pending;
-            if (t != 0xFFFFFFFFu) { k4_tile_flushed(sink, t, n_groups * (uint32_t)(kConsumers / 32)); *pending = 0xFFFFFFFFu; }
-        }
-    };
-    bool just_flushed = false;
     for (;;) {
         mbar_wait_a(sm0 + kFullOff + st * 8u, phase);
-        if (just_flushed) { publish_pending(); just_flushed = false; }
         const uint32_t stage_addr = sm0 + st * (uint32_t)kStageBytes;
         const uint32_t meta_addr = sm0 + kMetaOff + st * (uint32_t)kMetaStride;
         const StageMeta* mp = reinterpret_cast<const StageMeta*>(meta_base + st * kMetaStride);
@@ -1823,11 +1839,6 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                         acc[j][c] = 0;
                     }
                 }
-            }
-            if (sink.world) {                                    // the warp's bus writes are issued: its lane 0 may count them
-                __syncwarp();
-                if (lane == 0) *pending = a0_off / (uint32_t)kFT;
-                just_flushed = true;
             }
         } else if ((mode & 0xFF) == kModeReduce) {
             k4_reduce_tile(sink, a0_off);

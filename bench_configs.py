@@ -7,7 +7,7 @@ parameters come from X128P::new(0xC3) (synth.c3_voice_params).  Every entry carr
 achieved GB/s and the fraction of the measured HBM peak; each is checked by a size-independent property, not by the
 oracle (tests/ hold the oracle comparisons).
 
-At N > 1 only C3 runs, strong-scaled (voice v -> rank v mod N), with the bus reduced over peer memory inside the render
+At N > 1 only C3 runs, strong-scaled (voice v -> rank (v + v // N) mod N), with the bus reduced over peer memory inside the render
 kernel; `reduce_ms` is what the exchange adds to the same render without it."""
 from __future__ import annotations
 
@@ -120,7 +120,7 @@ def c2_true24(ctx, peak, quick):
 
 # ---------------------------------------------------------------------------------------------- C3
 class C3Scene:
-    """this rank's voices of the C3 scene (v mod world == rank): clips from X128P::new(0xC3_0000 + v) bytes in HBM"""
+    """this rank's voices of the C3 scene: clips from X128P::new(0xC3_0000 + v) bytes in HBM"""
 
     def __init__(self, ctx, rank, world, n_voices, frames, all_unit):
         import audio_decoder_b200 as blast
@@ -128,7 +128,9 @@ class C3Scene:
         import bench
         self.ctx = ctx
         params = synth.c3_voice_params(n_voices)
-        self.ids = list(range(rank, n_voices, world))
+        # voice v -> rank (v + v // world) mod world: round robin, rotated by one per row, so that the odd (interpolated,
+        # twice as expensive) voices do not all land on the odd ranks as they would with v mod world
+        self.ids = [v for v in range(n_voices) if (v + v // world) % world == rank]
         self.slabs = []
         self.src_bytes = 0.0
         track_of = {}
@@ -225,7 +227,7 @@ def c3(ctx, rank, world, local, dist, peak, quick, all_unit):
                  workload=f"C3: {n_voices} stereo voices x {frames} frames -> one stereo S16 bus, "
                           + ("velocity 1.0" if all_unit else "odd voices at velocity 0.5..1.5 (interpolated)")
                           + ", gains next_f32() * 2^-7 from X128P::new(0xC3), clips X128P::new(0xC3_0000 + v)"
-                          + (f"; voice v on rank v mod {world}" if world > 1 else ""),
+                          + (f"; voice v on rank (v + v // {world}) mod {world}" if world > 1 else ""),
                  kernel="voice_position_scan + voice_render_mix_tma (render + tile reduce + S16 wrap)",
                  ms_without_exchange=round(ms_local, 4), reduce_ms=round(ms - ms_local, 4), check=check,
                  frac_note=f"of {world} x the measured HBM peak" if world > 1 else None)
