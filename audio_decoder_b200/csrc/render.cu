@@ -1296,7 +1296,9 @@ __device__ __forceinline__ void consume_generic(const StageMeta& m, uint32_t sta
 // next one from a global counter and keeps the stage ring full ACROSS items, so a CTA has no prologue / epilogue
 // bubble per item (as one CTA per item this cost ~11 us per CTA round: C2's mix ran at 5.3 TB/s, C3 at 6.7).  A
 // kModeFlush item at the end of each work item makes the consumers add their accumulators into the bus.
-template <int OC>
+// kSink: the bus-sink code (tile counts, reduce items) is compiled in; kTables: so is the producer's piece-table path.
+// Both are rare configurations and both cost the producer warp registers (it spills) — the plain kernel carries neither.
+template <int OC, bool kSink, bool kTables>
 __global__ void __launch_bounds__(kTmaThreads, 3)
 voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uint32_t voices_per_group,
                      uint32_t n_groups, const Seg* __restrict__ segs, const uint32_t* __restrict__ nsegs,
@@ -1317,7 +1319,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
     // index than its own, i.e. is already held by a running CTA: no CTA ever waits for work nobody has taken.
     const uint32_t n_tiles = (frames + (uint32_t)kFT - 1u) / (uint32_t)kFT;
     const uint32_t n_render_items = n_tiles * n_groups;
-    const uint32_t n_items = sink.world ? (n_tiles + sink.lag) * n_groups : n_render_items;
+    const uint32_t n_items = (kSink && sink.world) ? (n_tiles + sink.lag) * n_groups : n_render_items;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -1345,7 +1347,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
         auto acquire = [&](uint32_t o_idx) {
             const uint32_t st = o_idx % kStages, round = o_idx / kStages;
             if (round > 0) mbar_wait(empty + st, (round - 1) & 1);
-            if (sink.world) {
+            if (kSink && sink.world) {
                 const uint32_t t = s_ft[st];
                 if (t != 0xFFFFFFFFu) { k4_tile_flushed(sink, t, n_groups); s_ft[st] = 0xFFFFFFFFu; }
             }
@@ -1353,7 +1355,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
         // one lane: every flush stage enqueued so far is consumed and counted (before this CTA's consumers are sent to
         // wait for a peer, and at the end): a CTA never waits for a tile while it holds a count back
         auto drain = [&](uint32_t o_now) {
-            if (!sink.world) return;
+            if (!kSink || !sink.world) return;
             for (uint32_t k = 1; k <= (uint32_t)kStages && k <= o_now; ++k) {
                 const uint32_t oi = o_now - k, st = oi % kStages;
                 const uint32_t t = s_ft[st];
@@ -1380,7 +1382,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
         if (item >= n_items) break;
         if (lane == 0) grabbed = atomicAdd(work, 1u);     // the item after this one: in flight while this one is staged
         const uint32_t tile = item / n_groups;
-        const bool render_item = tile < n_tiles;
+        const bool render_item = !kSink || tile < n_tiles;     // (virtual items exist only behind a sink)
         const uint32_t f0 = tile * (uint32_t)kFT;
         const uint32_t nf = render_item ? min((uint32_t)kFT, frames - f0) : 0u;
         const uint32_t vbeg = (item % n_groups) * voices_per_group;
@@ -1606,7 +1608,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                     // is computed here.  (Cutting these tiles in this warp, one voice at a time, was what K4 waited for on
                     // scenes with retriggers: a quarter of all voice-tiles, ~6 segments each.)
                     {
-                        const bool has_tab = hold_multi && pool != nullptr && (__float_as_uint(r.scale) & 0xFFC00000u) == kTabTag;
+                        const bool has_tab = kTables && hold_multi && pool != nullptr && (__float_as_uint(r.scale) & 0xFFC00000u) == kTabTag;
                         const uint4* vrows = has_tab ? pool + (size_t)vi * pool_rows + (uint32_t)r.d : nullptr;
                         uint4 hdr = make_uint4(0, 0, 0, 0);
                         if (has_tab) hdr = __ldg(vrows);                            // all lanes' first headers in one round trip
@@ -1762,13 +1764,13 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                 ms->mode = kModeFlush;
                 ms->a0_off = f0;
                 ms->frange = nf;
-                if (sink.world) s_ft[st] = tile;
+                if (kSink && sink.world) s_ft[st] = tile;
                 mbar_arrive(full + st);
             }
             __syncwarp();
             o += 1;
         }
-        if (sink.world && item % n_groups == 0 && tile >= sink.lag && (tile - sink.lag) % sink.world == sink.rank) {
+        if (kSink && sink.world && item % n_groups == 0 && tile >= sink.lag && (tile - sink.lag) % sink.world == sink.rank) {
             const uint32_t st = o % kStages;
             if (lane == 0) {
                 drain(o);
@@ -1840,7 +1842,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                     }
                 }
             }
-        } else if ((mode & 0xFF) == kModeReduce) {
+        } else if (kSink && (mode & 0xFF) == kModeReduce) {
             k4_reduce_tile(sink, a0_off);
         } else {
             const uint32_t path = (mode >> 8) & 0xFF;
@@ -2111,6 +2113,8 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         }
         groups = best;
     }
+    static const uint32_t forced_groups = getenv("BLAST_RENDER_GROUPS") ? (uint32_t)atoi(getenv("BLAST_RENDER_GROUPS")) : 0u;   // development
+    if (forced_groups) groups = std::max(1u, std::min(forced_groups, n_voices));
     const uint32_t per_group = (n_voices + groups - 1) / groups;
     groups = (n_voices + per_group - 1) / per_group;
     const int use_atomic = groups > 1;
@@ -2166,15 +2170,22 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
     dim3 grid_tma(std::min<uint32_t>(n_tiles * groups, resident), 1);
     if (oc <= 2 && !legacy) {
         // TMA pipeline kernel (one producer warp + eight consumer warps)
+#define BLAST_LAUNCH_TMA(OCV, SINK, TAB)                                                                                              \
+    do {                                                                                                                                \
+        BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<OCV, SINK, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem)); \
+        voice_render_mix_tma<OCV, SINK, TAB><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(                                      \
+            rb.d_voices, n_voices, per_group, groups, rb.d_segs, rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, \
+            d_err, rb.seg_cap, d_work, sink, -0.0f, tab_pool, rb.pool_rows);                                                         \
+    } while (0)
+        const bool with_tab = tab_pool != nullptr;
         if (oc == 1) {
-            BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
-            voice_render_mix_tma<1><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(rb.d_voices, n_voices, per_group, groups, rb.d_segs,
-                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, d_err, rb.seg_cap, d_work, sink, -0.0f, tab_pool, rb.pool_rows);
+            if (fused) BLAST_LAUNCH_TMA(1, true, false); else BLAST_LAUNCH_TMA(1, false, false);
+        } else if (fused) {
+            if (with_tab) BLAST_LAUNCH_TMA(2, true, true); else BLAST_LAUNCH_TMA(2, true, false);
         } else {
-            BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
-            voice_render_mix_tma<2><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(rb.d_voices, n_voices, per_group, groups, rb.d_segs,
-                                                                                  rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, d_err, rb.seg_cap, d_work, sink, -0.0f, tab_pool, rb.pool_rows);
+            if (with_tab) BLAST_LAUNCH_TMA(2, false, true); else BLAST_LAUNCH_TMA(2, false, false);
         }
+#undef BLAST_LAUNCH_TMA
     } else {
 #define BLAST_LAUNCH_MIX(OCV)                                                                              \
     voice_render_mix<OCV><<<grid, kThreads, 0, ctx->stream>>>(rb.d_voices, n_voices, per_group, rb.d_segs,  \
