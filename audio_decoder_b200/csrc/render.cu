@@ -2089,30 +2089,16 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         BLAST_CUDA_TRY(cudaMalloc(&rb.d_recs, need * sizeof(TileRec)));
         rb.recs_cap = need;
     }
-    // voice groups: enough work items to fill the GPU a few times over, groups of >= 64 voices
+    // voice groups: enough work items to fill the GPU a few times over
     uint32_t groups = 1;
     static const uint32_t ctas_per_sm = getenv("BLAST_RENDER_CTAS_PER_SM") ? (uint32_t)atoi(getenv("BLAST_RENDER_CTAS_PER_SM")) : 32u;
     const uint32_t want_ctas = (uint32_t)ctx->sm_count * ctas_per_sm;
-    static const uint32_t min_group = getenv("BLAST_RENDER_MIN_GROUP") ? (uint32_t)atoi(getenv("BLAST_RENDER_MIN_GROUP")) : 64u;
+    // groups of >= 16 voices: a sharded scene (1,024 files over 8 GPUs = 128 voices per rank) still gets ~6 work items per
+    // CTA for the queue to balance; smaller groups pay more per flush than they gain (profiles/r02_group_sweep.json)
+    static const uint32_t min_group = getenv("BLAST_RENDER_MIN_GROUP") ? (uint32_t)atoi(getenv("BLAST_RENDER_MIN_GROUP")) : 16u;
     while (n_tiles * groups < want_ctas && n_voices / (groups * 2) >= min_group) groups *= 2;
     // persistent: CTAs per SM (three fit: shared-memory bound) take (tile, group) items, tile-major, from a counter
     const uint32_t resident = (uint32_t)ctx->sm_count * (uint32_t)ctx->render_ctas_per_sm;
-    if (oc <= 2 && !legacy && n_tiles * groups < 8 * resident) {
-        // few equal items per CTA: a kernel as long as ceil(items / CTAs) items.  Among the group counts allowed (groups of
-        // >= 16 voices) take the one that wastes the least of the last round (1,024 files over 8 GPUs: 128 voices per rank,
-        // 352 tiles -> 704 items on 444 CTAs would leave 44 % of the second round idle).
-        uint32_t best = groups;
-        double best_cost = 1e30;
-        for (uint32_t g = 1; g <= 64 && n_voices / g >= 16; ++g) {
-            const uint32_t per = (n_voices + g - 1) / g, gg = (n_voices + per - 1) / per;
-            const uint64_t items = (uint64_t)n_tiles * gg;
-            const uint64_t rounds = (items + resident - 1) / resident;
-            // per item: `per` voice tiles of work + ~3 voice tiles' worth of fixed cost (flush, barriers, queue)
-            const double cost = (double)rounds * ((double)per + 3.0);
-            if (cost < best_cost) { best_cost = cost; best = gg; }
-        }
-        groups = best;
-    }
     static const uint32_t forced_groups = getenv("BLAST_RENDER_GROUPS") ? (uint32_t)atoi(getenv("BLAST_RENDER_GROUPS")) : 0u;   // development
     if (forced_groups) groups = std::max(1u, std::min(forced_groups, n_voices));
     const uint32_t per_group = (n_voices + groups - 1) / groups;
