@@ -498,7 +498,8 @@ def run_ours(args):
     shard.close()
     if not args.no_configs:
         import bench_configs
-        out["configs"] = bench_configs.run(ctx, rank, world, local, dist, peak, quick=args.quick_configs)
+        out["configs"] = bench_configs.run(ctx, rank, world, local, dist, peak, quick=args.quick_configs,
+                                           reduce=args.reduce if args.reduce in ("p2p", "p2p2") else "p2p2")
     if rank == 0:
         print(json.dumps(out))
     if peer is not None:

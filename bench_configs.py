@@ -163,7 +163,7 @@ class C3Scene:
             s.free()
 
 
-def c3(ctx, rank, world, local, dist, peak, quick, all_unit):
+def c3(ctx, rank, world, local, dist, peak, quick, all_unit, reduce="p2p"):
     from audio_decoder_b200 import audio_processing as ap, distributed as bd
     n_voices = synth.C3_VOICES if not quick else 512
     frames = synth.C3_FRAMES if not quick else 1 << 17
@@ -175,7 +175,12 @@ def c3(ctx, rank, world, local, dist, peak, quick, all_unit):
 
     def fused():
         sc.scene.restore_dev()
-        peer.render_reduce(sc.scene, frames)
+        if reduce == "p2p2":                                    # the tile exchange as two kernels after the render
+            peer.begin()
+            sc.scene.render_partial_dev(frames, peer.part_ptr)
+            peer.reduce(n_slots)
+        else:                                                   # ... or inside the render kernel
+            peer.render_reduce(sc.scene, frames)
         peer.wait()
 
     def local_only():                                           # the same render without the exchange: K3 + K4 + K5 on this rank's voices
@@ -228,7 +233,9 @@ def c3(ctx, rank, world, local, dist, peak, quick, all_unit):
                           + ("velocity 1.0" if all_unit else "odd voices at velocity 0.5..1.5 (interpolated)")
                           + ", gains next_f32() * 2^-7 from X128P::new(0xC3), clips X128P::new(0xC3_0000 + v)"
                           + (f"; voice v on rank (v + v // {world}) mod {world}" if world > 1 else ""),
-                 kernel="voice_position_scan + voice_render_mix_tma (render + tile reduce + S16 wrap)",
+                 kernel="voice_position_scan + voice_render_mix_tma + " + ("bus_finalize" if world == 1 else
+                        "peer_publish_tiles + bus_reduce_tiles (tile exchange over peer memory)" if reduce == "p2p2" else
+                        "tile publish / peer reduce / S16 wrap inside the render kernel"),
                  ms_without_exchange=round(ms_local, 4), reduce_ms=round(ms - ms_local, 4), check=check,
                  frac_note=f"of {world} x the measured HBM peak" if world > 1 else None)
     peer.close()
@@ -369,13 +376,13 @@ def c5(ctx, peak, quick):
     return out
 
 
-def run(ctx, rank, world, local, dist, peak, quick=False):
+def run(ctx, rank, world, local, dist, peak, quick=False, reduce="p2p"):
     out = {}
     if world == 1:
         out["c1"] = c1(ctx, peak, quick)
         out["c2_true24"] = c2_true24(ctx, peak, quick)
-    out["c3_unit"] = c3(ctx, rank, world, local, dist, peak, quick, True)
-    out["c3_mixed"] = c3(ctx, rank, world, local, dist, peak, quick, False)
+    out["c3_unit"] = c3(ctx, rank, world, local, dist, peak, quick, True, reduce)
+    out["c3_mixed"] = c3(ctx, rank, world, local, dist, peak, quick, False, reduce)
     if world == 1:
         out["c3_seq"] = c3_seq(ctx, peak, quick)
         ctx.trim()
