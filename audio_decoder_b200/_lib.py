@@ -168,6 +168,7 @@ SIGNATURES = {
     "blast_peer_bus_export": (C.c_int, [_vp, _vp, _vp]),
     "blast_peer_bus_connect_ipc": (C.c_int, [_vp, _vp, _vp]),
     "blast_peer_bus_connect_local": (C.c_int, [C.POINTER(_vp), _u32]),
+    "blast_peer_bus_set_fused": (C.c_int, [_vp, C.c_int]),
     "blast_peer_bus_partial": (_vp, [_vp]),
     "blast_peer_bus_bus": (_vp, [_vp]),
     "blast_scene_render_reduce_dev": (C.c_int, [_vp, _vp, _u64, _vp]),
@@ -178,6 +179,7 @@ SIGNATURES = {
     "blast_conductor_set_shard_by_track": (C.c_int, [_vp, _u32, _u32]),
     "blast_group_create": (C.c_int, [C.POINTER(_vp), C.POINTER(C.c_int), _u32]),
     "blast_group_destroy": (None, [_vp]),
+    "blast_group_set_fused": (C.c_int, [_vp, C.c_int]),
     "blast_group_size": (_u32, [_vp]),
     "blast_group_ctx": (_vp, [_vp, _u32]),
     "blast_group_pcm_decode_batch": (C.c_int, [_vp, _u32, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(PcmDesc), C.POINTER(_vp),

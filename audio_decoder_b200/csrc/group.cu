@@ -23,6 +23,7 @@ struct blast_group {
     std::vector<int> device;
     std::vector<blast_peer_bus*> pb;          // one per member, connected; sized for pb_slots
     uint64_t pb_slots = 0;
+    bool fused = false;                       // blast_group_render: the exchange inside the render kernel
     std::vector<std::vector<void*>> slabs;    // device memory handed out as tracks, per member
 };
 
@@ -67,6 +68,7 @@ int ensure_peer_buses(blast_group* g, uint64_t n_slots) {
     for (uint32_t m = 0; m < g->n; ++m)
         if (int rc = blast_peer_bus_create(g->ctx[m], std::max<uint64_t>(n_slots, 1), m, g->n, 0, &g->pb[m])) { free_peer_buses(g); return rc; }
     if (int rc = blast_peer_bus_connect_local(g->pb.data(), g->n)) { free_peer_buses(g); return rc; }
+    for (uint32_t m = 0; m < g->n; ++m) blast_peer_bus_set_fused(g->pb[m], g->fused ? 1 : 0);
     g->pb_slots = std::max<uint64_t>(n_slots, 1);
     return BLAST_OK;
 }
@@ -130,6 +132,14 @@ void blast_group_destroy(blast_group* g) {
     blast_group_free_tracks(g);
     for (auto* c : g->ctx) blast_ctx_destroy(c);
     delete g;
+}
+
+int blast_group_set_fused(blast_group* g, int fused) {
+    BLAST_REQUIRE(g != nullptr, BLAST_ERR_ARG, "blast_group_set_fused: null group");
+    g->fused = fused != 0;
+    for (uint32_t m = 0; m < g->pb.size(); ++m)
+        if (g->pb[m]) blast_peer_bus_set_fused(g->pb[m], g->fused ? 1 : 0);
+    return BLAST_OK;
 }
 
 uint32_t blast_group_size(const blast_group* g) { return g ? g->n : 0; }

@@ -27,6 +27,7 @@ struct blast_peer_bus {
     bool connected = false;
     uint32_t step = 0;
     uint32_t timeout_ms = 20000;
+    bool fused = false;                         // blast_scene_render_reduce_dev: the exchange inside the render kernel
 };
 
 namespace {
@@ -61,6 +62,7 @@ void layout(blast_peer_bus* pb) {
 namespace blast_rdr {
 
 int32_t* peer_bus_partial(blast_peer_bus* pb) { return reinterpret_cast<int32_t*>(pb->window); }
+bool peer_bus_fused(const blast_peer_bus* pb) { return pb->fused; }
 
 int peer_bus_next_step(blast_ctx* ctx, blast_peer_bus* pb, uint64_t frames, uint32_t oc, bool in_render, BusSink* out) {
     if (pb->ctx != ctx) return blast::set_error(BLAST_ERR_ARG, "the peer bus belongs to another context");
@@ -206,6 +208,12 @@ int blast_peer_bus_connect_local(blast_peer_bus* const* all, uint32_t world) {
         }
         all[r]->connected = true;
     }
+    return BLAST_OK;
+}
+
+int blast_peer_bus_set_fused(blast_peer_bus* pb, int fused) {
+    BLAST_REQUIRE(pb != nullptr, BLAST_ERR_ARG, "blast_peer_bus_set_fused: null peer bus");
+    pb->fused = fused != 0;
     return BLAST_OK;
 }
 

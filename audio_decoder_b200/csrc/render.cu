@@ -2359,13 +2359,17 @@ int blast_scene_render_reduce_dev(blast_ctx* ctx, blast_scene* sc, uint64_t fram
     if (int rc = peer_bus_next_step(ctx, pb, frames, sc->out_channels, true, &sink)) return rc;
     const VoiceDev* rewind = (sc->rewind && frames) ? sc->d_voices0 : nullptr;
     if (frames) sc->rewind = false;
-    static const bool fuse1 = getenv("BLAST_SINK_FUSE_SINGLE") != nullptr;
-    if (sink.world == 1 && !fuse1) {
-        // a single rank has nothing to exchange: render, then one finalize launch.  (The render kernel can finalize its
-        // own tiles — BLAST_SINK_FUSE_SINGLE=1 — but publishing every flush costs more than the 5 us launch it saves:
-        // C2's mix 0.537 ms fused vs 0.516 ms, profiles/r02_sink_lag_sweep.json.)
+    if (!peer_bus_fused(pb)) {
+        // Default: render, then the exchange as its own launches — one finalize on a single rank; tile publish + tile
+        // reduce over peer memory (after a wait for the peers' acknowledgements of the previous step) on several.  The
+        // render kernel can do the exchange itself (blast_peer_bus_set_fused), tile by tile as the tiles complete; measured
+        // on B200s that variant is the slower one: its producer warp carries the hand-off and spills
+        // (profiles/r02_sink_lag_sweep.json, r02_bench_n2_*.json).
+        if (sink.world > 1)
+            if (int rc = launch_flag_wait(ctx, sink.ack_mine, sink.world, sink.step - 1u, sink.timeout_ms, sink.err)) return rc;
         if (int rc = launch_render(ctx, sc->rb, sc->n_voices, 0, sc->out_channels, frames, peer_bus_partial(pb), nullptr, rewind)) return rc;
-        return blast_bus_finalize_dev(ctx, peer_bus_partial(pb), blast_peer_bus_bus(pb), frames * sc->out_channels);
+        if (sink.world == 1) return blast_bus_finalize_dev(ctx, peer_bus_partial(pb), blast_peer_bus_bus(pb), frames * sc->out_channels);
+        return launch_bus_reduce(ctx, sink);
     }
     return launch_render(ctx, sc->rb, sc->n_voices, 0, sc->out_channels, frames, peer_bus_partial(pb), &sink, rewind);
 }

@@ -137,6 +137,7 @@ int launch_flag_wait(blast_ctx* ctx, const uint32_t* d_flags, uint32_t n, uint32
 // sink the kernels take.  in_render: tiles are the render kernel's (kFT frames); else 4,096-slot tiles.
 int peer_bus_next_step(blast_ctx* ctx, blast_peer_bus* pb, uint64_t frames, uint32_t out_channels, bool in_render, BusSink* out);
 int32_t* peer_bus_partial(blast_peer_bus* pb);
+bool peer_bus_fused(const blast_peer_bus* pb);
 // VoiceDev routing fields (S, nch, adv) for a voice with C channels on an out_channels bus
 void route_voice(VoiceDev& v, uint32_t out_channels, bool has_seq);
 

@@ -170,15 +170,16 @@ class ShardedMpegIndex:
 class PeerBus:
     """The render's one exchange step without a collective library (include/blast_cuda.h, blast_peer_bus_*): every
     rank's window — int32 partial bus, S16 bus, flag tables — is mapped into every peer's address space (CUDA IPC over
-    NVLink / NVSwitch); the bus is cut into tiles, tile t is reduced by rank t mod world INSIDE the render kernel as the
-    tiles complete.  This class only creates the window and carries the 64-byte handles (torch.distributed, set-up
-    time); the protocol itself lives in the library.
+    NVLink / NVSwitch); the bus is cut into tiles, tile t is reduced by rank t mod world — by two small kernels after the
+    render, or (fused=True) inside the render kernel as the tiles complete.  This class only creates the window and
+    carries the 64-byte handles (torch.distributed, set-up time); the protocol itself lives in the library.
 
     Per step, on every rank:      pb.render_reduce(scene, frames)     then, on the root:   pb.wait();  bus = pb.bus_ptr
     or (Conductor spans):         pb.begin(); <render into pb.part_ptr>; pb.reduce(n_slots)
     """
 
-    def __init__(self, ctx, n_slots: int, rank: int, world: int, group=None, root: int = 0):
+    def __init__(self, ctx, n_slots: int, rank: int, world: int, group=None, root: int = 0, fused: bool = False):
+        """fused: render_reduce() does the exchange inside the render kernel instead of as two kernels after it"""
         import ctypes as C
         from .errors import check
         self.ctx, self.rank, self.world, self.root, self.n_slots = ctx, rank, world, root, n_slots
@@ -220,6 +221,7 @@ class PeerBus:
                 raise RuntimeError("peer memory (CUDA IPC) is not available on this box: " + "; ".join(bad))
         elif err:
             raise RuntimeError(err)
+        check(ctx.lib.blast_peer_bus_set_fused(self.h, int(fused)))
         self.part_ptr = ctx.lib.blast_peer_bus_partial(self.h)
         self.bus_ptr = ctx.lib.blast_peer_bus_bus(self.h)
 

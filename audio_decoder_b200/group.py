@@ -13,13 +13,15 @@ from .errors import check
 
 
 class Group:
-    def __init__(self, devices):
+    def __init__(self, devices, fused: bool = False):
+        """fused: render() does the bus exchange inside the render kernel instead of as two kernels after it"""
         self.lib = _lib.load()
         ids = (C.c_int * len(devices))(*devices)
         p = C.c_void_p()
         check(self.lib.blast_group_create(C.byref(p), ids, len(devices)))
         self.h = p.value
         self.n = len(devices)
+        check(self.lib.blast_group_set_fused(self.h, int(fused)))
 
     def close(self):
         if getattr(self, "h", None):

@@ -236,7 +236,7 @@ def run_ours(args):
     if mix:
         if args.reduce in ("p2p", "p2p2"):
             try:
-                peer = bd.PeerBus(ctx, n_slots, rank, world)
+                peer = bd.PeerBus(ctx, n_slots, rank, world, fused=(args.reduce == "p2p"))
             except RuntimeError as e:                                  # raised on EVERY rank or on none
                 if rank == 0:
                     print(f"bench.py: {e}; using the NCCL all-reduce instead", file=sys.stderr)
@@ -261,13 +261,8 @@ def run_ours(args):
         if peer is None:
             return mix_unfused(sh)
         sh.scene.restore_dev()
-        if args.reduce == "p2p2":                                       # the same exchange as two small kernels after the render
-            peer.begin()
-            sh.scene.render_partial_dev(frames, peer.part_ptr)
-            peer.reduce(n_slots)
-        else:
-            peer.render_reduce(sh.scene, frames)                        # K3 + K4 (render, publish, reduce, finalize)
-        peer.wait()                                                     # root: every rank's tiles are in the bus
+        peer.render_reduce(sh.scene, frames)     # K3, K4, then the tile exchange: two kernels (p2p2) or inside K4 (p2p)
+        peer.wait()                              # root: every rank's tiles are in the bus
 
     bus_ptr = (peer.bus_ptr if peer is not None else d_bus2.ptr) if mix else None
 
@@ -384,7 +379,7 @@ def run_ours(args):
         ach = alg_mix / (t["ms_mix"] * 1e-3) / 1e9
         roofline_mix = {"kernel": ("voice_position_scan + voice_render_mix_tma + bus_finalize" if world == 1 else
                                    "voice_position_scan + voice_render_mix_tma (render, tile publish, peer reduce, S16 wrap in one kernel)"
-                                   if args.reduce == "p2p" else "voice_position_scan + voice_render_mix_tma + peer_publish_tiles + bus_reduce_tiles")
+                                   if args.reduce == "p2p" else "voice_position_scan + voice_render_mix_tma + peer_publish_tiles + bus_reduce_tiles (tile exchange over peer memory)")
                         if peer is not None else "voice_position_scan + voice_render_mix_tma + NCCL all-reduce(int32) + bus_finalize",
                         "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                         "algorithmic_bytes_per_step": alg_mix, "ms_per_step": round(t["ms_mix"], 4),
@@ -483,7 +478,7 @@ def run_ours(args):
                          "samples written then re-read" + (": far larger than the 126 MB L2 (no flush needed)" if shard.n * data_len > 4e8 else
                                                            ": larger than the 126 MB L2 only in sum; no flush between steps — see the weak key for the > L2 per-GPU shard"),
                    "parallelism": f"strong scaling: the {n_files} files / voices sharded over {world} rank(s), file i -> rank i mod N" +
-                                  (("; partial buses reduced tile by tile inside the render kernel over peer memory (CUDA IPC / NVLink), no collective library"
+                                  (("; partial buses reduced tile by tile over peer memory (CUDA IPC / NVLink: " + ("inside the render kernel" if args.reduce == "p2p" else "two small kernels after the render") + "), no collective library"
                                     if peer is not None else "; one int32 all-reduce of the partial bus per step (NCCL)") if world > 1 and mix else "; no collective")},
         "roofline": roofline, "roofline_mix": roofline_mix, "roofline_step": roofline_step,
         "kernel_ms": {"decode": round(t["ms_decode_max"], 4), "mix": round(t["ms_mix_max"], 4),
@@ -664,9 +659,9 @@ def main():
     ap.add_argument("--quick-configs", action="store_true", help="other configs at reduced sizes (development)")
     ap.add_argument("--ref-files-per-thread", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--reduce", default="p2p", choices=["p2p", "p2p2", "nccl"],
-                    help="the mix reduction: inside the render kernel over peer memory (p2p), the same tile exchange as two "
-                         "kernels after the render (p2p2), or an NCCL all-reduce + finalize")
+    ap.add_argument("--reduce", default="p2p2", choices=["p2p2", "p2p", "nccl"],
+                    help="the mix reduction over peer memory as two small kernels after the render (p2p2, default: the fastest "
+                         "on B200s), the same tile exchange inside the render kernel (p2p), or an NCCL all-reduce + finalize")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

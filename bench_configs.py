@@ -169,18 +169,13 @@ def c3(ctx, rank, world, local, dist, peak, quick, all_unit, reduce="p2p"):
     frames = synth.C3_FRAMES if not quick else 1 << 17
     sc = C3Scene(ctx, rank, world, n_voices, frames, all_unit)
     n_slots = frames * 2
-    peer = bd.PeerBus(ctx, n_slots, rank, world)
+    peer = bd.PeerBus(ctx, n_slots, rank, world, fused=(reduce == "p2p"))
     part = ctx.alloc(4 * n_slots)
     bus2 = ctx.alloc(2 * n_slots)
 
     def fused():
         sc.scene.restore_dev()
-        if reduce == "p2p2":                                    # the tile exchange as two kernels after the render
-            peer.begin()
-            sc.scene.render_partial_dev(frames, peer.part_ptr)
-            peer.reduce(n_slots)
-        else:                                                   # ... or inside the render kernel
-            peer.render_reduce(sc.scene, frames)
+        peer.render_reduce(sc.scene, frames)                    # render + tile exchange (two kernels, or inside the render kernel)
         peer.wait()
 
     def local_only():                                           # the same render without the exchange: K3 + K4 + K5 on this rank's voices

@@ -205,18 +205,19 @@ int  blast_bus_finalize_dev(blast_ctx* ctx, const int32_t* d_partial, int16_t* d
  * access) owns a WINDOW: its int32 partial bus, an S16 bus (the result, complete on the root) and flag tables, mapped
  * into every peer's address space.  The bus is cut into tiles; tile t is reduced by rank t mod world.  Per step, on
  * every rank, in the same order on every rank:
- *     blast_scene_render_reduce_dev    the render kernel publishes each tile as its last voice group lands (a
- *                                      system-scope flag store to the tile's owner) and reduces the tiles it owns from
- *                                      the same work queue: wait for the tile's flags, sum the peers' int32 tiles with
- *                                      NVLink loads, wrap to S16 (engine.rs:441), store into the ROOT's bus.  The
- *                                      exchange overlaps the render tile by tile; no kernel sits between them.
+ *     blast_scene_render_reduce_dev    render + exchange.  The exchange: every rank raises, per tile, a system-scope
+ *                                      flag at the tile's owner; the owner waits for the tile's flags, sums the peers'
+ *                                      int32 tiles with NVLink loads, wraps to S16 (engine.rs:441) and stores into the
+ *                                      ROOT's bus.  Either two small kernels after the render (default) or inside the
+ *                                      render kernel's work queue, tile by tile as the tiles complete
+ *                                      (blast_peer_bus_set_fused).
  *  or blast_peer_bus_begin_dev, <stream work that fills blast_peer_bus_partial>, blast_peer_bus_reduce_dev
- *                                      the same protocol as two small kernels (Conductor spans, > 2 bus channels).
+ *                                      the exchange on its own (Conductor spans).
  *     blast_peer_bus_wait_dev          root only: the stream waits until every rank's tiles are in place.
  * A rank may overwrite its partial bus again only after every rank has finished reading it: the next step's first
  * kernel waits for those acknowledgements on the device.  All waits are bounded (BLAST_PEER_TIMEOUT_MS, default
  * 20,000): a rank that never publishes costs its peers the timeout and BLAST_ERR_TIMEOUT from blast_peer_bus_check,
- * not a hung GPU.  world == 1 is the single-GPU case: the render finalizes its own tiles (no bus_finalize launch). */
+ * not a hung GPU.  world == 1 is the single-GPU case: no exchange, the bus is finalized in place. */
 typedef struct blast_peer_bus blast_peer_bus;
 #define BLAST_PEER_HANDLE_BYTES 64
 int  blast_peer_bus_create(blast_ctx* ctx, uint64_t n_slots, uint32_t rank, uint32_t world, uint32_t root, blast_peer_bus** out);
@@ -226,6 +227,9 @@ int  blast_peer_bus_export(blast_ctx* ctx, blast_peer_bus* pb, uint8_t handle_ou
 int  blast_peer_bus_connect_ipc(blast_ctx* ctx, blast_peer_bus* pb, const uint8_t* handles /* world x 64 bytes */);
 /* one process: all[r] = rank r's peer bus (peer access between the GPUs is enabled here); call once, for all ranks */
 int  blast_peer_bus_connect_local(blast_peer_bus* const* all, uint32_t world);
+/* blast_scene_render_reduce_dev does the exchange inside the render kernel (1) or as launches of its own after it (0,
+ * the default: the faster one on B200s).  Same value on every rank. */
+int  blast_peer_bus_set_fused(blast_peer_bus* pb, int fused);
 int32_t* blast_peer_bus_partial(blast_peer_bus* pb);     /* this rank's int32 partial bus [n_slots] */
 int16_t* blast_peer_bus_bus(blast_peer_bus* pb);         /* this rank's S16 bus [n_slots]: the result on the root */
 int  blast_scene_render_reduce_dev(blast_ctx* ctx, blast_scene* scene, uint64_t frames, blast_peer_bus* pb);
@@ -446,6 +450,7 @@ int  blast_mpeg_parse(blast_ctx* ctx, const uint8_t* bytes, uint64_t len, int re
 typedef struct blast_group blast_group;
 int  blast_group_create(blast_group** out, const int* device_ids, uint32_t n_devices);
 void blast_group_destroy(blast_group* g);
+int  blast_group_set_fused(blast_group* g, int fused);   /* blast_group_render: see blast_peer_bus_set_fused */
 uint32_t   blast_group_size(const blast_group* g);
 blast_ctx* blast_group_ctx(blast_group* g, uint32_t member);
 /* main.rs:18-89 over the group: like blast_pcm_decode_batch; tracks_out[i] (nullable array) is file i's AudioFile.samples

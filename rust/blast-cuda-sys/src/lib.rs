@@ -148,6 +148,7 @@ extern "C" {
     pub fn blast_peer_bus_export(ctx: *mut blast_ctx, pb: *mut blast_peer_bus, handle_out: *mut u8) -> c_int;
     pub fn blast_peer_bus_connect_ipc(ctx: *mut blast_ctx, pb: *mut blast_peer_bus, handles: *const u8) -> c_int;
     pub fn blast_peer_bus_connect_local(all: *const *mut blast_peer_bus, world: u32) -> c_int;
+    pub fn blast_peer_bus_set_fused(pb: *mut blast_peer_bus, fused: c_int) -> c_int;
     pub fn blast_peer_bus_partial(pb: *mut blast_peer_bus) -> *mut i32;
     pub fn blast_peer_bus_bus(pb: *mut blast_peer_bus) -> *mut i16;
     pub fn blast_scene_render_reduce_dev(ctx: *mut blast_ctx, scene: *mut blast_scene, frames: u64, pb: *mut blast_peer_bus) -> c_int;
@@ -160,6 +161,7 @@ extern "C" {
     // several GPUs driven by this one process (main.rs is one process): decode by file, render by track, RNG by stream
     pub fn blast_group_create(out: *mut *mut blast_group, device_ids: *const c_int, n_devices: u32) -> c_int;
     pub fn blast_group_destroy(g: *mut blast_group);
+    pub fn blast_group_set_fused(g: *mut blast_group, fused: c_int) -> c_int;
     pub fn blast_group_size(g: *const blast_group) -> u32;
     pub fn blast_group_ctx(g: *mut blast_group, member: u32) -> *mut blast_ctx;
     pub fn blast_group_pcm_decode_batch(g: *mut blast_group, n: u32, files: *const *const u8, lens: *const usize,

@@ -30,15 +30,15 @@ if __name__ == "__main__":
     t_part = torch.empty(n, dtype=torch.int32, device=f"cuda:{local}")
     d_bus2 = ctx.alloc(2 * n)
     res = {"world": world}
-    for mode in ("fused", "two_kernel"):
-        peer = bd.PeerBus(ctx, n, rank, world)
+    for mode in ("fused", "two_kernel", "begin_reduce"):
+        peer = bd.PeerBus(ctx, n, rank, world, fused=(mode == "fused"))
         ok = True
         for step in range(5):
             vps = [ap.VoiceParams(v, True, 0.0, 1.0 if v % 3 else 0.77, float(np.float32(0.3 + 0.1 * step + 0.01 * v)))
                    for v in range(n_voices)]
             mine = [p if v % world == rank else ap.VoiceParams(v, False) for v, p in enumerate(vps)]
             sc = ap.Scene(ctx, tracks, mine, 2)
-            if mode == "fused":
+            if mode != "begin_reduce":
                 peer.render_reduce(sc, frames)
             else:
                 peer.begin()

@@ -67,14 +67,15 @@ def _oracle_bus(clips, voices, oc, frames):
     return c.coordinate(frames)
 
 
+@pytest.mark.parametrize("fused", [False, True], ids=["two_kernel", "fused"])
 @pytest.mark.parametrize("oc,frames", [(2, 1), (2, 2047), (2, 2048), (2, 40_001), (1, 9_000), (3, 5_000)])
-def test_world1_render_reduce_is_the_finalized_render(ctx, oc, frames):
-    """world == 1: the render kernel finalizes its own tiles (no bus_finalize launch) — same S16 bus as the oracle"""
+def test_world1_render_reduce_is_the_finalized_render(ctx, oc, frames, fused):
+    """world == 1: render + finalize, or (fused) the render kernel finalizes its own tiles — same S16 bus as the oracle"""
     rng = np.random.default_rng(frames + oc)
     clips, voices = _scene(rng, 70, frames, mono_every=7)
     tracks = [ap.Track.from_host(ctx, s, ch) for s, ch in clips]
     sc = ap.Scene(ctx, tracks, voices, oc)
-    pb = bd.PeerBus(ctx, frames * oc + 13, 0, 1)
+    pb = bd.PeerBus(ctx, frames * oc + 13, 0, 1, fused=fused)
     for _ in range(2):                                   # twice: flags are step counters, the voices are rewound
         sc.restore_dev()
         pb.render_reduce(sc, frames)
@@ -85,8 +86,9 @@ def test_world1_render_reduce_is_the_finalized_render(ctx, oc, frames):
     sc.close()
 
 
+@pytest.mark.parametrize("fused", [False, True], ids=["two_kernel", "fused"])
 @pytest.mark.parametrize("devices", member_sets(), ids=lambda d: "gpus_" + "_".join(map(str, d)))
-def test_group_decode_render_against_the_oracle(devices):
+def test_group_decode_render_against_the_oracle(devices, fused):
     """main.rs:18-89 + Conductor::coordinate over a group: files decoded on member i mod n, voices rendered where their
     track lives, bus reduced inside the render kernel — bit-identical to the oracle's single-threaded result"""
     rng = np.random.default_rng(len(devices) * 101 + sum(devices))
@@ -99,7 +101,7 @@ def test_group_decode_render_against_the_oracle(devices):
         else:
             images.append(synth.aiff_image(100 + i, n, bits=16)); kinds.append("aiff")
     descs = [fp.probe(k, im) for k, im in zip(kinds, images)]
-    with Group(devices) as g:
+    with Group(devices, fused=fused) as g:
         outs, tracks = g.decode_batch(images, descs)
         exp = [(oracle.wav_parse if k == "wav" else oracle.aiff_parse)(im)[1] for k, im in zip(kinds, images)]
         for o, e in zip(outs, exp):
@@ -196,7 +198,7 @@ def test_one_process_per_gpu_peer_bus_over_ipc():
     single-GPU render of the whole scene and against the oracle"""
     for n in [k for k in (2, 4, 8) if k <= n_gpus()]:
         res = _torchrun(n, "peer_bus_check.py", "--quick")
-        assert res["parity_fused"] and res["parity_two_kernel"] and res["parity_sharded_conductor"], res
+        assert res["parity_fused"] and res["parity_two_kernel"] and res["parity_begin_reduce"] and res["parity_sharded_conductor"], res
 
 
 @pytest.mark.skipif(n_gpus() < 2, reason="needs >= 2 GPUs")
