@@ -28,6 +28,11 @@ struct blast_peer_bus {
     uint32_t step = 0;
     uint32_t timeout_ms = 20000;
     bool fused = false;                         // blast_scene_render_reduce_dev: the exchange inside the render kernel
+    // The exchange runs on a stream of its own, behind the render and beside whatever the caller enqueues next: a rank
+    // waits for its slowest peer there, not in the stream that carries the next batch's decode.
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_render = nullptr, ev_exch = nullptr;
+    bool exch_pending = false;
 };
 
 namespace {
@@ -63,6 +68,20 @@ namespace blast_rdr {
 
 int32_t* peer_bus_partial(blast_peer_bus* pb) { return reinterpret_cast<int32_t*>(pb->window); }
 bool peer_bus_fused(const blast_peer_bus* pb) { return pb->fused; }
+
+int peer_bus_exchange(blast_ctx* ctx, blast_peer_bus* pb, const BusSink& sink) {
+    if (pb->world == 1) return launch_bus_reduce(ctx, sink);
+    BLAST_CUDA_TRY(cudaEventRecord(pb->ev_render, ctx->stream));
+    BLAST_CUDA_TRY(cudaStreamWaitEvent(pb->aux, pb->ev_render, 0));
+    if (int rc = launch_bus_reduce(ctx, sink, pb->aux)) return rc;
+    if (pb->rank == pb->root)                   // the root's bus is complete when every rank has stored its tiles
+        if (int rc = launch_flag_wait(ctx, reinterpret_cast<const uint32_t*>(pb->window + pb->off_done), pb->world, sink.step,
+                                      pb->timeout_ms, reinterpret_cast<uint32_t*>(pb->window + pb->off_err), pb->aux))
+            return rc;
+    BLAST_CUDA_TRY(cudaEventRecord(pb->ev_exch, pb->aux));
+    pb->exch_pending = true;
+    return BLAST_OK;
+}
 
 int peer_bus_next_step(blast_ctx* ctx, blast_peer_bus* pb, uint64_t frames, uint32_t oc, bool in_render, BusSink* out) {
     if (pb->ctx != ctx) return blast::set_error(BLAST_ERR_ARG, "the peer bus belongs to another context");
@@ -136,6 +155,15 @@ int blast_peer_bus_create(blast_ctx* ctx, uint64_t n_slots, uint32_t rank, uint3
     }
     pb->peer[rank] = pb->window;
     pb->connected = world == 1;
+    if (world > 1) {
+        if (cudaStreamCreateWithFlags(&pb->aux, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&pb->ev_render, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&pb->ev_exch, cudaEventDisableTiming) != cudaSuccess) {
+            const int rc = blast::set_error(BLAST_ERR_CUDA, "blast_peer_bus_create: stream / event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            blast_peer_bus_destroy(ctx, pb);
+            return rc;
+        }
+    }
     *out = pb;
     return BLAST_OK;
 }
@@ -146,6 +174,9 @@ void blast_peer_bus_destroy(blast_ctx* ctx, blast_peer_bus* pb) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
     }
+    if (pb->aux) { cudaStreamSynchronize(pb->aux); cudaStreamDestroy(pb->aux); }
+    if (pb->ev_render) cudaEventDestroy(pb->ev_render);
+    if (pb->ev_exch) cudaEventDestroy(pb->ev_exch);
     for (uint32_t r = 0; r < pb->world; ++r)
         if (pb->ipc[r] && pb->peer[r]) cudaIpcCloseMemHandle(pb->peer[r]);
     if (pb->window) cudaFree(pb->window);
@@ -233,15 +264,21 @@ int blast_peer_bus_reduce_dev(blast_ctx* ctx, blast_peer_bus* pb, uint64_t n_slo
     BLAST_REQUIRE(pb != nullptr, BLAST_ERR_ARG, "blast_peer_bus_reduce_dev: null peer bus");
     BusSink sink;
     if (int rc = peer_bus_next_step(ctx, pb, n_slots_used, 1, false, &sink)) return rc;
-    return launch_bus_reduce(ctx, sink);
+    return peer_bus_exchange(ctx, pb, sink);
 }
 
 int blast_peer_bus_wait_dev(blast_ctx* ctx, blast_peer_bus* pb) {
     if (int rc = blast::bind(ctx)) return rc;
     BLAST_REQUIRE(pb && pb->ctx == ctx, BLAST_ERR_ARG, "blast_peer_bus_wait_dev: no peer bus of this context");
-    if (pb->world == 1 || pb->rank != pb->root) return BLAST_OK;
+    if (pb->world == 1) return BLAST_OK;
+    if (pb->exch_pending) {                     // the exchange ran beside the stream: join it
+        BLAST_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, pb->ev_exch, 0));
+        pb->exch_pending = false;
+        return BLAST_OK;
+    }
+    if (pb->rank != pb->root) return BLAST_OK;
     return launch_flag_wait(ctx, reinterpret_cast<const uint32_t*>(pb->window + pb->off_done), pb->world, pb->step, pb->timeout_ms,
-                            reinterpret_cast<uint32_t*>(pb->window + pb->off_err));
+                            reinterpret_cast<uint32_t*>(pb->window + pb->off_err));   // (fused: the exchange was in the render kernel)
 }
 
 int blast_peer_bus_check(blast_ctx* ctx, blast_peer_bus* pb) {
@@ -249,6 +286,7 @@ int blast_peer_bus_check(blast_ctx* ctx, blast_peer_bus* pb) {
     BLAST_REQUIRE(pb && pb->ctx == ctx, BLAST_ERR_ARG, "blast_peer_bus_check: no peer bus of this context");
     uint32_t* mb = static_cast<uint32_t*>(blast::mailbox(ctx));
     if (!mb) return BLAST_ERR_CUDA;
+    if (pb->aux) BLAST_CUDA_TRY(cudaStreamSynchronize(pb->aux));
     BLAST_CUDA_TRY(cudaMemcpyAsync(mb, pb->window + pb->off_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (*mb & 4u) {

@@ -2032,30 +2032,33 @@ int reserve_buffers(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32
     return BLAST_OK;
 }
 
-int launch_flag_wait(blast_ctx* ctx, const uint32_t* d_flags, uint32_t n, uint32_t value, uint32_t timeout_ms, uint32_t* d_err) {
+int launch_flag_wait(blast_ctx* ctx, const uint32_t* d_flags, uint32_t n, uint32_t value, uint32_t timeout_ms, uint32_t* d_err,
+                     cudaStream_t stream) {
     if (n == 0) return BLAST_OK;
     if (n > 32) return blast::set_error(BLAST_ERR_CAPACITY, "at most 32 flags per wait");
-    flag_wait<<<1, 32, 0, ctx->stream>>>(d_flags, n, value, timeout_ms, d_err);
+    if (!stream) stream = ctx->stream;
+    flag_wait<<<1, 32, 0, stream>>>(d_flags, n, value, timeout_ms, d_err);
     BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
     return BLAST_OK;
 }
 
-static int launch_peer_raise(blast_ctx* ctx, const BusSink& sink) {
-    peer_raise<<<1, 2 * kMaxPeers, 0, ctx->stream>>>(sink);
+static int launch_peer_raise(blast_ctx* ctx, const BusSink& sink, cudaStream_t stream) {
+    peer_raise<<<1, 2 * kMaxPeers, 0, stream>>>(sink);
     BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
     return BLAST_OK;
 }
 
-int launch_bus_reduce(blast_ctx* ctx, const BusSink& sink) {
+int launch_bus_reduce(blast_ctx* ctx, const BusSink& sink, cudaStream_t stream) {
+    if (!stream) stream = ctx->stream;
     if (sink.n_tiles) {
-        peer_publish_tiles<<<(sink.n_tiles + 255) / 256, 256, 0, ctx->stream>>>(sink);
+        peer_publish_tiles<<<(sink.n_tiles + 255) / 256, 256, 0, stream>>>(sink);
         BLAST_CUDA_TRY(cudaGetLastError());
         ctx->launches += 1;
     }
-    if (sink.n_my_tiles == 0) return launch_peer_raise(ctx, sink);
-    bus_reduce_tiles<<<sink.n_my_tiles, 256, 0, ctx->stream>>>(sink);
+    if (sink.n_my_tiles == 0) return launch_peer_raise(ctx, sink, stream);
+    bus_reduce_tiles<<<sink.n_my_tiles, 256, 0, stream>>>(sink);
     BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
     return BLAST_OK;
@@ -2198,7 +2201,7 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         ctx->launches += 1;
     }
     if (sink_in && sink_in->world && !fused) return launch_bus_reduce(ctx, *sink_in);
-    if (fused && sink.n_my_tiles == 0) return launch_peer_raise(ctx, sink);
+    if (fused && sink.n_my_tiles == 0) return launch_peer_raise(ctx, sink, ctx->stream);
     return BLAST_OK;
 }
 
@@ -2369,7 +2372,7 @@ int blast_scene_render_reduce_dev(blast_ctx* ctx, blast_scene* sc, uint64_t fram
             if (int rc = launch_flag_wait(ctx, sink.ack_mine, sink.world, sink.step - 1u, sink.timeout_ms, sink.err)) return rc;
         if (int rc = launch_render(ctx, sc->rb, sc->n_voices, 0, sc->out_channels, frames, peer_bus_partial(pb), nullptr, rewind)) return rc;
         if (sink.world == 1) return blast_bus_finalize_dev(ctx, peer_bus_partial(pb), blast_peer_bus_bus(pb), frames * sc->out_channels);
-        return launch_bus_reduce(ctx, sink);
+        return peer_bus_exchange(ctx, pb, sink);
     }
     return launch_render(ctx, sc->rb, sc->n_voices, 0, sc->out_channels, frames, peer_bus_partial(pb), &sink, rewind);
 }

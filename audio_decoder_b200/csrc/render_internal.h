@@ -130,9 +130,14 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
                   uint64_t frames, int32_t* d_partial_bus, const BusSink* sink = nullptr, const VoiceDev* rewind = nullptr);
 // the reduction on its own: publish every tile of this rank's partial bus (filled by earlier stream work), reduce the
 // tiles this rank owns.  Async on ctx->stream.
-int launch_bus_reduce(blast_ctx* ctx, const BusSink& sink);
+int launch_bus_reduce(blast_ctx* ctx, const BusSink& sink, cudaStream_t stream = nullptr);   // nullptr: ctx->stream
 // async: the stream waits (on the device, bounded) until the n flags have reached `value`
-int launch_flag_wait(blast_ctx* ctx, const uint32_t* d_flags, uint32_t n, uint32_t value, uint32_t timeout_ms, uint32_t* d_err);
+int launch_flag_wait(blast_ctx* ctx, const uint32_t* d_flags, uint32_t n, uint32_t value, uint32_t timeout_ms, uint32_t* d_err,
+                     cudaStream_t stream = nullptr);
+// peer_bus.cu: the exchange of the step `sink` describes, on the peer bus's own stream behind everything enqueued on
+// ctx->stream so far — it overlaps whatever the caller enqueues next (the next batch's decode); blast_peer_bus_wait_dev
+// joins it.
+int peer_bus_exchange(blast_ctx* ctx, blast_peer_bus* pb, const BusSink& sink);
 // peer_bus.cu: starts the next step of a peer bus for a render of `frames` frames on an out_channels bus and fills the
 // sink the kernels take.  in_render: tiles are the render kernel's (kFT frames); else 4,096-slot tiles.
 int peer_bus_next_step(blast_ctx* ctx, blast_peer_bus* pb, uint64_t frames, uint32_t out_channels, bool in_render, BusSink* out);

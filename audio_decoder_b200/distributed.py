@@ -174,8 +174,9 @@ class PeerBus:
     render, or (fused=True) inside the render kernel as the tiles complete.  This class only creates the window and
     carries the 64-byte handles (torch.distributed, set-up time); the protocol itself lives in the library.
 
-    Per step, on every rank:      pb.render_reduce(scene, frames)     then, on the root:   pb.wait();  bus = pb.bus_ptr
+    Per step, on every rank:      pb.render_reduce(scene, frames)     before the bus is read:   pb.wait();  bus = pb.bus_ptr
     or (Conductor spans):         pb.begin(); <render into pb.part_ptr>; pb.reduce(n_slots)
+    The exchange runs on the peer bus's own stream, beside what is enqueued next; wait() joins it.
     """
 
     def __init__(self, ctx, n_slots: int, rank: int, world: int, group=None, root: int = 0, fused: bool = False):
@@ -241,7 +242,7 @@ class PeerBus:
         check(self.ctx.lib.blast_peer_bus_reduce_dev(self.ctx.h, self.h, self.n_slots if n_slots is None else n_slots))
 
     def wait(self):
-        """async, root: the stream waits until every rank's tiles of the current step are in the bus"""
+        """async: the stream joins the exchange of the current step (on the root: every rank's tiles are in the bus)"""
         from .errors import check
         check(self.ctx.lib.blast_peer_bus_wait_dev(self.ctx.h, self.h))
 

@@ -175,27 +175,30 @@ def c3(ctx, rank, world, local, dist, peak, quick, all_unit, reduce="p2p"):
 
     def fused():
         sc.scene.restore_dev()
-        peer.render_reduce(sc.scene, frames)                    # render + tile exchange (two kernels, or inside the render kernel)
-        peer.wait()
+        peer.render_reduce(sc.scene, frames)                    # render + tile exchange (two kernels beside the stream, or inside the render kernel)
 
     def local_only():                                           # the same render without the exchange: K3 + K4 + K5 on this rank's voices
         sc.scene.restore_dev()
         sc.scene.render_partial_dev(frames, part.ptr)
         ap.finalize_bus(ctx, part.ptr, bus2.ptr, n_slots)
 
-    def timed(fn, iters):
+    def timed(fn, iters, join=None):
         for _ in range(2):
             fn()
+        if join:
+            join()
         ctx.sync()
         if dist is not None:
             dist.barrier(device_ids=[local])
         e0 = ctx.event().record()
         for _ in range(iters):
             fn()
+        if join:
+            join()                                              # the last exchange belongs to the timed region
         e1 = ctx.event().record()
         return _max(dist, local, e0.elapsed_ms(e1) / iters)
 
-    ms = timed(fused, 5)
+    ms = timed(fused, 5, peer.wait)
     peer.check()
     sc.scene.check()
     bus = None

@@ -213,7 +213,11 @@ int  blast_bus_finalize_dev(blast_ctx* ctx, const int32_t* d_partial, int16_t* d
  *                                      (blast_peer_bus_set_fused).
  *  or blast_peer_bus_begin_dev, <stream work that fills blast_peer_bus_partial>, blast_peer_bus_reduce_dev
  *                                      the exchange on its own (Conductor spans).
- *     blast_peer_bus_wait_dev          root only: the stream waits until every rank's tiles are in place.
+ *     blast_peer_bus_wait_dev          joins the exchange: it runs on a stream of its own behind the render, BESIDE what
+ *                                      the caller enqueues next (the next batch's decode), so a rank waits for its slowest
+ *                                      peer there and not in the caller's stream.  After it, on the root, the bus of the
+ *                                      step is complete in stream order.  Call it before the bus is consumed (and at the
+ *                                      end of a run); the next step orders itself behind the exchange on its own.
  * A rank may overwrite its partial bus again only after every rank has finished reading it: the next step's first
  * kernel waits for those acknowledgements on the device.  All waits are bounded (BLAST_PEER_TIMEOUT_MS, default
  * 20,000): a rank that never publishes costs its peers the timeout and BLAST_ERR_TIMEOUT from blast_peer_bus_check,
