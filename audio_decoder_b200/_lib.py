@@ -128,6 +128,7 @@ SIGNATURES = {
     "blast_scene_restore_dev": (C.c_int, [_vp, _vp]),
     "blast_scene_get_voices": (C.c_int, [_vp, _vp, C.POINTER(Voice), _u32]),
     "blast_scene_render_dev": (C.c_int, [_vp, _vp, _u64, _vp]),
+    "blast_scene_reserve": (C.c_int, [_vp, _vp, _u64]),
     "blast_scene_check": (C.c_int, [_vp, _vp]),
     "blast_bus_finalize_dev": (C.c_int, [_vp, _vp, _vp, _u64]),
     "blast_x128p_seed": (None, [_u64, C.POINTER(X128PState)]),

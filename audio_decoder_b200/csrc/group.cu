@@ -214,6 +214,9 @@ int blast_group_render(blast_group* g, const blast_track* tracks, uint32_t n_tra
         for (uint32_t v = 0; v < n_voices; ++v)
             if (voices[v].track % g->n == m) mine.push_back(voices[v]);
         rc = blast_scene_create(g->ctx[m], tracks, n_tracks, mine.data(), (uint32_t)mine.size(), out_channels, &sc[m]);
+        // everything the render allocates, now: members may share a GPU, and an allocation behind a kernel that waits for
+        // a peer may never return
+        if (rc == BLAST_OK) rc = blast_scene_reserve(g->ctx[m], sc[m], frames);
     }
     // from here on every member takes its step of the peer protocol, whatever happens to another one
     for (uint32_t m = 0; m < g->n; ++m) {

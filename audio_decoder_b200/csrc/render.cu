@@ -2032,6 +2032,37 @@ int reserve_buffers(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32
     return BLAST_OK;
 }
 
+// Everything a render of `frames` frames allocates (grow-only): the per-(tile, voice) records and, when enabled, the
+// piece-table pool.  launch_render calls it; hosts that must not allocate while a kernel of theirs waits for a peer (group
+// members that share a GPU) call it up front.
+int reserve_frames(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t oc, uint64_t frames) {
+    if (n_voices == 0 || frames == 0) return BLAST_OK;
+    const size_t need = (size_t)((frames + kFT - 1) / kFT) * n_voices;
+    if (need > rb.recs_cap) {
+        BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (rb.d_recs) BLAST_CUDA_TRY(cudaFree(rb.d_recs));
+        rb.d_recs = nullptr;
+        rb.recs_cap = 0;
+        BLAST_CUDA_TRY(cudaMalloc(&rb.d_recs, need * sizeof(TileRec)));
+        rb.recs_cap = need;
+    }
+    static const bool tables = getenv("BLAST_RENDER_TABLES") != nullptr;
+    static const bool legacy = getenv("BLAST_RENDER_LEGACY") != nullptr;
+    if (oc == 2 && !legacy && tables) {
+        const uint32_t rows = pool_rows_for(rb.seg_cap);
+        if (rb.pool_voices < rb.voices_cap || rb.pool_rows != rows) {
+            BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (rb.d_pool) cudaFree(rb.d_pool);
+            rb.d_pool = nullptr;
+            rb.pool_voices = 0;
+            BLAST_CUDA_TRY(cudaMalloc(&rb.d_pool, rb.voices_cap * (size_t)rows * sizeof(uint4)));
+            rb.pool_voices = rb.voices_cap;
+            rb.pool_rows = rows;
+        }
+    }
+    return BLAST_OK;
+}
+
 int launch_flag_wait(blast_ctx* ctx, const uint32_t* d_flags, uint32_t n, uint32_t value, uint32_t timeout_ms, uint32_t* d_err,
                      cudaStream_t stream) {
     if (n == 0) return BLAST_OK;
@@ -2083,15 +2114,7 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         if (sink_in && sink_in->world) return launch_bus_reduce(ctx, *sink_in);
         return BLAST_OK;
     }
-    const size_t need = (size_t)n_tiles * n_voices;
-    if (need > rb.recs_cap) {
-        BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        if (rb.d_recs) BLAST_CUDA_TRY(cudaFree(rb.d_recs));
-        rb.d_recs = nullptr;
-        rb.recs_cap = 0;
-        BLAST_CUDA_TRY(cudaMalloc(&rb.d_recs, need * sizeof(TileRec)));
-        rb.recs_cap = need;
-    }
+    if (int rc = reserve_frames(ctx, rb, n_voices, oc, frames)) return rc;
     // voice groups: enough work items to fill the GPU a few times over
     uint32_t groups = 1;
     static const uint32_t ctas_per_sm = getenv("BLAST_RENDER_CTAS_PER_SM") ? (uint32_t)atoi(getenv("BLAST_RENDER_CTAS_PER_SM")) : 32u;
@@ -2119,21 +2142,8 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
     }
 
     // piece-table pool of the tiles with several segments (stereo bus, TMA kernel): grow-only, sized by voices x segments
-    uint4* tab_pool = nullptr;
     static const bool tables = getenv("BLAST_RENDER_TABLES") != nullptr;
-    if (oc == 2 && !legacy && tables) {
-        const uint32_t rows = pool_rows_for(rb.seg_cap);
-        if (rb.pool_voices < rb.voices_cap || rb.pool_rows != rows) {
-            BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-            if (rb.d_pool) cudaFree(rb.d_pool);
-            rb.d_pool = nullptr;
-            rb.pool_voices = 0;
-            BLAST_CUDA_TRY(cudaMalloc(&rb.d_pool, rb.voices_cap * (size_t)rows * sizeof(uint4)));
-            rb.pool_voices = rb.voices_cap;
-            rb.pool_rows = rows;
-        }
-        tab_pool = rb.d_pool;
-    }
+    uint4* tab_pool = (oc == 2 && !legacy && tables) ? rb.d_pool : nullptr;
     rb.parity ^= 1u;                                         // this render's error word; cleared by the previous render's K3
     uint32_t* d_err = rb.d_err + rb.parity;
     uint32_t* d_work = rb.d_err + 2;
@@ -2331,6 +2341,12 @@ int blast_scene_render_dev(blast_ctx* ctx, blast_scene* sc, uint64_t frames, int
     const VoiceDev* rewind = (sc->rewind && frames) ? sc->d_voices0 : nullptr;
     if (frames) sc->rewind = false;
     return launch_render(ctx, sc->rb, sc->n_voices, 0, sc->out_channels, frames, d_partial_bus, nullptr, rewind);
+}
+
+int blast_scene_reserve(blast_ctx* ctx, blast_scene* sc, uint64_t frames) {
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_REQUIRE(sc != nullptr, BLAST_ERR_ARG, "blast_scene_reserve: null scene");
+    return reserve_frames(ctx, sc->rb, sc->n_voices, sc->out_channels, frames);
 }
 
 int blast_scene_check(blast_ctx* ctx, blast_scene* sc) {

@@ -196,6 +196,9 @@ int  blast_scene_get_voices(blast_ctx* ctx, blast_scene* scene, blast_voice* out
  * iterations of coordinate()'s outer loop would.  Async: position scan + render/mix launches.
  * Partial buses of several GPUs may be summed (int32) before blast_bus_finalize_dev. */
 int  blast_scene_render_dev(blast_ctx* ctx, blast_scene* scene, uint64_t frames, int32_t* d_partial_bus);
+/* Allocates now what a render of `frames` frames would allocate on first use (grow-only scratch): the renders that
+ * follow neither allocate nor synchronise. */
+int  blast_scene_reserve(blast_ctx* ctx, blast_scene* scene, uint64_t frames);
 /* synchronises and reports deferred device-side errors of the last render (BLAST_ERR_CAPACITY) */
 int  blast_scene_check(blast_ctx* ctx, blast_scene* scene);
 /* S16 bus = low 16 bits of the int32 partial sums (== i16 wrapping accumulate, engine.rs:441) */

@@ -109,6 +109,7 @@ extern "C" {
     pub fn blast_scene_set_voices(ctx: *mut blast_ctx, scene: *mut blast_scene, voices: *const blast_voice, n: u32) -> c_int;
     pub fn blast_scene_get_voices(ctx: *mut blast_ctx, scene: *mut blast_scene, out: *mut blast_voice, n: u32) -> c_int;
     pub fn blast_scene_render_dev(ctx: *mut blast_ctx, scene: *mut blast_scene, frames: u64, d_partial_bus: *mut i32) -> c_int;
+    pub fn blast_scene_reserve(ctx: *mut blast_ctx, scene: *mut blast_scene, frames: u64) -> c_int;
     pub fn blast_scene_check(ctx: *mut blast_ctx, scene: *mut blast_scene) -> c_int;
     pub fn blast_bus_finalize_dev(ctx: *mut blast_ctx, d_partial: *const i32, d_bus: *mut i16, n_slots: u64) -> c_int;
     pub fn blast_render(ctx: *mut blast_ctx, tracks: *const blast_track, n_tracks: u32, voices: *const blast_voice,
