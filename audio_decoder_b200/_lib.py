@@ -176,6 +176,7 @@ SIGNATURES = {
     "blast_peer_bus_begin_dev": (C.c_int, [_vp, _vp]),
     "blast_peer_bus_reduce_dev": (C.c_int, [_vp, _vp, _u64]),
     "blast_peer_bus_wait_dev": (C.c_int, [_vp, _vp]),
+    "blast_peer_bus_flags": (C.c_int, [_vp, _vp, _vp, _u32]),
     "blast_peer_bus_check": (C.c_int, [_vp, _vp]),
     "blast_conductor_set_shard_by_track": (C.c_int, [_vp, _u32, _u32]),
     "blast_group_create": (C.c_int, [C.POINTER(_vp), C.POINTER(C.c_int), _u32]),

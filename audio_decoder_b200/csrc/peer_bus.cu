@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "render_internal.h"
 
@@ -279,6 +280,26 @@ int blast_peer_bus_wait_dev(blast_ctx* ctx, blast_peer_bus* pb) {
     if (pb->rank != pb->root) return BLAST_OK;
     return launch_flag_wait(ctx, reinterpret_cast<const uint32_t*>(pb->window + pb->off_done), pb->world, pb->step, pb->timeout_ms,
                             reinterpret_cast<uint32_t*>(pb->window + pb->off_err));   // (fused: the exchange was in the render kernel)
+}
+
+int blast_peer_bus_flags(blast_ctx* ctx, blast_peer_bus* pb, uint32_t* out, uint32_t cap) {
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_REQUIRE(pb && out && pb->ctx == ctx, BLAST_ERR_ARG, "blast_peer_bus_flags: bad argument");
+    // layout of the dump: step, world, then per rank r: ready[r][tile 0..3], done[r], ack[r]
+    std::vector<uint32_t> v;
+    v.push_back(pb->step);
+    v.push_back(pb->world);
+    cudaStream_t s = nullptr;
+    BLAST_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));       // beside whatever is still waiting
+    auto rd = [&](size_t off) { uint32_t x = 0xDEADBEEFu; cudaMemcpyAsync(&x, pb->window + off, 4, cudaMemcpyDeviceToHost, s); cudaStreamSynchronize(s); return x; };
+    for (uint32_t r = 0; r < pb->world; ++r) {
+        for (uint32_t t = 0; t < 4; ++t) v.push_back(rd(pb->off_ready + ((size_t)r * pb->max_tiles + t) * 4));
+        v.push_back(rd(pb->off_done + r * 4));
+        v.push_back(rd(pb->off_ack + r * 4));
+    }
+    cudaStreamDestroy(s);
+    for (uint32_t i = 0; i < cap && i < v.size(); ++i) out[i] = v[i];
+    return BLAST_OK;
 }
 
 int blast_peer_bus_check(blast_ctx* ctx, blast_peer_bus* pb) {

@@ -243,6 +243,9 @@ int  blast_scene_render_reduce_dev(blast_ctx* ctx, blast_scene* scene, uint64_t 
 int  blast_peer_bus_begin_dev(blast_ctx* ctx, blast_peer_bus* pb);
 int  blast_peer_bus_reduce_dev(blast_ctx* ctx, blast_peer_bus* pb, uint64_t n_slots_used);
 int  blast_peer_bus_wait_dev(blast_ctx* ctx, blast_peer_bus* pb);
+/* diagnostic: {step, world, then per rank r: ready[r][tile 0..3], done[r], ack[r]} of this rank's window, read beside
+ * whatever may still be waiting */
+int  blast_peer_bus_flags(blast_ctx* ctx, blast_peer_bus* pb, uint32_t* out, uint32_t cap);
 /* synchronises; BLAST_ERR_TIMEOUT if a device-side wait of this rank gave up since the last check */
 int  blast_peer_bus_check(blast_ctx* ctx, blast_peer_bus* pb);
 /* one-shot with a host bus (interleaved S16_LE like the ALSA area, runtime.rs:272-276) */

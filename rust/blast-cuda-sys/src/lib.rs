@@ -156,6 +156,7 @@ extern "C" {
     pub fn blast_peer_bus_begin_dev(ctx: *mut blast_ctx, pb: *mut blast_peer_bus) -> c_int;
     pub fn blast_peer_bus_reduce_dev(ctx: *mut blast_ctx, pb: *mut blast_peer_bus, n_slots_used: u64) -> c_int;
     pub fn blast_peer_bus_wait_dev(ctx: *mut blast_ctx, pb: *mut blast_peer_bus) -> c_int;
+    pub fn blast_peer_bus_flags(ctx: *mut blast_ctx, pb: *mut blast_peer_bus, out: *mut u32, cap: u32) -> c_int;
     pub fn blast_peer_bus_check(ctx: *mut blast_ctx, pb: *mut blast_peer_bus) -> c_int;
     pub fn blast_conductor_set_shard_by_track(c: *mut blast_conductor, rank: u32, world: u32) -> c_int;
 
