@@ -157,6 +157,7 @@ int blast_peer_bus_create(blast_ctx* ctx, uint64_t n_slots, uint32_t rank, uint3
     pb->peer[rank] = pb->window;
     pb->connected = world == 1;
     if (world > 1) {
+        if (int rc = preload_kernels(ctx)) { blast_peer_bus_destroy(ctx, pb); return rc; }
         if (cudaStreamCreateWithFlags(&pb->aux, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&pb->ev_render, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&pb->ev_exch, cudaEventDisableTiming) != cudaSuccess) {
@@ -285,7 +286,7 @@ int blast_peer_bus_wait_dev(blast_ctx* ctx, blast_peer_bus* pb) {
 int blast_peer_bus_flags(blast_ctx* ctx, blast_peer_bus* pb, uint32_t* out, uint32_t cap) {
     if (int rc = blast::bind(ctx)) return rc;
     BLAST_REQUIRE(pb && out && pb->ctx == ctx, BLAST_ERR_ARG, "blast_peer_bus_flags: bad argument");
-    // layout of the dump: step, world, then per rank r: ready[r][tile 0..3], done[r], ack[r]
+    // layout of the dump: step, world, then per rank r: ready[r][tile 0..3], done[r], ack[r]; then the error word and the reduce count
     std::vector<uint32_t> v;
     v.push_back(pb->step);
     v.push_back(pb->world);
@@ -297,6 +298,8 @@ int blast_peer_bus_flags(blast_ctx* ctx, blast_peer_bus* pb, uint32_t* out, uint
         v.push_back(rd(pb->off_done + r * 4));
         v.push_back(rd(pb->off_ack + r * 4));
     }
+    v.push_back(rd(pb->off_err));
+    v.push_back(rd(pb->off_red));
     cudaStreamDestroy(s);
     for (uint32_t i = 0; i < cap && i < v.size(); ++i) out[i] = v[i];
     return BLAST_OK;

@@ -2032,6 +2032,43 @@ int reserve_buffers(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32
     return BLAST_OK;
 }
 
+// CUDA loads a kernel's code at its first launch (lazy module loading), and that load can wait for the device to go idle.
+// A rank whose kernel waits for a peer must therefore never be the reason a peer's FIRST launch of some kernel cannot
+// load — which is exactly what happens when group members share a GPU (measured: a hang until the wait's time-out, only
+// in the first step; none with CUDA_MODULE_LOADING=EAGER).  Everything the render and the exchange launch is loaded here,
+// once per device, before the first step of a peer bus.
+int preload_kernels(blast_ctx* ctx) {
+    static bool done[64] = {};
+    if (ctx->device >= 0 && ctx->device < 64 && done[ctx->device]) return BLAST_OK;
+    cudaFuncAttributes a;
+#define BLAST_TOUCH(k) BLAST_CUDA_TRY(cudaFuncGetAttributes(&a, k))
+    BLAST_TOUCH(seq_event_scan);
+    BLAST_TOUCH(voice_position_scan);
+    BLAST_TOUCH(voice_split_fixup);
+    BLAST_TOUCH(bus_finalize);
+    BLAST_TOUCH(peer_publish_tiles);
+    BLAST_TOUCH(bus_reduce_tiles);
+    BLAST_TOUCH(peer_raise);
+    BLAST_TOUCH(flag_wait);
+    BLAST_TOUCH((voice_render_mix_tma<1, false, false>));
+    BLAST_TOUCH((voice_render_mix_tma<1, true, false>));
+    BLAST_TOUCH((voice_render_mix_tma<2, false, false>));
+    BLAST_TOUCH((voice_render_mix_tma<2, false, true>));
+    BLAST_TOUCH((voice_render_mix_tma<2, true, false>));
+    BLAST_TOUCH((voice_render_mix_tma<2, true, true>));
+    BLAST_TOUCH(voice_render_mix<1>);
+    BLAST_TOUCH(voice_render_mix<2>);
+    BLAST_TOUCH(voice_render_mix<3>);
+    BLAST_TOUCH(voice_render_mix<4>);
+    BLAST_TOUCH(voice_render_mix<5>);
+    BLAST_TOUCH(voice_render_mix<6>);
+    BLAST_TOUCH(voice_render_mix<7>);
+    BLAST_TOUCH(voice_render_mix<8>);
+#undef BLAST_TOUCH
+    if (ctx->device >= 0 && ctx->device < 64) done[ctx->device] = true;
+    return BLAST_OK;
+}
+
 // Everything a render of `frames` frames allocates (grow-only): the per-(tile, voice) records and, when enabled, the
 // piece-table pool.  launch_render calls it; hosts that must not allocate while a kernel of theirs waits for a peer (group
 // members that share a GPU) call it up front.

@@ -121,6 +121,7 @@ struct BusSink {
 
 int  reserve_buffers(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t n_seqs);
 int  reserve_frames(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t out_channels, uint64_t frames);
+int  preload_kernels(blast_ctx* ctx);
 void free_buffers(RenderBuffers& rb);
 // Seq event scan (when n_seqs > 0) + position scan + render/mix of the first n_voices records of rb.d_voices into
 // the int32 partial bus (overwritten); async on ctx->stream.  Device-side capacity errors land in rb.d_err.

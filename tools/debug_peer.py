@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """two peer buses on one GPU driven from one thread, step by step, with flag dumps (development)"""
 import ctypes as C
+import time
 import os
 import sys
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
@@ -36,17 +37,23 @@ def dump(tag):
     for r, c in enumerate(ctxs):
         out = (C.c_uint32 * 64)()
         L.blast_peer_bus_flags(c.h, pbs[r], out, 64)
-        print(tag, "rank", r, list(out[:2 + 6 * world]), flush=True)
+        print(tag, "rank", r, list(out[:2 + 6 * world]), "err/red", list(out[2 + 6 * world:4 + 6 * world]), flush=True)
 
 
+dump("created")
 for step in range(2):
     for r, c in enumerate(ctxs):
         check(L.blast_scene_render_reduce_dev(c.h, scenes[r][1].h, frames, pbs[r]))
         print("enqueued rank", r, flush=True)
-    import time
-    time.sleep(0.5)
-    dump(f"step {step} after 0.5 s")
+        if step == 0 and r == 0:
+            time.sleep(0.2)
+            dump("rank 0 alone")
+    time.sleep(0.05)
+    dump(f"step {step} after 0.05 s")
+    t0 = time.perf_counter()
     check(L.blast_peer_bus_wait_dev(ctxs[0].h, pbs[0]))
+    ctxs[0].sync()
+    print("wait+sync took", round(time.perf_counter() - t0, 3), "s", flush=True)
     bus = np.zeros(frames * 2, np.int16)
     check(L.blast_memcpy_d2h(ctxs[0].h, bus.ctypes.data, L.blast_peer_bus_bus(pbs[0]), bus.nbytes))
     for r, c in enumerate(ctxs):
