@@ -150,7 +150,7 @@ def sub_track(blast, ap, ctx, ptr, n_samples, channels, rate=48000):
 # ------------------------------------------------------------------ our arm: the C2 decode + mix workload
 class C2Shard:
     """the files `ids` of the C2 batch on this rank: file images in HBM (256-byte aligned slots, payload at +54) and in
-    pinned host memory (same layout), the decode plan, the scene of the decoded tracks"""
+    pinned host memory (back to back), the decode plan, the scene of the decoded tracks"""
 
     def __init__(self, ctx, ids, data_len, layout, gains, host_images=True):
         import audio_decoder_b200 as blast
@@ -170,17 +170,20 @@ class C2Shard:
         if n:
             br.Streams.from_seeds(ctx, [0xC20000 + i for i in self.ids]).fill_dev(draws, 0, 100, d_pay.ptr, None, None)
         self.d_in = ctx.alloc(max(1, n) * slot)
-        self.h_in = ctx.pinned(max(1, n) * slot) if host_images else None
+        # host images lie BACK TO BACK, like an asset directory read into one buffer: blast_pcm_decode_batch then moves
+        # several files per copy (the bytes between two payloads are the next file's own header)
+        self.h_in = ctx.pinned(max(1, n) * self.image_len) if host_images else None
         h_hdr = ctx.pinned(256)
         h_hdr.u8[:len(hdr)] = hdr
         for k in range(n):
             L.blast_memcpy_h2d(ctx.h, self.d_in.ptr + k * slot, h_hdr.ptr, len(hdr))
             L.blast_memcpy_d2d(ctx.h, self.d_in.ptr + k * slot + len(hdr), d_pay.ptr + k * draws * 8, data_len)
-        if host_images and n:
-            L.blast_memcpy_d2h(ctx.h, self.h_in.ptr, self.d_in.ptr, n * slot)
+        if host_images:
+            for k in range(n):
+                L.blast_memcpy_d2h(ctx.h, self.h_in.ptr + k * self.image_len, self.d_in.ptr + k * slot, self.image_len)
         ctx.sync()
         h_hdr.free()
-        self.view = self.h_in.u8.reshape(max(1, n), slot)[:n, :self.image_len] if host_images else None
+        self.view = self.h_in.u8.reshape(max(1, n), self.image_len)[:n] if host_images else None
         self.desc = fp.probe("aiff", self.view[0] if host_images and n else np.concatenate([hdr, np.zeros(data_len, np.uint8)]))
         off = self.off = self.desc.data_off
         self.d_out = ctx.alloc(max(1, n) * self.words * 2)
@@ -417,7 +420,7 @@ def run_ours(args):
         wpf = shard.words
         h_out = ctx.pinned(max(1, n) * wpf * 2)
         h_bus = ctx.pinned(2 * n_slots) if mix else None
-        files = (C.c_void_p * max(1, n))(*[shard.h_in.ptr + k * shard.slot for k in range(n)])
+        files = (C.c_void_p * max(1, n))(*[shard.h_in.ptr + k * shard.image_len for k in range(n)])
         lens = (C.c_size_t * max(1, n))(*([shard.image_len] * n))
         dd = (_lib.PcmDesc * max(1, n))(*([shard.desc] * n))
         host_out = (C.c_void_p * max(1, n))(*[h_out.ptr + k * wpf * 2 for k in range(n)])
