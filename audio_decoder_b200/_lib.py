@@ -154,6 +154,7 @@ SIGNATURES = {
     "blast_conductor_destroy": (None, [_vp, _vp]),
     "blast_conductor_apply": (C.c_int, [_vp, _vp, C.POINTER(Command)]),
     "blast_conductor_set_shard": (C.c_int, [_vp, _u32, _u32]),
+    "blast_conductor_reserve": (C.c_int, [_vp, _vp, _u64]),
     "blast_conductor_render_dev": (C.c_int, [_vp, _vp, _u64, _vp]),
     "blast_conductor_coordinate": (C.c_int, [_vp, _vp, _u64, _vp]),
     "blast_conductor_render_timeline_dev": (C.c_int, [_vp, _vp, C.POINTER(TimedCommand), _u32, _u64, _vp]),

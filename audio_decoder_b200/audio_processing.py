@@ -247,6 +247,10 @@ class Conductor:
         check(self.ctx.lib.blast_conductor_coordinate(self.ctx.h, self.h, frames, bus.ctypes.data if bus.size else None))
         return bus
 
+    def reserve(self, frames: int):
+        """allocate now what a span of `frames` frames of the current scene needs (the spans that follow allocate nothing)"""
+        check(self.ctx.lib.blast_conductor_reserve(self.ctx.h, self.h, frames))
+
     def render_partial_dev(self, frames: int, d_partial: int):
         check(self.ctx.lib.blast_conductor_render_dev(self.ctx.h, self.h, frames, d_partial))
 

@@ -540,6 +540,27 @@ int blast_conductor_set_shard_by_track(blast_conductor* c, uint32_t rank, uint32
     return BLAST_OK;
 }
 
+int blast_conductor_reserve(blast_ctx* ctx, blast_conductor* c, uint64_t frames) {
+    if (int rc = blast::bind(ctx)) return rc;
+    BLAST_REQUIRE(c != nullptr, BLAST_ERR_ARG, "blast_conductor_reserve: null conductor");
+    Flat f;
+    if (int rc = flatten(c, f)) return rc;
+    const uint32_t nv = (uint32_t)f.dev.size(), ns = (uint32_t)f.seqs.size();
+    if (int rc = reserve_buffers(ctx, c->rb, nv, ns)) return rc;
+    if (int rc = reserve_frames(ctx, c->rb, nv, c->out_channels, frames)) return rc;
+    const size_t vb = (size_t)nv * sizeof(VoiceDev), sb = (size_t)ns * sizeof(SeqDev), pb = f.pool.size() * sizeof(float);
+    if (int rc = ensure_pin(c, 2 * (vb + sb) + pb + 16)) return rc;
+    if (pb > c->fpool_cap * sizeof(float)) {
+        BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (c->d_fpool) cudaFree(c->d_fpool);
+        c->d_fpool = nullptr;
+        c->fpool_cap = 0;
+        BLAST_CUDA_TRY(cudaMalloc(&c->d_fpool, pb * 2));
+        c->fpool_cap = f.pool.size() * 2;
+    }
+    return BLAST_OK;
+}
+
 int blast_conductor_render_dev(blast_ctx* ctx, blast_conductor* c, uint64_t frames, int32_t* d_partial_bus) {
     if (int rc = blast::bind(ctx)) return rc;
     BLAST_REQUIRE(c && (d_partial_bus || frames == 0), BLAST_ERR_ARG, "blast_conductor_render_dev: null argument");

@@ -252,7 +252,7 @@ def c3_seq(ctx, peak, quick):
     sc = C3Scene(ctx, 0, 1, n_voices, frames, False)
     part = ctx.alloc(frames * 2 * 4)
     times = []
-    for it in range(2):
+    for it in range(3):
         c = ap.Conductor(ctx, 2, 48000, sc.tracks)
         for v, vp in enumerate(sc.voices):
             # a beat every 24,000..48,000 calls (0.25..0.5 s at 48 kHz stereo), period 4, all four steps armed
@@ -262,7 +262,7 @@ def c3_seq(ctx, peak, quick):
             c.velocity(v, vp.velocity)
             c.start(v)
             c.set_voice(v, gain=vp.gain)
-        c.render_partial_dev(4096, part.ptr)                    # warm-up span: the conductor's buffers are allocated here
+        c.reserve(frames)                                       # the timed span allocates nothing
         ctx.sync()
         e0 = ctx.event().record()
         c.render_partial_dev(frames, part.ptr)

@@ -336,6 +336,9 @@ int  blast_conductor_set_shard_by_track(blast_conductor* c, uint32_t rank, uint3
  * the device work has finished (the Seq / position state is read back). BLAST_ERR_REF_PANIC where a Seq would index
  * an empty step list (processes.rs:79). */
 int  blast_conductor_render_dev(blast_ctx* ctx, blast_conductor* c, uint64_t frames, int32_t* d_partial_bus);
+/* Allocates now what a span of `frames` frames of the current scene would allocate on first use (grow-only): the spans
+ * that follow neither allocate nor wait for an allocation. */
+int  blast_conductor_reserve(blast_ctx* ctx, blast_conductor* c, uint64_t frames);
 /* coordinate() with a host bus: interleaved S16_LE like the ALSA area (runtime.rs:272-276) */
 int  blast_conductor_coordinate(blast_ctx* ctx, blast_conductor* c, uint64_t frames, int16_t* host_bus_out);
 /* Offline render of a whole Command timeline (the reference applies queued commands between periods,

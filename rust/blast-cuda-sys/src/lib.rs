@@ -72,6 +72,7 @@ extern "C" {
     pub fn blast_conductor_destroy(ctx: *mut blast_ctx, c: *mut blast_conductor);
     pub fn blast_conductor_apply(ctx: *mut blast_ctx, c: *mut blast_conductor, cmd: *const blast_command) -> c_int;
     pub fn blast_conductor_set_shard(c: *mut blast_conductor, rank: u32, world: u32) -> c_int;
+    pub fn blast_conductor_reserve(ctx: *mut blast_ctx, c: *mut blast_conductor, frames: u64) -> c_int;
     pub fn blast_conductor_render_dev(ctx: *mut blast_ctx, c: *mut blast_conductor, frames: u64, d_partial_bus: *mut i32) -> c_int;
     pub fn blast_conductor_coordinate(ctx: *mut blast_ctx, c: *mut blast_conductor, frames: u64, host_bus_out: *mut i16) -> c_int;
     pub fn blast_conductor_render_timeline(ctx: *mut blast_ctx, c: *mut blast_conductor, events: *const blast_timed_command,
