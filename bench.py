@@ -426,7 +426,7 @@ def run_ours(args):
         host_out = (C.c_void_p * max(1, n))(*[h_out.ptr + k * wpf * 2 for k in range(n)])
         dev_out = (C.c_void_p * max(1, n))(*[shard.d_out.ptr + k * wpf * 2 for k in range(n)])
         pcie = {}
-        pp = os.path.join(ROOT, "profiles", "r01_pcie_probe.json")
+        pp = os.path.join(ROOT, "profiles", "r02_pcie_probe.json")
         if os.path.exists(pp):
             pcie = json.load(open(pp))
 
@@ -461,7 +461,7 @@ def run_ours(args):
             if pcie:
                 r["pcie_peak_GBps"] = pcie.get("bidir_each_GBps" if to_host else "h2d_GBps")
                 r["pcie_frac"] = round(r["pcie_GBps_per_gpu"] / r["pcie_peak_GBps"], 3)
-                r["pcie_peak_source"] = "tools/pcie_probe.py on this pool's B200 box (profiles/r01_pcie_probe.json)"
+                r["pcie_peak_source"] = "tools/pcie_probe.py on this pool's B200 box (profiles/r02_pcie_probe.json)"
             return r
 
         e2e = e2e_run(False)
