@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libblast_cuda.so")
+# BLAST_CUDA_LIB: development only (A/B timing of two builds of the same ABI on one box)
+SO_PATH = os.environ.get("BLAST_CUDA_LIB") or os.path.join(_HERE, "libblast_cuda.so")
 
 OK = 0
 ERR_IO, ERR_UNSUPPORTED_FORMAT, ERR_UNEXPECTED_EOF, ERR_INVALID_DATA, ERR_REF_PANIC = 1, 2, 3, 4, 5

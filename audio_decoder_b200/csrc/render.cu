@@ -942,7 +942,7 @@ static_assert(2 * kPairHalf <= kStageBytes, "two unit tiles per stage");
 
 struct StageMeta {            // written by the producer before it arrives on the stage's full barrier
     // hot header (one LDS.128)
-    uint32_t mode;            // kMode* | path << 8 | full-range flag << 16 | slow flag << 17
+    uint32_t mode;            // kMode* | path << 8 | full-range flag << 16 | slow flag << 17 | three-segment flag << 18
     float gain;
     uint32_t a0_off;          // byte offset in the stage such that frame fl of the tile maps to a0_off + fl*4 (unit path)
     uint32_t frange;          // fa | fb << 16: the piece covers tile frames [fa, fb)
@@ -960,12 +960,14 @@ struct StageMeta {            // written by the producer before it arrives on th
     uint32_t base_idx;        // frame index staged at byte_off
     uint32_t byte_off;
     uint32_t shape;           // C | S << 8 | nch << 16
+    // offset 72.  A three-segment kPathStereoLerp piece (mode bit 18) keeps (f1, f2, q1, d1, q2, d2) in these six words:
+    // q(fl) = q1 + fl * d1 from tile frame f1 on, q2 + fl * d2 from f2 on (consume_stereo_lerp reads them by offset)
     uint32_t nseg;
     uint32_t seg_hint;        // segment index at the piece start (slow pieces walk from here)
     uint32_t f0;              // first frame of the work item's tile (generic path; kModeFlush items carry it in a0_off)
     uint32_t pad_[3];
 };
-static_assert(sizeof(StageMeta) == 96, "StageMeta layout");
+static_assert(sizeof(StageMeta) == 96 && offsetof(StageMeta, nseg) == 72, "StageMeta layout");
 constexpr size_t kMetaStride = 96;
 constexpr size_t kTmaSmem = (size_t)kStages * kStageBytes + kStages * kMetaStride + 2 * kStages * sizeof(uint64_t) +
                             (size_t)kStages * kMaxPieces * sizeof(uint4) + 32;     // + the producer's uncounted-flush words
@@ -1140,8 +1142,15 @@ __device__ __forceinline__ void lerp_frame(uint32_t w0, uint32_t w1, uint32_t fb
 // The fraction without a conversion: with sh <= 23 fraction bits, (q & mask) | (150 - sh) << 23 is the float
 // 2^(23-sh) + fract, so fract = that - 2^(23-sh) and 1 - fract = (2^(23-sh) + 1) - that, both exact: one LOP3 and two
 // FADDs instead of LOP + I2FP (quarter rate) + FMUL + FSUB.
-template <bool kFull>
-__device__ __forceinline__ void consume_stereo_lerp(uint32_t stage_addr, const StageMeta& m, float nz, int32_t (&acc)[kFPT][2]) {
+// kThree: the piece is up to THREE consecutive segments of the voice brought to a common unit (the finest ulp 2^-sh among
+// them: a position of a coarser binade is a multiple of it as well), i.e. one trajectory whose (q0, d) changes at tile
+// frames f1 and f2.  That is the tile in which an interpolated voice crosses a power of two: the run up to the last
+// position of the old binade, mostly one odd step, the run in the new binade (build_epoch) — four of the thirteen tiles
+// between two retriggers of the C3 + Seq scene.  Two compares and four selects per frame; the table path
+// (consume_stereo_multi) is left with the tiles right after a retrigger.
+template <bool kFull, bool kThree>
+__device__ __forceinline__ void consume_stereo_lerp(uint32_t stage_addr, const StageMeta& m, uint32_t meta_addr, float nz,
+                                                    int32_t (&acc)[kFPT][2]) {
     const uint32_t mask = (1u << m.sh) - 1u;
     const uint32_t sbase = stage_addr + m.byte_off - m.base_idx * 4u;
     const int32_t q0 = m.q0, d = m.d;
@@ -1149,20 +1158,37 @@ __device__ __forceinline__ void consume_stereo_lerp(uint32_t stage_addr, const S
     const float gain = m.gain;
     const uint32_t magic = (150u - sh) << 23;
     const float neg_c = -__uint_as_float(magic), one_c = __fadd_rn(__uint_as_float(magic), 1.0f);
-    if (kFull) {
-        uint32_t w0[kFPT], w1[kFPT], fb[kFPT];
-#pragma unroll
-        for (int j = 0; j < kFPT; ++j) {
-            const uint32_t q = (uint32_t)(q0 + (int32_t)(threadIdx.x + j * kConsumers) * d);
-            const uint32_t a = sbase + (q >> sh) * 4u;
-            fb[j] = (q & mask) | magic;
-            w0[j] = lds_u32(a);
-            w1[j] = lds_u32(a + 4u);
+    uint32_t f1 = 0, f2 = 0, q1 = 0, d1 = 0, q2 = 0, d2 = 0;
+    if (kThree) {
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2+72];" : "=r"(f1), "=r"(f2) : "r"(meta_addr));
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+80];" : "=r"(q1), "=r"(d1), "=r"(q2), "=r"(d2) : "r"(meta_addr));
+    }
+    auto q_of = [&](uint32_t fl) -> uint32_t {
+        if (kThree) {
+            const bool s1 = fl >= f1, s2 = fl >= f2;
+            const uint32_t qq = s2 ? q2 : (s1 ? q1 : (uint32_t)q0), dd = s2 ? d2 : (s1 ? d1 : (uint32_t)d);
+            return qq + fl * dd;
         }
+        return (uint32_t)(q0 + (int32_t)fl * d);
+    };
+    if (kFull) {
+        constexpr int kB = kThree ? 4 : kFPT;          // frames in flight (the three-segment variant has six more live registers)
 #pragma unroll
-        for (int j = 0; j < kFPT; ++j) {
-            const float v = __uint_as_float(fb[j]);
-            lerp_math(w0[j], w1[j], __fadd_rn(v, neg_c), __fsub_rn(one_c, v), gain, nz, acc[j][0], acc[j][1]);
+        for (int h = 0; h < kFPT; h += kB) {
+            uint32_t w0[kB], w1[kB], fb[kB];
+#pragma unroll
+            for (int j = 0; j < kB; ++j) {
+                const uint32_t q = q_of(threadIdx.x + (uint32_t)(h + j) * kConsumers);
+                const uint32_t a = sbase + (q >> sh) * 4u;
+                fb[j] = (q & mask) | magic;
+                w0[j] = lds_u32(a);
+                w1[j] = lds_u32(a + 4u);
+            }
+#pragma unroll
+            for (int j = 0; j < kB; ++j) {
+                const float v = __uint_as_float(fb[j]);
+                lerp_math(w0[j], w1[j], __fadd_rn(v, neg_c), __fsub_rn(one_c, v), gain, nz, acc[h + j][0], acc[h + j][1]);
+            }
         }
     } else {
         const uint32_t fa = m.frange & 0xFFFF, fe = m.frange >> 16, span = fe - fa;
@@ -1172,7 +1198,7 @@ __device__ __forceinline__ void consume_stereo_lerp(uint32_t stage_addr, const S
             if ((uint32_t)j < j_lo || (uint32_t)j > j_hi) continue;
             const uint32_t fl = threadIdx.x + j * kConsumers;
             if ((fl - fa) < span) {
-                const uint32_t q = (uint32_t)(q0 + (int32_t)fl * d);
+                const uint32_t q = q_of(fl);
                 const uint32_t a = sbase + (q >> sh) * 4u;
                 const float v = __uint_as_float((q & mask) | magic);
                 lerp_math(lds_u32(a), lds_u32(a + 4u), __fadd_rn(v, neg_c), __fsub_rn(one_c, v), gain, nz, acc[j][0], acc[j][1]);
@@ -1305,7 +1331,7 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                      const TileRec* __restrict__ recs, uint32_t frames, int32_t* __restrict__ bus, int use_atomic,
                      const uint32_t* __restrict__ err, const uint32_t seg_cap, uint32_t* __restrict__ work,
                      const __grid_constant__ BusSink sink, const float nz, const uint4* __restrict__ pool,
-                     const uint32_t pool_rows) {
+                     const uint32_t pool_rows, const uint32_t opts) {
     extern __shared__ __align__(128) uint8_t smem[];
     if (*err) return;                                           // truncated trajectories must not be rendered (uniform exit)
     uint8_t* stages = smem;
@@ -1413,6 +1439,51 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                     cur = 0;
                 }
             }
+            // ---- issue the pieces of this round: items in lane order, two consecutive full unit tiles share one stage (adds
+            // commute, the lanes need not be adjacent).  Every lane that owns an item does all of it itself — wait for
+            // its stage, write the meta row, arm the barrier, start the copies — and kStages lanes do so at a time: the
+            // stages of one such wave are distinct and depend only on earlier waves.  (One item at a time, with the
+            // lanes taking turns between warp barriers, cost ~110 issue slots per item in a warp that gets one slot in
+            // thirteen cycles: a third of the time of the single producer warp K4 waits for on scenes with retriggers.)
+            auto issue_round = [&](StageMeta& m, const uint32_t bytes, const unsigned long long src) {
+                const uint32_t have = __ballot_sync(0xFFFFFFFFu, (m.mode & 0xFF) != 0);
+                constexpr uint32_t kUnitFull = kModeStaged | (kPathStereoUnit << 8) | (1u << 16);
+                const uint32_t pairable = OC == 2 ? __ballot_sync(0xFFFFFFFFu, m.mode == kUnitFull && bytes <= kPairHalf) : 0u;
+                const uint32_t lt = (1u << lane) - 1u;
+                const bool is_pair = (pairable >> lane) & 1u;
+                const bool second = is_pair && (__popc(pairable & lt) & 1);
+                const uint32_t above = pairable & ~lt & ~(1u << lane);
+                const int partner = (is_pair && !second && above) ? __ffs(above) - 1 : -1;
+                const uint32_t items = have & ~__ballot_sync(0xFFFFFFFFu, second);
+                const uint32_t irank = __popc(items & lt), n_it = __popc(items);
+                const bool mine = (items >> lane) & 1u;
+                const int from = partner >= 0 ? partner : (int)lane;
+                const unsigned long long src2 = __shfl_sync(0xFFFFFFFFu, src, from);
+                const uint32_t bytes2 = __shfl_sync(0xFFFFFFFFu, bytes, from), a0_2 = __shfl_sync(0xFFFFFFFFu, m.a0_off, from);
+                const float gain2 = __shfl_sync(0xFFFFFFFFu, m.gain, from);
+                if (mine && partner >= 0) {           // the second voice's stage offset and gain ride in the trajectory slots
+                    m.mode = kModeStaged | (kPathStereoUnit2 << 8);
+                    m.q0 = (int32_t)(kPairHalf + a0_2);
+                    m.scale = gain2;
+                }
+                for (uint32_t w0 = 0; w0 < n_it; w0 += (uint32_t)kStages) {
+                    if (mine && irank - w0 < (uint32_t)kStages) {
+                        const uint32_t oi = o + irank, st = oi % kStages;
+                        acquire(oi);
+                        *reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride) = m;
+                        if ((m.mode & 0xFF) == kModeStaged) {
+                            mbar_arrive_expect_tx(full + st, bytes + (partner >= 0 ? bytes2 : 0u));
+                            bulk_g2s(stages + (size_t)st * kStageBytes, reinterpret_cast<const void*>(src), bytes, full + st);
+                            if (partner >= 0)
+                                bulk_g2s(stages + (size_t)st * kStageBytes + kPairHalf, reinterpret_cast<const void*>(src2), bytes2, full + st);
+                        } else {
+                            mbar_arrive(full + st);
+                        }
+                    }
+                    __syncwarp();
+                }
+                o += n_it;
+            };
             bool first_round = true;
             bool hold_multi = false;      // stereo voice whose tile spans several segments: try ONE staged item first
             while (__any_sync(0xFFFFFFFFu, cur < nf)) {
@@ -1559,49 +1630,101 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                     m.seg_hint = seg_j;
                     m.f0 = f0;
                 }
-                // ---- issue the pieces of this round in lane order; two consecutive full unit tiles share one stage
-                const uint32_t have = __ballot_sync(0xFFFFFFFFu, (m.mode & 0xFF) != 0);
-                constexpr uint32_t kUnitFull = kModeStaged | (kPathStereoUnit << 8) | (1u << 16);
-                const uint32_t pairable = OC == 2 ? __ballot_sync(0xFFFFFFFFu, m.mode == kUnitFull && bytes <= kPairHalf) : 0u;
-                for (uint32_t rest = have; rest;) {
-                    const int i = __ffs(rest) - 1;
-                    rest &= rest - 1;
-                    int i2 = -1;
-                    if ((pairable >> i) & 1u) {           // the next full unit tile of this round, adjacent lane or not (adds commute)
-                        const uint32_t cand = rest & pairable;
-                        if (cand) { i2 = __ffs(cand) - 1; rest &= ~(1u << i2); }
-                    }
-                    const uint32_t st = o % kStages, round = o / kStages;
-                    StageMeta* ms = reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride);
-                    const uint32_t bytes2 = i2 >= 0 ? __shfl_sync(0xFFFFFFFFu, bytes, i2) : 0u;
-                    if (lane == i) {
-                        acquire(o);
-                        *ms = m;
-                        if (i2 >= 0) ms->mode = kModeStaged | (kPathStereoUnit2 << 8);
-                    }
-                    if (i2 >= 0) {
-                        __syncwarp();
-                        if (lane == i2) {                 // the second voice's stage offset and gain ride in the trajectory slots
-                            ms->q0 = (int32_t)(kPairHalf + m.a0_off);
-                            ms->scale = m.gain;
-                        }
-                        __syncwarp();
-                    }
-                    if (lane == i) {
-                        if ((m.mode & 0xFF) == kModeStaged) {
-                            mbar_arrive_expect_tx(full + st, bytes + bytes2);
-                            bulk_g2s(stages + (size_t)st * kStageBytes, reinterpret_cast<const void*>(src), bytes, full + st);
-                        } else {
-                            mbar_arrive(full + st);
-                        }
-                    }
-                    __syncwarp();
-                    if (i2 >= 0 && lane == i2)
-                        bulk_g2s(stages + (size_t)st * kStageBytes + kPairHalf, reinterpret_cast<const void*>(src), bytes, full + st);
-                    o += 1;
-                }
                 // ---- after the first round: voices held back for the multi-piece path, one at a time, with
                 // the whole warp cooperating (lane l looks at segment j0 + l of that voice)
+                issue_round(m, bytes, src);
+                if (first_round && (opts & 4u) && __any_sync(0xFFFFFFFFu, hold_multi)) {
+                    // Lane-local: a held tile that two or three segments cover — an interpolated voice crossing a power of
+                    // two: four of five multi-segment tiles on scenes with retriggers — is cut by its own lane into ONE
+                    // three-segment piece (consume_stereo_lerp<., true>) and issued like the single-segment pieces above,
+                    // all lanes at once.  (The cooperative path below takes ~375 issue slots of this warp per voice.)
+                    StageMeta m3{};
+                    uint32_t bytes3 = 0;
+                    unsigned long long src3 = 0;
+                    if (hold_multi && v.vel != 1.0f) {
+                        const uint32_t last_abs = f0 + nf - 1;                      // S == 1 for held voices
+                        uint32_t cnt = 1;
+                        Seg g[3];
+                        uint32_t nxt[3];
+                        g[0] = sg[seg_j];
+                        g[1] = g[0]; g[2] = g[0];
+                        nxt[0] = nxt[1] = nxt[2] = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int t = 1; t <= 3; ++t) {
+                            if (cnt == (uint32_t)t && seg_j + t < nseg) {
+                                const Seg gn = sg[seg_j + t];
+                                nxt[t - 1] = gn.step0;
+                                if (t < 3 && gn.step0 <= last_abs) { g[t] = gn; cnt = t + 1; }
+                            }
+                        }
+                        const uint32_t nxt_last = cnt == 3u ? nxt[2] : (cnt == 2u ? nxt[1] : nxt[0]);
+                        const bool covered = nxt_last > last_abs;                    // no fourth segment inside the tile
+                        bool ok3 = covered && cnt >= 2u;
+                        uint32_t lo_g = 0xFFFFFFFFu, hi_g = 0u, sh_c = 0u;
+                        uint32_t fa_[3] = {0, 0, 0}, fe_[3] = {0, 0, 0}, sh_[3] = {0, 0, 0};
+                        int32_t q_[3] = {0, 0, 0};
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) {
+                            if (ok3 && (uint32_t)t < cnt) {
+                                const uint32_t ls = max(g[t].step0, f0), le = min(nxt[t], f0 + nf);
+                                fa_[t] = ls - f0; fe_[t] = le - f0;
+                                const float p_a = seg_eval(g[t].p0, g[t].d, g[t].scale, ls - g[t].step0);
+                                const float p_l = seg_eval(g[t].p0, g[t].d, g[t].scale, le - 1 - g[t].step0);
+                                const uint32_t lo = f2u_sat(fminf(p_a, p_l)), hi = f2u_sat(fmaxf(p_a, p_l));
+                                // audible, inside the clip, non-negative (NaN fails the comparisons)
+                                bool good = p_a >= 0.0f && p_l >= 0.0f && hi < v.end;
+                                if (good) {
+                                    if (g[t].d != 0) {
+                                        const uint32_t eb = (__float_as_uint(g[t].scale) >> 23) & 0xFF;
+                                        good = eb >= 104 && eb <= 127;
+                                        sh_[t] = 127 - eb;
+                                    } else {
+                                        const int E = (int)((__float_as_uint(p_a) >> 23) & 0xFF);
+                                        const int s_ = p_a == 0.0f ? 0 : max(0, 150 - E);
+                                        good = s_ <= 23;
+                                        sh_[t] = (uint32_t)s_;
+                                    }
+                                }
+                                if (good) {
+                                    const int32_t qa = __float2int_rz(__fmul_rn(p_a, __uint_as_float((127u + sh_[t]) << 23)));
+                                    q_[t] = qa - (int32_t)fa_[t] * g[t].d;
+                                    lo_g = min(lo_g, lo); hi_g = max(hi_g, hi); sh_c = max(sh_c, sh_[t]);
+                                } else {
+                                    ok3 = false;
+                                }
+                            }
+                        }
+                        if (ok3 && ((hi_g + 2u) >> (31u - sh_c)) == 0u) {
+                            const unsigned long long base = (unsigned long long)v.smp;
+                            const unsigned long long b0 = base + (unsigned long long)lo_g * 4ull;
+                            const unsigned long long b1 = base + ((unsigned long long)hi_g + 2ull) * 4ull;
+                            const unsigned long long a0 = b0 & ~15ull, a1 = (b1 + 15ull) & ~15ull;
+                            if (a1 - a0 <= (unsigned long long)kStageBytes) {
+                                const uint32_t fe_all = cnt == 3u ? fe_[2] : fe_[1];
+                                const uint32_t fullr = (fa_[0] == 0u && fe_all == (uint32_t)kFT) ? 1u : 0u;
+                                m3.mode = kModeStaged | (kPathStereoLerp << 8) | (fullr << 16) | (1u << 18);
+                                m3.gain = v.gain;
+                                m3.frange = fa_[0] | (fe_all << 16);
+                                m3.base_idx = lo_g;
+                                m3.byte_off = (uint32_t)(b0 - a0);
+                                m3.sh = sh_c;
+                                m3.q0 = (int32_t)((uint32_t)q_[0] << (sh_c - sh_[0]));
+                                m3.d = (int32_t)((uint32_t)g[0].d << (sh_c - sh_[0]));
+                                m3.nseg = fa_[1];                                                  // f1
+                                m3.seg_hint = cnt == 3u ? fa_[2] : fe_all;                          // f2
+                                m3.f0 = (uint32_t)q_[1] << (sh_c - sh_[1]);
+                                m3.pad_[0] = (uint32_t)g[1].d << (sh_c - sh_[1]);
+                                m3.pad_[1] = (uint32_t)q_[2] << ((sh_c - sh_[2]) & 31u);
+                                m3.pad_[2] = (uint32_t)g[2].d << ((sh_c - sh_[2]) & 31u);
+                                src3 = a0;
+                                bytes3 = (uint32_t)(a1 - a0);
+                                cur = nf;
+                                hold_multi = false;
+                            }
+                        }
+                    }
+                    issue_round(m3, bytes3, src3);
+                }
                 if (first_round) {
                     // tiles whose piece table K3 has already built (TileRec.scale carries the tag): the lane reads its
                     // item headers and issues two bulk copies per item — the source span and the piece rows — nothing
@@ -1669,10 +1792,11 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                         bool ok = true, silent = true;
                         uint32_t idx_lo = 0xFFFFFFFFu, idx_hi = 0, shv = 0, fa = 0, fe = 0;
                         int32_t q0v = 0;
+                        float p_a = 0.0f;
                         if (ex) {
                             const uint32_t ls = max(g.step0, f0), le = min(nxt, f0 + nf);
                             fa = ls - f0; fe = le - f0;
-                            const float p_a = seg_eval(g.p0, g.d, g.scale, ls - g.step0);
+                            p_a = seg_eval(g.p0, g.d, g.scale, ls - g.step0);
                             const float p_l = seg_eval(g.p0, g.d, g.scale, le - 1 - g.step0);
                             const bool weird = (p_a != p_a) || (p_l != p_l);
                             const uint32_t lo = f2u_sat(fminf(p_a, p_l)), hi = f2u_sat(fmaxf(p_a, p_l));
@@ -1727,9 +1851,68 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                                     const uint32_t st = o % kStages;
                                     if (lane == 0) acquire(o);
                                     __syncwarp();
-                                    if (ex && lane >= g0 && lane <= L)
+                                    // A group of ONE audible segment needs no table: it is an ordinary partial piece, unit or
+                                    // interpolated, and the consumers skip the 256-frame slabs it does not touch (the part of a
+                                    // tile before a retrigger, whose source lies far from the home position's).  Two or three
+                                    // audible segments of an interpolated voice are ONE piece in their finest common unit.
+                                    uint32_t kind = 0;                    // 0: table, 1: unit piece, 2: interpolated piece, 3: three segments
+                                    const bool in_grp = lane >= g0 && lane <= L;
+                                    const bool lerp_seg = in_grp && ex && !silent && vel_i != 1.0f;       // (ok holds for every lane here)
+                                    uint32_t sh_c = lerp_seg ? shv : 0u;
+#pragma unroll
+                                    for (int dd = 16; dd >= 1; dd >>= 1) sh_c = max(sh_c, __shfl_xor_sync(0xFFFFFFFFu, sh_c, dd));
+                                    const bool all_lerp = __all_sync(0xFFFFFFFFu, !in_grp || lerp_seg);
+                                    // my segment in the common unit (wrap-around arithmetic: the true q of an in-range frame is below 2^31)
+                                    const uint32_t q_c = (uint32_t)q0v << ((sh_c - shv) & 31u), d_c = (uint32_t)g.d << ((sh_c - shv) & 31u);
+                                    const uint32_t l1 = min(g0 + 1u, L), l2 = min(g0 + 2u, L);
+                                    const uint32_t fa_1 = __shfl_sync(0xFFFFFFFFu, fa, l1), q_1 = __shfl_sync(0xFFFFFFFFu, q_c, l1),
+                                                   d_1 = __shfl_sync(0xFFFFFFFFu, d_c, l1);
+                                    const uint32_t fa_2 = __shfl_sync(0xFFFFFFFFu, fa, l2), q_2 = __shfl_sync(0xFFFFFFFFu, q_c, l2),
+                                                   d_2 = __shfl_sync(0xFFFFFFFFu, d_c, l2);
+                                    const uint32_t fe_L = __shfl_sync(0xFFFFFFFFu, fe, L);
+                                    if (lane == g0) {
+                                        if (cnt == 1u && (opts & 1u)) {
+                                            if (vel_i == 1.0f && __fmul_rn((float)g.d, g.scale) == 1.0f) kind = 1;
+                                            else if (lerp_seg && g.d != 0 && shv <= 23u) kind = 2;
+                                        } else if ((cnt == 2u || cnt == 3u) && (opts & 2u) && all_lerp && sh_c <= 23u &&
+                                                   ((hi_g + 2u) >> (31u - sh_c)) == 0u) {
+                                            kind = 3;
+                                        }
+                                        if (kind != 0u) {
+                                            StageMeta mm{};
+                                            const uint32_t fe_all = kind == 3u ? fe_L : fe;
+                                            const uint32_t fullr = (fa == 0u && fe_all == (uint32_t)kFT) ? 1u : 0u;
+                                            mm.gain = gain_i;
+                                            mm.frange = fa | (fe_all << 16);
+                                            mm.base_idx = lo_g;
+                                            mm.byte_off = (uint32_t)(b0 - a0);
+                                            if (kind == 1u) {
+                                                mm.mode = kModeStaged | (kPathStereoUnit << 8) | (fullr << 16);
+                                                mm.a0_off = mm.byte_off + (f2u_sat(p_a) - lo_g - fa) * 4u;
+                                            } else if (kind == 2u) {
+                                                mm.mode = kModeStaged | (kPathStereoLerp << 8) | (fullr << 16);
+                                                mm.sh = shv;
+                                                mm.q0 = q0v;
+                                                mm.d = g.d;
+                                            } else {
+                                                mm.mode = kModeStaged | (kPathStereoLerp << 8) | (fullr << 16) | (1u << 18);
+                                                mm.sh = sh_c;
+                                                mm.q0 = (int32_t)q_c;
+                                                mm.d = (int32_t)d_c;
+                                                mm.nseg = fa_1;                          // f1
+                                                mm.seg_hint = cnt == 3u ? fa_2 : fe_L;   // f2 (nothing switches at the end of the piece)
+                                                mm.f0 = q_1;
+                                                mm.pad_[0] = d_1;
+                                                mm.pad_[1] = q_2;
+                                                mm.pad_[2] = d_2;
+                                            }
+                                            *reinterpret_cast<StageMeta*>(meta_base + st * kMetaStride) = mm;
+                                        }
+                                    }
+                                    kind = __shfl_sync(0xFFFFFFFFu, kind, g0);
+                                    if (kind == 0u && ex && lane >= g0 && lane <= L)
                                         ptabs[st * kMaxPieces + lane - g0] = make_uint4(fa | (fe << 16), (uint32_t)q0v, (uint32_t)g.d, shv | (silent ? 0x100u : 0u));
-                                    if (lane == 0) {
+                                    if (kind == 0u && lane == 0) {
                                         StageMeta mm{};
                                         mm.mode = kModeStaged | (kPathStereoMulti << 8);
                                         mm.gain = gain_i;
@@ -1854,8 +2037,13 @@ voice_render_mix_tma(const VoiceDev* __restrict__ voices, uint32_t n_voices, uin
                 else { if (g1) consume_stereo_unit<false, true>(stage_addr, a0_off, gain, frange, a2); else consume_stereo_unit<false, false>(stage_addr, a0_off, gain, frange, a2); }
             } else if (OC == 2 && path == kPathStereoLerp) {
                 auto& a2 = reinterpret_cast<int32_t (&)[kFPT][2]>(acc);
-                if (fullr) consume_stereo_lerp<true>(stage_addr, *mp, nz, a2);
-                else consume_stereo_lerp<false>(stage_addr, *mp, nz, a2);
+                if ((mode >> 18) & 1u) {
+                    if (fullr) consume_stereo_lerp<true, true>(stage_addr, *mp, meta_addr, nz, a2);
+                    else consume_stereo_lerp<false, true>(stage_addr, *mp, meta_addr, nz, a2);
+                } else {
+                    if (fullr) consume_stereo_lerp<true, false>(stage_addr, *mp, meta_addr, nz, a2);
+                    else consume_stereo_lerp<false, false>(stage_addr, *mp, meta_addr, nz, a2);
+                }
             } else if (OC == 2 && path == kPathStereoMulti) {
                 auto& a2 = reinterpret_cast<int32_t (&)[kFPT][2]>(acc);
                 const uint32_t ptab = smem_u32(ptabs + st * kMaxPieces);
@@ -2180,6 +2368,9 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
 
     // piece-table pool of the tiles with several segments (stereo bus, TMA kernel): grow-only, sized by voices x segments
     static const bool tables = getenv("BLAST_RENDER_TABLES") != nullptr;
+    // development switch: bit 0 = one-segment groups of a multi-segment tile as ordinary pieces, bit 1 = two / three segments as
+    // one piece (cooperative path), bit 2 = the same cut by the voice's own lane
+    static const uint32_t opts = getenv("BLAST_RENDER_OPTS") ? (uint32_t)atoi(getenv("BLAST_RENDER_OPTS")) : 7u;
     uint4* tab_pool = (oc == 2 && !legacy && tables) ? rb.d_pool : nullptr;
     rb.parity ^= 1u;                                         // this render's error word; cleared by the previous render's K3
     uint32_t* d_err = rb.d_err + rb.parity;
@@ -2211,7 +2402,7 @@ int launch_render(blast_ctx* ctx, RenderBuffers& rb, uint32_t n_voices, uint32_t
         BLAST_CUDA_TRY(cudaFuncSetAttribute(voice_render_mix_tma<OCV, SINK, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem)); \
         voice_render_mix_tma<OCV, SINK, TAB><<<grid_tma, kTmaThreads, kTmaSmem, ctx->stream>>>(                                      \
             rb.d_voices, n_voices, per_group, groups, rb.d_segs, rb.d_nsegs, rb.d_recs, (uint32_t)frames, d_partial_bus, use_atomic, \
-            d_err, rb.seg_cap, d_work, sink, -0.0f, tab_pool, rb.pool_rows);                                                         \
+            d_err, rb.seg_cap, d_work, sink, -0.0f, tab_pool, rb.pool_rows, opts);                                                       \
     } while (0)
         const bool with_tab = tab_pool != nullptr;
         if (oc == 1) {
