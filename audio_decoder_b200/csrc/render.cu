@@ -1024,8 +1024,12 @@ __device__ __forceinline__ int32_t lds_s16(uint32_t addr) {
 __device__ __forceinline__ void unpack_pair(uint32_t w, float& l, float& r) {
     uint32_t lo;
     asm("lop3.b32 %0, %1, 0x0000FFFF, 0x4B008000, 0x6A;" : "=r"(lo) : "r"(w));      // (a & b) ^ c
-    l = __fadd_rn(__uint_as_float(lo), -8421376.0f);                                  // -(2^23 + 32768): exact
-    r = __int2float_rn((int32_t)w >> 16);
+    // R: 0x4B400000 + sext(R) is the float 2^23 + 2^22 + R (the two's-complement add borrows from mantissa bit 22 for a
+    // negative R): ONE LEA.HI.SX32 instead of SHF + I2FP (quarter rate on the ALU pipe).  The two magic constants are
+    // subtracted by ONE packed add: -(2^23 + 32768) | -(2^23 + 2^22) << 32, both exact.
+    const uint32_t hi = (uint32_t)(((int32_t)w >> 16) + 0x4B400000);
+    asm("{\n\t.reg .b64 t, c;\n\tmov.b64 t, {%2, %3};\n\tmov.b64 c, 0xCB400000CB008000;\n\tadd.rn.f32x2 t, t, c;\n\tmov.b64 {%0, %1}, t;\n\t}"
+        : "=f"(l), "=f"(r) : "r"(lo), "r"(hi));
 }
 
 // (a * s, b * s), each product rounded to nearest like the scalar FMUL: ONE issue slot (Blackwell FMUL2).  Never
