@@ -649,28 +649,45 @@ constexpr uint32_t kHdrBins = 1u << 21;         // the 11 sync bits are fixed: 2
 // per warp on ONE address serialised in L2 (1.14 ms for C5's 49 M candidates; the 197 MB of headers stream in 40 us).
 // A key that finds both of its slots taken by other keys goes to the global histogram directly.
 constexpr uint32_t kHotSlots = 512;
+constexpr int kHistPerThread = 4;               // headers per thread and round, one 128-bit load: with one 4-byte load per
+                                                // thread and round the pass was latency-bound at 1.3 TB/s (155 us on C5)
 __global__ void __launch_bounds__(256)
 mpeg_hist(const uint32_t* __restrict__ hdr, unsigned long long n, uint32_t* __restrict__ hist) {
     __shared__ uint32_t s_key[kHotSlots], s_cnt[kHotSlots];
     for (uint32_t i = threadIdx.x; i < kHotSlots; i += blockDim.x) { s_key[i] = 0xFFFFFFFFu; s_cnt[i] = 0u; }
     __syncthreads();
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const bool aligned = ((unsigned long long)hdr & 15ull) == 0ull;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x * kHistPerThread;
     const unsigned long long rounds = (n + stride - 1) / stride;
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long i = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * kHistPerThread;
     for (unsigned long long r = 0; r < rounds; ++r, i += stride) {
-        const bool on = i < n;
-        const uint32_t key = on ? (hdr[i] & (kHdrBins - 1)) : 0xFFFFFFFFu;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
-        if (on && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
-            const uint32_t c = (uint32_t)__popc(peers);
-            uint32_t slot = (key * 2654435761u) >> 23;                      // 9 bits
-            bool done = false;
+        uint32_t h4[kHistPerThread];
+        if (aligned && i + kHistPerThread <= n) {
+            const uint4 v = *reinterpret_cast<const uint4*>(hdr + i);
+            h4[0] = v.x; h4[1] = v.y; h4[2] = v.z; h4[3] = v.w;
+        } else {
 #pragma unroll
-            for (int probe = 0; probe < 2 && !done; ++probe, slot ^= 1u) {
-                const uint32_t prev = atomicCAS(&s_key[slot], 0xFFFFFFFFu, key);
-                if (prev == 0xFFFFFFFFu || prev == key) { atomicAdd(&s_cnt[slot], c); done = true; }
+            for (int k = 0; k < kHistPerThread; ++k) h4[k] = i + k < n ? hdr[i + k] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < kHistPerThread; ++k) {
+            // only a header that parses can win the vote (mpeg_pick_ref): the others — two thirds of the false syncs inside
+            // payload bytes, whose scattered global atomics were what this pass was bound by — are not counted at all
+            HdrInfo hi_;
+            const bool on = i + k < n && parse_header_bits(0xFFE00000u | h4[k], hi_);
+            const uint32_t key = on ? (h4[k] & (kHdrBins - 1)) : 0xFFFFFFFFu;
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+            if (on && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+                const uint32_t c = (uint32_t)__popc(peers);
+                uint32_t slot = (key * 2654435761u) >> 23;                      // 9 bits
+                bool done = false;
+#pragma unroll
+                for (int probe = 0; probe < 2 && !done; ++probe, slot ^= 1u) {
+                    const uint32_t prev = atomicCAS(&s_key[slot], 0xFFFFFFFFu, key);
+                    if (prev == 0xFFFFFFFFu || prev == key) { atomicAdd(&s_cnt[slot], c); done = true; }
+                }
+                if (!done) atomicAdd(hist + key, c);
             }
-            if (!done) atomicAdd(hist + key, c);
         }
     }
     __syncthreads();
@@ -743,30 +760,48 @@ mpeg_first_pos(const unsigned long long* __restrict__ pos, const uint32_t* __res
         unsigned long long* slot = first + key;
         if (*reinterpret_cast<volatile unsigned long long*>(slot) > p) atomicMin(slot, p);   // the table only ever decreases
     };
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    // four consecutive candidates per thread and round, loaded with three 128-bit loads (as one dependent 4-byte + 8-byte
+    // load per thread and round the pass ran at 2.9 TB/s: 207 us on C5).  In every one of the four match rounds the
+    // candidates still ascend with the lane, so the lowest lane of a key holds the key's smallest position of the round.
+    const bool aligned = (((unsigned long long)pos | (unsigned long long)hdr) & 15ull) == 0ull;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x * kHistPerThread;
     const unsigned long long rounds = (n + stride - 1) / stride;
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long i = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * kHistPerThread;
     const uint32_t lane = threadIdx.x & 31;
     for (unsigned long long r = 0; r < rounds; ++r, i += stride) {
-        uint32_t key = 0xFFFFFFFFu;
-        unsigned long long p = ~0ull;
-        if (i < n) {
-            const uint32_t h = hdr[i];
-            uint32_t pl, sk;
-            if (cand_valid_lut(h, ref_header, s_lut, pl, sk)) { key = h & (kHdrBins - 1); p = pos[i]; }
-        }
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
-        const int leader = __ffs(peers) - 1;
-        const unsigned long long p_lead = __shfl_sync(0xFFFFFFFFu, p, leader);
-        if (key != 0xFFFFFFFFu && ((int)lane == leader || p < p_lead)) {
-            uint32_t slot = (key * 2654435761u) >> 23;
-            bool done = false;
+        uint32_t h4[kHistPerThread];
+        unsigned long long p4[kHistPerThread];
+        if (aligned && i + kHistPerThread <= n) {
+            const uint4 v = *reinterpret_cast<const uint4*>(hdr + i);
+            h4[0] = v.x; h4[1] = v.y; h4[2] = v.z; h4[3] = v.w;
+            const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(pos + i), b2 = *reinterpret_cast<const ulonglong2*>(pos + i + 2);
+            p4[0] = a.x; p4[1] = a.y; p4[2] = b2.x; p4[3] = b2.y;
+        } else {
 #pragma unroll
-            for (int probe = 0; probe < 2 && !done; ++probe, slot ^= 1u) {
-                const uint32_t prev = atomicCAS(&s_key[slot], 0xFFFFFFFFu, key);
-                if (prev == 0xFFFFFFFFu || prev == key) { atomicMin(&s_min[slot], p); done = true; }
+            for (int k = 0; k < kHistPerThread; ++k) {
+                h4[k] = i + k < n ? hdr[i + k] : 0u;                    // 0 has no sync bits: never valid
+                p4[k] = i + k < n ? pos[i + k] : ~0ull;
             }
-            if (!done) global_min(key, p);
+        }
+#pragma unroll
+        for (int k = 0; k < kHistPerThread; ++k) {
+            uint32_t key = 0xFFFFFFFFu;
+            unsigned long long p = ~0ull;
+            uint32_t pl, sk;
+            if (i + k < n && cand_valid_lut(h4[k], ref_header, s_lut, pl, sk)) { key = h4[k] & (kHdrBins - 1); p = p4[k]; }
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+            const int leader = __ffs(peers) - 1;
+            const unsigned long long p_lead = __shfl_sync(0xFFFFFFFFu, p, leader);
+            if (key != 0xFFFFFFFFu && ((int)lane == leader || p < p_lead)) {
+                uint32_t slot = (key * 2654435761u) >> 23;
+                bool done = false;
+#pragma unroll
+                for (int probe = 0; probe < 2 && !done; ++probe, slot ^= 1u) {
+                    const uint32_t prev = atomicCAS(&s_key[slot], 0xFFFFFFFFu, key);
+                    if (prev == 0xFFFFFFFFu || prev == key) { atomicMin(&s_min[slot], p); done = true; }
+                }
+                if (!done) global_min(key, p);
+            }
         }
     }
     __syncthreads();
@@ -852,23 +887,37 @@ mpeg_classify(const unsigned long long* __restrict__ pos, const uint32_t* __rest
     }
 }
 
-// exclusive scan of the block counts (one block; the array is small)
+// exclusive scan of the block counts (one block of 1,024 threads; the array is small): per-thread sums, a two-level
+// shuffle scan across the block (one thread walking the 1,024 partial sums took 15 of the kernel's 39 us), per-thread write
 __global__ void mpeg_scan_blocks(const unsigned long long* __restrict__ counts, unsigned long long* __restrict__ base,
                                  unsigned long long nb, unsigned long long* __restrict__ total) {
-    __shared__ unsigned long long s_part[1024];
+    __shared__ unsigned long long s_warp[32];
     const unsigned long long per = (nb + blockDim.x - 1) / blockDim.x;
-    const unsigned long long a = threadIdx.x * per, b = min(nb, a + per);
+    const unsigned long long a = min(nb, threadIdx.x * per), b = min(nb, a + per);
     unsigned long long sum = 0;
     for (unsigned long long i = a; i < b; ++i) sum += counts[i];
-    s_part[threadIdx.x] = sum;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if ((int)lane >= d) inc += up;
+    }
+    if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long run = 0;
-        for (unsigned int t = 0; t < blockDim.x; ++t) { const unsigned long long v = s_part[t]; s_part[t] = run; run += v; }
-        *total = run;
+    if (warp == 0) {
+        const uint32_t n_warps = (blockDim.x + 31) / 32;
+        unsigned long long w = lane < n_warps ? s_warp[lane] : 0ull;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, w, d);
+            if ((int)lane >= d) w += up;
+        }
+        s_warp[lane] = w;                                   // inclusive over the warps
     }
     __syncthreads();
-    unsigned long long run = s_part[threadIdx.x];
+    unsigned long long run = (inc - sum) + (warp ? s_warp[warp - 1] : 0ull);
+    if (threadIdx.x == blockDim.x - 1) *total = run + sum;
     for (unsigned long long i = a; i < b; ++i) { base[i] = run; run += counts[i]; }
 }
 
@@ -1143,7 +1192,7 @@ int blast_mpeg_hist_dev(blast_ctx* ctx, const uint32_t* d_hdr, uint64_t n, uint3
     if (int rc = blast::bind(ctx)) return rc;
     BLAST_REQUIRE(d_hist && (d_hdr || n == 0), BLAST_ERR_ARG, "blast_mpeg_hist_dev: null argument");
     if (n == 0) return BLAST_OK;
-    const unsigned g = (unsigned)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)ctx->sm_count * 16);
+    const unsigned g = (unsigned)std::min<unsigned long long>((n + 256 * kHistPerThread - 1) / (256 * kHistPerThread), (unsigned long long)ctx->sm_count * 16);
     mpeg_hist<<<g, 256, 0, ctx->stream>>>(d_hdr, n, d_hist);
     BLAST_CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
@@ -1173,7 +1222,7 @@ int blast_mpeg_first_pos_dev(blast_ctx* ctx, const uint64_t* d_pos, const uint32
     if (int rc = blast::bind(ctx)) return rc;
     BLAST_REQUIRE(d_first && ((d_pos && d_hdr) || n == 0), BLAST_ERR_ARG, "blast_mpeg_first_pos_dev: null argument");
     if (n == 0) return BLAST_OK;
-    const unsigned g = (unsigned)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)ctx->sm_count * 16);
+    const unsigned g = (unsigned)std::min<unsigned long long>((n + 256 * kHistPerThread - 1) / (256 * kHistPerThread), (unsigned long long)ctx->sm_count * 16);
     mpeg_first_pos<<<g, 256, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long*>(d_pos), d_hdr, n, ref_header,
                                                reinterpret_cast<unsigned long long*>(d_first));
     BLAST_CUDA_TRY(cudaGetLastError());

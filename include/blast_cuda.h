@@ -413,7 +413,8 @@ int  blast_mpeg_index_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, 
                           uint64_t* d_offsets_out, uint64_t cap, uint64_t* n_offsets_out, uint32_t* ref_header_out,
                           uint64_t* n_candidates_out);
 /* The same in separate steps (blast_mpeg_index_dev = scan + these four).  The histogram has BLAST_MPEG_HDR_BINS
- * uint32 bins indexed by the low 21 header bits (the 11 sync bits are fixed) and is ACCUMULATED into; the
+ * uint32 bins indexed by the low 21 header bits (the 11 sync bits are fixed) and is ACCUMULATED into (headers that
+ * parse_header rejects cannot win the vote and are not counted: their bins stay as they were); the
  * first-position table has BLAST_MPEG_HDR_BINS uint64 entries, initialised by the caller to all-ones, and is
  * min-reduced into.  Both may be summed / min-reduced across GPUs between the steps (one NCCL all-reduce each). */
 #define BLAST_MPEG_HDR_BINS (1u << 21)
