@@ -41,6 +41,8 @@ struct blast_ctx {
     uint64_t x128p_split_sub = 0;     // the sub-stream jump matrices J^(2^b) held in scratch slot 5
     int x128p_split_mats = 0;
     void* x128p_split_ptr = nullptr;
+    std::vector<uint8_t> tab8_copy;   // the 24-bit unpack's job table as last uploaded into scratch slot 8 (a batch that is
+    const void* tab8_ptr = nullptr;   // unpacked again — the same buffers, step after step — uploads nothing)
     int render_ctas_per_sm = 3;       // K4's persistent CTAs per SM (3 fit); lowered when several contexts that wait for
                                       // each other inside K4 share one GPU (blast_group over a repeated device id)
 };

@@ -70,6 +70,7 @@ void* scratch(blast_ctx* ctx, int slot, size_t bytes) {
         // slot 5 caches the RNG's sub-stream jump matrices: a new allocation may come back at the same address with
         // undefined contents, so the cache key (which includes the pointer) is dropped with the memory
         if (slot == 5) ctx->x128p_split_ptr = nullptr;
+        if (slot == 8) ctx->tab8_ptr = nullptr;
     }
     size_t want = (bytes + (bytes >> 2) + 255) & ~(size_t)255;      // 25 % head-room
     if (cudaMalloc(&ctx->scratch[slot], want) != cudaSuccess) {
@@ -152,6 +153,7 @@ int blast_ctx_trim(blast_ctx* ctx) {
         ctx->scratch_cap[i] = 0;
     }
     ctx->x128p_split_ptr = nullptr;                 // the cached jump matrices lived in scratch
+    ctx->tab8_ptr = nullptr;                        // and so did the cached 24-bit job table
     blast::release_pipe(ctx);
     return BLAST_OK;
 }

@@ -389,6 +389,7 @@ int blast_pcm_decode_dev(blast_ctx* ctx, const blast_pcm_job* jobs, uint32_t n_j
     JobDev* d_jobs = static_cast<JobDev*>(blast::scratch(ctx, 8, hj.size() * sizeof(JobDev)));
     TileRef* d_tiles = static_cast<TileRef*>(blast::scratch(ctx, 9, ht.size() * sizeof(TileRef)));
     if (!d_jobs || !d_tiles) return BLAST_ERR_CUDA;
+    ctx->tab8_ptr = nullptr;                                           // slot 8 no longer holds a 24-bit job table
     BLAST_CUDA_TRY(cudaMemcpyAsync(d_jobs, hj.data(), hj.size() * sizeof(JobDev), cudaMemcpyHostToDevice, ctx->stream));
     BLAST_CUDA_TRY(cudaMemcpyAsync(d_tiles, ht.data(), ht.size() * sizeof(TileRef), cudaMemcpyHostToDevice, ctx->stream));
     const int grid = (int)std::min<uint64_t>(ht.size(), (uint64_t)ctx->sm_count * kCtasPerSm);
@@ -556,7 +557,16 @@ int blast_pcm24_unpack_dev(blast_ctx* ctx, const blast_pcm24_job* jobs, uint32_t
     // pageable vector, which the runtime stages before cudaMemcpyAsync returns
     Job24Dev* d_jobs = static_cast<Job24Dev*>(blast::scratch(ctx, 8, hj.size() * sizeof(Job24Dev)));
     if (!d_jobs) return BLAST_ERR_CUDA;
-    BLAST_CUDA_TRY(cudaMemcpyAsync(d_jobs, hj.data(), hj.size() * sizeof(Job24Dev), cudaMemcpyHostToDevice, ctx->stream));
+    // the same batch again (the same buffers, step after step): the table in slot 8 is still the one uploaded last time
+    const size_t tab_bytes = hj.size() * sizeof(Job24Dev);
+    const bool same = ctx->tab8_ptr == d_jobs && ctx->tab8_copy.size() == tab_bytes &&
+                      memcmp(ctx->tab8_copy.data(), hj.data(), tab_bytes) == 0;
+    if (!same) {
+        ctx->tab8_ptr = nullptr;
+        BLAST_CUDA_TRY(cudaMemcpyAsync(d_jobs, hj.data(), tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->tab8_copy.assign(reinterpret_cast<const uint8_t*>(hj.data()), reinterpret_cast<const uint8_t*>(hj.data()) + tab_bytes);
+        ctx->tab8_ptr = d_jobs;
+    }
     const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * k24CtasPerSm);
     pcm24_unpack_batch<<<grid, k24Threads, 0, ctx->stream>>>(d_jobs, (uint32_t)hj.size(), (uint32_t)n_tiles);
     BLAST_CUDA_TRY(cudaGetLastError());

@@ -174,6 +174,46 @@ def test_pcm24_extension(ctx, be, kind):
         assert np.array_equal(got, exp)
 
 
+def test_pcm24_job_table_is_reused_only_when_identical(ctx):
+    """the job table of a batch that is unpacked again is not uploaded again (pcm_decode.cu: tab8_copy); a batch of
+    the same size with other buffers, a 16-bit decode in between (it shares the scratch slot) and the first batch
+    again must all come out right"""
+    rng = np.random.default_rng(41)
+    raws = [rng.integers(0, 256, size=3 * 9000 + 16, dtype=np.uint8) for _ in range(2)]
+    d_src = [ctx.to_device(r) for r in raws]
+    shapes = [(0, 5000), (3, 4000)]
+    sets = []
+    for which in (0, 1):
+        jobs, expect, bufs = [], [], []
+        for sa, n in shapes:
+            dst = ctx.alloc(n * 4)
+            bufs.append(dst)
+            jobs.append((d_src[which].ptr + sa, dst.ptr, n, True, 0))
+            expect.append(oracle.pcm24_unpack(raws[which][sa:sa + 3 * n], True))
+        sets.append((jobs, expect, bufs))
+
+    def run_and_check(k):
+        jobs, expect, bufs = sets[k]
+        for b, e in zip(bufs, expect):
+            b.upload(np.zeros(len(e), np.int32))
+        fp.pcm24_unpack_dev(ctx, jobs)
+        for b, e in zip(bufs, expect):
+            assert np.array_equal(b.download(np.int32, len(e)), e)
+
+    run_and_check(0)
+    run_and_check(0)                                      # identical table: no upload
+    run_and_check(1)                                      # same size, other buffers
+    img = synth.aiff_image(77, 3000)
+    fp.decode_batch(ctx, [img], [fp.probe("aiff", img)])  # the 16-bit path between two unpacks
+    wav = synth.wav_image(78, 2000)
+    d_img = ctx.to_device(wav)
+    d_out = ctx.alloc(4000)
+    desc = fp.probe("wav", wav)
+    fp.decode_jobs_dev(ctx, [(d_img.ptr + desc.data_off, d_out.ptr, desc.data_len // 2, False)])   # writes scratch slot 8
+    run_and_check(1)
+    run_and_check(0)
+
+
 def test_back_to_back_images_are_coalesced_and_still_exact(ctx):
     """an asset directory read into ONE host buffer: consecutive images are adjacent, so their copies travel
     coalesced (payload + the next file's header bytes in one cudaMemcpyAsync); separate buffers in between"""
