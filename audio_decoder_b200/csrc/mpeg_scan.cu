@@ -887,6 +887,98 @@ mpeg_classify(const unsigned long long* __restrict__ pos, const uint32_t* __rest
     }
 }
 
+// One pass for the duplicate-first table AND the per-block counts of the single-GPU index (blast_mpeg_index_dev with
+// reference_compat): the blocks are mpeg_classify's (kClsBlock consecutive candidates, eight per thread, 128-bit loads),
+// so the count pass of mpeg_classify is not needed — its counts are the valid candidates of the block (written here) plus
+// one per header value whose FIRST position lies in the block (mpeg_dup_blocks, once the table is complete).
+__global__ void __launch_bounds__(kClsThreads)
+mpeg_first_count(const unsigned long long* __restrict__ pos, const uint32_t* __restrict__ hdr, unsigned long long n,
+                 uint32_t ref_header, unsigned long long file_len, unsigned long long* __restrict__ first,
+                 unsigned long long* __restrict__ block_counts, uint32_t* __restrict__ err) {
+    __shared__ uint32_t s_lut[32];
+    __shared__ uint32_t s_key[kHotSlots];
+    __shared__ unsigned long long s_min[kHotSlots];
+    __shared__ uint32_t s_valid;
+    for (uint32_t i = threadIdx.x; i < kHotSlots; i += blockDim.x) { s_key[i] = 0xFFFFFFFFu; s_min[i] = ~0ull; }
+    if (threadIdx.x == 0) s_valid = 0u;
+    build_len_lut(ref_header, s_lut);                            // (ends with __syncthreads)
+    auto global_min = [&](uint32_t key, unsigned long long p) {
+        unsigned long long* slot = first + key;
+        if (*reinterpret_cast<volatile unsigned long long*>(slot) > p) atomicMin(slot, p);   // the table only ever decreases
+    };
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * kClsBlock + (unsigned long long)threadIdx.x * kClsPerThread;
+    uint32_t h8[kClsPerThread];
+    unsigned long long p8[kClsPerThread];
+    const bool aligned = (((unsigned long long)pos | (unsigned long long)hdr) & 15ull) == 0ull;
+    if (aligned && i0 + kClsPerThread <= n) {
+        const uint4* hv = reinterpret_cast<const uint4*>(hdr + i0);
+        const uint4 ha = hv[0], hb = hv[1];
+        h8[0] = ha.x; h8[1] = ha.y; h8[2] = ha.z; h8[3] = ha.w; h8[4] = hb.x; h8[5] = hb.y; h8[6] = hb.z; h8[7] = hb.w;
+        const ulonglong2* pv = reinterpret_cast<const ulonglong2*>(pos + i0);
+#pragma unroll
+        for (int k = 0; k < kClsPerThread / 2; ++k) { const ulonglong2 t = pv[k]; p8[2 * k] = t.x; p8[2 * k + 1] = t.y; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kClsPerThread; ++k) {
+            const bool in = i0 + k < n;
+            h8[k] = in ? hdr[i0 + k] : 0u;                       // 0 has no sync bits: never valid
+            p8[k] = in ? pos[i0 + k] : ~0ull;
+        }
+    }
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t mine = 0;
+    // a thread's eight candidates ascend, and so do the k-th candidates of the lanes: in each of the eight match rounds the
+    // lowest lane of a key holds the key's smallest position of the round
+#pragma unroll
+    for (int k = 0; k < kClsPerThread; ++k) {
+        uint32_t key = 0xFFFFFFFFu;
+        unsigned long long p = ~0ull;
+        uint32_t pl, sk;
+        if (i0 + k < n && cand_valid_lut(h8[k], ref_header, s_lut, pl, sk)) {
+            key = h8[k] & (kHdrBins - 1);
+            p = p8[k];
+            mine += 1;
+            if (p + sk + pl > file_len) atomicExch(err, 1u);            // mpeg.rs:95-97 indexes past EOF
+        }
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+        const int leader = __ffs(peers) - 1;
+        const unsigned long long p_lead = __shfl_sync(0xFFFFFFFFu, p, leader);
+        if (key != 0xFFFFFFFFu && ((int)lane == leader || p < p_lead)) {
+            uint32_t slot = (key * 2654435761u) >> 23;
+            bool done = false;
+#pragma unroll
+            for (int probe = 0; probe < 2 && !done; ++probe, slot ^= 1u) {
+                const uint32_t prev = atomicCAS(&s_key[slot], 0xFFFFFFFFu, key);
+                if (prev == 0xFFFFFFFFu || prev == key) { atomicMin(&s_min[slot], p); done = true; }
+            }
+            if (!done) global_min(key, p);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
+    if (lane == 0 && mine) atomicAdd(&s_valid, mine);
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < kHotSlots; k += blockDim.x)
+        if (s_key[k] != 0xFFFFFFFFu) global_min(s_key[k], s_min[k]);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = s_valid;
+}
+
+// every header value with a first position adds one output (the duplicate, mpeg.rs:39) to the block that holds the position:
+// the largest block whose first candidate is not behind it
+__global__ void mpeg_dup_blocks(const unsigned long long* __restrict__ first, const unsigned long long* __restrict__ pos,
+                                unsigned long long n, unsigned long long n_blocks, unsigned long long* __restrict__ block_counts) {
+    const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= kHdrBins) return;
+    const unsigned long long p = first[key];
+    if (p == ~0ull) return;
+    unsigned long long lo = 0, hi = n_blocks;                    // invariant: pos[lo * kClsBlock] <= p < pos[hi * kClsBlock] (hi == n_blocks: +inf)
+    while (hi - lo > 1) {
+        const unsigned long long mid = (lo + hi) / 2;
+        if (pos[mid * kClsBlock] <= p) lo = mid; else hi = mid;
+    }
+    atomicAdd(block_counts + lo, 1ull);
+}
+
 // exclusive scan of the block counts (one block of 1,024 threads; the array is small): per-thread sums, a two-level
 // shuffle scan across the block (one thread walking the 1,024 partial sums took 15 of the kernel's 39 us), per-thread write
 __global__ void mpeg_scan_blocks(const unsigned long long* __restrict__ counts, unsigned long long* __restrict__ base,
@@ -1103,6 +1195,46 @@ int blast_mpeg_scan_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, ui
     return run_scan(ctx, d_bytes, len, d_pos_out, d_hdr_out, cap, n_out);
 }
 
+// first-position table + per-block counts in ONE pass over the candidates, then the duplicates per block, the scan of the
+// counts and mpeg_classify's emit pass (blast_mpeg_classify_dev's count pass is not run)
+static int index_compat_fused(blast_ctx* ctx, const uint64_t* d_pos, const uint32_t* d_hdr, uint64_t n, uint32_t ref_header,
+                              uint64_t* d_first, uint64_t stream_len, uint64_t* d_offsets_out, uint64_t cap, uint64_t* n_offsets_out) {
+    const unsigned long long n_blocks = (n + kClsBlock - 1) / kClsBlock;
+    const size_t bc_b = (n_blocks * 8 + 255) & ~255ull;
+    uint8_t* s7 = static_cast<uint8_t*>(blast::scratch(ctx, 7, 2 * bc_b + 256));
+    unsigned long long* h_box = static_cast<unsigned long long*>(blast::mailbox(ctx));
+    if (!s7 || !h_box) return BLAST_ERR_CUDA;
+    h_box += 64;
+    unsigned long long* d_bc = reinterpret_cast<unsigned long long*>(s7);
+    unsigned long long* d_bb = reinterpret_cast<unsigned long long*>(s7 + bc_b);
+    unsigned long long* d_total = reinterpret_cast<unsigned long long*>(s7 + 2 * bc_b);
+    uint32_t* d_err = reinterpret_cast<uint32_t*>(d_total + 1);
+    BLAST_CUDA_TRY(cudaMemsetAsync(d_total, 0, 16, ctx->stream));
+    const unsigned long long* pos = reinterpret_cast<const unsigned long long*>(d_pos);
+    unsigned long long* first = reinterpret_cast<unsigned long long*>(d_first);
+    mpeg_first_count<<<(unsigned)n_blocks, kClsThreads, 0, ctx->stream>>>(pos, d_hdr, n, ref_header, stream_len, first, d_bc, d_err);
+    mpeg_dup_blocks<<<kHdrBins / 256, 256, 0, ctx->stream>>>(first, pos, n, n_blocks, d_bc);
+    mpeg_scan_blocks<<<1, 1024, 0, ctx->stream>>>(d_bc, d_bb, n_blocks, d_total);
+    BLAST_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 3;
+    BLAST_CUDA_TRY(cudaMemcpyAsync(h_box, d_total, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long total = h_box[0];
+    const uint32_t err = (uint32_t)h_box[1];
+    *n_offsets_out = total;
+    if (err)
+        return blast::set_error(BLAST_ERR_REF_PANIC, "a frame payload extends past the end of the file (mpeg.rs:96 indexes out of bounds)");
+    if (d_offsets_out) {
+        if (total > cap) return blast::set_error(BLAST_ERR_CAPACITY, "mpeg index: %llu offsets, capacity %llu", total, (unsigned long long)cap);
+        mpeg_classify<<<(unsigned)n_blocks, kClsThreads, 0, ctx->stream>>>(pos, d_hdr, n, ref_header, first, 1, stream_len, d_bc, d_bb, 1,
+                                                                         reinterpret_cast<unsigned long long*>(d_offsets_out), cap, d_err);
+        BLAST_CUDA_TRY(cudaGetLastError());
+        ctx->launches += 1;
+        BLAST_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return BLAST_OK;
+}
+
 int blast_mpeg_index_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, int reference_compat,
                          uint64_t* d_offsets_out, uint64_t cap, uint64_t* n_offsets_out, uint32_t* ref_header_out,
                          uint64_t* n_candidates_out) {
@@ -1144,10 +1276,9 @@ int blast_mpeg_index_dev(blast_ctx* ctx, const uint8_t* d_bytes, uint64_t len, i
     if (ref_header_out) *ref_header_out = ref_header;
     if (reference_compat) {
         BLAST_CUDA_TRY(cudaMemsetAsync(d_first, 0xFF, first_b, ctx->stream));
-        if ((rc = blast_mpeg_first_pos_dev(ctx, d_pos, d_hdr, n_cand, ref_header, d_first)) != BLAST_OK) return rc;
+        return index_compat_fused(ctx, d_pos, d_hdr, n_cand, ref_header, d_first, len, d_offsets_out, cap, n_offsets_out);
     }
-    return blast_mpeg_classify_dev(ctx, d_pos, d_hdr, n_cand, ref_header, reference_compat ? d_first : nullptr, len, d_offsets_out, cap,
-                                   n_offsets_out);
+    return blast_mpeg_classify_dev(ctx, d_pos, d_hdr, n_cand, ref_header, nullptr, len, d_offsets_out, cap, n_offsets_out);
 }
 
 // ---- sharded scan (SURVEY §8 e): one contiguous byte range per GPU, one small exchange between the two phases
