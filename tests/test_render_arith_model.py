@@ -112,3 +112,88 @@ def test_three_segments_in_a_common_unit(seed):
                 assert np.array_equal(frac, p - np.trunc(p))
                 n_checked += 1
     assert n_checked > 20
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The producer warp of K4: which lanes issue an item in a round, which pair up, which stage each item takes
+# (render.cu, issue_round) and which held tiles the voice's own lane may cut (the segment discovery of the lane-local cut).
+K_STAGES = 4
+
+
+def _issue_round_model(have: int, pairable: int, o: int):
+    """-> [(stage item index, first lane, second lane or None)] in issue order, as the 32 lanes compute it"""
+    items = []
+    lanes = {}
+    for lane in range(32):
+        lt = (1 << lane) - 1
+        is_pair = (pairable >> lane) & 1
+        second = bool(is_pair and (bin(pairable & lt).count("1") & 1))
+        above = pairable & ~lt & ~(1 << lane) & 0xFFFFFFFF
+        partner = ((above & -above).bit_length() - 1) if (is_pair and not second and above) else -1
+        lanes[lane] = (second, partner)
+    second_mask = sum(1 << l for l, (s, _) in lanes.items() if s)
+    item_mask = have & ~second_mask
+    for lane in range(32):
+        if (item_mask >> lane) & 1:
+            irank = bin(item_mask & ((1 << lane) - 1)).count("1")
+            items.append((o + irank, lane, lanes[lane][1] if lanes[lane][1] >= 0 else None))
+    return items
+
+
+def test_issue_round_pairs_and_stages():
+    rng = np.random.default_rng(77)
+    for _ in range(400):
+        have = int(rng.integers(0, 1 << 32))
+        pairable = int(rng.integers(0, 1 << 32)) & have
+        o = int(rng.integers(0, 1000))
+        got = _issue_round_model(have, pairable, o)
+        # the sequential rule it replaces: lanes in ascending order; a pairable lane takes the next pairable lane along
+        want, rest, k = [], have, o
+        while rest:
+            i = (rest & -rest).bit_length() - 1
+            rest &= rest - 1
+            i2 = None
+            if (pairable >> i) & 1:
+                cand = rest & pairable
+                if cand:
+                    i2 = (cand & -cand).bit_length() - 1
+                    rest &= ~(1 << i2)
+            want.append((k, i, i2))
+            k += 1
+        assert got == want
+        # the lanes of one wave (K_STAGES consecutive items) take distinct stages
+        for w0 in range(0, len(got), K_STAGES):
+            stages = [idx % K_STAGES for idx, _, _ in got[w0:w0 + K_STAGES]]
+            assert len(set(stages)) == len(stages)
+
+
+def _lane_local_discovery(step0s, seg_j, last_abs):
+    """cnt (1..3 segments that overlap the tile from seg_j on) and whether no further segment starts inside the tile"""
+    nseg = len(step0s)
+    cnt, nxt = 1, [0xFFFFFFFF] * 3
+    for t in (1, 2, 3):
+        if cnt == t and seg_j + t < nseg:
+            s0 = step0s[seg_j + t]
+            nxt[t - 1] = s0
+            if t < 3 and s0 <= last_abs:
+                cnt = t + 1
+    nxt_last = nxt[2] if cnt == 3 else (nxt[1] if cnt == 2 else nxt[0])
+    return cnt, nxt_last > last_abs
+
+
+def test_lane_local_segment_discovery():
+    rng = np.random.default_rng(5)
+    for _ in range(2000):
+        nseg = int(rng.integers(1, 9))
+        gaps = rng.integers(1, 1500, size=nseg - 1) if nseg > 1 else np.array([], dtype=np.int64)
+        step0s = [0] + list(np.cumsum(gaps).astype(int))
+        f0 = int(rng.integers(0, max(1, step0s[-1] + 500)))
+        nf = 2048
+        last_abs = f0 + nf - 1
+        seg_j = max(j for j in range(nseg) if step0s[j] <= f0)                 # the segment that holds the tile's first step
+        inside = [j for j in range(seg_j, nseg) if j == seg_j or step0s[j] <= last_abs]
+        cnt, covered = _lane_local_discovery(step0s, seg_j, last_abs)
+        if len(inside) <= 3:
+            assert (cnt, covered) == (len(inside), True)
+        else:
+            assert cnt == 3 and not covered
